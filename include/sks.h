@@ -1,0 +1,206 @@
+/*
+ * sks.h -- C ABI of the B200-native spaced k-mer sketch + ANI engine (libsks.so).
+ *
+ * This is the drop-in boundary for the reference's sketch-and-compare path.  The reference
+ * (bensonlzl/spaced-kmer-sketching) has no FFI of its own: its boundary is the C++ free-function
+ * API of src/kmer.hpp / src/fasta_processing.hpp / src/ani_estimator.hpp.  The C++ headers next to
+ * this file (include/kmer.hpp, ...) re-export that API with the reference's signatures and are
+ * implemented on top of the entry points below; every entry point names the reference interface it
+ * replaces (file:line under /root/reference).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types.
+ *   - every function that can fail returns an int status (SKS_OK == 0); sks_last_error() gives a
+ *     thread-local message.  Nothing here throws or exits.
+ *   - a 128-bit kmer_bitset value (src/kmer.hpp:27,37) crosses the ABI as uint64_t[2] = {bits 0..63,
+ *     bits 64..127}, the block order of boost::dynamic_bitset<unsigned long>.
+ *   - there is NO CPU fallback: compute entry points fail with SKS_ERR_CUDA when no device is usable.
+ */
+#ifndef SKS_H
+#define SKS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKS_VERSION 100
+
+/* status codes */
+#define SKS_OK 0
+#define SKS_ERR_INVALID 1   /* bad argument (the message says which)                         */
+#define SKS_ERR_CUDA 2      /* CUDA runtime / launch failure, or no device                   */
+#define SKS_ERR_CAPACITY 3  /* an output buffer was too small                                */
+#define SKS_ERR_MISMATCH 4  /* list lengths / set kinds differ (src/kmer_set.cpp:147-150)    */
+#define SKS_ERR_IO 5        /* unreadable file (src/fasta_processing.cpp:86-90)              */
+
+/* Sketching predicate: the recognised forms of `std::function<bool(const kmer)>`
+ * (src/kmer.hpp:93-103,195-212).  SKS_PRED_FMH is the driver's condition
+ * `frac_min_hash(nonce)(k) % modulus == 0` (src/kmer-sketching.cpp:29-34, src/kmer.hpp:135-149). */
+#define SKS_PRED_ALL 0
+#define SKS_PRED_FMH 1
+
+/* boost::hash_combine flavour behind frac_min_hash (the reference pins no Boost version). */
+#define SKS_HASH_BOOST_171 171 /* Boost 1.71 .. 1.80 */
+#define SKS_HASH_BOOST_181 181 /* Boost >= 1.81 (default) */
+
+/* Device representation of a kmer_set (src/kmer.hpp:160-190). */
+#define SKS_REPR_AUTO 0   /* SORTED for FMH, BITSET for ALL when weight <= 16, else SORTED      */
+#define SKS_REPR_SORTED 1 /* ascending distinct masked_bits, 8 B (window <= 32) or 16 B per key  */
+#define SKS_REPR_BITSET 2 /* 4^weight-bit presence bitset indexed by PEXT(masked_bits, mask)     */
+
+typedef struct sks_pred {
+  int32_t kind;         /* SKS_PRED_*                                   */
+  int32_t nonce;        /* frac_min_hash(int n), src/kmer.hpp:141        */
+  uint64_t modulus;     /* c in `fmh(k) % c == 0`; must be non-zero      */
+  int32_t hash_variant; /* SKS_HASH_BOOST_*; 0 selects the default (181) */
+  int32_t reserved;
+} sks_pred;
+
+typedef struct sks_ctx sks_ctx;     /* one per (thread, device): stream, scratch, timers */
+typedef struct sks_batch sks_batch; /* genomes resident in HBM, 2-bit packed + segment tables */
+typedef struct sks_set sks_set;     /* one device-resident kmer_set */
+
+/* ---- library / context --------------------------------------------------------------------- */
+int sks_version(void);
+const char *sks_last_error(void);
+int sks_device_count(void);
+/* Creates a context on CUDA device `device` with its own non-blocking stream. */
+int sks_ctx_create(int device, sks_ctx **out);
+void sks_ctx_destroy(sks_ctx *ctx);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all later work. */
+int sks_ctx_set_stream(sks_ctx *ctx, void *cuda_stream);
+int sks_ctx_sync(sks_ctx *ctx);
+/* CUDA-event timing on the context's stream: begin/end bracket a region, end returns ms. */
+int sks_timer_begin(sks_ctx *ctx);
+int sks_timer_end(sks_ctx *ctx, float *out_ms);
+/* Number of kernels launched by this context so far (bench.py's gpu_launches). */
+int64_t sks_ctx_launch_count(const sks_ctx *ctx);
+
+/* ---- host-side helpers: masks, packing, FASTA, ANI (no device needed) ------------------------ */
+/* Seed string in README notation ("11001011", README.md:25-41) -> 128-bit mask with two bits per
+ * used position; s[i]=='1' sets bits 2(w-1-i), 2(w-1-i)+1.  The reference has no parser. */
+int sks_seed_to_mask(const char *seed, uint64_t out_mask[2], int *out_window);
+/* mask.count() / NUCLEOTIDE_BIT_SIZE, src/kmer-sketching.cpp:164 */
+int sks_mask_weight(const uint64_t mask[2]);
+/* contiguous_kmer(k), src/kmer_bitset.cpp:51-56 (k > 64 -> SKS_ERR_INVALID) */
+int sks_contiguous_mask(int k, uint64_t out_mask[2]);
+/* generate_random_spaced_seed_mask, src/kmer_bitset.cpp:132-152 (libstdc++ shuffle + mt19937) */
+int sks_random_mask(int window, int k, uint64_t seed, uint64_t out_mask[2]);
+/* reverse_kmer_bitset, src/kmer_bitset.cpp:105-119 */
+void sks_reverse_bitset(const uint64_t in[2], uint64_t out[2]);
+/* frac_min_hash::operator(), src/kmer.hpp:144-148, on the host (for the C++ functor type). */
+uint64_t sks_fmh_hash(const uint64_t masked[2], const uint64_t mask[2], int window, int nonce,
+                      int hash_variant);
+/* containment / binomial_estimator, src/ani_estimation.cpp:24-42 (host double arithmetic) */
+double sks_containment(int intersection, int set_size);
+double sks_binomial_estimator(double containment, int kmer_num_ones);
+
+/* 2-bit packing: 16 bases per uint32 word, base i in bits 2(i%16)..2(i%16)+1 of word i/16.
+ * `codes` are the reference's 1-byte codes 0..3 (acgt_string, src/fasta_processing.hpp:18). */
+size_t sks_packed_words(uint64_t n_bases);
+int sks_pack_codes(const uint8_t *codes, uint64_t n_bases, uint32_t *out_words);
+int sks_unpack_codes(const uint32_t *words, uint64_t n_bases, uint8_t *out_codes);
+/* FASTA text -> packed bases + segment table with the reference's record and split rules
+ * (strings_from_fasta + cut_nucleotide_strings, src/fasta_processing.cpp:79-211).  Two-call
+ * protocol: with out_* NULL it only reports *n_bases / *n_segs.  Segments are the maximal ACGT
+ * runs in file order; their bases are packed back to back. */
+int sks_fasta_parse(const char *text, size_t n, uint64_t *n_bases, uint64_t *n_segs,
+                    uint32_t *out_words, uint64_t *out_seg_len);
+/* Same, reading the file; an unreadable file returns SKS_ERR_IO (the C++ wrapper turns that into
+ * the reference's stderr message + exit(1)). */
+int sks_fasta_parse_file(const char *path, uint64_t *n_bases, uint64_t *n_segs, uint32_t **out_words,
+                         uint64_t **out_seg_len); /* malloc'ed; release with sks_free */
+void sks_free(void *p);
+
+/* ---- batches: genomes in HBM ---------------------------------------------------------------- */
+/* Uploads n_genomes packed genomes (HOST buffers).  packed[g] holds sks_packed_words(n_bases[g])
+ * words; seg_len[g][0..n_segs[g]) are the ACGT-run lengths (NULL / 0 => one segment of n_bases).
+ * Replaces the host side of kmer_set_from_fasta_file up to the sliding loop
+ * (src/kmer_set.cpp:54-68). */
+int sks_batch_upload(sks_ctx *ctx, int n_genomes, const uint32_t *const *packed, const uint64_t *n_bases,
+                     const uint64_t *const *seg_len, const uint64_t *n_segs, sks_batch **out);
+/* Synthetic genomes generated ON DEVICE (benchmark inputs, SURVEY.md 4.2 KAT-3 generator):
+ * genome g = mutate(gen(n_bases, gen_seed[g]), mut_seed[g], mut_D[g]); mut_D[g]==0 => no mutation. */
+int sks_batch_synth(sks_ctx *ctx, int n_genomes, uint64_t n_bases, const uint64_t *gen_seed,
+                    const uint64_t *mut_seed, const uint64_t *mut_D, sks_batch **out);
+/* A window [first_base, first_base + n_starts + window - 1) of one genome of `src` as a new
+ * single-genome batch (position sharding of one long sequence with a (w-1)-base halo). */
+int sks_batch_slice(sks_ctx *ctx, const sks_batch *src, int genome, uint64_t first_base, uint64_t n_starts,
+                    int window, sks_batch **out);
+int sks_batch_n_genomes(const sks_batch *b);
+uint64_t sks_batch_n_bases(const sks_batch *b, int genome);
+/* D2H copy of one genome's packed words (tests). */
+int sks_batch_download(sks_ctx *ctx, const sks_batch *b, int genome, uint32_t *out_words);
+void sks_batch_destroy(sks_ctx *ctx, sks_batch *b);
+
+/* ---- sketching: the hot path ----------------------------------------------------------------- */
+/* For every genome of the batch: slide the spaced seed, canonicalise, filter, and build the set.
+ * Replaces nucleotide_string_list_to_kmers + kmer_set::insert_kmers
+ * (src/kmer_sliding.cpp:112-238, src/kmer.hpp:170-178) == the body of kmer_set_from_fasta_file
+ * (src/kmer_set.cpp:54-68) and its loop/cilk_for over files (:81-133).
+ * out_sets[0..n_genomes) receive new sets (release each with sks_set_destroy). */
+int sks_sketch(sks_ctx *ctx, const sks_batch *batch, const uint64_t mask[2], int window, const sks_pred *pred,
+               int repr, sks_set **out_sets);
+/* The ordered, duplicate-preserving list of nucleotide_string_list_to_kmers
+ * (src/kmer_sliding.cpp:224-238) for one genome: masked_bits and kmer_bits (2 words each) in sequence
+ * order.  Two-call protocol: out_* NULL => only *out_n is written. */
+int sks_kmer_list(sks_ctx *ctx, const sks_batch *batch, int genome, const uint64_t mask[2], int window,
+                  const sks_pred *pred, uint64_t *out_n, uint64_t *out_masked, uint64_t *out_bits,
+                  uint64_t capacity);
+
+/* ---- sets ------------------------------------------------------------------------------------ */
+int sks_set_repr(const sks_set *s);
+int sks_set_window(const sks_set *s);
+int sks_set_weight(const sks_set *s);
+/* kmer_set::kmer_set_size, src/kmer.hpp:186-189 */
+int sks_set_size(sks_ctx *ctx, sks_set *s, int64_t *out);
+/* Members as ascending 128-bit masked_bits (2 words per key), D2H.  For BITSET sets the indices are
+ * expanded back through the mask (PDEP).  capacity in keys. */
+int sks_set_keys(sks_ctx *ctx, sks_set *s, uint64_t *out_lohi, uint64_t capacity);
+/* Raw device view of a SORTED set (for collectives): pointer, key count, words (uint64) per key. */
+int sks_set_device_keys(sks_ctx *ctx, sks_set *s, const void **dptr, int64_t *n_keys, int *words_per_key);
+/* Builds a SORTED set from ascending distinct keys already on the device (copied). */
+int sks_set_from_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int words_per_key,
+                             const uint64_t mask[2], int window, sks_set **out);
+/* Builds a SORTED set from UNSORTED, possibly duplicated device keys (sort + unique on device);
+ * the merge step after an all-gather of per-rank partial sketches of one sequence. */
+int sks_set_from_unsorted_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int words_per_key,
+                                      const uint64_t mask[2], int window, sks_set **out);
+void sks_set_destroy(sks_ctx *ctx, sks_set *s);
+
+/* ---- comparison ------------------------------------------------------------------------------ */
+/* kmer_set_intersection, src/kmer_set.cpp:23-41 */
+int sks_intersect(sks_ctx *ctx, sks_set *a, sks_set *b, int64_t *out);
+/* (parallel_)compute_pairwise_kmer_set_intersections, src/kmer_set.cpp:143-184: out[i] =
+ * |a[i] n b[i]|; na != nb returns SKS_ERR_MISMATCH (the reference throws std::runtime_error). */
+int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *const *b, int64_t nb, int32_t *out);
+/* All n*n ordered pairs in generate_all_pairs_from_vector order (src/generators.hpp:44-58):
+ * out[i*n + j] = |sets[i] n sets[j]|.  Rows [row_begin, row_end) only (rank tiling); other
+ * entries are left untouched. */
+int sks_intersect_all_pairs(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end,
+                            int32_t *out);
+/* ANI matrix from counts, src/kmer-sketching.cpp:196-200: containment on the FIRST set of the
+ * ordered pair, then ^(1/weight).  Host double arithmetic. */
+void sks_ani_from_counts(const int32_t *intersections, const int32_t *first_set_sizes, int64_t n_pairs,
+                         int weight, double *out_ani);
+
+/* ---- one-call pair pipeline (bench / e2e) ---------------------------------------------------- */
+typedef struct sks_pair_result {
+  int64_t size_a, size_b, intersection;
+  double ani_ab, ani_ba; /* binomial_estimator(containment(I, |A|), weight), and with |B| */
+} sks_pair_result;
+/* HOST packed genomes in, counts + ANI out: upload, sketch both, intersect, sizes, ANI. */
+int sks_pair_ani(sks_ctx *ctx, const uint32_t *packed_a, uint64_t n_bases_a, const uint32_t *packed_b,
+                 uint64_t n_bases_b, const uint64_t mask[2], int window, const sks_pred *pred, int repr,
+                 sks_pair_result *out);
+/* Same on a resident 2-genome batch (inputs already in HBM). */
+int sks_pair_ani_resident(sks_ctx *ctx, const sks_batch *batch, const uint64_t mask[2], int window,
+                          const sks_pred *pred, int repr, sks_pair_result *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKS_H */

@@ -1,0 +1,857 @@
+// extern "C" entry points of libsks.so that touch the device: contexts, batches, sketching, sets,
+// intersections.  Host-only entry points live in sks_host.cpp.  See include/sks.h for the contract
+// and the reference interfaces each call replaces.
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "sks_internal.cuh"
+
+namespace sks {
+
+DeviceBuffer::~DeviceBuffer() {
+  if (ptr) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cur != device) cudaSetDevice(device);
+    if (cudaFreeAsync(ptr, stream) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(ptr);
+    }
+    if (cur != device) cudaSetDevice(cur);
+  }
+}
+
+int alloc_buffer(sks_ctx *ctx, size_t bytes, BufferRef *out) {
+  auto buf = std::make_shared<DeviceBuffer>();
+  if (bytes == 0) bytes = 16;
+  SKS_CUDA_TRY(cudaMallocAsync(&buf->ptr, bytes, ctx->stream));
+  buf->bytes = bytes;
+  buf->device = ctx->device;
+  buf->stream = ctx->stream;
+  *out = buf;
+  return SKS_OK;
+}
+
+int ctx_scratch(sks_ctx *ctx, size_t bytes, void **out) {
+  if (bytes > ctx->scratch_bytes) {
+    if (ctx->scratch) SKS_CUDA_TRY(cudaFreeAsync(ctx->scratch, ctx->stream));
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    SKS_CUDA_TRY(cudaMallocAsync(&ctx->scratch, want, ctx->stream));
+    ctx->scratch_bytes = want;
+  }
+  *out = ctx->scratch;
+  return SKS_OK;
+}
+
+int ctx_pinned(sks_ctx *ctx, size_t bytes, void **out) {
+  if (bytes > ctx->pinned_bytes) {
+    if (ctx->pinned) {
+      SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      SKS_CUDA_TRY(cudaFreeHost(ctx->pinned));
+    }
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+    const size_t want = bytes + 4096;
+    SKS_CUDA_TRY(cudaMallocHost(&ctx->pinned, want));
+    ctx->pinned_bytes = want;
+  }
+  *out = ctx->pinned;
+  return SKS_OK;
+}
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+// Lays genomes out in one word buffer: [kPreWords zero][genome 0 data, zero padded to 4 words]
+// [kPreWords zero][genome 1 ...] ...  Fills h_genomes / h_seg_end / n_tiles; returns total words.
+int layout_batch(sks_batch *b, int n_genomes, const uint64_t *n_bases, const uint64_t *const *seg_len,
+                 const uint64_t *n_segs, uint64_t *total_words) {
+  b->n_genomes = n_genomes;
+  b->h_genomes.resize(n_genomes);
+  b->h_seg_end.clear();
+  uint64_t off = 0, tiles = 0;
+  b->total_bases = 0;
+  for (int g = 0; g < n_genomes; ++g) {
+    if (n_bases[g] >= 0xFFFF0000ull)
+      return set_error(SKS_ERR_INVALID, "genome %d has %llu bases; the limit per genome is 2^32 - 2^16", g,
+                       (unsigned long long)n_bases[g]);
+    GenomeDesc &gd = b->h_genomes[g];
+    off += kPreWords;
+    gd.word_off = off;
+    gd.n_bases = (uint32_t)n_bases[g];
+    gd.n_words = (uint32_t)round_up((n_bases[g] + 15) / 16, 4);
+    off += gd.n_words;
+    gd.seg_first = (uint32_t)b->h_seg_end.size();
+    const uint64_t ns = (seg_len && seg_len[g] && n_segs) ? n_segs[g] : 0;
+    if (ns == 0) {
+      b->h_seg_end.push_back(gd.n_bases);
+      gd.n_segs = 1;
+    } else {
+      uint64_t e = 0;
+      for (uint64_t s = 0; s < ns; ++s) {
+        e += seg_len[g][s];
+        b->h_seg_end.push_back((uint32_t)e);
+      }
+      if (e != n_bases[g])
+        return set_error(SKS_ERR_INVALID, "genome %d: segment lengths sum to %llu, expected %llu bases", g,
+                         (unsigned long long)e, (unsigned long long)n_bases[g]);
+      gd.n_segs = (uint32_t)ns;
+    }
+    gd.tile_first = (uint32_t)tiles;
+    gd.n_tiles = (uint32_t)((n_bases[g] + kTileWindows - 1) / kTileWindows);
+    tiles += gd.n_tiles;
+    b->total_bases += n_bases[g];
+  }
+  off += kPreWords + kPostWords;
+  if (tiles >= 0xFFFFFFFFull) return set_error(SKS_ERR_INVALID, "batch too large (%llu tiles)", (unsigned long long)tiles);
+  b->n_tiles = (uint32_t)tiles;
+  *total_words = off;
+  return SKS_OK;
+}
+
+int upload_tables(sks_ctx *ctx, sks_batch *b) {
+  const int G = b->n_genomes;
+  SKS_TRY(alloc_buffer(ctx, sizeof(GenomeDesc) * (size_t)std::max(G, 1), &b->genomes));
+  SKS_TRY(alloc_buffer(ctx, 4 * std::max<size_t>(b->h_seg_end.size(), 1), &b->seg_end));
+  if (G > 0)
+    SKS_CUDA_TRY(cudaMemcpyAsync(b->genomes->ptr, b->h_genomes.data(), sizeof(GenomeDesc) * G, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+  if (!b->h_seg_end.empty())
+    SKS_CUDA_TRY(cudaMemcpyAsync(b->seg_end->ptr, b->h_seg_end.data(), 4 * b->h_seg_end.size(), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+  if (G > 1 && b->n_tiles > 0) {
+    std::vector<uint32_t> tg(b->n_tiles);
+    for (int g = 0; g < G; ++g)
+      std::fill(tg.begin() + b->h_genomes[g].tile_first, tg.begin() + b->h_genomes[g].tile_first + b->h_genomes[g].n_tiles,
+                (uint32_t)g);
+    SKS_TRY(alloc_buffer(ctx, 4 * (size_t)b->n_tiles, &b->tile_genome));
+    SKS_CUDA_TRY(cudaMemcpyAsync(b->tile_genome->ptr, tg.data(), 4 * (size_t)b->n_tiles, cudaMemcpyHostToDevice, ctx->stream));
+    SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // tg is a local
+  }
+  return SKS_OK;
+}
+
+// Number of windows a genome can yield: sum over segments of max(0, len - w + 1)
+// (src/kmer_sliding.cpp:121-125,144).
+uint64_t genome_windows(const sks_batch *b, int g, int w) {
+  const GenomeDesc &gd = b->h_genomes[g];
+  uint64_t total = 0, prev = 0;
+  for (uint32_t s = 0; s < gd.n_segs; ++s) {
+    const uint64_t e = b->h_seg_end[gd.seg_first + s], len = e - prev;
+    if (len >= (uint64_t)w) total += len - w + 1;
+    prev = e;
+  }
+  return total;
+}
+
+struct SketchPlan {
+  int n_limbs, pred_mode, weight;
+  SketchParams p;
+};
+
+int make_plan(const sks_batch *batch, const uint64_t mask[2], int window, const sks_pred *pred, SketchPlan *plan) {
+  if (!batch || !mask || !pred) return set_error(SKS_ERR_INVALID, "null argument");
+  if (window < 1 || window > 64) return set_error(SKS_ERR_INVALID, "window length %d outside 1..64", window);
+  if (window < 64) {
+    const unsigned __int128 m = ((unsigned __int128)mask[1] << 64) | mask[0];
+    if (m >> (2 * window)) return set_error(SKS_ERR_INVALID, "mask has bits at or above 2*window");
+  }
+  memset(&plan->p, 0, sizeof(plan->p));
+  SketchParams &p = plan->p;
+  plan->n_limbs = (2 * window + 31) / 32;
+  plan->weight = sks_mask_weight(mask);
+  p.words = static_cast<const uint32_t *>(batch->words->ptr);
+  p.genomes = static_cast<const GenomeDesc *>(batch->genomes->ptr);
+  p.seg_end = static_cast<const uint32_t *>(batch->seg_end->ptr);
+  p.n_genomes = batch->n_genomes;
+  p.n_tiles = batch->n_tiles;
+  p.window = window;
+  p.mask[0] = (uint32_t)mask[0];
+  p.mask[1] = (uint32_t)(mask[0] >> 32);
+  p.mask[2] = (uint32_t)mask[1];
+  p.mask[3] = (uint32_t)(mask[1] >> 32);
+  if (pred->kind == SKS_PRED_ALL) {
+    plan->pred_mode = PRED_ALL;
+  } else if (pred->kind == SKS_PRED_FMH) {
+    if (pred->modulus == 0) return set_error(SKS_ERR_INVALID, "FracMinHash modulus must be non-zero");
+    const int variant = pred->hash_variant == 0 ? SKS_HASH_BOOST_181 : pred->hash_variant;
+    if (variant != SKS_HASH_BOOST_171 && variant != SKS_HASH_BOOST_181)
+      return set_error(SKS_ERR_INVALID, "unknown hash variant %d", pred->hash_variant);
+    plan->pred_mode = variant == SKS_HASH_BOOST_171 ? PRED_FMH171 : PRED_FMH181;
+    // frac_min_hash::operator(), src/kmer.hpp:146: everything but H(masked_bits) is constant per launch
+    p.hconst = boost_hash_bitset(mask[0], mask[1], variant) ^ (uint64_t)(int64_t)window ^ (uint64_t)(int64_t)pred->nonce;
+    modulus_magic(pred->modulus, &p.minv, &p.mbound, &p.mshift);
+  } else {
+    return set_error(SKS_ERR_INVALID, "unknown predicate kind %d", pred->kind);
+  }
+  return SKS_OK;
+}
+
+sks_set *new_set(const sks_ctx *ctx, int repr, const uint64_t mask[2], int window, int weight) {
+  sks_set *s = new (std::nothrow) sks_set();
+  if (!s) return nullptr;
+  s->device = ctx->device;
+  s->repr = repr;
+  s->window = window;
+  s->weight = weight;
+  s->mask[0] = mask[0];
+  s->mask[1] = mask[1];
+  return s;
+}
+
+int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const uint64_t mask[2], int window,
+                  sks_set **out_sets) {
+  int index_bits = 0;
+  SKS_TRY(build_pext_table(mask, plan.n_limbs, &plan.p.pext, &index_bits));
+  const int G = batch->n_genomes;
+  const uint64_t bits = 1ull << index_bits;           // 4^weight
+  const uint64_t words = bits < 32 ? 1 : bits / 32;   // per genome
+  BufferRef buf;
+  SKS_TRY(alloc_buffer(ctx, (size_t)words * 4 * G, &buf));
+  SKS_TRY(launch_fill_zero(ctx, buf->ptr, (size_t)words * 4 * G));
+  plan.p.bitset = static_cast<uint32_t *>(buf->ptr);
+  plan.p.bitset_words = words;
+  SKS_TRY(launch_sketch(ctx, plan.p, batch->tile_genome ? static_cast<const uint32_t *>(batch->tile_genome->ptr) : nullptr,
+                        plan.n_limbs, plan.pred_mode, OUT_BITSET));
+  for (int g = 0; g < G; ++g) {
+    sks_set *s = new_set(ctx, SKS_REPR_BITSET, mask, window, plan.weight);
+    if (!s) return set_error(SKS_ERR_INVALID, "out of host memory");
+    s->buf = buf;
+    s->byte_off = (size_t)g * words * 4;
+    s->bitset_words = words;
+    s->count = -1;
+    out_sets[g] = s;
+  }
+  return SKS_OK;
+}
+
+// Runs the sketch kernel in OUT_KEYS / OUT_LIST mode into per-genome regions; re-runs once with
+// exact capacities when a region overflowed.  Leaves raw keys (unsorted, duplicated) in *keys.
+int sketch_raw_keys(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const sks_pred *pred, int window,
+                    int out_mode, BufferRef *keys, BufferRef *pos, std::vector<uint64_t> *off,
+                    std::vector<uint64_t> *count, uint64_t *span) {
+  const int G = batch->n_genomes;
+  const int key_words = plan.n_limbs <= 2 ? 1 : 2;
+  std::vector<uint64_t> cap(G);
+  for (int g = 0; g < G; ++g) {
+    const uint64_t wins = genome_windows(batch, g, window);
+    uint64_t c = wins;
+    if (plan.pred_mode != PRED_ALL && pred->modulus > 1) {
+      const double expect = (double)wins / (double)pred->modulus;
+      c = std::min<uint64_t>(wins, (uint64_t)(expect * 1.25) + 1024);
+    }
+    cap[g] = c;
+  }
+  off->assign(G, 0);
+  count->assign(G, 0);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    uint64_t total = 0;
+    for (int g = 0; g < G; ++g) {
+      (*off)[g] = total;
+      total += cap[g];
+    }
+    *span = total;
+    SKS_TRY(alloc_buffer(ctx, (size_t)total * 8 * key_words, keys));
+    if (out_mode == OUT_LIST) SKS_TRY(alloc_buffer(ctx, (size_t)total * 4, pos));
+    // device tables: off | cap | count
+    char *tab = nullptr;
+    SKS_TRY(ctx_scratch(ctx, (size_t)G * 24 + 64, reinterpret_cast<void **>(&tab)));
+    uint64_t *d_off = reinterpret_cast<uint64_t *>(tab), *d_cap = d_off + G;
+    unsigned long long *d_count = reinterpret_cast<unsigned long long *>(d_cap + G);
+    char *stage = nullptr;
+    SKS_TRY(ctx_pinned(ctx, (size_t)G * 24, reinterpret_cast<void **>(&stage)));
+    memcpy(stage, off->data(), (size_t)G * 8);
+    memcpy(stage + (size_t)G * 8, cap.data(), (size_t)G * 8);
+    memset(stage + (size_t)G * 16, 0, (size_t)G * 8);
+    SKS_CUDA_TRY(cudaMemcpyAsync(tab, stage, (size_t)G * 24, cudaMemcpyHostToDevice, ctx->stream));
+    plan.p.out_keys = (*keys)->ptr;
+    plan.p.out_pos = out_mode == OUT_LIST ? static_cast<uint32_t *>((*pos)->ptr) : nullptr;
+    plan.p.out_off = d_off;
+    plan.p.out_cap = d_cap;
+    plan.p.out_count = d_count;
+    SKS_TRY(launch_sketch(ctx, plan.p, batch->tile_genome ? static_cast<const uint32_t *>(batch->tile_genome->ptr) : nullptr,
+                          plan.n_limbs, plan.pred_mode, out_mode));
+    SKS_CUDA_TRY(cudaMemcpyAsync(stage, d_count, (size_t)G * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    memcpy(count->data(), stage, (size_t)G * 8);
+    bool overflow = false;
+    for (int g = 0; g < G; ++g)
+      if ((*count)[g] > cap[g]) overflow = true;
+    if (!overflow) return SKS_OK;
+    for (int g = 0; g < G; ++g) cap[g] = std::max(cap[g], (*count)[g]);  // counts are exact even past cap
+  }
+  return set_error(SKS_ERR_CAPACITY, "sketch output overflowed twice");
+}
+
+int sketch_sorted(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const sks_pred *pred,
+                  const uint64_t mask[2], int window, sks_set **out_sets) {
+  const int G = batch->n_genomes;
+  const int key_words = plan.n_limbs <= 2 ? 1 : 2;
+  BufferRef raw, pos, uniq;
+  std::vector<uint64_t> off, count, uoff, ucount;
+  uint64_t span = 0;
+  SKS_TRY(sketch_raw_keys(ctx, batch, plan, pred, window, OUT_KEYS, &raw, &pos, &off, &count, &span));
+  SKS_TRY(sort_unique_regions(ctx, key_words, raw->ptr, off.data(), count.data(), G, span, &uniq, &uoff, &ucount));
+  for (int g = 0; g < G; ++g) {
+    sks_set *s = new_set(ctx, SKS_REPR_SORTED, mask, window, plan.weight);
+    if (!s) return set_error(SKS_ERR_INVALID, "out of host memory");
+    s->buf = uniq;
+    s->key_words = key_words;
+    s->byte_off = (size_t)uoff[g] * 8 * key_words;
+    s->count = (int64_t)ucount[g];
+    out_sets[g] = s;
+  }
+  return SKS_OK;
+}
+
+int check_pair(const sks_set *a, const sks_set *b) {
+  if (!a || !b) return set_error(SKS_ERR_INVALID, "null set");
+  if (a->repr != b->repr || a->window != b->window || a->mask[0] != b->mask[0] || a->mask[1] != b->mask[1] ||
+      a->key_words != b->key_words || a->device != b->device)
+    return set_error(SKS_ERR_MISMATCH, "sets were built with different masks, windows, representations or devices");
+  return SKS_OK;
+}
+
+}  // namespace
+}  // namespace sks
+
+using namespace sks;
+
+extern "C" {
+
+int sks_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int sks_ctx_create(int device, sks_ctx **out) {
+  if (!out) return set_error(SKS_ERR_INVALID, "null argument");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return set_error(SKS_ERR_CUDA, "no CUDA device is available; libsks has no CPU fallback");
+  }
+  if (device < 0 || device >= n) return set_error(SKS_ERR_INVALID, "device %d outside 0..%d", device, n - 1);
+  SKS_CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SKS_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return set_error(SKS_ERR_CUDA, "device %d is sm_%d%d; libsks is built for sm_100a (B200) only", device, prop.major,
+                     prop.minor);
+  sks_ctx *ctx = new (std::nothrow) sks_ctx();
+  if (!ctx) return set_error(SKS_ERR_INVALID, "out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  SKS_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  SKS_CUDA_TRY(cudaEventCreate(&ctx->ev0));
+  SKS_CUDA_TRY(cudaEventCreate(&ctx->ev1));
+  // keep freed blocks cached in the stream-ordered pool: steady-state calls allocate nothing
+  cudaMemPool_t pool;
+  SKS_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t threshold = UINT64_MAX;
+  SKS_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  *out = ctx;
+  return SKS_OK;
+}
+
+void sks_ctx_destroy(sks_ctx *ctx) {
+  if (!ctx) return;
+  DeviceGuard guard(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->scratch) cudaFreeAsync(ctx->scratch, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int sks_ctx_set_stream(sks_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return set_error(SKS_ERR_INVALID, "null context");
+  DeviceGuard guard(ctx->device);
+  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (ctx->scratch) {
+    SKS_CUDA_TRY(cudaFreeAsync(ctx->scratch, ctx->stream));
+    SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+  }
+  if (ctx->owns_stream && ctx->stream) SKS_CUDA_TRY(cudaStreamDestroy(ctx->stream));
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  ctx->owns_stream = false;
+  return SKS_OK;
+}
+
+int sks_ctx_sync(sks_ctx *ctx) {
+  if (!ctx) return set_error(SKS_ERR_INVALID, "null context");
+  DeviceGuard guard(ctx->device);
+  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return SKS_OK;
+}
+
+int sks_timer_begin(sks_ctx *ctx) {
+  DeviceGuard guard(ctx->device);
+  SKS_CUDA_TRY(cudaEventRecord(ctx->ev0, ctx->stream));
+  return SKS_OK;
+}
+int sks_timer_end(sks_ctx *ctx, float *out_ms) {
+  DeviceGuard guard(ctx->device);
+  SKS_CUDA_TRY(cudaEventRecord(ctx->ev1, ctx->stream));
+  SKS_CUDA_TRY(cudaEventSynchronize(ctx->ev1));
+  SKS_CUDA_TRY(cudaEventElapsedTime(out_ms, ctx->ev0, ctx->ev1));
+  return SKS_OK;
+}
+int64_t sks_ctx_launch_count(const sks_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- batches -------------------------------------------------------------------------------------
+int sks_batch_upload(sks_ctx *ctx, int n_genomes, const uint32_t *const *packed, const uint64_t *n_bases,
+                     const uint64_t *const *seg_len, const uint64_t *n_segs, sks_batch **out) {
+  if (!ctx || !out || n_genomes < 0 || (n_genomes > 0 && (!packed || !n_bases)))
+    return set_error(SKS_ERR_INVALID, "bad argument");
+  DeviceGuard guard(ctx->device);
+  sks_batch *b = new (std::nothrow) sks_batch();
+  if (!b) return set_error(SKS_ERR_INVALID, "out of host memory");
+  b->device = ctx->device;
+  uint64_t total_words = 0;
+  int st = layout_batch(b, n_genomes, n_bases, seg_len, n_segs, &total_words);
+  if (st == SKS_OK) st = alloc_buffer(ctx, (size_t)total_words * 4, &b->words);
+  if (st == SKS_OK) {
+    uint32_t *d = static_cast<uint32_t *>(b->words->ptr);
+    // zero only the pads (history words, 16-byte rounding, halo); the data words are overwritten
+    uint64_t prev_end = 0;
+    auto fail = [&](cudaError_t e) { return e == cudaSuccess ? SKS_OK : set_error(SKS_ERR_CUDA, "batch upload: %s", cudaGetErrorString(e)); };
+    for (int g = 0; g < n_genomes && st == SKS_OK; ++g) {
+      const GenomeDesc &gd = b->h_genomes[g];
+      const uint64_t data_words = (n_bases[g] + 15) / 16;
+      st = fail(cudaMemsetAsync(d + prev_end, 0, (gd.word_off - prev_end) * 4, ctx->stream));
+      if (st == SKS_OK && data_words)
+        st = fail(cudaMemcpyAsync(d + gd.word_off, packed[g], data_words * 4, cudaMemcpyHostToDevice, ctx->stream));
+      prev_end = gd.word_off + data_words;
+    }
+    if (st == SKS_OK) st = fail(cudaMemsetAsync(d + prev_end, 0, (total_words - prev_end) * 4, ctx->stream));
+  }
+  if (st == SKS_OK) st = upload_tables(ctx, b);
+  if (st != SKS_OK) {
+    delete b;
+    return st;
+  }
+  *out = b;
+  return SKS_OK;
+}
+
+int sks_batch_synth(sks_ctx *ctx, int n_genomes, uint64_t n_bases, const uint64_t *gen_seed, const uint64_t *mut_seed,
+                    const uint64_t *mut_D, sks_batch **out) {
+  if (!ctx || !out || n_genomes < 0 || (n_genomes > 0 && (!gen_seed || !mut_seed || !mut_D)))
+    return set_error(SKS_ERR_INVALID, "bad argument");
+  DeviceGuard guard(ctx->device);
+  sks_batch *b = new (std::nothrow) sks_batch();
+  if (!b) return set_error(SKS_ERR_INVALID, "out of host memory");
+  b->device = ctx->device;
+  std::vector<uint64_t> nb(n_genomes, n_bases);
+  uint64_t total_words = 0;
+  int st = layout_batch(b, n_genomes, nb.data(), nullptr, nullptr, &total_words);
+  if (st == SKS_OK) st = alloc_buffer(ctx, (size_t)total_words * 4, &b->words);
+  if (st == SKS_OK) st = launch_fill_zero(ctx, b->words->ptr, (size_t)total_words * 4);
+  if (st == SKS_OK) st = upload_tables(ctx, b);
+  if (st == SKS_OK && n_genomes > 0) {
+    uint64_t *d_seeds = nullptr;
+    st = ctx_scratch(ctx, (size_t)n_genomes * 24, reinterpret_cast<void **>(&d_seeds));
+    auto cp = [&](uint64_t *dst, const uint64_t *src) {
+      return cudaMemcpyAsync(dst, src, (size_t)n_genomes * 8, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+    };
+    if (st == SKS_OK && !(cp(d_seeds, gen_seed) && cp(d_seeds + n_genomes, mut_seed) && cp(d_seeds + 2 * n_genomes, mut_D)))
+      st = set_error(SKS_ERR_CUDA, "seed upload failed");
+    if (st == SKS_OK)
+      st = launch_synth(ctx, static_cast<uint32_t *>(b->words->ptr), static_cast<const GenomeDesc *>(b->genomes->ptr),
+                        n_genomes, b->h_genomes[0].n_words, d_seeds, d_seeds + n_genomes, d_seeds + 2 * n_genomes);
+    if (st == SKS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = set_error(SKS_ERR_CUDA, "synth failed");
+  }
+  if (st != SKS_OK) {
+    delete b;
+    return st;
+  }
+  *out = b;
+  return SKS_OK;
+}
+
+int sks_batch_n_genomes(const sks_batch *b) { return b ? b->n_genomes : 0; }
+uint64_t sks_batch_n_bases(const sks_batch *b, int genome) {
+  return (b && genome >= 0 && genome < b->n_genomes) ? b->h_genomes[genome].n_bases : 0;
+}
+
+int sks_batch_download(sks_ctx *ctx, const sks_batch *b, int genome, uint32_t *out_words) {
+  if (!ctx || !b || genome < 0 || genome >= b->n_genomes || !out_words) return set_error(SKS_ERR_INVALID, "bad argument");
+  DeviceGuard guard(ctx->device);
+  const GenomeDesc &gd = b->h_genomes[genome];
+  const uint64_t data_words = ((uint64_t)gd.n_bases + 15) / 16;
+  SKS_CUDA_TRY(cudaMemcpyAsync(out_words, static_cast<const uint32_t *>(b->words->ptr) + gd.word_off, data_words * 4,
+                               cudaMemcpyDeviceToHost, ctx->stream));
+  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return SKS_OK;
+}
+
+int sks_batch_slice(sks_ctx *ctx, const sks_batch *src, int genome, uint64_t first_base, uint64_t n_starts, int window,
+                    sks_batch **out) {
+  if (!ctx || !src || !out || genome < 0 || genome >= src->n_genomes || window < 1 || window > 64)
+    return set_error(SKS_ERR_INVALID, "bad argument");
+  if (first_base % 16 != 0) return set_error(SKS_ERR_INVALID, "slice start must be a multiple of 16 bases");
+  DeviceGuard guard(ctx->device);
+  const GenomeDesc &sg = src->h_genomes[genome];
+  if (first_base > sg.n_bases) first_base = sg.n_bases - sg.n_bases % 16;
+  uint64_t end = first_base + n_starts + window - 1;  // exclusive: the (w-1)-base halo after the last start
+  if (end > sg.n_bases || n_starts == 0) end = n_starts == 0 ? first_base : sg.n_bases;
+  const uint64_t nb = end - first_base;
+  // segments clipped to [first_base, end)
+  std::vector<uint64_t> segs;
+  uint64_t prev = 0;
+  for (uint32_t s = 0; s < sg.n_segs; ++s) {
+    const uint64_t e = src->h_seg_end[sg.seg_first + s];
+    const uint64_t lo = std::max<uint64_t>(prev, first_base), hi = std::min<uint64_t>(e, end);
+    if (hi > lo) segs.push_back(hi - lo);
+    prev = e;
+  }
+  sks_batch *b = new (std::nothrow) sks_batch();
+  if (!b) return set_error(SKS_ERR_INVALID, "out of host memory");
+  b->device = ctx->device;
+  const uint64_t *seg_ptr = segs.data();
+  const uint64_t ns = segs.size();
+  uint64_t total_words = 0;
+  int st = layout_batch(b, 1, &nb, ns ? &seg_ptr : nullptr, ns ? &ns : nullptr, &total_words);
+  if (st == SKS_OK) st = alloc_buffer(ctx, (size_t)total_words * 4, &b->words);
+  if (st == SKS_OK) st = launch_fill_zero(ctx, b->words->ptr, (size_t)total_words * 4);
+  if (st == SKS_OK && nb > 0) {
+    const uint64_t data_words = (nb + 15) / 16;
+    if (cudaMemcpyAsync(static_cast<uint32_t *>(b->words->ptr) + b->h_genomes[0].word_off,
+                        static_cast<const uint32_t *>(src->words->ptr) + sg.word_off + first_base / 16, data_words * 4,
+                        cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+      st = set_error(SKS_ERR_CUDA, "slice copy failed");
+  }
+  if (st == SKS_OK) st = upload_tables(ctx, b);
+  if (st != SKS_OK) {
+    delete b;
+    return st;
+  }
+  *out = b;
+  return SKS_OK;
+}
+
+void sks_batch_destroy(sks_ctx *ctx, sks_batch *b) {
+  (void)ctx;
+  delete b;
+}
+
+// ---- sketching -----------------------------------------------------------------------------------
+int sks_sketch(sks_ctx *ctx, const sks_batch *batch, const uint64_t mask[2], int window, const sks_pred *pred, int repr,
+               sks_set **out_sets) {
+  if (!ctx || !out_sets) return set_error(SKS_ERR_INVALID, "null argument");
+  DeviceGuard guard(ctx->device);
+  SketchPlan plan;
+  SKS_TRY(make_plan(batch, mask, window, pred, &plan));
+  if (batch->device != ctx->device) return set_error(SKS_ERR_INVALID, "batch lives on another device");
+  if (repr == SKS_REPR_AUTO)
+    repr = (pred->kind == SKS_PRED_ALL && plan.weight <= 16) ? SKS_REPR_BITSET : SKS_REPR_SORTED;
+  for (int g = 0; g < batch->n_genomes; ++g) out_sets[g] = nullptr;
+  int st;
+  if (repr == SKS_REPR_BITSET) {
+    if (plan.weight > 16)
+      return set_error(SKS_ERR_INVALID, "bitset representation needs weight <= 16 (4^%d bits do not fit)", plan.weight);
+    st = sketch_bitset(ctx, batch, plan, mask, window, out_sets);
+  } else if (repr == SKS_REPR_SORTED) {
+    st = sketch_sorted(ctx, batch, plan, pred, mask, window, out_sets);
+  } else {
+    return set_error(SKS_ERR_INVALID, "unknown representation %d", repr);
+  }
+  if (st != SKS_OK)
+    for (int g = 0; g < batch->n_genomes; ++g) {
+      delete out_sets[g];
+      out_sets[g] = nullptr;
+    }
+  return st;
+}
+
+// ---- sets ----------------------------------------------------------------------------------------
+int sks_set_repr(const sks_set *s) { return s ? s->repr : 0; }
+int sks_set_window(const sks_set *s) { return s ? s->window : 0; }
+int sks_set_weight(const sks_set *s) { return s ? s->weight : 0; }
+
+int sks_set_size(sks_ctx *ctx, sks_set *s, int64_t *out) {
+  if (!ctx || !s || !out) return set_error(SKS_ERR_INVALID, "null argument");
+  if (s->count < 0) {
+    DeviceGuard guard(ctx->device);
+    unsigned long long *d_cnt = nullptr, *h_cnt = nullptr;
+    SKS_TRY(ctx_scratch(ctx, 64, reinterpret_cast<void **>(&d_cnt)));
+    SKS_TRY(ctx_pinned(ctx, 64, reinterpret_cast<void **>(&h_cnt)));
+    SKS_TRY(launch_bitset_popcount(ctx, reinterpret_cast<const uint32_t *>(static_cast<const char *>(s->buf->ptr) + s->byte_off),
+                                   s->bitset_words, d_cnt));
+    SKS_CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    s->count = (int64_t)h_cnt[0];
+  }
+  *out = s->count;
+  return SKS_OK;
+}
+
+int sks_set_keys(sks_ctx *ctx, sks_set *s, uint64_t *out_lohi, uint64_t capacity) {
+  if (!ctx || !s || (!out_lohi && capacity)) return set_error(SKS_ERR_INVALID, "null argument");
+  DeviceGuard guard(ctx->device);
+  int64_t n = 0;
+  SKS_TRY(sks_set_size(ctx, s, &n));
+  if ((uint64_t)n > capacity) return set_error(SKS_ERR_CAPACITY, "set has %lld keys, capacity %llu", (long long)n, (unsigned long long)capacity);
+  const char *base = static_cast<const char *>(s->buf->ptr) + s->byte_off;
+  if (s->repr == SKS_REPR_SORTED) {
+    if (n == 0) return SKS_OK;
+    if (s->key_words == 2) {
+      SKS_CUDA_TRY(cudaMemcpyAsync(out_lohi, base, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+      SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    } else {
+      std::vector<uint64_t> tmp((size_t)n);
+      SKS_CUDA_TRY(cudaMemcpyAsync(tmp.data(), base, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      for (int64_t i = 0; i < n; ++i) {
+        out_lohi[2 * i] = tmp[(size_t)i];
+        out_lohi[2 * i + 1] = 0;
+      }
+    }
+    return SKS_OK;
+  }
+  // BITSET: download and expand set bits through the mask (PDEP); ascending index == ascending key
+  std::vector<uint32_t> words((size_t)s->bitset_words);
+  SKS_CUDA_TRY(cudaMemcpyAsync(words.data(), base, (size_t)s->bitset_words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  int bitpos[128], nb = 0;
+  for (int b = 0; b < 128; ++b)
+    if ((s->mask[b >> 6] >> (b & 63)) & 1) bitpos[nb++] = b;
+  uint64_t k = 0;
+  for (uint64_t wi = 0; wi < s->bitset_words; ++wi) {
+    uint32_t v = words[(size_t)wi];
+    while (v) {
+      const int bit = __builtin_ctz(v);
+      v &= v - 1;
+      const uint64_t idx = wi * 32 + bit;
+      uint64_t lo = 0, hi = 0;
+      for (int t = 0; t < nb; ++t)
+        if ((idx >> t) & 1) {
+          if (bitpos[t] < 64) lo |= 1ull << bitpos[t]; else hi |= 1ull << (bitpos[t] - 64);
+        }
+      if (k < capacity) {
+        out_lohi[2 * k] = lo;
+        out_lohi[2 * k + 1] = hi;
+      }
+      ++k;
+    }
+  }
+  return SKS_OK;
+}
+
+int sks_set_device_keys(sks_ctx *ctx, sks_set *s, const void **dptr, int64_t *n_keys, int *words_per_key) {
+  if (!ctx || !s || !dptr || !n_keys || !words_per_key) return set_error(SKS_ERR_INVALID, "null argument");
+  if (s->repr != SKS_REPR_SORTED) return set_error(SKS_ERR_INVALID, "only sorted sets expose device keys");
+  *dptr = static_cast<const char *>(s->buf->ptr) + s->byte_off;
+  *n_keys = s->count;
+  *words_per_key = s->key_words;
+  return SKS_OK;
+}
+
+int sks_set_from_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int words_per_key, const uint64_t mask[2],
+                             int window, sks_set **out) {
+  if (!ctx || !out || !mask || n_keys < 0 || (n_keys > 0 && !dptr) || (words_per_key != 1 && words_per_key != 2))
+    return set_error(SKS_ERR_INVALID, "bad argument");
+  DeviceGuard guard(ctx->device);
+  sks_set *s = new_set(ctx, SKS_REPR_SORTED, mask, window, sks_mask_weight(mask));
+  if (!s) return set_error(SKS_ERR_INVALID, "out of host memory");
+  s->key_words = words_per_key;
+  s->count = n_keys;
+  int st = alloc_buffer(ctx, (size_t)n_keys * 8 * words_per_key, &s->buf);
+  if (st == SKS_OK && n_keys > 0 &&
+      cudaMemcpyAsync(s->buf->ptr, dptr, (size_t)n_keys * 8 * words_per_key, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
+    st = set_error(SKS_ERR_CUDA, "device copy failed");
+  if (st != SKS_OK) {
+    delete s;
+    return st;
+  }
+  *out = s;
+  return SKS_OK;
+}
+
+int sks_set_from_unsorted_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int words_per_key,
+                                      const uint64_t mask[2], int window, sks_set **out) {
+  if (!ctx || !out || !mask || n_keys < 0 || (n_keys > 0 && !dptr) || (words_per_key != 1 && words_per_key != 2))
+    return set_error(SKS_ERR_INVALID, "bad argument");
+  DeviceGuard guard(ctx->device);
+  BufferRef raw, uniq;
+  SKS_TRY(alloc_buffer(ctx, (size_t)n_keys * 8 * words_per_key, &raw));
+  if (n_keys > 0)
+    SKS_CUDA_TRY(cudaMemcpyAsync(raw->ptr, dptr, (size_t)n_keys * 8 * words_per_key, cudaMemcpyDeviceToDevice, ctx->stream));
+  const uint64_t off = 0, cnt = (uint64_t)n_keys;
+  std::vector<uint64_t> uoff, ucount;
+  SKS_TRY(sort_unique_regions(ctx, words_per_key, raw->ptr, &off, &cnt, 1, cnt, &uniq, &uoff, &ucount));
+  sks_set *s = new_set(ctx, SKS_REPR_SORTED, mask, window, sks_mask_weight(mask));
+  if (!s) return set_error(SKS_ERR_INVALID, "out of host memory");
+  s->buf = uniq;
+  s->key_words = words_per_key;
+  s->byte_off = (size_t)uoff[0] * 8 * words_per_key;
+  s->count = (int64_t)ucount[0];
+  *out = s;
+  return SKS_OK;
+}
+
+void sks_set_destroy(sks_ctx *ctx, sks_set *s) {
+  (void)ctx;
+  delete s;
+}
+
+// ---- comparison ----------------------------------------------------------------------------------
+int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *const *b, int64_t nb, int32_t *out) {
+  if (!ctx || (na > 0 && (!a || !b || !out))) return set_error(SKS_ERR_INVALID, "null argument");
+  // src/kmer_set.cpp:147-150,174-177
+  if (na != nb) return set_error(SKS_ERR_MISMATCH, "Lists of kmer sets for intersection computation have different lengths");
+  if (na == 0) return SKS_OK;
+  DeviceGuard guard(ctx->device);
+  for (int64_t i = 0; i < na; ++i) SKS_TRY(check_pair(a[i], b[i]));
+  const int repr = a[0]->repr;
+  for (int64_t i = 0; i < na; ++i)
+    if (a[i]->repr != repr || a[i]->key_words != a[0]->key_words)
+      return set_error(SKS_ERR_MISMATCH, "pair list mixes set representations");
+
+  if (repr == SKS_REPR_BITSET) {
+    unsigned long long *d_cnt = nullptr, *h_cnt = nullptr;
+    SKS_TRY(ctx_scratch(ctx, (size_t)na * 24, reinterpret_cast<void **>(&d_cnt)));
+    SKS_TRY(ctx_pinned(ctx, (size_t)na * 24, reinterpret_cast<void **>(&h_cnt)));
+    for (int64_t i = 0; i < na; ++i) {
+      const uint32_t *pa = reinterpret_cast<const uint32_t *>(static_cast<const char *>(a[i]->buf->ptr) + a[i]->byte_off);
+      const uint32_t *pb = reinterpret_cast<const uint32_t *>(static_cast<const char *>(b[i]->buf->ptr) + b[i]->byte_off);
+      SKS_TRY(launch_bitset_pair_counts(ctx, pa, pb, a[i]->bitset_words, d_cnt + 3 * i));
+    }
+    SKS_CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)na * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < na; ++i) {
+      a[i]->count = (int64_t)h_cnt[3 * i];  // the same pass yields both set sizes
+      b[i]->count = (int64_t)h_cnt[3 * i + 1];
+      out[i] = (int32_t)h_cnt[3 * i + 2];
+    }
+    return SKS_OK;
+  }
+
+  // SORTED: one launch over the whole pair list
+  const size_t tab_bytes = (size_t)na * 32, out_bytes = (size_t)na * 4;
+  char *d_tab = nullptr, *h_tab = nullptr;
+  SKS_TRY(ctx_scratch(ctx, tab_bytes + out_bytes, reinterpret_cast<void **>(&d_tab)));
+  SKS_TRY(ctx_pinned(ctx, tab_bytes + out_bytes, reinterpret_cast<void **>(&h_tab)));
+  const void **h_pa = reinterpret_cast<const void **>(h_tab);
+  const void **h_pb = h_pa + na;
+  int64_t *h_na = reinterpret_cast<int64_t *>(h_pb + na), *h_nb = h_na + na;
+  for (int64_t i = 0; i < na; ++i) {
+    h_pa[i] = static_cast<const char *>(a[i]->buf->ptr) + a[i]->byte_off;
+    h_pb[i] = static_cast<const char *>(b[i]->buf->ptr) + b[i]->byte_off;
+    h_na[i] = a[i]->count;
+    h_nb[i] = b[i]->count;
+  }
+  SKS_CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const void **d_pa = reinterpret_cast<const void **>(d_tab);
+  const void **d_pb = d_pa + na;
+  int64_t *d_na = reinterpret_cast<int64_t *>(d_pb + na), *d_nb = d_na + na;
+  int32_t *d_out = reinterpret_cast<int32_t *>(d_tab + tab_bytes);
+  SKS_TRY(launch_sorted_intersect_pairs(ctx, a[0]->key_words, d_pa, d_na, d_pb, d_nb, na, d_out));
+  SKS_CUDA_TRY(cudaMemcpyAsync(h_tab + tab_bytes, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  memcpy(out, h_tab + tab_bytes, out_bytes);
+  return SKS_OK;
+}
+
+int sks_intersect(sks_ctx *ctx, sks_set *a, sks_set *b, int64_t *out) {
+  if (!out) return set_error(SKS_ERR_INVALID, "null argument");
+  int32_t r = 0;
+  sks_set *pa[1] = {a}, *pb[1] = {b};
+  SKS_TRY(sks_intersect_pairs(ctx, pa, 1, pb, 1, &r));
+  *out = r;
+  return SKS_OK;
+}
+
+int sks_intersect_all_pairs(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end,
+                            int32_t *out) {
+  if (!ctx || (n > 0 && (!sets || !out))) return set_error(SKS_ERR_INVALID, "null argument");
+  if (row_begin < 0 || row_end > n || row_begin > row_end) return set_error(SKS_ERR_INVALID, "bad row range");
+  // |A n B| is symmetric: evaluate each unordered pair touching the row range once, mirror inside it.
+  std::vector<sks_set *> pa, pb;
+  std::vector<std::pair<int64_t, int64_t>> ij;
+  for (int64_t i = row_begin; i < row_end; ++i)
+    for (int64_t j = 0; j < n; ++j) {
+      if (j == i) continue;
+      if (j >= row_begin && j < row_end && j < i) continue;
+      pa.push_back(sets[i]);
+      pb.push_back(sets[j]);
+      ij.emplace_back(i, j);
+    }
+  std::vector<int32_t> r(pa.size());
+  SKS_TRY(sks_intersect_pairs(ctx, pa.data(), (int64_t)pa.size(), pb.data(), (int64_t)pb.size(), r.data()));
+  for (size_t k = 0; k < ij.size(); ++k) {
+    const int64_t i = ij[k].first, j = ij[k].second;
+    out[i * n + j] = r[k];
+    if (j >= row_begin && j < row_end) out[j * n + i] = r[k];
+  }
+  for (int64_t i = row_begin; i < row_end; ++i) {  // |A n A| = |A|
+    int64_t sz = 0;
+    SKS_TRY(sks_set_size(ctx, sets[i], &sz));
+    out[i * n + i] = (int32_t)sz;
+  }
+  return SKS_OK;
+}
+
+// ---- one-call pair pipeline ----------------------------------------------------------------------
+int sks_pair_ani_resident(sks_ctx *ctx, const sks_batch *batch, const uint64_t mask[2], int window, const sks_pred *pred,
+                          int repr, sks_pair_result *out) {
+  if (!ctx || !batch || !out) return set_error(SKS_ERR_INVALID, "null argument");
+  if (batch->n_genomes != 2) return set_error(SKS_ERR_INVALID, "pair pipeline needs a 2-genome batch");
+  sks_set *sets[2] = {nullptr, nullptr};
+  SKS_TRY(sks_sketch(ctx, batch, mask, window, pred, repr, sets));
+  int64_t inter = 0, sa = 0, sb = 0;
+  int st = sks_intersect(ctx, sets[0], sets[1], &inter);
+  if (st == SKS_OK) st = sks_set_size(ctx, sets[0], &sa);
+  if (st == SKS_OK) st = sks_set_size(ctx, sets[1], &sb);
+  const int weight = sets[0]->weight;
+  sks_set_destroy(ctx, sets[0]);
+  sks_set_destroy(ctx, sets[1]);
+  if (st != SKS_OK) return st;
+  out->size_a = sa;
+  out->size_b = sb;
+  out->intersection = inter;
+  out->ani_ab = sks_binomial_estimator(sks_containment((int)inter, (int)sa), weight);
+  out->ani_ba = sks_binomial_estimator(sks_containment((int)inter, (int)sb), weight);
+  return SKS_OK;
+}
+
+int sks_pair_ani(sks_ctx *ctx, const uint32_t *packed_a, uint64_t n_bases_a, const uint32_t *packed_b, uint64_t n_bases_b,
+                 const uint64_t mask[2], int window, const sks_pred *pred, int repr, sks_pair_result *out) {
+  const uint32_t *packed[2] = {packed_a, packed_b};
+  const uint64_t nb[2] = {n_bases_a, n_bases_b};
+  sks_batch *batch = nullptr;
+  SKS_TRY(sks_batch_upload(ctx, 2, packed, nb, nullptr, nullptr, &batch));
+  const int st = sks_pair_ani_resident(ctx, batch, mask, window, pred, repr, out);
+  sks_batch_destroy(ctx, batch);
+  return st;
+}
+
+int sks_kmer_list(sks_ctx *ctx, const sks_batch *batch, int genome, const uint64_t mask[2], int window,
+                  const sks_pred *pred, uint64_t *out_n, uint64_t *out_masked, uint64_t *out_bits, uint64_t capacity);
+
+}  // extern "C"

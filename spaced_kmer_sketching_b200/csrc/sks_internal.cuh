@@ -1,0 +1,180 @@
+// Internal declarations shared by the CUDA translation units of libsks.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/sks.h"
+
+namespace sks {
+
+// ------------------------------------------------------------------------------------------------
+// Errors.  The C ABI never throws: internal code returns a status and records a thread-local text.
+// ------------------------------------------------------------------------------------------------
+int set_error(int code, const char *fmt, ...);
+#define SKS_CUDA_TRY(expr)                                                                         \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::sks::set_error(SKS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                              __FILE__, __LINE__);                                                 \
+  } while (0)
+#define SKS_TRY(expr)              \
+  do {                             \
+    int _s = (expr);               \
+    if (_s != SKS_OK) return _s;   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Geometry of the sketch kernel (see DESIGN.md "K1-K4").
+// A genome is cut into tiles of kTileWindows window start positions; one CTA pass handles one tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int kBasesPerWord = 16;    // 2-bit bases in a uint32 word
+constexpr int kSketchThreads = 256;  // threads per CTA
+constexpr int kGroup = 16;           // windows per unrolled group == bases per word
+constexpr int kTileWindows = 8192;   // window starts per tile (all instantiations)
+constexpr int kTileWords = kTileWindows / kBasesPerWord;  // 512
+constexpr int kPreWords = 4;         // 16 B of history before the tile (only 1 word is ever read)
+constexpr int kPostWords = 8;        // halo after the tile: <= 64+16 bases -> 5 words, rounded to 16 B
+constexpr int kStageWords = kPreWords + kTileWords + kPostWords;  // 524 words = 2096 B per stage
+
+// Per-genome descriptor in HBM.  Bases of a genome are packed 16 per word, all of its ACGT segments
+// back to back; the words live at batch.words + word_off, preceded by >= kPreWords readable words
+// and padded with zero words to a multiple of 4 (so every bulk copy is 16-byte granular).
+struct GenomeDesc {
+  uint64_t word_off;    // multiple of 4
+  uint32_t n_bases;     // < 2^32 - 2^16
+  uint32_t n_words;     // readable data words from word_off, multiple of 4
+  uint32_t seg_first;   // first entry of this genome in the segment tables
+  uint32_t n_segs;      // >= 1 (a genome without bases has one empty segment)
+  uint32_t tile_first;  // id of the genome's first tile in the batch-wide tile numbering
+  uint32_t n_tiles;
+};
+
+enum OutMode : int { OUT_KEYS = 0, OUT_BITSET = 1, OUT_LIST = 2 };
+enum PredMode : int { PRED_ALL = 0, PRED_FMH181 = 1, PRED_FMH171 = 2 };
+
+constexpr int kMaxPieces = 40;  // <= 32 runs, each split at most once per 32-bit limb boundary
+
+// One piece of the PEXT table: bits of limb `limb` selected by (rotr(x, rot) & dmask) land in the
+// compacted index.  Pieces are grouped by limb: limb k owns [piece_begin[k], piece_begin[k+1]).
+struct PextTable {
+  uint32_t dmask[kMaxPieces];
+  uint8_t rot[kMaxPieces];
+  uint8_t piece_begin[5];
+  uint8_t pad[3];
+};
+
+struct SketchParams {
+  const uint32_t *words;       // batch buffer
+  const GenomeDesc *genomes;   // [n_genomes]
+  const uint32_t *seg_end;     // exclusive end of every segment, relative to its genome start
+  int n_genomes;
+  uint32_t n_tiles;            // over the whole batch
+  int window;                  // w, 1..64
+  uint32_t mask[4];            // 128-bit mask as four 32-bit limbs
+  // predicate (FMH): pass <=> ror((H(masked) ^ hconst) * minv, mshift) <= mbound
+  uint64_t hconst;             // H(mask) ^ window ^ (int64)nonce
+  uint64_t minv;               // inverse of the odd part of the modulus mod 2^64
+  uint64_t mbound;             // floor((2^64-1) / modulus)
+  int mshift;                  // log2 of the power-of-two part of the modulus
+  // OUT_KEYS / OUT_LIST: per-genome output regions
+  void *out_keys;                       // uint64 (NL<=2) or ulonglong2 (NL>2) slots
+  uint32_t *out_pos;                    // OUT_LIST only: (strand<<31 | start position) per slot
+  const uint64_t *out_off;              // [n_genomes] first slot of the genome's region
+  const uint64_t *out_cap;              // [n_genomes] slots in the region
+  unsigned long long *out_count;        // [n_genomes] kept k-mers (keeps counting past out_cap)
+  // OUT_BITSET
+  uint32_t *bitset;            // n_genomes consecutive bitsets
+  uint64_t bitset_words;       // words per genome
+  PextTable pext;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Host-side objects behind the opaque C handles.
+// ------------------------------------------------------------------------------------------------
+struct DeviceBuffer {  // ref-counted cudaMalloc block shared by the sets of one sketch call
+  void *ptr = nullptr;
+  size_t bytes = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;  // stream the block was allocated on; it is freed in that stream's order
+  ~DeviceBuffer();
+};
+using BufferRef = std::shared_ptr<DeviceBuffer>;
+int alloc_buffer(sks_ctx *ctx, size_t bytes, BufferRef *out);
+
+}  // namespace sks
+
+struct sks_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = true;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  // reusable scratch (grown on demand)
+  void *scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // pinned staging for small D2H/H2D traffic
+  void *pinned = nullptr;
+  size_t pinned_bytes = 0;
+};
+
+struct sks_batch {
+  int device = 0;
+  int n_genomes = 0;
+  sks::BufferRef words;      // uint32 words of all genomes
+  sks::BufferRef genomes;    // GenomeDesc[n_genomes]
+  sks::BufferRef seg_end;    // uint32[total_segs]
+  sks::BufferRef tile_genome;  // uint32[n_tiles] (only when n_genomes > 1)
+  std::vector<sks::GenomeDesc> h_genomes;
+  std::vector<uint32_t> h_seg_end;
+  uint32_t n_tiles = 0;
+  uint64_t total_bases = 0;
+};
+
+struct sks_set {
+  int device = 0;
+  int repr = SKS_REPR_SORTED;
+  int window = 0;
+  int weight = 0;
+  uint64_t mask[2] = {0, 0};
+  // SORTED: `count` ascending distinct keys of `key_words` uint64 each at buf + byte_off
+  // BITSET: 4^weight bits at buf + byte_off
+  sks::BufferRef buf;
+  size_t byte_off = 0;
+  int key_words = 1;
+  int64_t count = -1;  // -1: not yet known (BITSET before the first popcount)
+  uint64_t bitset_words = 0;
+};
+
+namespace sks {
+// scratch / pinned helpers
+int ctx_scratch(sks_ctx *ctx, size_t bytes, void **out);
+int ctx_pinned(sks_ctx *ctx, size_t bytes, void **out);
+
+// kernels' host launchers (sks_sketch.cu, sks_sets.cu, sks_synth.cu)
+int launch_sketch(sks_ctx *ctx, const SketchParams &p, const uint32_t *tile_genome, int n_limbs, int pred_mode,
+                  int out_mode);
+int launch_fill_zero(sks_ctx *ctx, void *ptr, size_t bytes);
+int launch_synth(sks_ctx *ctx, uint32_t *words, const GenomeDesc *genomes, int n_genomes, uint32_t max_words,
+                 const uint64_t *gen_seed, const uint64_t *mut_seed, const uint64_t *mut_D);
+int launch_bitset_pair_counts(sks_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n_words,
+                              unsigned long long *out3);
+int launch_bitset_popcount(sks_ctx *ctx, const uint32_t *a, uint64_t n_words, unsigned long long *out1);
+int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t *h_off, const uint64_t *h_count,
+                        int n_regions, uint64_t span, BufferRef *out_buf, std::vector<uint64_t> *out_off,
+                        std::vector<uint64_t> *out_count);
+int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const *d_a, const int64_t *d_na,
+                                  const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out);
+
+// host-only helpers (sks_host.cpp)
+uint64_t boost_hash_bitset(uint64_t lo, uint64_t hi, int variant);
+void modulus_magic(uint64_t modulus, uint64_t *minv, uint64_t *mbound, int *mshift);
+int build_pext_table(const uint64_t mask[2], int n_limbs, PextTable *out, int *n_index_bits);
+}  // namespace sks

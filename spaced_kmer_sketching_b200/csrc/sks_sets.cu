@@ -1,0 +1,454 @@
+// Set-side kernels: presence-bitset clear / popcount / AND-popcount (K4 clear, K5 bitset),
+// sort + unique of sketched keys (the sorted-keys representation of kmer_set), and the
+// sorted-set intersection count (K5 sorted).
+//
+// Reference semantics reproduced:
+//   kmer_set::insert_kmers   src/kmer.hpp:170-178   (set of distinct (masked_bits, mask))
+//   kmer_set::kmer_set_size  src/kmer.hpp:186-189
+//   kmer_set_intersection    src/kmer_set.cpp:23-41 (|A n B|)
+#include <cub/cub.cuh>
+
+#include "sks_internal.cuh"
+
+namespace sks {
+namespace {
+
+constexpr int kStreamThreads = 256;
+
+// ---- streaming clear ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kStreamThreads) fill_zero_kernel(uint4 *__restrict__ p, size_t n16) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {
+    p[i] = z;
+    p[i + stride] = z;
+    p[i + 2 * stride] = z;
+    p[i + 3 * stride] = z;
+  }
+  for (; i < n16; i += stride) p[i] = z;
+}
+
+__device__ __forceinline__ uint32_t popc4(uint4 v) { return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+
+__device__ __forceinline__ void block_add3(unsigned long long a, unsigned long long b, unsigned long long c,
+                                           unsigned long long *out, int n_out) {
+  __shared__ unsigned long long s[3][kStreamThreads / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, o);
+    b += __shfl_down_sync(0xffffffffu, b, o);
+    c += __shfl_down_sync(0xffffffffu, c, o);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) {
+    s[0][wid] = a;
+    s[1][wid] = b;
+    s[2][wid] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 && threadIdx.x < n_out) {
+    unsigned long long t = 0;
+#pragma unroll
+    for (int i = 0; i < kStreamThreads / 32; ++i) t += s[threadIdx.x][i];
+    if (t) atomicAdd(out + threadIdx.x, t);
+  }
+}
+
+// |A|, |B|, |A n B| of two presence bitsets in ONE pass over both (2 * n16 * 16 bytes of traffic).
+__global__ void __launch_bounds__(kStreamThreads)
+    bitset_pair_counts_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b, size_t n16,
+                              unsigned long long *__restrict__ out3) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  uint32_t ca = 0, cb = 0, ci = 0;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {
+    uint4 va[4], vb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      va[u] = __ldcs(a + i + u * stride);
+      vb[u] = __ldcs(b + i + u * stride);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      ca += popc4(va[u]);
+      cb += popc4(vb[u]);
+      ci += popc4(make_uint4(va[u].x & vb[u].x, va[u].y & vb[u].y, va[u].z & vb[u].z, va[u].w & vb[u].w));
+    }
+  }
+  for (; i < n16; i += stride) {
+    const uint4 va = __ldcs(a + i), vb = __ldcs(b + i);
+    ca += popc4(va);
+    cb += popc4(vb);
+    ci += popc4(make_uint4(va.x & vb.x, va.y & vb.y, va.z & vb.z, va.w & vb.w));
+  }
+  block_add3(ca, cb, ci, out3, 3);
+}
+
+__global__ void __launch_bounds__(kStreamThreads)
+    bitset_popcount_kernel(const uint4 *__restrict__ a, size_t n16, unsigned long long *__restrict__ out1) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  uint32_t ca = 0;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {
+    uint4 va[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) va[u] = __ldcs(a + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ca += popc4(va[u]);
+  }
+  for (; i < n16; i += stride) ca += popc4(__ldcs(a + i));
+  block_add3(ca, 0, 0, out1, 1);
+}
+
+// Small bitsets (fewer than 4 words, e.g. weight 1..3): scalar word loop.
+__global__ void bitset_small_counts_kernel(const uint32_t *a, const uint32_t *b, uint64_t n_words,
+                                           unsigned long long *out3) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long ca = 0, cb = 0, ci = 0;
+    for (uint64_t i = 0; i < n_words; ++i) {
+      const uint32_t x = a[i], y = b ? b[i] : 0u;
+      ca += __popc(x);
+      cb += __popc(y);
+      ci += __popc(x & y);
+    }
+    out3[0] += ca;
+    if (b) {
+      out3[1] += cb;
+      out3[2] += ci;
+    }
+  }
+}
+
+int stream_grid(const sks_ctx *ctx, size_t n16) {
+  size_t want = (n16 + kStreamThreads - 1) / kStreamThreads;
+  size_t cap = (size_t)ctx->sm_count * 8;  // 8 resident CTAs of 256 threads per SM
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+// ---- sort + unique --------------------------------------------------------------------------------
+struct Region {
+  unsigned long long begin, end;  // slots
+};
+
+template <int KW>
+__device__ __forceinline__ bool key_ne(const unsigned long long *k, unsigned long long i, unsigned long long j) {
+  if (KW == 1) return k[i] != k[j];
+  return k[2 * i] != k[2 * j] || k[2 * i + 1] != k[2 * j + 1];
+}
+
+// flags[i] = 1 when slot i is the first occurrence of its key inside its region.
+template <int KW>
+__global__ void mark_heads_kernel(const unsigned long long *__restrict__ keys, const Region *__restrict__ regions,
+                                  uint32_t *__restrict__ flags) {
+  const Region r = regions[blockIdx.y];
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = r.begin + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < r.end;
+       i += stride)
+    flags[i] = (i == r.begin || key_ne<KW>(keys, i, i - 1)) ? 1u : 0u;
+}
+
+template <int KW>
+__global__ void scatter_heads_kernel(const unsigned long long *__restrict__ keys, const Region *__restrict__ regions,
+                                     const uint32_t *__restrict__ flags, const uint32_t *__restrict__ pos,
+                                     unsigned long long *__restrict__ out, unsigned long long *__restrict__ uoff,
+                                     unsigned long long *__restrict__ ucount) {
+  const Region r = regions[blockIdx.y];
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = r.begin + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < r.end;
+       i += stride) {
+    if (flags[i]) {
+      const unsigned long long d = pos[i];
+      if (KW == 1) {
+        out[d] = keys[i];
+      } else {
+        out[2 * d] = keys[2 * i];
+        out[2 * d + 1] = keys[2 * i + 1];
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (r.end > r.begin) {
+      uoff[blockIdx.y] = pos[r.begin];
+      ucount[blockIdx.y] = (unsigned long long)pos[r.end - 1] + flags[r.end - 1] - pos[r.begin];
+    } else {
+      uoff[blockIdx.y] = 0;
+      ucount[blockIdx.y] = 0;
+    }
+  }
+}
+
+// Split / join 16-byte keys into (lo, hi) planes for the two-pass stable radix sort.
+__global__ void split_keys_kernel(const ulonglong2 *__restrict__ in, unsigned long long *__restrict__ lo,
+                                  unsigned long long *__restrict__ hi, unsigned long long n) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const ulonglong2 v = in[i];
+    lo[i] = v.x;
+    hi[i] = v.y;
+  }
+}
+__global__ void join_keys_kernel(const unsigned long long *__restrict__ lo, const unsigned long long *__restrict__ hi,
+                                 ulonglong2 *__restrict__ out, unsigned long long n) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_ulonglong2(lo[i], hi[i]);
+}
+
+// ---- sorted-set intersection ------------------------------------------------------------------------
+template <int KW>
+__device__ __forceinline__ int key_cmp(const unsigned long long *a, long long i, const unsigned long long *b,
+                                       long long j) {
+  if (KW == 1) {
+    const unsigned long long x = a[i], y = b[j];
+    return x < y ? -1 : (x > y ? 1 : 0);
+  }
+  const unsigned long long xh = a[2 * i + 1], yh = b[2 * j + 1];
+  if (xh != yh) return xh < yh ? -1 : 1;
+  const unsigned long long xl = a[2 * i], yl = b[2 * j];
+  return xl < yl ? -1 : (xl > yl ? 1 : 0);
+}
+
+// One CTA per pair: every thread takes a slice of the smaller set, locates its first key in the
+// larger set by binary search and then merges forward.
+template <int KW>
+__global__ void __launch_bounds__(256)
+    sorted_intersect_kernel(const void *const *__restrict__ pa, const long long *__restrict__ na,
+                            const void *const *__restrict__ pb, const long long *__restrict__ nb,
+                            int32_t *__restrict__ out) {
+  const long long pair = blockIdx.x;
+  const unsigned long long *A = static_cast<const unsigned long long *>(pa[pair]);
+  const unsigned long long *B = static_cast<const unsigned long long *>(pb[pair]);
+  long long nA = na[pair], nB = nb[pair];
+  if (nA > nB) {  // probe with the smaller set (src/kmer_set.cpp:26-27)
+    const unsigned long long *t = A; A = B; B = t;
+    long long tn = nA; nA = nB; nB = tn;
+  }
+  uint32_t cnt = 0;
+  if (nA > 0 && nB > 0) {
+    const long long per = (nA + blockDim.x - 1) / blockDim.x;
+    long long i = (long long)threadIdx.x * per, iend = i + per < nA ? i + per : nA;
+    if (i < iend) {
+      long long lo = 0, hi = nB;  // lower_bound of A[i] in B
+      while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (key_cmp<KW>(B, mid, A, i) < 0) lo = mid + 1; else hi = mid;
+      }
+      long long j = lo;
+      while (i < iend && j < nB) {
+        const int c = key_cmp<KW>(A, i, B, j);
+        if (c == 0) { ++cnt; ++i; ++j; } else if (c < 0) ++i; else ++j;
+      }
+    }
+  }
+  __shared__ uint32_t s[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int k = 0; k < 8; ++k) t += s[k];
+    out[pair] = (int32_t)t;
+  }
+}
+
+}  // namespace
+
+int launch_fill_zero(sks_ctx *ctx, void *ptr, size_t bytes) {
+  if (bytes == 0) return SKS_OK;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (bytes & 15)) {
+    SKS_CUDA_TRY(cudaMemsetAsync(ptr, 0, bytes, ctx->stream));
+    return SKS_OK;
+  }
+  const size_t n16 = bytes / 16;
+  fill_zero_kernel<<<stream_grid(ctx, n16), kStreamThreads, 0, ctx->stream>>>(static_cast<uint4 *>(ptr), n16);
+  SKS_CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  return SKS_OK;
+}
+
+int launch_bitset_pair_counts(sks_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n_words,
+                              unsigned long long *out3) {
+  SKS_CUDA_TRY(cudaMemsetAsync(out3, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  if (n_words % 4 != 0 || n_words < 4) {
+    bitset_small_counts_kernel<<<1, 32, 0, ctx->stream>>>(a, b, n_words, out3);
+  } else {
+    const size_t n16 = n_words / 4;
+    bitset_pair_counts_kernel<<<stream_grid(ctx, n16), kStreamThreads, 0, ctx->stream>>>(
+        reinterpret_cast<const uint4 *>(a), reinterpret_cast<const uint4 *>(b), n16, out3);
+  }
+  SKS_CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  return SKS_OK;
+}
+
+int launch_bitset_popcount(sks_ctx *ctx, const uint32_t *a, uint64_t n_words, unsigned long long *out1) {
+  SKS_CUDA_TRY(cudaMemsetAsync(out1, 0, sizeof(unsigned long long), ctx->stream));
+  if (n_words % 4 != 0 || n_words < 4) {
+    bitset_small_counts_kernel<<<1, 32, 0, ctx->stream>>>(a, nullptr, n_words, out1);
+  } else {
+    const size_t n16 = n_words / 4;
+    bitset_popcount_kernel<<<stream_grid(ctx, n16), kStreamThreads, 0, ctx->stream>>>(
+        reinterpret_cast<const uint4 *>(a), n16, out1);
+  }
+  SKS_CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  return SKS_OK;
+}
+
+// Sorts and de-duplicates n_regions independent key regions that live in one buffer.
+//   keys      : device buffer of `span` slots (key_words uint64 per slot); region g occupies slots
+//               [h_off[g], h_off[g] + h_count[g]).
+//   out_buf   : receives the distinct keys of all regions back to back (region order kept);
+//   out_off / out_count: per-region slot offset and count inside out_buf.
+int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t *h_off, const uint64_t *h_count,
+                        int n_regions, uint64_t span, BufferRef *out_buf, std::vector<uint64_t> *out_off,
+                        std::vector<uint64_t> *out_count) {
+  out_off->assign(n_regions, 0);
+  out_count->assign(n_regions, 0);
+  uint64_t total = 0;
+  for (int g = 0; g < n_regions; ++g) total += h_count[g];
+  if (total == 0) {
+    SKS_TRY(alloc_buffer(ctx, 16, out_buf));
+    return SKS_OK;
+  }
+  if (span >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "sort span of %llu slots exceeds 2^31", (unsigned long long)span);
+
+  const size_t kb = (size_t)key_words * 8;
+  // scratch: regions | begin/end offsets | alt keys (| lo/hi planes) | flags | pos | uoff | ucount | cub temp
+  std::vector<Region> h_regions(n_regions);
+  std::vector<long long> h_begin(n_regions), h_end(n_regions);
+  for (int g = 0; g < n_regions; ++g) {
+    h_regions[g] = {h_off[g], h_off[g] + h_count[g]};
+    h_begin[g] = (long long)h_off[g];
+    h_end[g] = (long long)(h_off[g] + h_count[g]);
+  }
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t cub_bytes = 0, t = 0;
+  {
+    unsigned long long *kp = nullptr;
+    long long *op = nullptr;
+    uint32_t *fp = nullptr;
+    if (n_regions == 1) {
+      cub::DeviceRadixSort::SortPairs(nullptr, t, kp, kp, kp, kp, (int)span, 0, 64, ctx->stream);
+    } else {
+      cub::DeviceSegmentedRadixSort::SortPairs(nullptr, t, kp, kp, kp, kp, (int)span, n_regions, op, op, 0, 64,
+                                               ctx->stream);
+    }
+    cub_bytes = t;
+    cub::DeviceScan::ExclusiveSum(nullptr, t, fp, fp, (int)span, ctx->stream);
+    if (t > cub_bytes) cub_bytes = t;
+  }
+  const size_t sz_regions = align(sizeof(Region) * n_regions), sz_offs = align(sizeof(long long) * n_regions);
+  const size_t sz_plane = align(8 * span), sz_keys = align(kb * span), sz_u32 = align(4 * span);
+  const size_t n_planes = key_words == 1 ? 1 : 4;  // K64: alt keys; K128: lo, hi, lo', hi'
+  const size_t need = sz_regions + 2 * sz_offs + n_planes * sz_plane + 2 * sz_u32 + 2 * sz_offs + align(cub_bytes);
+  (void)sz_keys;
+  char *base = nullptr;
+  SKS_TRY(ctx_scratch(ctx, need, reinterpret_cast<void **>(&base)));
+  size_t o = 0;
+  Region *d_regions = reinterpret_cast<Region *>(base + o); o += sz_regions;
+  long long *d_begin = reinterpret_cast<long long *>(base + o); o += sz_offs;
+  long long *d_end = reinterpret_cast<long long *>(base + o); o += sz_offs;
+  unsigned long long *plane[4];
+  for (size_t i = 0; i < n_planes; ++i) { plane[i] = reinterpret_cast<unsigned long long *>(base + o); o += sz_plane; }
+  uint32_t *d_flags = reinterpret_cast<uint32_t *>(base + o); o += sz_u32;
+  uint32_t *d_pos = reinterpret_cast<uint32_t *>(base + o); o += sz_u32;
+  unsigned long long *d_uoff = reinterpret_cast<unsigned long long *>(base + o); o += sz_offs;
+  unsigned long long *d_ucount = reinterpret_cast<unsigned long long *>(base + o); o += sz_offs;
+  void *d_cub = base + o;
+
+  SKS_CUDA_TRY(cudaMemcpyAsync(d_regions, h_regions.data(), sizeof(Region) * n_regions, cudaMemcpyHostToDevice, ctx->stream));
+  SKS_CUDA_TRY(cudaMemcpyAsync(d_begin, h_begin.data(), sizeof(long long) * n_regions, cudaMemcpyHostToDevice, ctx->stream));
+  SKS_CUDA_TRY(cudaMemcpyAsync(d_end, h_end.data(), sizeof(long long) * n_regions, cudaMemcpyHostToDevice, ctx->stream));
+
+  unsigned long long *sorted = nullptr;  // [span] slots of key_words
+  unsigned long long *d_keys = static_cast<unsigned long long *>(keys);
+  const int nblk = (int)((span + 255) / 256);
+  if (key_words == 1) {
+    size_t tb = cub_bytes;
+    if (n_regions == 1) {
+      cub::DeviceRadixSort::SortKeys(d_cub, tb, d_keys + h_off[0], plane[0] + h_off[0], (int)h_count[0], 0, 64, ctx->stream);
+    } else {
+      cub::DeviceSegmentedRadixSort::SortKeys(d_cub, tb, d_keys, plane[0], (int)span, n_regions, d_begin, d_end, 0, 64,
+                                              ctx->stream);
+    }
+    ctx->launches += 8;
+    sorted = plane[0];
+  } else {
+    split_keys_kernel<<<nblk, 256, 0, ctx->stream>>>(static_cast<const ulonglong2 *>(keys), plane[0], plane[1], span);
+    size_t tb = cub_bytes;
+    if (n_regions == 1) {
+      const uint64_t b = h_off[0];
+      const int n = (int)h_count[0];
+      cub::DeviceRadixSort::SortPairs(d_cub, tb, plane[0] + b, plane[2] + b, plane[1] + b, plane[3] + b, n, 0, 64, ctx->stream);
+      tb = cub_bytes;
+      cub::DeviceRadixSort::SortPairs(d_cub, tb, plane[3] + b, plane[1] + b, plane[2] + b, plane[0] + b, n, 0, 64, ctx->stream);
+    } else {
+      cub::DeviceSegmentedRadixSort::SortPairs(d_cub, tb, plane[0], plane[2], plane[1], plane[3], (int)span, n_regions,
+                                               d_begin, d_end, 0, 64, ctx->stream);
+      tb = cub_bytes;
+      cub::DeviceSegmentedRadixSort::SortPairs(d_cub, tb, plane[3], plane[1], plane[2], plane[0], (int)span, n_regions,
+                                               d_begin, d_end, 0, 64, ctx->stream);
+    }
+    // now plane[0] = lo, plane[1] = hi, sorted by (hi, lo); re-interleave into the caller's buffer
+    join_keys_kernel<<<nblk, 256, 0, ctx->stream>>>(plane[0], plane[1], static_cast<ulonglong2 *>(keys), span);
+    ctx->launches += 18;
+    sorted = d_keys;
+  }
+  SKS_CUDA_TRY(cudaGetLastError());
+
+  SKS_CUDA_TRY(cudaMemsetAsync(d_flags, 0, 4 * span, ctx->stream));
+  uint64_t max_count = 0;
+  for (int g = 0; g < n_regions; ++g) max_count = h_count[g] > max_count ? h_count[g] : max_count;
+  dim3 grid((unsigned)std::min<uint64_t>((max_count + 255) / 256, 65535 / 8), (unsigned)n_regions);
+  if (grid.x < 1) grid.x = 1;
+  if (key_words == 1) mark_heads_kernel<1><<<grid, 256, 0, ctx->stream>>>(sorted, d_regions, d_flags);
+  else mark_heads_kernel<2><<<grid, 256, 0, ctx->stream>>>(sorted, d_regions, d_flags);
+  {
+    size_t tb = cub_bytes;
+    cub::DeviceScan::ExclusiveSum(d_cub, tb, d_flags, d_pos, (int)span, ctx->stream);
+  }
+  SKS_TRY(alloc_buffer(ctx, kb * total, out_buf));
+  unsigned long long *d_out = static_cast<unsigned long long *>((*out_buf)->ptr);
+  if (key_words == 1)
+    scatter_heads_kernel<1><<<grid, 256, 0, ctx->stream>>>(sorted, d_regions, d_flags, d_pos, d_out, d_uoff, d_ucount);
+  else
+    scatter_heads_kernel<2><<<grid, 256, 0, ctx->stream>>>(sorted, d_regions, d_flags, d_pos, d_out, d_uoff, d_ucount);
+  SKS_CUDA_TRY(cudaGetLastError());
+  ctx->launches += 4;
+
+  std::vector<unsigned long long> h_uoff(n_regions), h_ucount(n_regions);
+  SKS_CUDA_TRY(cudaMemcpyAsync(h_uoff.data(), d_uoff, 8 * n_regions, cudaMemcpyDeviceToHost, ctx->stream));
+  SKS_CUDA_TRY(cudaMemcpyAsync(h_ucount.data(), d_ucount, 8 * n_regions, cudaMemcpyDeviceToHost, ctx->stream));
+  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  for (int g = 0; g < n_regions; ++g) {
+    (*out_off)[g] = h_uoff[g];
+    (*out_count)[g] = h_ucount[g];
+  }
+  return SKS_OK;
+}
+
+int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const *d_a, const int64_t *d_na,
+                                  const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out) {
+  if (n_pairs == 0) return SKS_OK;
+  for (int64_t done = 0; done < n_pairs;) {
+    const int64_t chunk = std::min<int64_t>(n_pairs - done, 1 << 30);
+    if (key_words == 1)
+      sorted_intersect_kernel<1><<<(unsigned)chunk, 256, 0, ctx->stream>>>(
+          d_a + done, reinterpret_cast<const long long *>(d_na + done), d_b + done,
+          reinterpret_cast<const long long *>(d_nb + done), d_out + done);
+    else
+      sorted_intersect_kernel<2><<<(unsigned)chunk, 256, 0, ctx->stream>>>(
+          d_a + done, reinterpret_cast<const long long *>(d_na + done), d_b + done,
+          reinterpret_cast<const long long *>(d_nb + done), d_out + done);
+    SKS_CUDA_TRY(cudaGetLastError());
+    ctx->launches++;
+    done += chunk;
+  }
+  return SKS_OK;
+}
+
+}  // namespace sks

@@ -1,0 +1,363 @@
+// The sketch kernel: fused K1 (stage 2-bit bases) + K2 (spaced-seed gather, canonical strand) +
+// K3 (Boost-compatible FracMinHash filter, compaction) + K4 (presence-bitset insert).
+//
+// Replaces the reference's hot loop nucleotide_string_to_kmers (src/kmer_sliding.cpp:112-186):
+//   per base  : update_kmer_window / update_complement_kmer_window        (:26-47,144-151)
+//   per window: fwd & mask, rc & mask (same mask), canonical = min, ties -> rc (:159-175)
+//               sketching_cond(kmer) -> push_back                          (:182-184)
+// and, for OUT_BITSET, kmer_set::insert_kmers (src/kmer.hpp:170-178).
+//
+// Formulation (DESIGN.md has the derivation): with bases packed 16 per word, base i in bits
+// 2(i%16), the reverse-complement window of start i is a plain right funnel shift of the
+// complemented words, and the forward window is a left funnel shift of the 2-bit-group-reversed
+// words.  A thread owns 16 consecutive window starts whose first is word aligned, so after one
+// per-group alignment shift every per-window shift amount is a compile-time constant.
+#include "sks_internal.cuh"
+
+namespace sks {
+namespace {
+
+// ---- mbarrier + 1-D bulk copy (TMA engine, no tensor map needed) ---------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// Reverse the sixteen 2-bit groups of a word: LE-packed bases -> MSB-first bases.
+__device__ __forceinline__ uint32_t rev_groups(uint32_t x) {
+  x = __brev(x);
+  return ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+}
+
+// ---- Boost hash restatement (src/kmer.hpp:137-148 call sites; see oracle/oracle.c header) --------
+__device__ __forceinline__ uint64_t hc181(uint64_t h, uint64_t k) {
+  const uint64_t M = 0x0e9846af9b1a615dULL;
+  uint64_t x = h + 0x9e3779b9ULL + k;
+  x ^= x >> 32;
+  x *= M;
+  x ^= x >> 32;
+  x *= M;
+  x ^= x >> 28;
+  return x;
+}
+__device__ __forceinline__ uint64_t hc171(uint64_t h, uint64_t k) {
+  const uint64_t m = 0xc6a4a7935bd1e995ULL;
+  k *= m;
+  k ^= k >> 47;
+  k *= m;
+  h ^= k;
+  h *= m;
+  h += 0xe6546b64ULL;
+  return h;
+}
+template <int PRED>
+__device__ __forceinline__ uint64_t bitset_hash(uint64_t b0, uint64_t b1) {
+  if (PRED == PRED_FMH171) return hc171(128, hc171(hc171(0, b0), b1));
+  return hc181(128, hc181(hc181(0, b0), b1));
+}
+
+struct TileMeta {
+  uint32_t genome;
+  uint32_t t0;       // first window start of the tile, relative to the genome
+  uint32_t n_bases;  // of the genome
+  uint32_t seg_first;
+  uint32_t n_segs;
+  uint32_t pad[3];
+};
+
+template <int NL>
+struct KeyType {
+  using type = unsigned long long;
+};
+template <>
+struct KeyType<3> {
+  using type = ulonglong2;
+};
+template <>
+struct KeyType<4> {
+  using type = ulonglong2;
+};
+
+constexpr int kStageSlots = kSketchThreads * kGroup;  // kept k-mers staged per round (4096)
+
+template <int NL, int OUT>
+constexpr size_t sketch_smem_bytes() {
+  size_t b = 2 * kStageWords * 4 + 2 * sizeof(TileMeta) + 64;
+  if (OUT != OUT_BITSET) b += kStageSlots * sizeof(typename KeyType<NL>::type);
+  if (OUT == OUT_LIST) b += kStageSlots * 4;
+  return b;
+}
+
+template <int NL, int PRED, int OUT>
+__global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_constant__ SketchParams P,
+                                                               const uint32_t *__restrict__ tile_genome) {
+  using key_t = typename KeyType<NL>::type;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t *s_words = reinterpret_cast<uint32_t *>(smem_raw);                        // [2][kStageWords]
+  TileMeta *s_meta = reinterpret_cast<TileMeta *>(smem_raw + 2 * kStageWords * 4);    // [2]
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem_raw + 2 * kStageWords * 4 + 2 * sizeof(TileMeta));  // [2]
+  uint32_t *s_count = reinterpret_cast<uint32_t *>(s_bar + 2);
+  unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_bar + 3);
+  key_t *s_keys = reinterpret_cast<key_t *>(smem_raw + 2 * kStageWords * 4 + 2 * sizeof(TileMeta) + 64);
+  uint32_t *s_pos = reinterpret_cast<uint32_t *>(s_keys + kStageSlots);
+
+  const int tid = threadIdx.x;
+  const int w = P.window;
+  const int d2 = 2 * (w & 15);  // alignment shift of the forward stream
+  const int wq = w >> 4;
+
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    *s_count = 0;
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // Producer: describe tile `tile` in s_meta[stage] and start its bulk copy into s_words[stage].
+  auto issue = [&](uint32_t tile, int stage) {
+    const uint32_t g = (P.n_genomes == 1) ? 0u : tile_genome[tile];
+    const GenomeDesc gd = P.genomes[g];
+    const uint32_t tw = (tile - gd.tile_first) * (uint32_t)kTileWords;  // first data word of the tile
+    TileMeta m;
+    m.genome = g;
+    m.t0 = tw * kBasesPerWord;
+    m.n_bases = gd.n_bases;
+    m.seg_first = gd.seg_first;
+    m.n_segs = gd.n_segs;
+    s_meta[stage] = m;
+    uint32_t avail = gd.n_words + kPreWords - tw;  // words readable from (word_off + tw - kPreWords)
+    uint32_t copy_words = avail < (uint32_t)kStageWords ? avail : (uint32_t)kStageWords;
+    const uint32_t *src = P.words + gd.word_off + tw - kPreWords;
+    fence_proxy_async();
+    mbar_expect_tx(&s_bar[stage], copy_words * 4);
+    bulk_g2s(s_words + stage * kStageWords, src, copy_words * 4, &s_bar[stage]);
+  };
+
+  if (tid == 0 && blockIdx.x < P.n_tiles) issue(blockIdx.x, 0);
+
+  for (uint32_t it = 0;; ++it) {
+    const uint32_t tile = blockIdx.x + it * gridDim.x;
+    if (tile >= P.n_tiles) break;
+    const int stage = it & 1;
+    if (tid == 0 && tile + gridDim.x < P.n_tiles) issue(tile + gridDim.x, stage ^ 1);
+    mbar_wait(&s_bar[stage], (it >> 1) & 1);
+
+    const TileMeta tm = s_meta[stage];
+    const uint32_t *sm = s_words + stage * kStageWords;
+    const uint32_t n_bases = tm.n_bases;
+
+    // Per-thread segment cursor: [.., seg_e) is the end of the segment holding the current position.
+    uint32_t seg_i = tm.seg_first, seg_last = tm.seg_first + tm.n_segs - 1, seg_e = n_bases;
+    const uint32_t first_pos = tm.t0 + tid * 32;
+    if (tm.n_segs > 1 && first_pos < n_bases) {
+      uint32_t lo = tm.seg_first, hi = seg_last;  // first segment whose end is > first_pos
+      while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(P.seg_end + mid) > first_pos) hi = mid; else lo = mid + 1;
+      }
+      seg_i = lo;
+      seg_e = __ldg(P.seg_end + lo);
+    }
+
+#pragma unroll 1
+    for (int gi = 0; gi < 2; ++gi) {
+      const uint32_t p0 = first_pos + gi * kGroup;
+      const int wl = kPreWords + tid * 2 + gi;
+
+      // ---- which of the 16 windows exist (inside one segment, fully) --------------------------
+      uint32_t vmask = 0;
+      if (p0 < n_bases) {
+        while (seg_i < seg_last && p0 >= seg_e) seg_e = __ldg(P.seg_end + (++seg_i));
+        if (p0 + (kGroup - 1) + w <= seg_e) {
+          vmask = 0xFFFFu;
+        } else {
+          for (int j = 0; j < kGroup; ++j) {
+            const uint32_t p = p0 + j;
+            while (seg_i < seg_last && p >= seg_e) seg_e = __ldg(P.seg_end + (++seg_i));
+            if (p < seg_e && p + w <= seg_e) vmask |= 1u << j;
+          }
+        }
+      }
+
+      if (vmask != 0) {
+        // ---- stage the words of this group in registers ------------------------------------
+        uint32_t rw[NL + 1], fa[NL + 1];
+#pragma unroll
+        for (int x = 0; x <= NL; ++x) rw[x] = sm[wl + x];
+        {
+          const int fb = wl + wq - NL;
+          uint32_t be_prev = rev_groups(sm[fb]);
+#pragma unroll
+          for (int x = 0; x <= NL; ++x) {
+            const uint32_t be = rev_groups(sm[fb + x + 1]);
+            fa[x] = __funnelshift_l(be, be_prev, d2);
+            be_prev = be;
+          }
+        }
+
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+          // ---- K2: both strands through the same mask, canonical = smaller, ties -> rc ---------
+          uint32_t f[NL], r[NL], c[NL];
+#pragma unroll
+          for (int k = 0; k < NL; ++k) {
+            f[k] = __funnelshift_l(fa[NL - k], fa[NL - 1 - k], 2 * j) & P.mask[k];
+            r[k] = ~__funnelshift_r(rw[k], rw[k + 1], 2 * j) & P.mask[k];
+          }
+          bool lt;
+          if (NL == 1) {
+            lt = f[0] < r[0];
+          } else if (NL == 2) {
+            lt = (((uint64_t)f[1] << 32) | f[0]) < (((uint64_t)r[1] << 32) | r[0]);
+          } else if (NL == 3) {
+            const uint64_t fl = ((uint64_t)f[1] << 32) | f[0], rl = ((uint64_t)r[1] << 32) | r[0];
+            lt = (f[2] < r[2]) || (f[2] == r[2] && fl < rl);
+          } else {
+            const uint64_t fl = ((uint64_t)f[1] << 32) | f[0], rl = ((uint64_t)r[1] << 32) | r[0];
+            const uint64_t fh = ((uint64_t)f[NL - 1] << 32) | f[NL > 2 ? 2 : 0];
+            const uint64_t rh = ((uint64_t)r[NL - 1] << 32) | r[NL > 2 ? 2 : 0];
+            lt = (fh < rh) || (fh == rh && fl < rl);
+          }
+#pragma unroll
+          for (int k = 0; k < NL; ++k) c[k] = lt ? f[k] : r[k];
+
+          const uint64_t b0 = (NL >= 2) ? ((((uint64_t)c[NL >= 2 ? 1 : 0]) << 32) | c[0]) : (uint64_t)c[0];
+          const uint64_t b1 = (NL == 3)   ? (uint64_t)c[NL >= 3 ? 2 : 0]
+                              : (NL == 4) ? ((((uint64_t)c[NL >= 4 ? 3 : 0]) << 32) | c[NL >= 3 ? 2 : 0])
+                                          : 0ull;
+
+          // ---- K3: predicate -------------------------------------------------------------------
+          bool pass = (vmask >> j) & 1u;
+          if (PRED != PRED_ALL) {
+            const uint64_t h = bitset_hash<PRED>(b0, b1) ^ P.hconst;
+            uint64_t t = h * P.minv;
+            t = (t >> P.mshift) | (t << ((64 - P.mshift) & 63));
+            pass = pass && (t <= P.mbound);
+          }
+
+          // ---- K3/K4: emit ---------------------------------------------------------------------
+          if (pass) {
+            if (OUT == OUT_BITSET) {
+              uint32_t idx = 0;
+#pragma unroll
+              for (int k = 0; k < NL; ++k) {
+                for (int p = P.pext.piece_begin[k]; p < P.pext.piece_begin[k + 1]; ++p)
+                  idx |= __funnelshift_r(c[k], c[k], P.pext.rot[p]) & P.pext.dmask[p];
+              }
+              atomicOr(P.bitset + (uint64_t)tm.genome * P.bitset_words + (idx >> 5), 1u << (idx & 31));
+            } else {
+              const uint32_t slot = atomicAdd(s_count, 1u);
+              if (NL <= 2) {
+                reinterpret_cast<unsigned long long *>(s_keys)[slot] = b0;
+              } else {
+                reinterpret_cast<ulonglong2 *>(s_keys)[slot] = make_ulonglong2(b0, b1);
+              }
+              if (OUT == OUT_LIST) s_pos[slot] = (p0 + j) | (lt ? 0u : 0x80000000u);
+            }
+          }
+        }
+      }
+
+      // ---- flush the round's kept k-mers: one global reservation per CTA -------------------------
+      if (OUT != OUT_BITSET) {
+        __syncthreads();
+        const uint32_t n = *s_count;
+        if (n > 0) {  // uniform
+          if (tid == 0) *s_base = atomicAdd(P.out_count + tm.genome, (unsigned long long)n);
+          __syncthreads();
+          const unsigned long long base = *s_base;
+          const unsigned long long cap = P.out_cap[tm.genome], off = P.out_off[tm.genome];
+          if (tid == 0) *s_count = 0;
+          key_t *out = reinterpret_cast<key_t *>(P.out_keys);
+          for (uint32_t i = tid; i < n; i += kSketchThreads) {
+            if (base + i < cap) {
+              out[off + base + i] = s_keys[i];
+              if (OUT == OUT_LIST) P.out_pos[off + base + i] = s_pos[i];
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with s_words[stage] / s_meta[stage] before it is refilled
+  }
+}
+
+template <int NL, int PRED, int OUT>
+int launch_one(sks_ctx *ctx, const SketchParams &p, const uint32_t *tile_genome) {
+  auto kern = sketch_kernel<NL, PRED, OUT>;
+  constexpr size_t smem = sketch_smem_bytes<NL, OUT>();
+  static thread_local int ctas_per_sm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int &occ = ctas_per_sm[ctx->device & 7];
+  if (occ == 0) {
+    SKS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SKS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSketchThreads, smem));
+    if (occ < 1) occ = 1;
+  }
+  if (p.n_tiles == 0) return SKS_OK;
+  // Persistent CTAs: a whole number of waves of resident CTAs, capped by the tile count.
+  uint32_t grid = (uint32_t)(ctx->sm_count * occ);
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  kern<<<grid, kSketchThreads, smem, ctx->stream>>>(p, tile_genome);
+  SKS_CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  return SKS_OK;
+}
+
+template <int NL, int PRED>
+int launch_out(sks_ctx *ctx, const SketchParams &p, const uint32_t *tg, int out_mode) {
+  switch (out_mode) {
+    case OUT_KEYS: return launch_one<NL, PRED, OUT_KEYS>(ctx, p, tg);
+    case OUT_BITSET: return launch_one<NL, PRED, OUT_BITSET>(ctx, p, tg);
+    case OUT_LIST: return launch_one<NL, PRED, OUT_LIST>(ctx, p, tg);
+  }
+  return set_error(SKS_ERR_INVALID, "bad output mode %d", out_mode);
+}
+template <int NL>
+int launch_pred(sks_ctx *ctx, const SketchParams &p, const uint32_t *tg, int pred_mode, int out_mode) {
+  switch (pred_mode) {
+    case PRED_ALL: return launch_out<NL, PRED_ALL>(ctx, p, tg, out_mode);
+    case PRED_FMH181: return launch_out<NL, PRED_FMH181>(ctx, p, tg, out_mode);
+    case PRED_FMH171: return launch_out<NL, PRED_FMH171>(ctx, p, tg, out_mode);
+  }
+  return set_error(SKS_ERR_INVALID, "bad predicate mode %d", pred_mode);
+}
+
+}  // namespace
+
+int launch_sketch(sks_ctx *ctx, const SketchParams &p, const uint32_t *tile_genome, int n_limbs, int pred_mode,
+                  int out_mode) {
+  switch (n_limbs) {
+    case 1: return launch_pred<1>(ctx, p, tile_genome, pred_mode, out_mode);
+    case 2: return launch_pred<2>(ctx, p, tile_genome, pred_mode, out_mode);
+    case 3: return launch_pred<3>(ctx, p, tile_genome, pred_mode, out_mode);
+    case 4: return launch_pred<4>(ctx, p, tile_genome, pred_mode, out_mode);
+  }
+  return set_error(SKS_ERR_INVALID, "window needs %d limbs", n_limbs);
+}
+
+}  // namespace sks
