@@ -79,6 +79,23 @@ int sks_timer_end(sks_ctx *ctx, float *out_ms);
 /* Number of kernels launched by this context so far (bench.py's gpu_launches). */
 int64_t sks_ctx_launch_count(const sks_ctx *ctx);
 
+/* Per-kernel CUDA-event timing (bench.py's roofline numbers).  While enabled, every kernel launch of
+ * the context is bracketed by a pair of events on the context's stream; sks_ctx_kernel_stats
+ * synchronises, returns launches and summed duration of one kernel kind since the last query and
+ * resets it. */
+#define SKS_KERNEL_SKETCH 0       /* fused unpack / gather / hash-filter / emit (K1-K4)  */
+#define SKS_KERNEL_FILL 1         /* bitset clear                                        */
+#define SKS_KERNEL_PAIR_COUNTS 2  /* bitset AND/popcount (K5, bitset)                    */
+#define SKS_KERNEL_POPCOUNT 3     /* bitset popcount (set size)                          */
+#define SKS_KERNEL_SORT_UNIQUE 4  /* radix sort + unique of sketched keys                */
+#define SKS_KERNEL_INTERSECT 5    /* sorted-set intersection (K5, sorted)                */
+#define SKS_KERNEL_SYNTH 6        /* synthetic genome generator                          */
+#define SKS_KERNEL_LIST 7         /* ordered-list finalisation                           */
+#define SKS_KERNEL_KINDS 8
+int sks_ctx_profile(sks_ctx *ctx, int enable);
+int sks_ctx_kernel_stats(sks_ctx *ctx, int kind, int64_t *out_launches, double *out_total_ms);
+const char *sks_kernel_name(int kind);
+
 /* ---- host-side helpers: masks, packing, FASTA, ANI (no device needed) ------------------------ */
 /* Seed string in README notation ("11001011", README.md:25-41) -> 128-bit mask with two bits per
  * used position; s[i]=='1' sets bits 2(w-1-i), 2(w-1-i)+1.  The reference has no parser. */
@@ -126,6 +143,10 @@ int sks_batch_upload(sks_ctx *ctx, int n_genomes, const uint32_t *const *packed,
  * genome g = mutate(gen(n_bases, gen_seed[g]), mut_seed[g], mut_D[g]); mut_D[g]==0 => no mutation. */
 int sks_batch_synth(sks_ctx *ctx, int n_genomes, uint64_t n_bases, const uint64_t *gen_seed,
                     const uint64_t *mut_seed, const uint64_t *mut_D, sks_batch **out);
+/* Same, but genome g holds bases [first_base[g], first_base[g] + n_bases) of its (unbounded) stream:
+ * a rank's slice of one long synthetic sequence without generating the rest. */
+int sks_batch_synth_at(sks_ctx *ctx, int n_genomes, uint64_t n_bases, const uint64_t *first_base,
+                       const uint64_t *gen_seed, const uint64_t *mut_seed, const uint64_t *mut_D, sks_batch **out);
 /* A window [first_base, first_base + n_starts + window - 1) of one genome of `src` as a new
  * single-genome batch (position sharding of one long sequence with a (w-1)-base halo). */
 int sks_batch_slice(sks_ctx *ctx, const sks_batch *src, int genome, uint64_t first_base, uint64_t n_starts,

@@ -62,6 +62,28 @@ int ctx_pinned(sks_ctx *ctx, size_t bytes, void **out) {
   return SKS_OK;
 }
 
+static cudaEvent_t take_event(sks_ctx *ctx) {
+  if (!ctx->event_pool.empty()) {
+    cudaEvent_t e = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+KernelTimer::KernelTimer(sks_ctx *c, int k) : ctx(c), kind(k) {
+  if (!ctx->profile) return;
+  e0 = take_event(ctx);
+  e1 = take_event(ctx);
+  cudaEventRecord(e0, ctx->stream);
+}
+KernelTimer::~KernelTimer() {
+  if (!e0) return;
+  cudaEventRecord(e1, ctx->stream);
+  ctx->prof[kind].emplace_back(e0, e1);
+}
+
 namespace {
 
 struct DeviceGuard {
@@ -382,6 +404,12 @@ void sks_ctx_destroy(sks_ctx *ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (auto &v : ctx->prof)
+    for (auto &pr : v) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->owns_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -423,6 +451,35 @@ int sks_timer_end(sks_ctx *ctx, float *out_ms) {
 }
 int64_t sks_ctx_launch_count(const sks_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int sks_ctx_profile(sks_ctx *ctx, int enable) {
+  if (!ctx) return set_error(SKS_ERR_INVALID, "null context");
+  ctx->profile = enable != 0;
+  return SKS_OK;
+}
+int sks_ctx_kernel_stats(sks_ctx *ctx, int kind, int64_t *out_launches, double *out_total_ms) {
+  if (!ctx || kind < 0 || kind >= SKS_KERNEL_KINDS) return set_error(SKS_ERR_INVALID, "bad argument");
+  DeviceGuard guard(ctx->device);
+  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  double total = 0;
+  for (auto &pr : ctx->prof[kind]) {
+    float ms = 0;
+    SKS_CUDA_TRY(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    total += ms;
+    ctx->event_pool.push_back(pr.first);
+    ctx->event_pool.push_back(pr.second);
+  }
+  if (out_launches) *out_launches = (int64_t)ctx->prof[kind].size();
+  if (out_total_ms) *out_total_ms = total;
+  ctx->prof[kind].clear();
+  return SKS_OK;
+}
+const char *sks_kernel_name(int kind) {
+  static const char *names[SKS_KERNEL_KINDS] = {"sketch_kernel", "fill_zero_kernel", "bitset_pair_counts_kernel",
+                                                "bitset_popcount_kernel", "sort_unique", "sorted_intersect_kernel",
+                                                "synth_kernel", "list_finalize"};
+  return (kind >= 0 && kind < SKS_KERNEL_KINDS) ? names[kind] : "?";
+}
+
 // ---- batches -------------------------------------------------------------------------------------
 int sks_batch_upload(sks_ctx *ctx, int n_genomes, const uint32_t *const *packed, const uint64_t *n_bases,
                      const uint64_t *const *seg_len, const uint64_t *n_segs, sks_batch **out) {
@@ -461,6 +518,13 @@ int sks_batch_upload(sks_ctx *ctx, int n_genomes, const uint32_t *const *packed,
 
 int sks_batch_synth(sks_ctx *ctx, int n_genomes, uint64_t n_bases, const uint64_t *gen_seed, const uint64_t *mut_seed,
                     const uint64_t *mut_D, sks_batch **out) {
+  std::vector<uint64_t> zeros(n_genomes > 0 ? n_genomes : 1, 0);
+  return sks_batch_synth_at(ctx, n_genomes, n_bases, zeros.data(), gen_seed, mut_seed, mut_D, out);
+}
+
+int sks_batch_synth_at(sks_ctx *ctx, int n_genomes, uint64_t n_bases, const uint64_t *first_base,
+                       const uint64_t *gen_seed, const uint64_t *mut_seed, const uint64_t *mut_D, sks_batch **out) {
+  if (!first_base && n_genomes > 0) return set_error(SKS_ERR_INVALID, "bad argument");
   if (!ctx || !out || n_genomes < 0 || (n_genomes > 0 && (!gen_seed || !mut_seed || !mut_D)))
     return set_error(SKS_ERR_INVALID, "bad argument");
   DeviceGuard guard(ctx->device);
@@ -475,15 +539,17 @@ int sks_batch_synth(sks_ctx *ctx, int n_genomes, uint64_t n_bases, const uint64_
   if (st == SKS_OK) st = upload_tables(ctx, b);
   if (st == SKS_OK && n_genomes > 0) {
     uint64_t *d_seeds = nullptr;
-    st = ctx_scratch(ctx, (size_t)n_genomes * 24, reinterpret_cast<void **>(&d_seeds));
+    st = ctx_scratch(ctx, (size_t)n_genomes * 32, reinterpret_cast<void **>(&d_seeds));
     auto cp = [&](uint64_t *dst, const uint64_t *src) {
       return cudaMemcpyAsync(dst, src, (size_t)n_genomes * 8, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
     };
-    if (st == SKS_OK && !(cp(d_seeds, gen_seed) && cp(d_seeds + n_genomes, mut_seed) && cp(d_seeds + 2 * n_genomes, mut_D)))
+    if (st == SKS_OK && !(cp(d_seeds, gen_seed) && cp(d_seeds + n_genomes, mut_seed) && cp(d_seeds + 2 * n_genomes, mut_D) &&
+                            cp(d_seeds + 3 * n_genomes, first_base)))
       st = set_error(SKS_ERR_CUDA, "seed upload failed");
     if (st == SKS_OK)
       st = launch_synth(ctx, static_cast<uint32_t *>(b->words->ptr), static_cast<const GenomeDesc *>(b->genomes->ptr),
-                        n_genomes, b->h_genomes[0].n_words, d_seeds, d_seeds + n_genomes, d_seeds + 2 * n_genomes);
+                        n_genomes, b->h_genomes[0].n_words, d_seeds, d_seeds + n_genomes, d_seeds + 2 * n_genomes,
+                        d_seeds + 3 * n_genomes);
     if (st == SKS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = set_error(SKS_ERR_CUDA, "synth failed");
   }
   if (st != SKS_OK) {
@@ -851,7 +917,55 @@ int sks_pair_ani(sks_ctx *ctx, const uint32_t *packed_a, uint64_t n_bases_a, con
   return st;
 }
 
+// nucleotide_string_list_to_kmers, src/kmer_sliding.cpp:224-238: ordered list with duplicates.
 int sks_kmer_list(sks_ctx *ctx, const sks_batch *batch, int genome, const uint64_t mask[2], int window,
-                  const sks_pred *pred, uint64_t *out_n, uint64_t *out_masked, uint64_t *out_bits, uint64_t capacity);
+                  const sks_pred *pred, uint64_t *out_n, uint64_t *out_masked, uint64_t *out_bits, uint64_t capacity) {
+  if (!ctx || !batch || !out_n) return set_error(SKS_ERR_INVALID, "null argument");
+  if (genome < 0 || genome >= batch->n_genomes) return set_error(SKS_ERR_INVALID, "genome %d outside the batch", genome);
+  DeviceGuard guard(ctx->device);
+  const sks_batch *one = batch;
+  sks_batch *tmp = nullptr;
+  if (batch->n_genomes > 1) {  // the kernel numbers tiles batch-wide: work on a single-genome copy
+    SKS_TRY(sks_batch_slice(ctx, batch, genome, 0, batch->h_genomes[genome].n_bases, 1, &tmp));
+    one = tmp;
+  }
+  SketchPlan plan;
+  BufferRef raw, pos, outbuf;
+  std::vector<uint64_t> off, count;
+  uint64_t span = 0;
+  int st = make_plan(one, mask, window, pred, &plan);
+  if (st == SKS_OK) st = sketch_raw_keys(ctx, one, plan, pred, window, OUT_LIST, &raw, &pos, &off, &count, &span);
+  if (st == SKS_OK) {
+    const uint64_t n = count[0];
+    *out_n = n;
+    if (out_masked || out_bits) {
+      if (n > capacity) {
+        st = set_error(SKS_ERR_CAPACITY, "list has %llu k-mers, capacity %llu", (unsigned long long)n, (unsigned long long)capacity);
+      } else if (n > 0) {
+        const GenomeDesc &gd = one->h_genomes[0];
+        st = alloc_buffer(ctx, (size_t)n * 32, &outbuf);
+        unsigned long long *d_masked = nullptr, *d_bits = nullptr;
+        if (st == SKS_OK) {
+          d_masked = static_cast<unsigned long long *>(outbuf->ptr);
+          d_bits = d_masked + 2 * n;
+          st = launch_list_finalize(ctx, static_cast<const uint32_t *>(one->words->ptr) + gd.word_off,
+                                    static_cast<const uint32_t *>(one->seg_end->ptr) + gd.seg_first, gd.n_segs, window,
+                                    plan.n_limbs <= 2 ? 1 : 2, raw->ptr, static_cast<const uint32_t *>(pos->ptr),
+                                    (uint32_t)n, d_masked, d_bits);
+        }
+        auto d2h = [&](uint64_t *dst, const unsigned long long *src) {
+          if (!dst || st != SKS_OK) return;
+          if (cudaMemcpyAsync(dst, src, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+            st = set_error(SKS_ERR_CUDA, "list download failed");
+        };
+        d2h(out_masked, d_masked);
+        d2h(out_bits, d_bits);
+        if (st == SKS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = set_error(SKS_ERR_CUDA, "list download failed");
+      }
+    }
+  }
+  if (tmp) sks_batch_destroy(ctx, tmp);
+  return st;
+}
 
 }  // extern "C"

@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <memory>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -123,6 +124,10 @@ struct sks_ctx {
   // pinned staging for small D2H/H2D traffic
   void *pinned = nullptr;
   size_t pinned_bytes = 0;
+  // optional per-kernel event timing (sks_ctx_profile)
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[SKS_KERNEL_KINDS];
+  std::vector<cudaEvent_t> event_pool;
 };
 
 struct sks_batch {
@@ -154,6 +159,15 @@ struct sks_set {
 };
 
 namespace sks {
+// Brackets the kernel launches of one scope with events when the context is being profiled.
+struct KernelTimer {
+  sks_ctx *ctx;
+  int kind;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  KernelTimer(sks_ctx *c, int k);
+  ~KernelTimer();
+};
+
 // scratch / pinned helpers
 int ctx_scratch(sks_ctx *ctx, size_t bytes, void **out);
 int ctx_pinned(sks_ctx *ctx, size_t bytes, void **out);
@@ -163,7 +177,7 @@ int launch_sketch(sks_ctx *ctx, const SketchParams &p, const uint32_t *tile_geno
                   int out_mode);
 int launch_fill_zero(sks_ctx *ctx, void *ptr, size_t bytes);
 int launch_synth(sks_ctx *ctx, uint32_t *words, const GenomeDesc *genomes, int n_genomes, uint32_t max_words,
-                 const uint64_t *gen_seed, const uint64_t *mut_seed, const uint64_t *mut_D);
+                 const uint64_t *gen_seed, const uint64_t *mut_seed, const uint64_t *mut_D, const uint64_t *first_base);
 int launch_bitset_pair_counts(sks_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n_words,
                               unsigned long long *out3);
 int launch_bitset_popcount(sks_ctx *ctx, const uint32_t *a, uint64_t n_words, unsigned long long *out1);
@@ -172,6 +186,10 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
                         std::vector<uint64_t> *out_count);
 int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const *d_a, const int64_t *d_na,
                                   const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out);
+
+int launch_list_finalize(sks_ctx *ctx, const uint32_t *words, const uint32_t *seg_end, uint32_t n_segs, int window,
+                         int key_words, const void *raw_keys, const uint32_t *raw_pos, uint32_t n,
+                         unsigned long long *out_masked, unsigned long long *out_bits);
 
 // host-only helpers (sks_host.cpp)
 uint64_t boost_hash_bitset(uint64_t lo, uint64_t hi, int variant);

@@ -263,6 +263,7 @@ int launch_fill_zero(sks_ctx *ctx, void *ptr, size_t bytes) {
     return SKS_OK;
   }
   const size_t n16 = bytes / 16;
+  KernelTimer timer(ctx, SKS_KERNEL_FILL);
   fill_zero_kernel<<<stream_grid(ctx, n16), kStreamThreads, 0, ctx->stream>>>(static_cast<uint4 *>(ptr), n16);
   SKS_CUDA_TRY(cudaGetLastError());
   ctx->launches++;
@@ -272,6 +273,7 @@ int launch_fill_zero(sks_ctx *ctx, void *ptr, size_t bytes) {
 int launch_bitset_pair_counts(sks_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n_words,
                               unsigned long long *out3) {
   SKS_CUDA_TRY(cudaMemsetAsync(out3, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  KernelTimer timer(ctx, SKS_KERNEL_PAIR_COUNTS);
   if (n_words % 4 != 0 || n_words < 4) {
     bitset_small_counts_kernel<<<1, 32, 0, ctx->stream>>>(a, b, n_words, out3);
   } else {
@@ -286,6 +288,7 @@ int launch_bitset_pair_counts(sks_ctx *ctx, const uint32_t *a, const uint32_t *b
 
 int launch_bitset_popcount(sks_ctx *ctx, const uint32_t *a, uint64_t n_words, unsigned long long *out1) {
   SKS_CUDA_TRY(cudaMemsetAsync(out1, 0, sizeof(unsigned long long), ctx->stream));
+  KernelTimer timer(ctx, SKS_KERNEL_POPCOUNT);
   if (n_words % 4 != 0 || n_words < 4) {
     bitset_small_counts_kernel<<<1, 32, 0, ctx->stream>>>(a, nullptr, n_words, out1);
   } else {
@@ -364,6 +367,7 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
   SKS_CUDA_TRY(cudaMemcpyAsync(d_begin, h_begin.data(), sizeof(long long) * n_regions, cudaMemcpyHostToDevice, ctx->stream));
   SKS_CUDA_TRY(cudaMemcpyAsync(d_end, h_end.data(), sizeof(long long) * n_regions, cudaMemcpyHostToDevice, ctx->stream));
 
+  KernelTimer timer(ctx, SKS_KERNEL_SORT_UNIQUE);
   unsigned long long *sorted = nullptr;  // [span] slots of key_words
   unsigned long long *d_keys = static_cast<unsigned long long *>(keys);
   const int nblk = (int)((span + 255) / 256);
@@ -434,6 +438,7 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
 int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const *d_a, const int64_t *d_na,
                                   const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out) {
   if (n_pairs == 0) return SKS_OK;
+  KernelTimer timer(ctx, SKS_KERNEL_INTERSECT);
   for (int64_t done = 0; done < n_pairs;) {
     const int64_t chunk = std::min<int64_t>(n_pairs - done, 1 << 30);
     if (key_words == 1)

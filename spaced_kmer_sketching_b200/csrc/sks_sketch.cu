@@ -322,6 +322,7 @@ int launch_one(sks_ctx *ctx, const SketchParams &p, const uint32_t *tile_genome)
   // Persistent CTAs: a whole number of waves of resident CTAs, capped by the tile count.
   uint32_t grid = (uint32_t)(ctx->sm_count * occ);
   if (grid > p.n_tiles) grid = p.n_tiles;
+  KernelTimer timer(ctx, SKS_KERNEL_SKETCH);
   kern<<<grid, kSketchThreads, smem, ctx->stream>>>(p, tile_genome);
   SKS_CUDA_TRY(cudaGetLastError());
   ctx->launches++;

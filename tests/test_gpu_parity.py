@@ -1,0 +1,293 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libsks.so) against the CPU oracle on the same
+seeded inputs, against the golden fixtures produced by the unmodified reference, and -- at the
+BASELINE.json sizes -- through size-independent properties.  Integer results are compared bit-exactly;
+ANI within 1e-12 (it is computed on the host in double from identical integer counts)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+import spaced_kmer_sketching_b200 as sks
+from oracle import port
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+CODE = {"A": 0, "C": 1, "G": 2, "T": 3}
+C2_SEED = "011101110010111110011011"          # (24,16,seed 0)
+C3_SEED = "0011111011010111111011001011101"   # (31,21,seed 0)
+
+
+def ival(h):
+    return int(h, 16)
+
+
+def to_int(a):
+    return [int(x[0]) | (int(x[1]) << 64) for x in a]
+
+
+def key_digest(keys):
+    return hashlib.sha256(np.ascontiguousarray(keys, dtype="<u8").tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = sks.Context(0)
+    yield c
+    c.close()
+
+
+def opred(pred):
+    if pred.kind == sks.PRED_ALL:
+        return (port.ALL,)
+    return (port.FMH, pred.nonce, pred.modulus, pred.hash_variant)
+
+
+# ---- ordered lists: the most direct view of the hot loop --------------------------------------
+def test_kmer_lists_golden(ctx):
+    g = load_golden("kmer_lists.json")
+    seqs = {k: np.array([CODE[c] for c in v], dtype=np.uint8) for k, v in g["sequences"].items()}
+    for case in g["cases"]:
+        mask, w = sks.seed_to_mask(case["seed"])
+        batch = ctx.upload_codes([seqs[case["seq"]]], [np.array(case["segs"], dtype=np.uint64)])
+        masked, bits = ctx.kmer_list(batch, 0, mask, w, sks.all_kmers())
+        tag = (case["seq"], case["seed"], case["segs"])
+        assert to_int(masked) == [ival(x) for x in case["masked"]], tag
+        assert to_int(bits) == [ival(x) for x in case["bits"]], tag
+        for variant in (171, 181):
+            fm, _ = ctx.kmer_list(batch, 0, mask, w, sks.frac_min_hash(1, 4, variant))
+            assert to_int(fm) == [ival(x) for x in case["fmh4_%d" % variant]], tag + (variant,)
+        batch.close()
+
+
+def test_kat1_readme(ctx):
+    mask, w = sks.seed_to_mask("11001011")
+    codes = np.array([CODE[c] for c in "AAACGTACGTTT"], dtype=np.uint8)
+    batch = ctx.upload_codes([codes])
+    masked, bits = ctx.kmer_list(batch, 0, mask, w, sks.all_kmers())
+    assert to_int(masked) == [0x81, 0xC6, 0x100B, 0xC6, 0x81]   # SURVEY.md 4.2 KAT-1 (tie -> rc at i=2)
+    (s,) = ctx.sketch(batch, mask, w, sks.all_kmers(), sks.REPR_SORTED)
+    assert to_int(s.keys()) == [0x81, 0xC6, 0x100B]
+    (s2,) = ctx.sketch(batch, mask, w, sks.all_kmers(), sks.REPR_BITSET)
+    assert to_int(s2.keys()) == [0x81, 0xC6, 0x100B] and s2.kmer_set_size() == 3
+
+
+def random_case(rng, trial):
+    w = int(rng.integers(1, 65))
+    k = int(rng.integers(1, w + 1))
+    mask = sks.generate_random_spaced_seed_mask(w, k, trial)
+    nseg = int(rng.integers(1, 6))
+    lens = []
+    for _ in range(nseg):
+        kind = int(rng.integers(0, 6))
+        lens.append([w - 1, w, w + 1, int(rng.integers(1, 300)), int(rng.integers(300, 9000)),
+                     int(rng.integers(8000, 40000))][kind])
+    lens = [L for L in lens if L > 0] or [w]
+    codes = rng.integers(0, 4, sum(lens), dtype=np.uint8)
+    if trial % 5 == 0:   # low-complexity stretches: duplicates and strand ties
+        codes[: len(codes) // 2] = np.tile(np.array([0, 3], dtype=np.uint8), len(codes))[: len(codes) // 2]
+    return w, k, mask, codes, lens
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_fuzz_lists_and_sets_vs_oracle(ctx, block):
+    rng = np.random.default_rng(100 + block)
+    for t in range(12):
+        trial = block * 12 + t
+        w, k, mask, codes, lens = random_case(rng, trial)
+        variant = 171 if trial % 2 else 181
+        preds = [sks.all_kmers(), sks.frac_min_hash(int(rng.integers(-3, 5)), int(rng.integers(1, 12)), variant)]
+        batch = ctx.upload_codes([codes], [np.array(lens, dtype=np.uint64)])
+        for pred in preds:
+            om, ob = port.kmers(codes, lens, mask, w, *opred(pred), want_bits=True)
+            gm, gb = ctx.kmer_list(batch, 0, mask, w, pred)
+            tag = (trial, w, k, lens, pred.kind)
+            assert np.array_equal(gm, om), tag
+            assert np.array_equal(gb, ob), tag
+            oset = port.sort_unique(om)
+            (s,) = ctx.sketch(batch, mask, w, pred, sks.REPR_SORTED)
+            assert s.kmer_set_size() == len(oset) and np.array_equal(s.keys(), oset), tag
+            if k <= 13:
+                (b,) = ctx.sketch(batch, mask, w, pred, sks.REPR_BITSET)
+                assert b.kmer_set_size() == len(oset) and np.array_equal(b.keys(), oset), tag
+        batch.close()
+
+
+def test_multi_genome_batch_and_intersections(ctx):
+    rng = np.random.default_rng(7)
+    base = rng.integers(0, 4, 30000, dtype=np.uint8)
+    genomes, seglens = [], []
+    for i in range(7):
+        g = base.copy()
+        flips = rng.random(len(g)) < 0.01 * i
+        g[flips] = (g[flips] + 1) & 3
+        n = [30000, 8192, 8193, 16384 + 23, 5, 29999, 12000][i]
+        genomes.append(g[:n])
+        seglens.append(np.array([n // 3, n - n // 3], dtype=np.uint64) if i % 2 else None)
+    batch = ctx.upload_codes(genomes, seglens)
+    for seed, pred, reprs in ((C2_SEED, sks.all_kmers(), (sks.REPR_SORTED,)),
+                              ("110101101", sks.all_kmers(), (sks.REPR_SORTED, sks.REPR_BITSET)),
+                              (C3_SEED, sks.frac_min_hash(1, 20), (sks.REPR_SORTED,)),
+                              ("1" * 40, sks.frac_min_hash(2, 7, 171), (sks.REPR_SORTED,))):
+        mask, w = sks.seed_to_mask(seed)
+        osets = [port.sketch_set(g, [len(g)] if s is None else list(s), mask, w, *opred(pred))
+                 for g, s in zip(genomes, seglens)]
+        want = np.array([[port.intersection(a, b) for b in osets] for a in osets], dtype=np.int32)
+        for r in reprs:
+            sets = ctx.sketch(batch, mask, w, pred, r)
+            for s, o in zip(sets, osets):
+                assert np.array_equal(s.keys(), o)
+            got = ctx.intersect_all_pairs(sets)
+            assert np.array_equal(got, want)
+            f, s2 = sks.generate_all_pairs_from_vector(list(range(len(sets))))
+            flat = ctx.intersect_pairs([sets[i] for i in f], [sets[j] for j in s2])
+            assert np.array_equal(flat, want.ravel())
+            # row tiling (rank tiling of the pair matrix) fills exactly its rows
+            part = np.full_like(want, -1)
+            ctx.intersect_all_pairs(sets, 2, 5, part)
+            assert np.array_equal(part[2:5], want[2:5]) and (part[:2] == -1).all() and (part[5:] == -1).all()
+    with pytest.raises(sks.SksError) as e:   # src/kmer_set.cpp:147-150,174-177
+        ctx.intersect_pairs(sets[:2], sets[:3])
+    assert e.value.code == 4 and "different lengths" in str(e.value)
+
+
+def test_multi_golden(ctx):
+    g = load_golden("multi.json")
+    n = len(g["Ds"])
+    batch = ctx.synth(g["L"], [g["base_seed"]] * n, [2000 + i for i in range(n)], g["Ds"])
+    for case in g["cases"]:
+        mask, w = sks.seed_to_mask(case["seed"])
+        pred = sks.all_kmers() if case["pred"] == "ALL" else sks.frac_min_hash(case["nonce"], case["modulus"], case["variant"])
+        sets = ctx.sketch(batch, mask, w, pred)
+        assert [s.kmer_set_size() for s in sets] == case["sizes"]
+        assert [key_digest(s.keys()) for s in sets] == case["digests"]
+        ints = ctx.intersect_all_pairs(sets)
+        assert ints.ravel().tolist() == case["intersections"]
+        sizes = np.repeat(np.array(case["sizes"], dtype=np.int32), n)
+        ani = sks.ani_from_counts(ints.ravel(), sizes, sks.mask_weight(mask))
+        assert np.max(np.abs(ani - np.array([float(x) for x in case["ani"]]))) <= 1e-12
+
+
+def test_synth_matches_oracle_generator(ctx):
+    batch = ctx.synth(100_003, [42, 42, 9], [0, 43, 5], [0, 100, 3])
+    A = port.gen(100_003, 42)
+    assert np.array_equal(sks.unpack_codes(batch.download(0), 100_003), A)
+    assert np.array_equal(sks.unpack_codes(batch.download(1), 100_003), port.mutate(A, 43, 100))
+    assert np.array_equal(sks.unpack_codes(batch.download(2), 100_003), port.mutate(port.gen(100_003, 9), 5, 3))
+
+
+@pytest.mark.parametrize("name", ["sets_100k.json", "sets_5m.json"])
+def test_sets_golden(ctx, name):
+    """KAT-3 / KAT-4: counts and key digests produced by the unmodified reference."""
+    g = load_golden(name)
+    batch = ctx.synth(g["L"], [g["gen_seed"]] * 2, [0, g["mut_seed"]], [0, g["D"]])
+    for case in g["cases"]:
+        mask, w = sks.seed_to_mask(case["seed"])
+        pred = sks.all_kmers() if case["pred"] == "ALL" else sks.frac_min_hash(case["nonce"], case["modulus"], case["variant"])
+        weight = sks.mask_weight(mask)
+        reprs = [sks.REPR_SORTED] + ([sks.REPR_BITSET] if weight <= 16 and pred.kind == sks.PRED_ALL else [])
+        for r in reprs:
+            sa, sb = ctx.sketch(batch, mask, w, pred, r)
+            inter = ctx.intersect(sa, sb)
+            tag = (case["seed"], case["pred"], case["variant"], r)
+            assert (sa.kmer_set_size(), sb.kmer_set_size(), inter) == (case["size_a"], case["size_b"], case["intersection"]), tag
+            if r == sks.REPR_SORTED or g["L"] <= 10 ** 6:
+                assert key_digest(sa.keys()) == case["digest_a"] and key_digest(sb.keys()) == case["digest_b"], tag
+            ab = sks.binomial_estimator(sks.containment(inter, sa.kmer_set_size()), weight)
+            ba = sks.binomial_estimator(sks.containment(inter, sb.kmer_set_size()), weight)
+            assert abs(ab - float(case["ani_ab"])) <= 1e-12 and abs(ba - float(case["ani_ba"])) <= 1e-12, tag
+            sa.close()
+            sb.close()
+    # the one-call pipelines (resident and host-buffer) on C2
+    case = [c for c in g["cases"] if c["seed"] == C2_SEED and c["pred"] == "ALL"][0]
+    mask, w = sks.seed_to_mask(C2_SEED)
+    r = ctx.pair_ani_resident(batch, mask, w, sks.all_kmers(), sks.REPR_BITSET)
+    assert (r.size_a, r.size_b, r.intersection) == (case["size_a"], case["size_b"], case["intersection"])
+    assert abs(r.ani_ab - float(case["ani_ab"])) <= 1e-12 and abs(r.ani_ba - float(case["ani_ba"])) <= 1e-12
+    wa, wb = batch.download(0), batch.download(1)
+    r2 = ctx.pair_ani(wa, g["L"], wb, g["L"], mask, w, sks.all_kmers())
+    assert (r2.size_a, r2.size_b, r2.intersection, r2.ani_ab) == (r.size_a, r.size_b, r.intersection, r.ani_ab)
+
+
+def test_fasta_files_to_sets(ctx, tmp_path):
+    A = port.gen(50_000, 5)
+    B = port.mutate(A, 6, 50)
+    port.write_fasta(str(tmp_path / "a.fna"), A)
+    text = port.codes_to_text(B)
+    # N runs, lower case, CRLF, blank line, second record: the section 3.6 quirks
+    messy = b">b one\r\n" + text[:1000] + b"\r\n" + text[1000:3000].lower() + b"\n\n" + text[3000:20000] + \
+            b"NNNN" + text[20000:] + b"\n>b2\n" + text[:777] + b"\n"
+    (tmp_path / "b.fna").write_bytes(messy)
+    files = [str(tmp_path / "a.fna"), str(tmp_path / "b.fna")]
+    for seed, pred in ((C2_SEED, sks.all_kmers()), (C3_SEED, sks.frac_min_hash(1, 10))):
+        mask, w = sks.seed_to_mask(seed)
+        sets = sks.kmer_sets_from_fasta_files(ctx, files, mask, w, pred, sks.REPR_SORTED)
+        osets = []
+        for f in files:
+            codes, segs = port.fasta_parse(open(f, "rb").read())
+            osets.append(port.sketch_set(codes, list(segs), mask, w, *opred(pred)))
+        for s, o in zip(sets, osets):
+            assert np.array_equal(s.keys(), o)
+        assert sks.kmer_set_intersection(ctx, sets[0], sets[1]) == port.intersection(osets[0], osets[1])
+    one = sks.kmer_set_from_fasta_file(ctx, files[1], mask, w, pred, sks.REPR_SORTED)
+    assert np.array_equal(one.keys(), osets[1])
+
+
+# ---- properties at the BASELINE.json sizes -----------------------------------------------------
+def test_properties_full_size(ctx):
+    L = 5_000_000
+    batch = ctx.synth(L, [42, 42], [0, 43], [0, 100])
+    mask, w = sks.seed_to_mask(C2_SEED)
+    sa, sb = ctx.sketch(batch, mask, w, sks.all_kmers(), sks.REPR_SORTED)
+    ba, bb = ctx.sketch(batch, mask, w, sks.all_kmers(), sks.REPR_BITSET)
+    # representation equivalence: bitset popcount == sorted-unique count, same members
+    assert ba.kmer_set_size() == sa.kmer_set_size() and bb.kmer_set_size() == sb.kmer_set_size()
+    assert ctx.intersect(ba, bb) == ctx.intersect(sa, sb)
+    ka = sa.keys()
+    assert np.array_equal(ba.keys(), ka)
+    # sortedness, distinctness, idempotence, symmetry
+    assert (ka[1:, 0] > ka[:-1, 0]).all() and (ka[:, 1] == 0).all()
+    assert ctx.intersect(sa, sa) == sa.kmer_set_size()
+    assert ctx.intersect(sa, sb) == ctx.intersect(sb, sa)
+    # strand independence: the reverse complement gives the same set (src/kmer_sliding.cpp:159-175)
+    A = sks.unpack_codes(batch.download(0), L)
+    rc = (3 - A[::-1]).astype(np.uint8)
+    (sr,) = ctx.sketch(ctx.upload_codes([rc]), mask, w, sks.all_kmers(), sks.REPR_SORTED)
+    assert np.array_equal(sr.keys(), ka)
+    # position sharding with a (w-1)-base halo: union of slices == whole (C3-style long sequence)
+    mask3, w3 = sks.seed_to_mask(C3_SEED)
+    pred = sks.frac_min_hash(1, 200)
+    (whole,) = ctx.sketch(ctx.upload_codes([A]), mask3, w3, pred)
+    parts = []
+    n_starts = L - w3 + 1
+    cuts = [0, 1_250_000 - 1_250_000 % 16, 2_500_000, 3_750_016, n_starts]
+    full = ctx.upload_codes([A])
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        (p,) = ctx.sketch(full.slice(0, lo, hi - lo, w3), mask3, w3, pred)
+        parts.append(p.keys())
+    union = np.unique(np.concatenate(parts)[:, 0])
+    assert np.array_equal(union, whole.keys()[:, 0])
+
+
+def test_c3_chromosome_scale(ctx):
+    """250 Mbp, weight-21 span-31 seed, FMH(200): sampled against the oracle + global properties."""
+    L = 250_000_000
+    batch = ctx.synth(L, [7], [0], [0])
+    mask, w = sks.seed_to_mask(C3_SEED)
+    pred = sks.frac_min_hash(1, 200)
+    (s,) = ctx.sketch(batch, mask, w, pred)
+    keys = s.keys()
+    n = len(keys)
+    assert abs(n - (L - w + 1) / 200) < 6 * ((L / 200) ** 0.5) + 0.001 * n   # ~1/200 of the windows survive
+    assert (keys[1:, 0] > keys[:-1, 0]).all()
+    # every member passes the predicate (host restatement of frac_min_hash in libsks itself is not the
+    # checker: use the oracle's hash)
+    for i in np.linspace(0, n - 1, 2000).astype(int):
+        assert port.fmh(int(keys[i, 0]), mask, w, 1, 181) % 200 == 0
+    # a 1 Mbp window of the chromosome, sketched by the oracle, must be a subset of the whole sketch
+    lo = 123_456_784
+    sub = sks.unpack_codes(batch.slice(0, lo, 1_000_000, w).download(0), 1_000_000 + w - 1)
+    assert np.array_equal(sub[:64], port.gen(lo + 64, 7)[lo:])
+    osub = port.sketch_set(sub, [len(sub)], mask, w, port.FMH, 1, 200, 181)
+    assert len(osub) > 4000 and np.isin(osub[:, 0], keys[:, 0]).all()
