@@ -91,7 +91,8 @@ int64_t sks_ctx_launch_count(const sks_ctx *ctx);
 #define SKS_KERNEL_INTERSECT 5    /* sorted-set intersection (K5, sorted)                */
 #define SKS_KERNEL_SYNTH 6        /* synthetic genome generator                          */
 #define SKS_KERNEL_LIST 7         /* ordered-list finalisation                           */
-#define SKS_KERNEL_KINDS 8
+#define SKS_KERNEL_BITSET_BUILD 8 /* bucket sort + slice-wise bitset assembly (K4, bucketed) */
+#define SKS_KERNEL_KINDS 9
 int sks_ctx_profile(sks_ctx *ctx, int enable);
 int sks_ctx_kernel_stats(sks_ctx *ctx, int kind, int64_t *out_launches, double *out_total_ms);
 const char *sks_kernel_name(int kind);

@@ -2,6 +2,7 @@
 // intersections.  Host-only entry points live in sks_host.cpp.  See include/sks.h for the contract
 // and the reference interfaces each call replaces.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -46,19 +47,28 @@ int ctx_scratch(sks_ctx *ctx, size_t bytes, void **out) {
   return SKS_OK;
 }
 
+// Pinned staging is a ring: blocks handed out since the last wrap stay untouched, so several
+// asynchronous H2D parameter uploads can be in flight without a stream sync between them.
 int ctx_pinned(sks_ctx *ctx, size_t bytes, void **out) {
-  if (bytes > ctx->pinned_bytes) {
+  bytes = (bytes + 63) & ~(size_t)63;
+  if (bytes > ctx->pinned_bytes / 2) {
     if (ctx->pinned) {
       SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
       SKS_CUDA_TRY(cudaFreeHost(ctx->pinned));
     }
     ctx->pinned = nullptr;
     ctx->pinned_bytes = 0;
-    const size_t want = bytes + 4096;
+    const size_t want = std::max<size_t>(2 * bytes, (size_t)1 << 20);
     SKS_CUDA_TRY(cudaMallocHost(&ctx->pinned, want));
     ctx->pinned_bytes = want;
+    ctx->pinned_off = 0;
   }
-  *out = ctx->pinned;
+  if (ctx->pinned_off + bytes > ctx->pinned_bytes) {
+    SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // everything staged so far has been consumed
+    ctx->pinned_off = 0;
+  }
+  *out = static_cast<char *>(ctx->pinned) + ctx->pinned_off;
+  ctx->pinned_off += bytes;
   return SKS_OK;
 }
 
@@ -236,20 +246,38 @@ sks_set *new_set(const sks_ctx *ctx, int repr, const uint64_t mask[2], int windo
   return s;
 }
 
-int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const uint64_t mask[2], int window,
-                  sks_set **out_sets) {
+int sketch_raw_keys(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const sks_pred *pred, int window,
+                    int out_mode, BufferRef *keys, BufferRef *pos, std::vector<uint64_t> *off,
+                    std::vector<uint64_t> *count, uint64_t *span);
+
+int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const sks_pred *pred, const uint64_t mask[2],
+                  int window, sks_set **out_sets) {
   int index_bits = 0;
   SKS_TRY(build_pext_table(mask, plan.n_limbs, &plan.p.pext, &index_bits));
   const int G = batch->n_genomes;
   const uint64_t bits = 1ull << index_bits;           // 4^weight
   const uint64_t words = bits < 32 ? 1 : bits / 32;   // per genome
-  BufferRef buf;
+  BufferRef buf, count_buf;
   SKS_TRY(alloc_buffer(ctx, (size_t)words * 4 * G, &buf));
-  SKS_TRY(launch_fill_zero(ctx, buf->ptr, (size_t)words * 4 * G));
-  plan.p.bitset = static_cast<uint32_t *>(buf->ptr);
-  plan.p.bitset_words = words;
-  SKS_TRY(launch_sketch(ctx, plan.p, batch->tile_genome ? static_cast<const uint32_t *>(batch->tile_genome->ptr) : nullptr,
-                        plan.n_limbs, plan.pred_mode, OUT_BITSET));
+  const uint32_t *tg = batch->tile_genome ? static_cast<const uint32_t *>(batch->tile_genome->ptr) : nullptr;
+  const bool bucketed = index_bits > kSliceBits && index_bits >= ctx->bucket_min_bits;
+  if (bucketed) {
+    // K2/K3 emit 32-bit PEXT indices; K4 = bucket by slice + assemble every 64 KB slice in smem
+    BufferRef raw, pos, sorted;
+    std::vector<uint64_t> off, count;
+    uint64_t span = 0;
+    SKS_TRY(sketch_raw_keys(ctx, batch, plan, pred, window, OUT_INDEX, &raw, &pos, &off, &count, &span));
+    SKS_TRY(alloc_buffer(ctx, (size_t)span * 4, &sorted));
+    SKS_TRY(alloc_buffer(ctx, sizeof(unsigned long long) * (size_t)G, &count_buf));
+    SKS_TRY(launch_bitset_build(ctx, static_cast<const uint32_t *>(raw->ptr), static_cast<uint32_t *>(sorted->ptr),
+                                off.data(), count.data(), G, index_bits, static_cast<uint32_t *>(buf->ptr), words,
+                                static_cast<unsigned long long *>(count_buf->ptr)));
+  } else {
+    SKS_TRY(launch_fill_zero(ctx, buf->ptr, (size_t)words * 4 * G));
+    plan.p.bitset = static_cast<uint32_t *>(buf->ptr);
+    plan.p.bitset_words = words;
+    SKS_TRY(launch_sketch(ctx, plan.p, tg, plan.n_limbs, plan.pred_mode, OUT_BITSET));
+  }
   for (int g = 0; g < G; ++g) {
     sks_set *s = new_set(ctx, SKS_REPR_BITSET, mask, window, plan.weight);
     if (!s) return set_error(SKS_ERR_INVALID, "out of host memory");
@@ -257,6 +285,8 @@ int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
     s->byte_off = (size_t)g * words * 4;
     s->bitset_words = words;
     s->count = -1;
+    s->count_buf = count_buf;
+    s->count_off = (size_t)g * sizeof(unsigned long long);
     out_sets[g] = s;
   }
   return SKS_OK;
@@ -268,7 +298,7 @@ int sketch_raw_keys(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, cons
                     int out_mode, BufferRef *keys, BufferRef *pos, std::vector<uint64_t> *off,
                     std::vector<uint64_t> *count, uint64_t *span) {
   const int G = batch->n_genomes;
-  const int key_words = plan.n_limbs <= 2 ? 1 : 2;
+  const size_t key_bytes = out_mode == OUT_INDEX ? 4 : (plan.n_limbs <= 2 ? 8 : 16);
   std::vector<uint64_t> cap(G);
   for (int g = 0; g < G; ++g) {
     const uint64_t wins = genome_windows(batch, g, window);
@@ -288,7 +318,7 @@ int sketch_raw_keys(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, cons
       total += cap[g];
     }
     *span = total;
-    SKS_TRY(alloc_buffer(ctx, (size_t)total * 8 * key_words, keys));
+    SKS_TRY(alloc_buffer(ctx, (size_t)total * key_bytes, keys));
     if (out_mode == OUT_LIST) SKS_TRY(alloc_buffer(ctx, (size_t)total * 4, pos));
     // device tables: off | cap | count
     char *tab = nullptr;
@@ -308,6 +338,10 @@ int sketch_raw_keys(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, cons
     plan.p.out_count = d_count;
     SKS_TRY(launch_sketch(ctx, plan.p, batch->tile_genome ? static_cast<const uint32_t *>(batch->tile_genome->ptr) : nullptr,
                           plan.n_limbs, plan.pred_mode, out_mode));
+    if (plan.pred_mode == PRED_ALL) {  // every window is kept: the counts are known without a read-back
+      for (int g = 0; g < G; ++g) (*count)[g] = cap[g];
+      return SKS_OK;
+    }
     SKS_CUDA_TRY(cudaMemcpyAsync(stage, d_count, (size_t)G * 8, cudaMemcpyDeviceToHost, ctx->stream));
     SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     memcpy(count->data(), stage, (size_t)G * 8);
@@ -391,6 +425,7 @@ int sks_ctx_create(int device, sks_ctx **out) {
   SKS_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t threshold = UINT64_MAX;
   SKS_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  if (const char *e = getenv("SKS_BUCKET_MIN_BITS")) ctx->bucket_min_bits = atoi(e);
   *out = ctx;
   return SKS_OK;
 }
@@ -476,7 +511,7 @@ int sks_ctx_kernel_stats(sks_ctx *ctx, int kind, int64_t *out_launches, double *
 const char *sks_kernel_name(int kind) {
   static const char *names[SKS_KERNEL_KINDS] = {"sketch_kernel", "fill_zero_kernel", "bitset_pair_counts_kernel",
                                                 "bitset_popcount_kernel", "sort_unique", "sorted_intersect_kernel",
-                                                "synth_kernel", "list_finalize"};
+                                                "synth_kernel", "list_finalize", "bitset_build"};
   return (kind >= 0 && kind < SKS_KERNEL_KINDS) ? names[kind] : "?";
 }
 
@@ -641,7 +676,7 @@ int sks_sketch(sks_ctx *ctx, const sks_batch *batch, const uint64_t mask[2], int
   if (repr == SKS_REPR_BITSET) {
     if (plan.weight > 16)
       return set_error(SKS_ERR_INVALID, "bitset representation needs weight <= 16 (4^%d bits do not fit)", plan.weight);
-    st = sketch_bitset(ctx, batch, plan, mask, window, out_sets);
+    st = sketch_bitset(ctx, batch, plan, pred, mask, window, out_sets);
   } else if (repr == SKS_REPR_SORTED) {
     st = sketch_sorted(ctx, batch, plan, pred, mask, window, out_sets);
   } else {
@@ -667,8 +702,12 @@ int sks_set_size(sks_ctx *ctx, sks_set *s, int64_t *out) {
     unsigned long long *d_cnt = nullptr, *h_cnt = nullptr;
     SKS_TRY(ctx_scratch(ctx, 64, reinterpret_cast<void **>(&d_cnt)));
     SKS_TRY(ctx_pinned(ctx, 64, reinterpret_cast<void **>(&h_cnt)));
-    SKS_TRY(launch_bitset_popcount(ctx, reinterpret_cast<const uint32_t *>(static_cast<const char *>(s->buf->ptr) + s->byte_off),
-                                   s->bitset_words, d_cnt));
+    if (s->count_buf) {  // the bucketed build already counted the bits
+      d_cnt = reinterpret_cast<unsigned long long *>(static_cast<char *>(s->count_buf->ptr) + s->count_off);
+    } else {
+      SKS_TRY(launch_bitset_popcount(ctx, reinterpret_cast<const uint32_t *>(static_cast<const char *>(s->buf->ptr) + s->byte_off),
+                                     s->bitset_words, d_cnt));
+    }
     SKS_CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
     SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     s->count = (int64_t)h_cnt[0];

@@ -57,8 +57,13 @@ struct GenomeDesc {
   uint32_t n_tiles;
 };
 
-enum OutMode : int { OUT_KEYS = 0, OUT_BITSET = 1, OUT_LIST = 2 };
+enum OutMode : int { OUT_KEYS = 0, OUT_BITSET = 1, OUT_LIST = 2, OUT_INDEX = 3 };
 enum PredMode : int { PRED_ALL = 0, PRED_FMH181 = 1, PRED_FMH171 = 2 };
+
+// Bucketed bitset build: the 4^weight-bit bitset is cut into slices of 2^kSliceBits bits (64 KB) that
+// are assembled in shared memory and streamed out once (sks_sets.cu, bitset_build_kernel).
+constexpr int kSliceBits = 19;
+constexpr int kSliceWords = (1 << kSliceBits) / 32;  // 16384
 
 constexpr int kMaxPieces = 40;  // <= 32 runs, each split at most once per 32-bit limb boundary
 
@@ -85,7 +90,7 @@ struct SketchParams {
   uint64_t mbound;             // floor((2^64-1) / modulus)
   int mshift;                  // log2 of the power-of-two part of the modulus
   // OUT_KEYS / OUT_LIST: per-genome output regions
-  void *out_keys;                       // uint64 (NL<=2) or ulonglong2 (NL>2) slots
+  void *out_keys;                       // uint64 (NL<=2) / ulonglong2 (NL>2) slots; uint32 for OUT_INDEX
   uint32_t *out_pos;                    // OUT_LIST only: (strand<<31 | start position) per slot
   const uint64_t *out_off;              // [n_genomes] first slot of the genome's region
   const uint64_t *out_cap;              // [n_genomes] slots in the region
@@ -121,9 +126,11 @@ struct sks_ctx {
   // reusable scratch (grown on demand)
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
+  int bucket_min_bits = 26;  // bitsets of >= 2^this bits are built by the bucketed path (SKS_BUCKET_MIN_BITS)
   // pinned staging for small D2H/H2D traffic
   void *pinned = nullptr;
   size_t pinned_bytes = 0;
+  size_t pinned_off = 0;
   // optional per-kernel event timing (sks_ctx_profile)
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[SKS_KERNEL_KINDS];
@@ -156,6 +163,9 @@ struct sks_set {
   int key_words = 1;
   int64_t count = -1;  // -1: not yet known (BITSET before the first popcount)
   uint64_t bitset_words = 0;
+  // BITSET built by the bucketed path: the build kernel left the popcount on the device
+  sks::BufferRef count_buf;
+  size_t count_off = 0;
 };
 
 namespace sks {
@@ -180,6 +190,9 @@ int launch_synth(sks_ctx *ctx, uint32_t *words, const GenomeDesc *genomes, int n
                  const uint64_t *gen_seed, const uint64_t *mut_seed, const uint64_t *mut_D, const uint64_t *first_base);
 int launch_bitset_pair_counts(sks_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n_words,
                               unsigned long long *out3);
+int launch_bitset_build(sks_ctx *ctx, const uint32_t *raw_idx, uint32_t *sorted_idx, const uint64_t *h_off,
+                        const uint64_t *h_count, int n_genomes, int index_bits, uint32_t *bitset, uint64_t bitset_words,
+                        unsigned long long *d_set_count);
 int launch_bitset_popcount(sks_ctx *ctx, const uint32_t *a, uint64_t n_words, unsigned long long *out1);
 int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t *h_off, const uint64_t *h_count,
                         int n_regions, uint64_t span, BufferRef *out_buf, std::vector<uint64_t> *out_off,

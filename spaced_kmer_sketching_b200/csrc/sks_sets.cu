@@ -6,6 +6,8 @@
 //   kmer_set::insert_kmers   src/kmer.hpp:170-178   (set of distinct (masked_bits, mask))
 //   kmer_set::kmer_set_size  src/kmer.hpp:186-189
 //   kmer_set_intersection    src/kmer_set.cpp:23-41 (|A n B|)
+#include <algorithm>
+
 #include <cub/cub.cuh>
 
 #include "sks_internal.cuh"
@@ -126,6 +128,238 @@ int stream_grid(const sks_ctx *ctx, size_t n16) {
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return (int)want;
+}
+
+// ---- bucketed bitset build --------------------------------------------------------------------------
+// Random atomicOr into a 512 MiB bitset costs a 64 B DRAM read + a 32 B write per k-mer (measured:
+// 1 GB of DRAM traffic for 10 M k-mers at 29 % of HBM, latency bound).  Instead:
+//   1. the 32-bit PEXT indices of a genome are partitioned into <= 256 coarse buckets by their top
+//      bits (a counting pass, a scan and a scatter pass over an L2-resident 20 MB list).  A finer
+//      partition (one bucket per 64 KB slice) was measured too: its one-atomic-per-index scatter cost
+//      276 us, more than it saved;
+//   2. a CTA takes a group of slices of one coarse bucket, keeps the group's indices in shared memory,
+//      and assembles every 64 KB slice there before streaming it to HBM exactly once.
+// The clear and the insert become ONE sequential write pass, and the slice popcounts give
+// kmer_set_size() for free.
+constexpr int kCoarseBitsMax = 8;                    // <= 256 coarse buckets
+constexpr int kCoarseSliceBitsMax = 5;               // <= 32 slices (2 MiB of bitset) per coarse bucket
+constexpr int kGroupSlices = 8;                      // slices assembled by one work item
+constexpr int kBuildThreads = 512;
+constexpr int kKeyCap = 11264;                       // indices of one work item kept in shared memory (44 KB)
+
+struct BuildGenome {
+  const uint32_t *raw;      // PEXT indices as emitted by the sketch kernel
+  uint32_t *bucketed;       // the same, grouped by coarse bucket
+  uint32_t *starts;         // [n_coarse + 1] first position of every coarse bucket in `bucketed`
+  uint32_t *cursor;         // [n_coarse] histogram, then scatter cursors (= bucket ends afterwards)
+  uint32_t *bitset;
+  unsigned long long *set_count;
+  uint32_t n;               // number of indices
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(256)
+    coarse_hist_kernel(const BuildGenome *__restrict__ genomes, int coarse_shift, uint32_t n_coarse) {
+  __shared__ uint32_t s_hist[1 << kCoarseBitsMax];
+  const BuildGenome g = genomes[blockIdx.y];
+  for (uint32_t i = threadIdx.x; i < n_coarse; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += stride)
+    atomicAdd(&s_hist[__ldg(g.raw + i) >> coarse_shift], 1u);
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < n_coarse; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(g.cursor + i, s_hist[i]);  // cursor doubles as the histogram until the scan
+}
+
+// One CTA per genome: exclusive scan of the histogram -> starts[0..n_coarse], cursor = starts.
+__global__ void __launch_bounds__(256) coarse_scan_kernel(const BuildGenome *__restrict__ genomes, uint32_t n_coarse) {
+  __shared__ uint32_t s[1 << kCoarseBitsMax];
+  const BuildGenome g = genomes[blockIdx.x];
+  const uint32_t t = threadIdx.x;
+  const uint32_t v = t < n_coarse ? g.cursor[t] : 0u;
+  s[t] = v;
+  __syncthreads();
+  for (uint32_t o = 1; o < 256; o <<= 1) {
+    const uint32_t add = t >= o ? s[t - o] : 0u;
+    __syncthreads();
+    s[t] += add;
+    __syncthreads();
+  }
+  if (t < n_coarse) {
+    g.starts[t] = s[t] - v;
+    g.cursor[t] = s[t] - v;
+  }
+  if (t == 0) g.starts[n_coarse] = g.n;
+}
+
+constexpr int kScatterKeys = 4096;  // indices per CTA pass
+
+__global__ void __launch_bounds__(256)
+    coarse_scatter_kernel(const BuildGenome *__restrict__ genomes, int coarse_shift, uint32_t n_coarse) {
+  __shared__ uint32_t s_hist[1 << kCoarseBitsMax];
+  __shared__ uint32_t s_base[1 << kCoarseBitsMax];
+  const BuildGenome g = genomes[blockIdx.y];
+  const uint32_t n_chunks = (g.n + kScatterKeys - 1) / kScatterKeys;
+  for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    for (uint32_t i = threadIdx.x; i < n_coarse; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    uint32_t key[kScatterKeys / 256], rank[kScatterKeys / 256];
+    const uint32_t base = chunk * kScatterKeys;
+#pragma unroll
+    for (int u = 0; u < kScatterKeys / 256; ++u) {
+      const uint32_t i = base + u * 256 + threadIdx.x;
+      if (i < g.n) key[u] = __ldg(g.raw + i);
+    }
+#pragma unroll
+    for (int u = 0; u < kScatterKeys / 256; ++u) {
+      const uint32_t i = base + u * 256 + threadIdx.x;
+      if (i < g.n) rank[u] = atomicAdd(&s_hist[key[u] >> coarse_shift], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n_coarse; i += blockDim.x)
+      s_base[i] = s_hist[i] ? atomicAdd(g.cursor + i, s_hist[i]) : 0u;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kScatterKeys / 256; ++u) {
+      const uint32_t i = base + u * 256 + threadIdx.x;
+      if (i < g.n) g.bucketed[s_base[key[u] >> coarse_shift] + rank[u]] = key[u];
+    }
+    __syncthreads();
+  }
+}
+
+// Work item = (genome, coarse bucket, group of <= kGroupSlices slices), handed out by an atomic counter.
+// Two ~108 KB CTAs per SM: one assembles while the other streams its slice out.  The slice leaves shared
+// memory through registers (LDS.128 -> popcount -> STG.128): plain vector stores are fire-and-forget,
+// whereas a 64 KB bulk (TMA) store per CTA measured ~6 us of latency with one store in flight per CTA.
+__global__ void __launch_bounds__(kBuildThreads, 2)
+    bitset_build_kernel(const BuildGenome *__restrict__ genomes, uint32_t n_genomes, uint32_t n_coarse,
+                        uint32_t slices_per_coarse, uint32_t group_slices, unsigned int *__restrict__ work_counter) {
+  extern __shared__ __align__(128) uint32_t s_dyn[];
+  uint32_t *s_slice = s_dyn;                 // [kSliceWords]
+  uint32_t *s_keys = s_dyn + kSliceWords;    // [kKeyCap]
+  __shared__ uint32_t s_item, s_nkeys;
+  __shared__ unsigned long long s_tot[kBuildThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t groups = slices_per_coarse / group_slices;
+  const uint32_t n_items = n_genomes * n_coarse * groups;
+  const uint32_t slice_mask = slices_per_coarse - 1;
+  unsigned long long total = 0;
+  uint32_t cur_genome = 0xFFFFFFFFu;
+  uint4 *b4 = reinterpret_cast<uint4 *>(s_slice);
+
+  auto flush_total = [&](uint32_t genome) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_down_sync(0xffffffffu, total, o);
+    if (lane == 0) s_tot[tid >> 5] = total;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long t = 0;
+      for (int i = 0; i < kBuildThreads / 32; ++i) t += s_tot[i];
+      if (t) atomicAdd(genomes[genome].set_count, t);
+    }
+    __syncthreads();
+    total = 0;
+  };
+
+  for (;;) {
+    __syncthreads();  // everyone is done with s_item / s_keys of the previous item
+    if (tid == 0) s_item = atomicAdd(work_counter, 1u);
+    __syncthreads();
+    const uint32_t item = s_item;
+    if (item >= n_items) break;
+    const uint32_t genome = item / (n_coarse * groups);
+    const uint32_t rem = item - genome * (n_coarse * groups);
+    const uint32_t coarse = rem / groups, group = rem - coarse * groups;
+    if (genome != cur_genome) {
+      if (cur_genome != 0xFFFFFFFFu) flush_total(cur_genome);
+      cur_genome = genome;
+    }
+    const BuildGenome g = genomes[genome];
+    const uint32_t lo = __ldg(g.starts + coarse), hi = __ldg(g.cursor + coarse);  // cursor = bucket end after the scatter
+    const uint32_t *__restrict__ bk = g.bucketed;
+
+    // Stages the indices of slices [first, first + span) of this coarse bucket in s_keys (warp-aggregated
+    // compaction, four independent loads in flight per lane); returns how many there are.
+    auto stage = [&](uint32_t first, uint32_t span) -> uint32_t {
+      __syncthreads();
+      if (tid == 0) s_nkeys = 0;
+      __syncthreads();
+      for (uint32_t i0 = lo + (tid >> 5) * 128; i0 < hi; i0 += (kBuildThreads / 32) * 128) {
+        uint32_t key[4];
+        bool keep[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t i = i0 + u * 32 + lane;
+          key[u] = i < hi ? __ldg(bk + i) : 0xFFFFFFFFu;
+          keep[u] = i < hi && (((key[u] >> kSliceBits) & slice_mask) - first) < span;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t m = __ballot_sync(0xffffffffu, keep[u]);
+          if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_nkeys, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t slot = base + __popc(m & ((1u << lane) - 1));
+            if (keep[u] && slot < kKeyCap) s_keys[slot] = key[u];
+          }
+        }
+      }
+      __syncthreads();
+      return s_nkeys;
+    };
+
+    // Assembles one slice in shared memory and streams it out.
+    auto assemble = [&](uint32_t slice, uint32_t nkeys, bool direct) {
+#pragma unroll
+      for (int i = tid; i < kSliceWords / 4; i += kBuildThreads) b4[i] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      if (!direct) {
+        for (uint32_t i = tid; i < nkeys; i += kBuildThreads) {
+          const uint32_t key = s_keys[i];
+          if (((key >> kSliceBits) & slice_mask) == slice) {
+            const uint32_t bit = key & ((1u << kSliceBits) - 1);
+            atomicOr(&s_slice[bit >> 5], 1u << (bit & 31));
+          }
+        }
+      } else {  // more indices in ONE slice than shared memory holds: read them from the bucket
+        for (uint32_t i = lo + tid; i < hi; i += kBuildThreads) {
+          const uint32_t key = __ldg(bk + i);
+          if (((key >> kSliceBits) & slice_mask) == slice) {
+            const uint32_t bit = key & ((1u << kSliceBits) - 1);
+            atomicOr(&s_slice[bit >> 5], 1u << (bit & 31));
+          }
+        }
+      }
+      __syncthreads();
+      uint4 *dst = reinterpret_cast<uint4 *>(g.bitset + ((size_t)coarse * slices_per_coarse + slice) * kSliceWords);
+      uint32_t c = 0;
+#pragma unroll
+      for (int i = tid; i < kSliceWords / 4; i += kBuildThreads) {
+        const uint4 v = b4[i];
+        c += popc4(v);
+        __stcs(dst + i, v);
+      }
+      total += c;
+      __syncthreads();  // the slice buffer is zeroed again
+    };
+
+    const uint32_t first_slice = group * group_slices;  // within the coarse bucket
+    uint32_t done = 0;
+    while (done < group_slices) {  // normally one pass; skewed buckets are staged in smaller spans
+      uint32_t span = group_slices - done, nkeys;
+      for (;;) {
+        nkeys = stage(first_slice + done, span);
+        if (nkeys <= kKeyCap || span == 1) break;
+        span >>= 1;
+      }
+      for (uint32_t t = 0; t < span; ++t) assemble(first_slice + done + t, nkeys, nkeys > kKeyCap);
+      done += span;
+    }
+  }
+  if (cur_genome != 0xFFFFFFFFu) flush_total(cur_genome);
 }
 
 // ---- sort + unique --------------------------------------------------------------------------------
@@ -281,6 +515,75 @@ int launch_bitset_pair_counts(sks_ctx *ctx, const uint32_t *a, const uint32_t *b
     bitset_pair_counts_kernel<<<stream_grid(ctx, n16), kStreamThreads, 0, ctx->stream>>>(
         reinterpret_cast<const uint4 *>(a), reinterpret_cast<const uint4 *>(b), n16, out3);
   }
+  SKS_CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  return SKS_OK;
+}
+
+// Builds n_genomes bitsets of 2^index_bits bits each (index_bits > kSliceBits) from the raw PEXT
+// indices of every genome: raw_idx + h_off[g] holds h_count[g] indices; bucketed_idx is scratch of the
+// same size.  d_set_count[g] receives |set g| (zeroed here).
+int launch_bitset_build(sks_ctx *ctx, const uint32_t *raw_idx, uint32_t *bucketed_idx, const uint64_t *h_off,
+                        const uint64_t *h_count, int n_genomes, int index_bits, uint32_t *bitset, uint64_t bitset_words,
+                        unsigned long long *d_set_count) {
+  if (n_genomes == 0) return SKS_OK;
+  const int coarse_bits = std::max(index_bits - kSliceBits - kCoarseSliceBitsMax, 0);
+  if (coarse_bits > kCoarseBitsMax || index_bits <= kSliceBits)
+    return set_error(SKS_ERR_INVALID, "bucketed bitset build handles 20..32 index bits, not %d", index_bits);
+  const uint32_t n_coarse = 1u << coarse_bits;
+  const int coarse_shift = index_bits - coarse_bits;  // coarse bucket = idx >> coarse_shift
+  const uint32_t slices_per_coarse = 1u << (coarse_shift - kSliceBits);
+  const uint32_t group_slices = std::min<uint32_t>(slices_per_coarse, kGroupSlices);
+  uint64_t max_n = 0;
+  for (int g = 0; g < n_genomes; ++g) max_n = std::max(max_n, h_count[g]);
+  if (max_n >= (1ull << 32)) return set_error(SKS_ERR_CAPACITY, "too many k-mers in one genome for the bucketed build");
+
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t sz_desc = align(sizeof(BuildGenome) * n_genomes);
+  const size_t sz_tab = align((size_t)(2 * n_coarse + 1) * 4);  // starts | cursor per genome
+  char *base = nullptr;
+  SKS_TRY(ctx_scratch(ctx, sz_desc + sz_tab * n_genomes + 256, reinterpret_cast<void **>(&base)));
+  BuildGenome *d_desc = reinterpret_cast<BuildGenome *>(base);
+  char *d_tabs = base + sz_desc;
+  unsigned int *d_counter = reinterpret_cast<unsigned int *>(d_tabs + sz_tab * n_genomes);
+  BuildGenome *h_desc = nullptr;
+  SKS_TRY(ctx_pinned(ctx, sizeof(BuildGenome) * n_genomes, reinterpret_cast<void **>(&h_desc)));
+  for (int g = 0; g < n_genomes; ++g) {
+    uint32_t *tab = reinterpret_cast<uint32_t *>(d_tabs + sz_tab * g);
+    h_desc[g].raw = raw_idx + h_off[g];
+    h_desc[g].bucketed = bucketed_idx + h_off[g];
+    h_desc[g].starts = tab;
+    h_desc[g].cursor = tab + n_coarse + 1;
+    h_desc[g].bitset = bitset + (size_t)g * bitset_words;
+    h_desc[g].set_count = d_set_count + g;
+    h_desc[g].n = (uint32_t)h_count[g];
+    h_desc[g].pad = 0;
+  }
+
+  KernelTimer timer(ctx, SKS_KERNEL_BITSET_BUILD);
+  SKS_CUDA_TRY(cudaMemsetAsync(d_set_count, 0, sizeof(unsigned long long) * n_genomes, ctx->stream));
+  SKS_CUDA_TRY(cudaMemsetAsync(d_tabs, 0, sz_tab * n_genomes + 256, ctx->stream));
+  SKS_CUDA_TRY(cudaMemcpyAsync(d_desc, h_desc, sizeof(BuildGenome) * n_genomes, cudaMemcpyHostToDevice, ctx->stream));
+  constexpr int smem = (kSliceWords + kKeyCap) * 4;
+  static thread_local bool attr_set[8] = {false, false, false, false, false, false, false, false};
+  if (!attr_set[ctx->device & 7]) {
+    SKS_CUDA_TRY(cudaFuncSetAttribute(bitset_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set[ctx->device & 7] = true;
+  }
+  const unsigned gx_stream = (unsigned)std::min<uint64_t>((max_n + kScatterKeys - 1) / kScatterKeys + 1,
+                                                          (uint64_t)ctx->sm_count * 8);
+  for (int g0 = 0; g0 < n_genomes; g0 += 32768) {
+    const int ng = std::min(n_genomes - g0, 32768);
+    coarse_hist_kernel<<<dim3(gx_stream, ng), 256, 0, ctx->stream>>>(d_desc + g0, coarse_shift, n_coarse);
+    coarse_scan_kernel<<<ng, 256, 0, ctx->stream>>>(d_desc + g0, n_coarse);
+    coarse_scatter_kernel<<<dim3(gx_stream, ng), 256, 0, ctx->stream>>>(d_desc + g0, coarse_shift, n_coarse);
+    ctx->launches += 3;
+  }
+  const uint64_t n_items = (uint64_t)n_genomes * n_coarse * (slices_per_coarse / group_slices);
+  if (n_items >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "too many bitset slices in one batch");
+  const unsigned gx = (unsigned)std::min<uint64_t>(n_items, (uint64_t)ctx->sm_count * 2);  // two ~108 KB CTAs per SM
+  bitset_build_kernel<<<gx, kBuildThreads, smem, ctx->stream>>>(d_desc, (uint32_t)n_genomes, n_coarse, slices_per_coarse,
+                                                               group_slices, d_counter);
   SKS_CUDA_TRY(cudaGetLastError());
   ctx->launches++;
   return SKS_OK;

@@ -88,17 +88,35 @@ struct TileMeta {
   uint32_t pad[3];
 };
 
-template <int NL>
+// Staged / emitted element: the masked key (8 B up to 32 bases, else 16 B), or -- OUT_INDEX -- the
+// 32-bit PEXT index of the key.
+template <int NL, int OUT>
 struct KeyType {
   using type = unsigned long long;
 };
-template <>
-struct KeyType<3> {
+template <int OUT>
+struct KeyType<3, OUT> {
+  using type = ulonglong2;
+};
+template <int OUT>
+struct KeyType<4, OUT> {
   using type = ulonglong2;
 };
 template <>
-struct KeyType<4> {
-  using type = ulonglong2;
+struct KeyType<1, OUT_INDEX> {
+  using type = uint32_t;
+};
+template <>
+struct KeyType<2, OUT_INDEX> {
+  using type = uint32_t;
+};
+template <>
+struct KeyType<3, OUT_INDEX> {
+  using type = uint32_t;
+};
+template <>
+struct KeyType<4, OUT_INDEX> {
+  using type = uint32_t;
 };
 
 constexpr int kStageSlots = kSketchThreads * kGroup;  // kept k-mers staged per round (4096)
@@ -106,7 +124,7 @@ constexpr int kStageSlots = kSketchThreads * kGroup;  // kept k-mers staged per 
 template <int NL, int OUT>
 constexpr size_t sketch_smem_bytes() {
   size_t b = 2 * kStageWords * 4 + 2 * sizeof(TileMeta) + 64;
-  if (OUT != OUT_BITSET) b += kStageSlots * sizeof(typename KeyType<NL>::type);
+  if (OUT != OUT_BITSET) b += kStageSlots * sizeof(typename KeyType<NL, OUT>::type);
   if (OUT == OUT_LIST) b += kStageSlots * 4;
   return b;
 }
@@ -114,7 +132,7 @@ constexpr size_t sketch_smem_bytes() {
 template <int NL, int PRED, int OUT>
 __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_constant__ SketchParams P,
                                                                const uint32_t *__restrict__ tile_genome) {
-  using key_t = typename KeyType<NL>::type;
+  using key_t = typename KeyType<NL, OUT>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t *s_words = reinterpret_cast<uint32_t *>(smem_raw);                        // [2][kStageWords]
   TileMeta *s_meta = reinterpret_cast<TileMeta *>(smem_raw + 2 * kStageWords * 4);    // [2]
@@ -261,17 +279,21 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
 
           // ---- K3/K4: emit ---------------------------------------------------------------------
           if (pass) {
-            if (OUT == OUT_BITSET) {
-              uint32_t idx = 0;
+            uint32_t idx = 0;
+            if (OUT == OUT_BITSET || OUT == OUT_INDEX) {  // PEXT(masked, mask): rotate-and-mask pieces
 #pragma unroll
               for (int k = 0; k < NL; ++k) {
                 for (int p = P.pext.piece_begin[k]; p < P.pext.piece_begin[k + 1]; ++p)
                   idx |= __funnelshift_r(c[k], c[k], P.pext.rot[p]) & P.pext.dmask[p];
               }
+            }
+            if (OUT == OUT_BITSET) {
               atomicOr(P.bitset + (uint64_t)tm.genome * P.bitset_words + (idx >> 5), 1u << (idx & 31));
             } else {
               const uint32_t slot = atomicAdd(s_count, 1u);
-              if (NL <= 2) {
+              if (OUT == OUT_INDEX) {
+                reinterpret_cast<uint32_t *>(s_keys)[slot] = idx;
+              } else if (NL <= 2) {
                 reinterpret_cast<unsigned long long *>(s_keys)[slot] = b0;
               } else {
                 reinterpret_cast<ulonglong2 *>(s_keys)[slot] = make_ulonglong2(b0, b1);
@@ -335,6 +357,7 @@ int launch_out(sks_ctx *ctx, const SketchParams &p, const uint32_t *tg, int out_
     case OUT_KEYS: return launch_one<NL, PRED, OUT_KEYS>(ctx, p, tg);
     case OUT_BITSET: return launch_one<NL, PRED, OUT_BITSET>(ctx, p, tg);
     case OUT_LIST: return launch_one<NL, PRED, OUT_LIST>(ctx, p, tg);
+    case OUT_INDEX: return launch_one<NL, PRED, OUT_INDEX>(ctx, p, tg);
   }
   return set_error(SKS_ERR_INVALID, "bad output mode %d", out_mode);
 }

@@ -38,6 +38,21 @@ def ctx():
     c.close()
 
 
+@pytest.fixture(scope="module")
+def ctx_bucket():
+    """A context that builds every bitset above one slice through the bucketed (slice-assembly) path."""
+    import os
+    old = os.environ.get("SKS_BUCKET_MIN_BITS")
+    os.environ["SKS_BUCKET_MIN_BITS"] = "20"
+    c = sks.Context(0)
+    if old is None:
+        del os.environ["SKS_BUCKET_MIN_BITS"]
+    else:
+        os.environ["SKS_BUCKET_MIN_BITS"] = old
+    yield c
+    c.close()
+
+
 def opred(pred):
     if pred.kind == sks.PRED_ALL:
         return (port.ALL,)
@@ -91,7 +106,7 @@ def random_case(rng, trial):
 
 
 @pytest.mark.parametrize("block", range(4))
-def test_fuzz_lists_and_sets_vs_oracle(ctx, block):
+def test_fuzz_lists_and_sets_vs_oracle(ctx, ctx_bucket, block):
     rng = np.random.default_rng(100 + block)
     for t in range(12):
         trial = block * 12 + t
@@ -111,7 +126,36 @@ def test_fuzz_lists_and_sets_vs_oracle(ctx, block):
             if k <= 13:
                 (b,) = ctx.sketch(batch, mask, w, pred, sks.REPR_BITSET)
                 assert b.kmer_set_size() == len(oset) and np.array_equal(b.keys(), oset), tag
+                if k >= 10:   # same through the bucketed build (atomic path above when 2k < 26)
+                    b2 = ctx_bucket.upload_codes([codes], [np.array(lens, dtype=np.uint64)])
+                    (b,) = ctx_bucket.sketch(b2, mask, w, pred, sks.REPR_BITSET)
+                    assert b.kmer_set_size() == len(oset) and np.array_equal(b.keys(), oset), tag
+                    b2.close()
         batch.close()
+
+
+def test_bitset_paths_agree_multi_genome(ctx, ctx_bucket):
+    """Atomic-insert and bucketed bitset builds give identical bitsets (sizes, members, intersections)."""
+    rng = np.random.default_rng(11)
+    genomes = [rng.integers(0, 4, n, dtype=np.uint8) for n in (70000, 5, 8192, 33333)]
+    genomes.append(genomes[0].copy())
+    genomes[4][::97] = (genomes[4][::97] + 1) & 3
+    # skewed index distributions: one slice / one coarse bucket holds (nearly) every index, which drives
+    # the bucketed build through its span-halving and direct-scan paths
+    genomes.append(np.zeros(60000, dtype=np.uint8))                                  # poly-A
+    genomes.append((rng.integers(0, 2, 90000) * 3).astype(np.uint8))                 # A/T only
+    genomes.append(np.where(rng.random(120000) < 0.9, 0, rng.integers(0, 4, 120000)).astype(np.uint8))
+    segl = [None, None, np.array([4000, 4192], dtype=np.uint64), None, None, None, None, None]
+    for seed, pred in (("1101100111011", sks.all_kmers()), ("110110011101101", sks.frac_min_hash(1, 3))):
+        mask, w = sks.seed_to_mask(seed)
+        osets = [port.sketch_set(g, [len(g)] if s is None else list(s), mask, w, *opred(pred))
+                 for g, s in zip(genomes, segl)]
+        for c in (ctx, ctx_bucket):
+            sets = c.sketch(c.upload_codes(genomes, segl), mask, w, pred, sks.REPR_BITSET)
+            assert [s.kmer_set_size() for s in sets] == [len(o) for o in osets]
+            for s, o in zip(sets, osets):
+                assert np.array_equal(s.keys(), o)
+            assert c.intersect(sets[0], sets[4]) == port.intersection(osets[0], osets[4])
 
 
 def test_multi_genome_batch_and_intersections(ctx):
