@@ -109,6 +109,8 @@ int sks_contiguous_mask(int k, uint64_t out_mask[2]);
 int sks_random_mask(int window, int k, uint64_t seed, uint64_t out_mask[2]);
 /* reverse_kmer_bitset, src/kmer_bitset.cpp:105-119 */
 void sks_reverse_bitset(const uint64_t in[2], uint64_t out[2]);
+/* boost::hash<boost::dynamic_bitset<>> of a 128-bit value (call sites src/kmer.hpp:137,146). */
+uint64_t sks_boost_hash_bitset(const uint64_t value[2], int hash_variant);
 /* frac_min_hash::operator(), src/kmer.hpp:144-148, on the host (for the C++ functor type). */
 uint64_t sks_fmh_hash(const uint64_t masked[2], const uint64_t mask[2], int window, int nonce,
                       int hash_variant);
@@ -191,6 +193,10 @@ int sks_set_from_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int
  * the merge step after an all-gather of per-rank partial sketches of one sequence. */
 int sks_set_from_unsorted_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int words_per_key,
                                       const uint64_t mask[2], int window, sks_set **out);
+/* Same from HOST keys (2 words per key: lo, hi), e.g. kmer_set::insert_kmers (src/kmer.hpp:170-178) on a
+ * host-built list, or the survivors of a host-evaluated sketching condition. */
+int sks_set_from_host_keys(sks_ctx *ctx, const uint64_t *keys_lohi, int64_t n_keys, const uint64_t mask[2], int window,
+                           sks_set **out);
 void sks_set_destroy(sks_ctx *ctx, sks_set *s);
 
 /* ---- comparison ------------------------------------------------------------------------------ */

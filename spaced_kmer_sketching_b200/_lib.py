@@ -59,6 +59,7 @@ PROTOTYPES = {
     "sks_contiguous_mask": (ci, [ci, u64p]),
     "sks_random_mask": (ci, [ci, ci, u64, u64p]),
     "sks_reverse_bitset": (None, [u64p, u64p]),
+    "sks_boost_hash_bitset": (u64, [u64p, ci]),
     "sks_fmh_hash": (u64, [u64p, u64p, ci, ci, ci]),
     "sks_containment": (C.c_double, [ci, ci]),
     "sks_binomial_estimator": (C.c_double, [C.c_double, ci]),
@@ -86,6 +87,7 @@ PROTOTYPES = {
     "sks_set_device_keys": (ci, [vp, vp, C.POINTER(vp), i64p, C.POINTER(ci)]),
     "sks_set_from_device_keys": (ci, [vp, vp, i64, ci, u64p, ci, C.POINTER(vp)]),
     "sks_set_from_unsorted_device_keys": (ci, [vp, vp, i64, ci, u64p, ci, C.POINTER(vp)]),
+    "sks_set_from_host_keys": (ci, [vp, vp, i64, u64p, ci, C.POINTER(vp)]),
     "sks_set_destroy": (None, [vp, vp]),
     "sks_intersect": (ci, [vp, vp, vp, i64p]),
     "sks_intersect_pairs": (ci, [vp, C.POINTER(vp), i64, C.POINTER(vp), i64, vp]),

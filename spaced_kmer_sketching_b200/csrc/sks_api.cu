@@ -377,9 +377,10 @@ int sketch_sorted(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
 
 int check_pair(const sks_set *a, const sks_set *b) {
   if (!a || !b) return set_error(SKS_ERR_INVALID, "null set");
-  if (a->repr != b->repr || a->window != b->window || a->mask[0] != b->mask[0] || a->mask[1] != b->mask[1] ||
-      a->key_words != b->key_words || a->device != b->device)
-    return set_error(SKS_ERR_MISMATCH, "sets were built with different masks, windows, representations or devices");
+  // window_length is not part of k-mer equality (src/kmer.hpp:82-85); mask and layout are
+  if (a->repr != b->repr || a->mask[0] != b->mask[0] || a->mask[1] != b->mask[1] || a->key_words != b->key_words ||
+      a->device != b->device)
+    return set_error(SKS_ERR_MISMATCH, "sets were built with different masks, representations or devices");
   return SKS_OK;
 }
 
@@ -818,6 +819,30 @@ int sks_set_from_unsorted_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_
   s->count = (int64_t)ucount[0];
   *out = s;
   return SKS_OK;
+}
+
+int sks_set_from_host_keys(sks_ctx *ctx, const uint64_t *keys_lohi, int64_t n_keys, const uint64_t mask[2], int window,
+                           sks_set **out) {
+  if (!ctx || !out || !mask || n_keys < 0 || (n_keys > 0 && !keys_lohi)) return set_error(SKS_ERR_INVALID, "bad argument");
+  if (window < 1 || window > 64) return set_error(SKS_ERR_INVALID, "window length %d outside 1..64", window);
+  DeviceGuard guard(ctx->device);
+  const int kw = window <= 32 ? 1 : 2;  // same key width the sketch kernel uses for this window
+  BufferRef raw;
+  SKS_TRY(alloc_buffer(ctx, (size_t)std::max<int64_t>(n_keys, 1) * 8 * kw, &raw));
+  if (n_keys > 0) {
+    if (kw == 2) {
+      SKS_CUDA_TRY(cudaMemcpyAsync(raw->ptr, keys_lohi, (size_t)n_keys * 16, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      std::vector<uint64_t> lo((size_t)n_keys);
+      for (int64_t i = 0; i < n_keys; ++i) {
+        if (keys_lohi[2 * i + 1]) return set_error(SKS_ERR_INVALID, "key %lld has bits above 2*window", (long long)i);
+        lo[(size_t)i] = keys_lohi[2 * i];
+      }
+      SKS_CUDA_TRY(cudaMemcpyAsync(raw->ptr, lo.data(), (size_t)n_keys * 8, cudaMemcpyHostToDevice, ctx->stream));
+      SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // lo is a local
+    }
+  }
+  return sks_set_from_unsorted_device_keys(ctx, raw->ptr, n_keys, kw, mask, window, out);
 }
 
 void sks_set_destroy(sks_ctx *ctx, sks_set *s) {

@@ -169,6 +169,10 @@ void sks_reverse_bitset(const uint64_t in[2], uint64_t out[2]) {
   out[1] = rev64(lo);
 }
 
+uint64_t sks_boost_hash_bitset(const uint64_t value[2], int hash_variant) {
+  return sks::boost_hash_bitset(value[0], value[1], hash_variant == SKS_HASH_BOOST_171 ? SKS_HASH_BOOST_171 : SKS_HASH_BOOST_181);
+}
+
 uint64_t sks_fmh_hash(const uint64_t masked[2], const uint64_t mask[2], int window, int nonce, int hash_variant) {
   const int v = hash_variant == SKS_HASH_BOOST_171 ? SKS_HASH_BOOST_171 : SKS_HASH_BOOST_181;
   return sks::boost_hash_bitset(masked[0], masked[1], v) ^ sks::boost_hash_bitset(mask[0], mask[1], v) ^

@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
   unsigned long long total = 0;
   uint32_t cur_genome = 0xFFFFFFFFu;
   uint4 *b4 = reinterpret_cast<uint4 *>(s_slice);
+  for (int i = tid; i < kSliceWords / 4; i += kBuildThreads) b4[i] = make_uint4(0, 0, 0, 0);  // invariant of assemble()
 
   auto flush_total = [&](uint32_t genome) {
 #pragma unroll
@@ -311,26 +312,15 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
       return s_nkeys;
     };
 
-    // Assembles one slice in shared memory and streams it out.
+    // Assembles one slice in shared memory (all-zero on entry and again on exit) and streams it out.
     auto assemble = [&](uint32_t slice, uint32_t nkeys, bool direct) {
-#pragma unroll
-      for (int i = tid; i < kSliceWords / 4; i += kBuildThreads) b4[i] = make_uint4(0, 0, 0, 0);
-      __syncthreads();
-      if (!direct) {
-        for (uint32_t i = tid; i < nkeys; i += kBuildThreads) {
-          const uint32_t key = s_keys[i];
-          if (((key >> kSliceBits) & slice_mask) == slice) {
-            const uint32_t bit = key & ((1u << kSliceBits) - 1);
-            atomicOr(&s_slice[bit >> 5], 1u << (bit & 31));
-          }
-        }
-      } else {  // more indices in ONE slice than shared memory holds: read them from the bucket
-        for (uint32_t i = lo + tid; i < hi; i += kBuildThreads) {
-          const uint32_t key = __ldg(bk + i);
-          if (((key >> kSliceBits) & slice_mask) == slice) {
-            const uint32_t bit = key & ((1u << kSliceBits) - 1);
-            atomicOr(&s_slice[bit >> 5], 1u << (bit & 31));
-          }
+      const uint32_t *__restrict__ src = direct ? bk + lo : s_keys;
+      const uint32_t n = direct ? hi - lo : nkeys;  // direct: more indices in ONE slice than smem holds
+      for (uint32_t i = tid; i < n; i += kBuildThreads) {
+        const uint32_t key = src[i];
+        if (((key >> kSliceBits) & slice_mask) == slice) {
+          const uint32_t bit = key & ((1u << kSliceBits) - 1);
+          atomicOr(&s_slice[bit >> 5], 1u << (bit & 31));
         }
       }
       __syncthreads();
@@ -339,11 +329,12 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
 #pragma unroll
       for (int i = tid; i < kSliceWords / 4; i += kBuildThreads) {
         const uint4 v = b4[i];
+        b4[i] = make_uint4(0, 0, 0, 0);
         c += popc4(v);
         __stcs(dst + i, v);
       }
       total += c;
-      __syncthreads();  // the slice buffer is zeroed again
+      __syncthreads();
     };
 
     const uint32_t first_slice = group * group_slices;  // within the coarse bucket

@@ -111,7 +111,9 @@ def gather_rows(counts: np.ndarray, rows: Tuple[int, int], world: int) -> np.nda
     import torch
     import torch.distributed as dist
     n = counts.shape[0]
-    block = torch.from_numpy(np.ascontiguousarray(counts[rows[0]:rows[1]])).reshape(-1).cuda()
+    block = torch.from_numpy(np.ascontiguousarray(counts[rows[0]:rows[1]])).reshape(-1)
+    if dist.get_backend() == "nccl":
+        block = block.cuda()
     parts = allgather_varlen(block, world, dist)
     full = torch.cat(parts).reshape(n, n)
     return full.cpu().numpy()

@@ -1,0 +1,117 @@
+// Exercises the reference-shaped C++ API (include/kmer.hpp ...) exactly as a user of the reference
+// would, and prints one JSON object; tests/test_gpu_cpp_api.py compares it with the CPU oracle.
+//   test_cpp_api A.fna B.fna
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+
+#include "ani_estimator.hpp"
+#include "fasta_processing.hpp"
+#include "generators.hpp"
+#include "kmer.hpp"
+
+static std::string hex128(const kmer_bitset &b)
+{
+    std::ostringstream os;
+    os << std::hex << std::setfill('0') << std::setw(16) << b.word(1) << std::setw(16) << b.word(0);
+    return os.str();
+}
+
+static frac_min_hash fmh(1);
+static bool driver_condition(const kmer &k) { return fmh(k) % 200 == 0; } // src/kmer-sketching.cpp:29-34
+
+int main(int argc, char *argv[])
+{
+    if (argc < 3) return 2;
+    initialise_contiguous_kmer_array();
+    initialise_reversing_kmer_array();
+    std::cout << std::setprecision(17) << "{";
+
+    // masks
+    std::cout << "\"mask_24_16\":\"" << hex128(generate_random_spaced_seed_mask(24, 16)) << "\",";
+    std::cout << "\"mask_31_21_s3\":\"" << hex128(generate_random_spaced_seed_mask(31, 21, 3)) << "\",";
+    std::cout << "\"contig_33\":\"" << hex128(contiguous_kmer(33)) << "\",";
+    bool threw = false;
+    try { contiguous_kmer(65); } catch (const std::runtime_error &) { threw = true; }
+    std::cout << "\"contig_65_throws\":" << (threw ? "true" : "false") << ",";
+    const kmer_bitset seed_mask = sks::seed_string_to_mask("11001011");
+    std::cout << "\"seed_mask\":\"" << hex128(seed_mask) << "\",\"seed_weight\":" << seed_mask.count() / NUCLEOTIDE_BIT_SIZE << ",";
+    { std::ostringstream os; os << seed_mask; std::cout << "\"seed_mask_printed_len\":" << os.str().size() << ","; }
+
+    // ordered list on strings (segments): KAT-1 plus a second segment
+    {
+        std::vector<std::vector<uint8_t>> strings = {{0, 0, 0, 1, 2, 3, 0, 1, 2, 3, 3, 3}, {}, {3, 2, 1, 0, 0, 1, 2, 3, 1}};
+        std::vector<kmer> ks = nucleotide_string_list_to_kmers(strings, seed_mask, 8, sks::all_kmers());
+        std::cout << "\"list_masked\":[";
+        for (size_t i = 0; i < ks.size(); ++i) std::cout << (i ? "," : "") << "\"" << hex128(ks[i].masked_bits) << "\"";
+        std::cout << "],\"list_bits\":[";
+        for (size_t i = 0; i < ks.size(); ++i) std::cout << (i ? "," : "") << "\"" << hex128(ks[i].kmer_bits) << "\"";
+        std::cout << "],";
+        // legacy canonicalisation agrees with the sliding version (src/kmers.cpp:31-35)
+        bool legacy_ok = true;
+        for (const kmer &k : ks) legacy_ok = legacy_ok && canonical_kmer(k).masked_bits == k.masked_bits;
+        std::cout << "\"legacy_ok\":" << (legacy_ok ? "true" : "false") << ",";
+    }
+
+    // FASTA -> sets under four kinds of sketching condition
+    const kmer_bitset mask = generate_random_spaced_seed_mask(24, 16);
+    char *files[2] = {argv[1], argv[2]};
+    struct cond_case { const char *name; std::function<bool(const kmer)> f; };
+    const cond_case cases[] = {
+        {"all", sks::all_kmers()},
+        {"fmh_struct", sks::fmh_condition(1, 50)},
+        {"driver", driver_condition},
+        {"lambda_fmh7", [](const kmer k) { return frac_min_hash(-2)(k) % 7 == 0; }},
+        {"parity", [](const kmer k) { return k.masked_bits.count() % 2 == 0; }},
+    };
+    std::cout << "\"cases\":{";
+    bool first_case = true;
+    for (const cond_case &c : cases)
+    {
+        std::vector<kmer_set> sets = parallel_kmer_sets_from_fasta_files(2, files, mask, 24, c.f);
+        const std::string path = sks::last_predicate_path();
+        std::vector<kmer_set *> ptrs = {&sets[0], &sets[1]};
+        const auto pairs = generate_all_pairs_from_vector(ptrs);
+        const std::vector<int> inter = compute_pairwise_kmer_set_intersections(pairs.first, pairs.second);
+        std::cout << (first_case ? "" : ",") << "\"" << c.name << "\":{\"path\":\"" << path << "\",\"sizes\":["
+                  << sets[0].kmer_set_size() << "," << sets[1].kmer_set_size() << "],\"inter\":[";
+        for (size_t i = 0; i < inter.size(); ++i) std::cout << (i ? "," : "") << inter[i];
+        std::cout << "],\"ani\":[";
+        for (size_t i = 0; i < inter.size(); ++i)
+            std::cout << (i ? "," : "") << binomial_estimator(containment(inter[i], pairs.first[i]->kmer_set_size()), 16);
+        std::cout << "]}";
+        first_case = false;
+    }
+    std::cout << "},";
+
+    // host-side sets: insert_kmers on a host list, the lazily materialised table, mixed use
+    {
+        const kmer_bitset m8 = sks::seed_string_to_mask("110101101");
+        std::vector<acgt_string> strings = nucleotide_strings_from_fasta_file(argv[1]);
+        std::vector<kmer> list = nucleotide_string_list_to_kmers(strings, m8, 9, sks::all_kmers());
+        kmer_set host_set;
+        host_set.insert_kmers(list);
+        kmer_set dev_set = kmer_set_from_fasta_file(argv[1], m8, 9, sks::all_kmers());
+        size_t found = 0, walked = 0;
+        for (const auto &kv : dev_set.kmer_hashes) { ++walked; found += host_set.kmer_hashes.count(kv.first); }
+        std::cout << "\"host_list_len\":" << list.size() << ",\"host_set_size\":" << host_set.kmer_set_size()
+                  << ",\"dev_set_size\":" << dev_set.kmer_set_size() << ",\"walked\":" << walked << ",\"found\":" << found
+                  << ",\"host_dev_inter\":" << kmer_set_intersection(host_set, dev_set)
+                  << ",\"n_strings\":" << strings.size() << ",";
+        kmer_set other = kmer_set_from_fasta_file(argv[2], mask, 24, sks::all_kmers());
+        std::cout << "\"different_mask_inter\":" << kmer_set_intersection(dev_set, other) << ",";
+        kmer_set empty;
+        std::cout << "\"empty_inter\":" << kmer_set_intersection(empty, dev_set) << ",\"empty_size\":" << empty.kmer_set_size() << ",";
+    }
+    bool mismatch_threw = false;
+    try
+    {
+        kmer_set a, b;
+        std::vector<kmer_set *> one = {&a}, two = {&a, &b};
+        compute_pairwise_kmer_set_intersections(one, two);
+    }
+    catch (const std::runtime_error &) { mismatch_threw = true; }
+    std::cout << "\"mismatch_throws\":" << (mismatch_threw ? "true" : "false") << ",";
+    std::cout << "\"containment_0\":" << containment(0, 10) << ",\"estimator_neg\":" << binomial_estimator(-1.0, 5) << "}" << std::endl;
+    return 0;
+}
