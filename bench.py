@@ -31,6 +31,9 @@ C2_SEED = "011101110010111110011011"          # generate_random_spaced_seed_mask
 C3_SEED = "0011111011010111111011001011101"   # generate_random_spaced_seed_mask(31, 21, 0)
 C2_L = 5_000_000
 KAT4_C2 = (4994572, 4994591, 4244791)         # |A|, |B|, |A n B| from the reference
+WORKLOAD = ("C2: synthetic 5 Mbp genome vs 1%-mutated copy per GPU, weight-16 span-24 seed " + C2_SEED +
+            ", predicate ALL, one kmer_set per genome (4^16-bit presence bitset, 512 MiB, on the GPU), "
+            "intersection (AND/popcount), containment^(1/16) ANI")
 METRIC = "spaced_kmers_per_s_sketch_plus_ani"
 UNIT = "kmers/s"
 
@@ -146,8 +149,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "C2: synthetic 5 Mbp pair, weight-16 span-24 seed, predicate ALL, set build + "
-                               "intersection + ANI (reference CPU path: unordered_map sets)", "sample": sample},
+        "config": {"workload": WORKLOAD, "sample": sample,
+                   "note": "reference CPU path: parallel_kmer_sets_from_fasta_files (unordered_map sets) + "
+                           "kmer_set_intersection + containment/binomial_estimator"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "result": {"size_a": counts[0], "size_b": counts[1], "intersection": counts[2], "ani_ab": counts[3]},
@@ -305,9 +309,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "C2: synthetic 5 Mbp genome vs 1%-mutated copy per GPU, weight-16 span-24 seed "
-                                   + C2_SEED + ", predicate ALL, 4^16-bit presence bitset per genome (512 MiB), "
-                                   "AND/popcount, containment^(1/16) ANI",
+            "config": {"workload": WORKLOAD,
                        "bases_per_step_per_gpu": 2 * L, "l2": "1 GiB of bitsets per step (> 126 MB L2) and a 256 MiB "
                        "flush write between timed steps", "parallelism": "genome pairs sharded over ranks, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

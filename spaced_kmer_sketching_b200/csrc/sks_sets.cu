@@ -133,25 +133,26 @@ int stream_grid(const sks_ctx *ctx, size_t n16) {
 // ---- bucketed bitset build --------------------------------------------------------------------------
 // Random atomicOr into a 512 MiB bitset costs a 64 B DRAM read + a 32 B write per k-mer (measured:
 // 1 GB of DRAM traffic for 10 M k-mers at 29 % of HBM, latency bound).  Instead:
-//   1. the 32-bit PEXT indices of a genome are partitioned into <= 256 coarse buckets by their top
-//      bits (a counting pass, a scan and a scatter pass over an L2-resident 20 MB list).  A finer
-//      partition (one bucket per 64 KB slice) was measured too: its one-atomic-per-index scatter cost
-//      276 us, more than it saved;
-//   2. a CTA takes a group of slices of one coarse bucket, keeps the group's indices in shared memory,
-//      and assembles every 64 KB slice there before streaming it to HBM exactly once.
+//   1. the 32-bit PEXT indices of a genome are partitioned into <= 1024 buckets by their top bits (a
+//      counting pass, a scan and a scatter pass over an L2-resident 20 MB list); a bucket covers a GROUP
+//      of kGroupSlices consecutive 64 KB slices of the bitset;
+//   2. a CTA takes one bucket, copies its indices into shared memory, and assembles each of the group's
+//      slices there before streaming it to HBM exactly once.
 // The clear and the insert become ONE sequential write pass, and the slice popcounts give
-// kmer_set_size() for free.
-constexpr int kCoarseBitsMax = 8;                    // <= 256 coarse buckets
-constexpr int kCoarseSliceBitsMax = 5;               // <= 32 slices (2 MiB of bitset) per coarse bucket
-constexpr int kGroupSlices = 8;                      // slices assembled by one work item
+// kmer_set_size() for free.  (Measured alternatives: radix sort by slice with cub, 205 us of sort; one
+// bucket per slice with a per-index global cursor bump, 276 us of scatter; 256 coarse buckets with the
+// group's indices filtered out of the bucket by every CTA, 265 us of build of which ~60 us was the filter.)
+constexpr int kGroupSliceBits = 3;                   // 8 slices (512 KB of bitset) per bucket
+constexpr int kMaxPartBits = 32 - kSliceBits - kGroupSliceBits;  // <= 1024 buckets
+constexpr int kMaxParts = 1 << kMaxPartBits;
 constexpr int kBuildThreads = 512;
-constexpr int kKeyCap = 11264;                       // indices of one work item kept in shared memory (44 KB)
+constexpr int kKeyCap = 11264;                       // indices of one bucket kept in shared memory (44 KB)
 
 struct BuildGenome {
   const uint32_t *raw;      // PEXT indices as emitted by the sketch kernel
-  uint32_t *bucketed;       // the same, grouped by coarse bucket
-  uint32_t *starts;         // [n_coarse + 1] first position of every coarse bucket in `bucketed`
-  uint32_t *cursor;         // [n_coarse] histogram, then scatter cursors (= bucket ends afterwards)
+  uint32_t *bucketed;       // the same, grouped by bucket
+  uint32_t *starts;         // [n_parts + 1] first position of every bucket in `bucketed`
+  uint32_t *cursor;         // [n_parts] histogram, then scatter cursors (= bucket ends afterwards)
   uint32_t *bitset;
   unsigned long long *set_count;
   uint32_t n;               // number of indices
@@ -159,50 +160,61 @@ struct BuildGenome {
 };
 
 __global__ void __launch_bounds__(256)
-    coarse_hist_kernel(const BuildGenome *__restrict__ genomes, int coarse_shift, uint32_t n_coarse) {
-  __shared__ uint32_t s_hist[1 << kCoarseBitsMax];
+    part_hist_kernel(const BuildGenome *__restrict__ genomes, int part_shift, uint32_t n_parts) {
+  __shared__ uint32_t s_hist[kMaxParts];
   const BuildGenome g = genomes[blockIdx.y];
-  for (uint32_t i = threadIdx.x; i < n_coarse; i += blockDim.x) s_hist[i] = 0;
+  for (uint32_t i = threadIdx.x; i < n_parts; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n; i += stride)
-    atomicAdd(&s_hist[__ldg(g.raw + i) >> coarse_shift], 1u);
+    atomicAdd(&s_hist[__ldg(g.raw + i) >> part_shift], 1u);
   __syncthreads();
-  for (uint32_t i = threadIdx.x; i < n_coarse; i += blockDim.x)
+  for (uint32_t i = threadIdx.x; i < n_parts; i += blockDim.x)
     if (s_hist[i]) atomicAdd(g.cursor + i, s_hist[i]);  // cursor doubles as the histogram until the scan
 }
 
-// One CTA per genome: exclusive scan of the histogram -> starts[0..n_coarse], cursor = starts.
-__global__ void __launch_bounds__(256) coarse_scan_kernel(const BuildGenome *__restrict__ genomes, uint32_t n_coarse) {
-  __shared__ uint32_t s[1 << kCoarseBitsMax];
+// One 1024-thread CTA per genome: exclusive scan of the histogram -> starts[0..n_parts], cursor = starts.
+__global__ void __launch_bounds__(kMaxParts) part_scan_kernel(const BuildGenome *__restrict__ genomes, uint32_t n_parts) {
+  __shared__ uint32_t s_warp[32];
   const BuildGenome g = genomes[blockIdx.x];
-  const uint32_t t = threadIdx.x;
-  const uint32_t v = t < n_coarse ? g.cursor[t] : 0u;
-  s[t] = v;
+  const uint32_t t = threadIdx.x, lane = t & 31;
+  const uint32_t v = t < n_parts ? g.cursor[t] : 0u;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += x;
+  }
+  if (lane == 31) s_warp[t >> 5] = incl;
   __syncthreads();
-  for (uint32_t o = 1; o < 256; o <<= 1) {
-    const uint32_t add = t >= o ? s[t - o] : 0u;
-    __syncthreads();
-    s[t] += add;
-    __syncthreads();
+  if (t < 32) {
+    uint32_t w = s_warp[t];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, w, o);
+      if (t >= (uint32_t)o) w += x;
+    }
+    s_warp[t] = w;
   }
-  if (t < n_coarse) {
-    g.starts[t] = s[t] - v;
-    g.cursor[t] = s[t] - v;
+  __syncthreads();
+  const uint32_t excl = incl - v + ((t >> 5) ? s_warp[(t >> 5) - 1] : 0u);
+  if (t < n_parts) {
+    g.starts[t] = excl;
+    g.cursor[t] = excl;
   }
-  if (t == 0) g.starts[n_coarse] = g.n;
+  if (t == 0) g.starts[n_parts] = g.n;
 }
 
 constexpr int kScatterKeys = 4096;  // indices per CTA pass
 
 __global__ void __launch_bounds__(256)
-    coarse_scatter_kernel(const BuildGenome *__restrict__ genomes, int coarse_shift, uint32_t n_coarse) {
-  __shared__ uint32_t s_hist[1 << kCoarseBitsMax];
-  __shared__ uint32_t s_base[1 << kCoarseBitsMax];
+    part_scatter_kernel(const BuildGenome *__restrict__ genomes, int part_shift, uint32_t n_parts) {
+  __shared__ uint32_t s_hist[kMaxParts];
+  __shared__ uint32_t s_base[kMaxParts];
   const BuildGenome g = genomes[blockIdx.y];
   const uint32_t n_chunks = (g.n + kScatterKeys - 1) / kScatterKeys;
   for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    for (uint32_t i = threadIdx.x; i < n_coarse; i += blockDim.x) s_hist[i] = 0;
+    for (uint32_t i = threadIdx.x; i < n_parts; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
     uint32_t key[kScatterKeys / 256], rank[kScatterKeys / 256];
     const uint32_t base = chunk * kScatterKeys;
@@ -214,41 +226,41 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int u = 0; u < kScatterKeys / 256; ++u) {
       const uint32_t i = base + u * 256 + threadIdx.x;
-      if (i < g.n) rank[u] = atomicAdd(&s_hist[key[u] >> coarse_shift], 1u);
+      if (i < g.n) rank[u] = atomicAdd(&s_hist[key[u] >> part_shift], 1u);
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n_coarse; i += blockDim.x)
+    for (uint32_t i = threadIdx.x; i < n_parts; i += blockDim.x)
       s_base[i] = s_hist[i] ? atomicAdd(g.cursor + i, s_hist[i]) : 0u;
     __syncthreads();
 #pragma unroll
     for (int u = 0; u < kScatterKeys / 256; ++u) {
       const uint32_t i = base + u * 256 + threadIdx.x;
-      if (i < g.n) g.bucketed[s_base[key[u] >> coarse_shift] + rank[u]] = key[u];
+      if (i < g.n) g.bucketed[s_base[key[u] >> part_shift] + rank[u]] = key[u];
     }
     __syncthreads();
   }
 }
 
-// Work item = (genome, coarse bucket, group of <= kGroupSlices slices), handed out by an atomic counter.
-// Two ~108 KB CTAs per SM: one assembles while the other streams its slice out.  The slice leaves shared
-// memory through registers (LDS.128 -> popcount -> STG.128): plain vector stores are fire-and-forget,
-// whereas a 64 KB bulk (TMA) store per CTA measured ~6 us of latency with one store in flight per CTA.
+// Work item = (genome, bucket), handed out by an atomic counter.  Two ~108 KB CTAs per SM: one assembles
+// while the other streams its slice out.  A slice leaves shared memory through registers
+// (LDS.128 -> popcount -> STG.128, the buffer zeroed behind the read): plain vector stores are
+// fire-and-forget, whereas a 64 KB bulk (TMA) store per slice measured ~6 us of latency with one store in
+// flight per CTA.
 __global__ void __launch_bounds__(kBuildThreads, 2)
-    bitset_build_kernel(const BuildGenome *__restrict__ genomes, uint32_t n_genomes, uint32_t n_coarse,
-                        uint32_t slices_per_coarse, uint32_t group_slices, unsigned int *__restrict__ work_counter) {
+    bitset_build_kernel(const BuildGenome *__restrict__ genomes, uint32_t n_genomes, uint32_t n_parts,
+                        uint32_t group_slices, unsigned int *__restrict__ work_counter) {
   extern __shared__ __align__(128) uint32_t s_dyn[];
   uint32_t *s_slice = s_dyn;                 // [kSliceWords]
   uint32_t *s_keys = s_dyn + kSliceWords;    // [kKeyCap]
-  __shared__ uint32_t s_item, s_nkeys;
+  __shared__ uint32_t s_item;
   __shared__ unsigned long long s_tot[kBuildThreads / 32];
   const int tid = threadIdx.x, lane = tid & 31;
-  const uint32_t groups = slices_per_coarse / group_slices;
-  const uint32_t n_items = n_genomes * n_coarse * groups;
-  const uint32_t slice_mask = slices_per_coarse - 1;
+  const uint32_t n_items = n_genomes * n_parts;
+  const uint32_t slice_mask = group_slices - 1;
   unsigned long long total = 0;
   uint32_t cur_genome = 0xFFFFFFFFu;
   uint4 *b4 = reinterpret_cast<uint4 *>(s_slice);
-  for (int i = tid; i < kSliceWords / 4; i += kBuildThreads) b4[i] = make_uint4(0, 0, 0, 0);  // invariant of assemble()
+  for (int i = tid; i < kSliceWords / 4; i += kBuildThreads) b4[i] = make_uint4(0, 0, 0, 0);  // invariant: zero between slices
 
   auto flush_total = [&](uint32_t genome) {
 #pragma unroll
@@ -270,61 +282,45 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
     __syncthreads();
     const uint32_t item = s_item;
     if (item >= n_items) break;
-    const uint32_t genome = item / (n_coarse * groups);
-    const uint32_t rem = item - genome * (n_coarse * groups);
-    const uint32_t coarse = rem / groups, group = rem - coarse * groups;
+    const uint32_t genome = item / n_parts, part = item - genome * n_parts;
     if (genome != cur_genome) {
       if (cur_genome != 0xFFFFFFFFu) flush_total(cur_genome);
       cur_genome = genome;
     }
     const BuildGenome g = genomes[genome];
-    const uint32_t lo = __ldg(g.starts + coarse), hi = __ldg(g.cursor + coarse);  // cursor = bucket end after the scatter
-    const uint32_t *__restrict__ bk = g.bucketed;
-
-    // Stages the indices of slices [first, first + span) of this coarse bucket in s_keys (warp-aggregated
-    // compaction, four independent loads in flight per lane); returns how many there are.
-    auto stage = [&](uint32_t first, uint32_t span) -> uint32_t {
-      __syncthreads();
-      if (tid == 0) s_nkeys = 0;
-      __syncthreads();
-      for (uint32_t i0 = lo + (tid >> 5) * 128; i0 < hi; i0 += (kBuildThreads / 32) * 128) {
-        uint32_t key[4];
-        bool keep[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t i = i0 + u * 32 + lane;
-          key[u] = i < hi ? __ldg(bk + i) : 0xFFFFFFFFu;
-          keep[u] = i < hi && (((key[u] >> kSliceBits) & slice_mask) - first) < span;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t m = __ballot_sync(0xffffffffu, keep[u]);
-          if (m) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&s_nkeys, (uint32_t)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const uint32_t slot = base + __popc(m & ((1u << lane) - 1));
-            if (keep[u] && slot < kKeyCap) s_keys[slot] = key[u];
-          }
-        }
+    const uint32_t lo = __ldg(g.starts + part), hi = __ldg(g.cursor + part);  // cursor = bucket end after the scatter
+    const uint32_t n = hi - lo;
+    const uint32_t *__restrict__ bk = g.bucketed + lo;
+    const bool direct = n > kKeyCap;  // more indices than shared memory holds (heavily skewed genome)
+    uint32_t n4 = 0;
+    if (!direct && n > 0) {
+      // straight copy; the tail is padded with copies of the last index (OR is idempotent) so that the
+      // scans below can read whole uint4s
+      n4 = (n + 3) / 4;
+      for (uint32_t i = tid; i < n4 * 4; i += kBuildThreads) s_keys[i] = __ldg(bk + (i < n ? i : n - 1));
+    }
+    __syncthreads();
+    const uint4 *k4 = reinterpret_cast<const uint4 *>(s_keys);
+    auto put = [&](uint32_t key, uint32_t slice) {
+      if (((key >> kSliceBits) & slice_mask) == slice) {
+        const uint32_t bit = key & ((1u << kSliceBits) - 1);
+        atomicOr(&s_slice[bit >> 5], 1u << (bit & 31));
       }
-      __syncthreads();
-      return s_nkeys;
     };
-
-    // Assembles one slice in shared memory (all-zero on entry and again on exit) and streams it out.
-    auto assemble = [&](uint32_t slice, uint32_t nkeys, bool direct) {
-      const uint32_t *__restrict__ src = direct ? bk + lo : s_keys;
-      const uint32_t n = direct ? hi - lo : nkeys;  // direct: more indices in ONE slice than smem holds
-      for (uint32_t i = tid; i < n; i += kBuildThreads) {
-        const uint32_t key = src[i];
-        if (((key >> kSliceBits) & slice_mask) == slice) {
-          const uint32_t bit = key & ((1u << kSliceBits) - 1);
-          atomicOr(&s_slice[bit >> 5], 1u << (bit & 31));
+    for (uint32_t slice = 0; slice < group_slices; ++slice) {
+      if (!direct) {
+        for (uint32_t i = tid; i < n4; i += kBuildThreads) {
+          const uint4 v = k4[i];
+          put(v.x, slice);
+          put(v.y, slice);
+          put(v.z, slice);
+          put(v.w, slice);
         }
+      } else {
+        for (uint32_t i = tid; i < n; i += kBuildThreads) put(__ldg(bk + i), slice);
       }
       __syncthreads();
-      uint4 *dst = reinterpret_cast<uint4 *>(g.bitset + ((size_t)coarse * slices_per_coarse + slice) * kSliceWords);
+      uint4 *dst = reinterpret_cast<uint4 *>(g.bitset + ((size_t)part * group_slices + slice) * kSliceWords);
       uint32_t c = 0;
 #pragma unroll
       for (int i = tid; i < kSliceWords / 4; i += kBuildThreads) {
@@ -335,19 +331,6 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
       }
       total += c;
       __syncthreads();
-    };
-
-    const uint32_t first_slice = group * group_slices;  // within the coarse bucket
-    uint32_t done = 0;
-    while (done < group_slices) {  // normally one pass; skewed buckets are staged in smaller spans
-      uint32_t span = group_slices - done, nkeys;
-      for (;;) {
-        nkeys = stage(first_slice + done, span);
-        if (nkeys <= kKeyCap || span == 1) break;
-        span >>= 1;
-      }
-      for (uint32_t t = 0; t < span; ++t) assemble(first_slice + done + t, nkeys, nkeys > kKeyCap);
-      done += span;
     }
   }
   if (cur_genome != 0xFFFFFFFFu) flush_total(cur_genome);
@@ -518,20 +501,19 @@ int launch_bitset_build(sks_ctx *ctx, const uint32_t *raw_idx, uint32_t *buckete
                         const uint64_t *h_count, int n_genomes, int index_bits, uint32_t *bitset, uint64_t bitset_words,
                         unsigned long long *d_set_count) {
   if (n_genomes == 0) return SKS_OK;
-  const int coarse_bits = std::max(index_bits - kSliceBits - kCoarseSliceBitsMax, 0);
-  if (coarse_bits > kCoarseBitsMax || index_bits <= kSliceBits)
+  if (index_bits <= kSliceBits || index_bits > 32)
     return set_error(SKS_ERR_INVALID, "bucketed bitset build handles 20..32 index bits, not %d", index_bits);
-  const uint32_t n_coarse = 1u << coarse_bits;
-  const int coarse_shift = index_bits - coarse_bits;  // coarse bucket = idx >> coarse_shift
-  const uint32_t slices_per_coarse = 1u << (coarse_shift - kSliceBits);
-  const uint32_t group_slices = std::min<uint32_t>(slices_per_coarse, kGroupSlices);
+  const int group_bits = std::min(kGroupSliceBits, index_bits - kSliceBits);
+  const int part_shift = kSliceBits + group_bits;  // bucket = idx >> part_shift
+  const uint32_t n_parts = 1u << (index_bits - part_shift);
+  const uint32_t group_slices = 1u << group_bits;
   uint64_t max_n = 0;
   for (int g = 0; g < n_genomes; ++g) max_n = std::max(max_n, h_count[g]);
   if (max_n >= (1ull << 32)) return set_error(SKS_ERR_CAPACITY, "too many k-mers in one genome for the bucketed build");
 
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t sz_desc = align(sizeof(BuildGenome) * n_genomes);
-  const size_t sz_tab = align((size_t)(2 * n_coarse + 1) * 4);  // starts | cursor per genome
+  const size_t sz_tab = align((size_t)(2 * n_parts + 1) * 4);  // starts | cursor per genome
   char *base = nullptr;
   SKS_TRY(ctx_scratch(ctx, sz_desc + sz_tab * n_genomes + 256, reinterpret_cast<void **>(&base)));
   BuildGenome *d_desc = reinterpret_cast<BuildGenome *>(base);
@@ -544,7 +526,7 @@ int launch_bitset_build(sks_ctx *ctx, const uint32_t *raw_idx, uint32_t *buckete
     h_desc[g].raw = raw_idx + h_off[g];
     h_desc[g].bucketed = bucketed_idx + h_off[g];
     h_desc[g].starts = tab;
-    h_desc[g].cursor = tab + n_coarse + 1;
+    h_desc[g].cursor = tab + n_parts + 1;
     h_desc[g].bitset = bitset + (size_t)g * bitset_words;
     h_desc[g].set_count = d_set_count + g;
     h_desc[g].n = (uint32_t)h_count[g];
@@ -565,16 +547,16 @@ int launch_bitset_build(sks_ctx *ctx, const uint32_t *raw_idx, uint32_t *buckete
                                                           (uint64_t)ctx->sm_count * 8);
   for (int g0 = 0; g0 < n_genomes; g0 += 32768) {
     const int ng = std::min(n_genomes - g0, 32768);
-    coarse_hist_kernel<<<dim3(gx_stream, ng), 256, 0, ctx->stream>>>(d_desc + g0, coarse_shift, n_coarse);
-    coarse_scan_kernel<<<ng, 256, 0, ctx->stream>>>(d_desc + g0, n_coarse);
-    coarse_scatter_kernel<<<dim3(gx_stream, ng), 256, 0, ctx->stream>>>(d_desc + g0, coarse_shift, n_coarse);
+    part_hist_kernel<<<dim3(gx_stream, ng), 256, 0, ctx->stream>>>(d_desc + g0, part_shift, n_parts);
+    part_scan_kernel<<<ng, kMaxParts, 0, ctx->stream>>>(d_desc + g0, n_parts);
+    part_scatter_kernel<<<dim3(gx_stream, ng), 256, 0, ctx->stream>>>(d_desc + g0, part_shift, n_parts);
     ctx->launches += 3;
   }
-  const uint64_t n_items = (uint64_t)n_genomes * n_coarse * (slices_per_coarse / group_slices);
+  const uint64_t n_items = (uint64_t)n_genomes * n_parts;
   if (n_items >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "too many bitset slices in one batch");
   const unsigned gx = (unsigned)std::min<uint64_t>(n_items, (uint64_t)ctx->sm_count * 2);  // two ~108 KB CTAs per SM
-  bitset_build_kernel<<<gx, kBuildThreads, smem, ctx->stream>>>(d_desc, (uint32_t)n_genomes, n_coarse, slices_per_coarse,
-                                                               group_slices, d_counter);
+  bitset_build_kernel<<<gx, kBuildThreads, smem, ctx->stream>>>(d_desc, (uint32_t)n_genomes, n_parts, group_slices,
+                                                               d_counter);
   SKS_CUDA_TRY(cudaGetLastError());
   ctx->launches++;
   return SKS_OK;
