@@ -369,7 +369,7 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
     b3.close()
 
     # C4-style: G genomes per rank, all-gather, rank-tiled all-vs-all
-    G = 64
+    G = 125   # 125 genomes per GPU: 1000 genomes on 8 GPUs is BASELINE.json configs[3]
     Lg = 5_000_000
     ids = list(range(rank * G, (rank + 1) * G))
     Ds = [[0, 1000, 200, 100, 50, 20][g % 6] for g in ids]

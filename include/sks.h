@@ -189,6 +189,10 @@ int sks_set_device_keys(sks_ctx *ctx, sks_set *s, const void **dptr, int64_t *n_
 /* Builds a SORTED set from ascending distinct keys already on the device (copied). */
 int sks_set_from_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int words_per_key,
                              const uint64_t mask[2], int window, sks_set **out);
+/* n_sets SORTED sets whose keys lie back to back at dptr (set i has counts[i] keys): one device copy, the
+ * sets share the buffer.  The receive side of an all-gather of sketches. */
+int sks_sets_from_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_sets, const int64_t *counts, int words_per_key,
+                              const uint64_t mask[2], int window, sks_set **out);
 /* Builds a SORTED set from UNSORTED, possibly duplicated device keys (sort + unique on device);
  * the merge step after an all-gather of per-rank partial sketches of one sequence. */
 int sks_set_from_unsorted_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int words_per_key,

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "sks_set_keys": (ci, [vp, vp, vp, u64]),
     "sks_set_device_keys": (ci, [vp, vp, C.POINTER(vp), i64p, C.POINTER(ci)]),
     "sks_set_from_device_keys": (ci, [vp, vp, i64, ci, u64p, ci, C.POINTER(vp)]),
+    "sks_sets_from_device_keys": (ci, [vp, vp, i64, i64p, ci, u64p, ci, C.POINTER(vp)]),
     "sks_set_from_unsorted_device_keys": (ci, [vp, vp, i64, ci, u64p, ci, C.POINTER(vp)]),
     "sks_set_from_host_keys": (ci, [vp, vp, i64, u64p, ci, C.POINTER(vp)]),
     "sks_set_destroy": (None, [vp, vp]),

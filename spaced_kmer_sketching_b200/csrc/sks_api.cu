@@ -799,6 +799,40 @@ int sks_set_from_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int
   return SKS_OK;
 }
 
+int sks_sets_from_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_sets, const int64_t *counts, int words_per_key,
+                              const uint64_t mask[2], int window, sks_set **out) {
+  if (!ctx || !out || !mask || n_sets < 0 || (n_sets > 0 && !counts) || (words_per_key != 1 && words_per_key != 2))
+    return set_error(SKS_ERR_INVALID, "bad argument");
+  DeviceGuard guard(ctx->device);
+  int64_t total = 0;
+  for (int64_t i = 0; i < n_sets; ++i) {
+    if (counts[i] < 0) return set_error(SKS_ERR_INVALID, "negative key count");
+    total += counts[i];
+  }
+  if (total > 0 && !dptr) return set_error(SKS_ERR_INVALID, "null key pointer");
+  BufferRef buf;
+  const size_t kb = (size_t)8 * words_per_key;
+  SKS_TRY(alloc_buffer(ctx, (size_t)total * kb, &buf));
+  if (total > 0)
+    SKS_CUDA_TRY(cudaMemcpyAsync(buf->ptr, dptr, (size_t)total * kb, cudaMemcpyDeviceToDevice, ctx->stream));
+  const int weight = sks_mask_weight(mask);
+  int64_t off = 0;
+  for (int64_t i = 0; i < n_sets; ++i) {
+    sks_set *s = new_set(ctx, SKS_REPR_SORTED, mask, window, weight);
+    if (!s) {
+      for (int64_t j = 0; j < i; ++j) delete out[j];
+      return set_error(SKS_ERR_INVALID, "out of host memory");
+    }
+    s->buf = buf;
+    s->key_words = words_per_key;
+    s->byte_off = (size_t)off * kb;
+    s->count = counts[i];
+    out[i] = s;
+    off += counts[i];
+  }
+  return SKS_OK;
+}
+
 int sks_set_from_unsorted_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int words_per_key,
                                       const uint64_t mask[2], int window, sks_set **out) {
   if (!ctx || !out || !mask || n_keys < 0 || (n_keys > 0 && !dptr) || (words_per_key != 1 && words_per_key != 2))

@@ -418,46 +418,108 @@ __device__ __forceinline__ int key_cmp(const unsigned long long *a, long long i,
   return xl < yl ? -1 : (xl > yl ? 1 : 0);
 }
 
-// One CTA per pair: every thread takes a slice of the smaller set, locates its first key in the
-// larger set by binary search and then merges forward.
+// One CTA per pair, one slice of the smaller set per warp.  A warp walks its slice of A and the matching
+// range of B in chunks of 32 keys (coalesced 256 B loads, one key per lane): every lane locates its A key in
+// the B chunk with a 5-step shuffle search, then whichever chunk has the smaller maximum is advanced
+// (both on a tie).  The kernel is issue bound (~65 instructions per step of 32 + 32 keys; a register
+// prefetch queue for the next chunks was measured and changed nothing), the sets are L2 resident.
 template <int KW>
-__global__ void __launch_bounds__(256)
+struct WarpKey;
+template <>
+struct WarpKey<1> {
+  unsigned long long v;
+  __device__ __forceinline__ static WarpKey load(const unsigned long long *p, long long i) { return {p[i]}; }
+  __device__ __forceinline__ static WarpKey max() { return {~0ull}; }
+  __device__ __forceinline__ WarpKey shfl(int src) const { return {__shfl_sync(0xffffffffu, v, src)}; }
+  __device__ __forceinline__ bool lt(const WarpKey &o) const { return v < o.v; }
+  __device__ __forceinline__ bool eq(const WarpKey &o) const { return v == o.v; }
+};
+template <>
+struct WarpKey<2> {
+  unsigned long long lo, hi;
+  __device__ __forceinline__ static WarpKey load(const unsigned long long *p, long long i) {
+    const ulonglong2 t = reinterpret_cast<const ulonglong2 *>(p)[i];
+    return {t.x, t.y};
+  }
+  __device__ __forceinline__ static WarpKey max() { return {~0ull, ~0ull}; }
+  __device__ __forceinline__ WarpKey shfl(int src) const {
+    return {__shfl_sync(0xffffffffu, lo, src), __shfl_sync(0xffffffffu, hi, src)};
+  }
+  __device__ __forceinline__ bool lt(const WarpKey &o) const { return hi != o.hi ? hi < o.hi : lo < o.lo; }
+  __device__ __forceinline__ bool eq(const WarpKey &o) const { return lo == o.lo && hi == o.hi; }
+};
+
+constexpr int kIntersectThreads = 256;
+
+template <int KW>
+__global__ void __launch_bounds__(kIntersectThreads)
     sorted_intersect_kernel(const void *const *__restrict__ pa, const long long *__restrict__ na,
                             const void *const *__restrict__ pb, const long long *__restrict__ nb,
                             int32_t *__restrict__ out) {
+  using K = WarpKey<KW>;
   const long long pair = blockIdx.x;
   const unsigned long long *A = static_cast<const unsigned long long *>(pa[pair]);
   const unsigned long long *B = static_cast<const unsigned long long *>(pb[pair]);
   long long nA = na[pair], nB = nb[pair];
-  if (nA > nB) {  // probe with the smaller set (src/kmer_set.cpp:26-27)
+  if (nA > nB) {  // walk the smaller set (src/kmer_set.cpp:26-27)
     const unsigned long long *t = A; A = B; B = t;
-    long long tn = nA; nA = nB; nB = tn;
+    const long long tn = nA; nA = nB; nB = tn;
   }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kIntersectThreads / 32;
   uint32_t cnt = 0;
   if (nA > 0 && nB > 0) {
-    const long long per = (nA + blockDim.x - 1) / blockDim.x;
-    long long i = (long long)threadIdx.x * per, iend = i + per < nA ? i + per : nA;
-    if (i < iend) {
-      long long lo = 0, hi = nB;  // lower_bound of A[i] in B
-      while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        if (key_cmp<KW>(B, mid, A, i) < 0) lo = mid + 1; else hi = mid;
+    const long long per = ((nA + kWarps - 1) / kWarps + 31) & ~31ll;
+    long long ai = (long long)warp * per;
+    const long long a_end = ai + per < nA ? ai + per : nA;
+    if (ai < a_end) {
+      // bi = lower_bound(B, A[ai]) by a 32-ary search: every lane probes one splitter
+      const K first = K::load(A, ai);
+      long long lo = 0, hi = nB;  // answer in [lo, hi]
+      while (hi - lo > 0) {
+        const long long span = hi - lo, step = (span + 31) / 32;
+        const long long probe = lo + (long long)lane * step;  // splitters lo, lo+step, ...
+        const bool less = probe < hi && K::load(B, probe).lt(first);
+        const uint32_t m = __ballot_sync(0xffffffffu, less);
+        const int k = __popc(m);  // splitters 0..k-1 are < first (monotone)
+        if (k == 0) { hi = lo; break; }
+        const long long nlo = lo + (long long)(k - 1) * step + 1;
+        const long long nhi = (lo + (long long)k * step) < hi ? lo + (long long)k * step : hi;
+        lo = nlo;
+        hi = nhi;
       }
-      long long j = lo;
-      while (i < iend && j < nB) {
-        const int c = key_cmp<KW>(A, i, B, j);
-        if (c == 0) { ++cnt; ++i; ++j; } else if (c < 0) ++i; else ++j;
+      long long bi = lo;
+      K a = K::max(), b = K::max();
+      bool load_a = true, load_b = true;
+      while (ai < a_end && bi < nB) {
+        if (load_a) a = ai + lane < a_end ? K::load(A, ai + lane) : K::max();
+        if (load_b) b = bi + lane < nB ? K::load(B, bi + lane) : K::max();
+        // position of a among the 32 b's: number of b_j < a, capped at 31 (an a above every b cannot match)
+        int pos = 0;
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+          const K probe = b.shfl(pos + s - 1);
+          if (probe.lt(a)) pos += s;
+        }
+        const K hit = b.shfl(pos);
+        if (ai + lane < a_end && hit.eq(a) && bi + pos < nB) ++cnt;
+        const long long a_last = (a_end - ai < 32 ? a_end - ai : 32) - 1, b_last = (nB - bi < 32 ? nB - bi : 32) - 1;
+        const K a_max = a.shfl((int)a_last), b_max = b.shfl((int)b_last);
+        load_a = !b_max.lt(a_max);  // a_max <= b_max: this A chunk is done
+        load_b = !a_max.lt(b_max);  // b_max <= a_max: this B chunk is done
+        if (load_a) ai += 32;
+        if (load_b) bi += 32;
       }
     }
   }
-  __shared__ uint32_t s[8];
+  __shared__ uint32_t s[kWarps];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
+  if (lane == 0) s[warp] = cnt;
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t t = 0;
-    for (int k = 0; k < 8; ++k) t += s[k];
+    for (int k = 0; k < kWarps; ++k) t += s[k];
     out[pair] = (int32_t)t;
   }
 }
@@ -718,11 +780,11 @@ int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const
   for (int64_t done = 0; done < n_pairs;) {
     const int64_t chunk = std::min<int64_t>(n_pairs - done, 1 << 30);
     if (key_words == 1)
-      sorted_intersect_kernel<1><<<(unsigned)chunk, 256, 0, ctx->stream>>>(
+      sorted_intersect_kernel<1><<<(unsigned)chunk, kIntersectThreads, 0, ctx->stream>>>(
           d_a + done, reinterpret_cast<const long long *>(d_na + done), d_b + done,
           reinterpret_cast<const long long *>(d_nb + done), d_out + done);
     else
-      sorted_intersect_kernel<2><<<(unsigned)chunk, 256, 0, ctx->stream>>>(
+      sorted_intersect_kernel<2><<<(unsigned)chunk, kIntersectThreads, 0, ctx->stream>>>(
           d_a + done, reinterpret_cast<const long long *>(d_na + done), d_b + done,
           reinterpret_cast<const long long *>(d_nb + done), d_out + done);
     SKS_CUDA_TRY(cudaGetLastError());

@@ -272,6 +272,15 @@ class Context:
         check(fn(self.h, C.c_void_p(dptr), n_keys, words_per_key, _w2(mask), window, C.byref(h)))
         return KmerSet(self, h)
 
+    def sets_from_device_keys(self, dptr: int, counts: Sequence[int], words_per_key: int, mask: int,
+                              window: int) -> List["KmerSet"]:
+        """Sets whose sorted keys lie back to back at `dptr` (one device copy, shared buffer)."""
+        n = len(counts)
+        cnt = (C.c_int64 * max(n, 1))(*[int(c) for c in counts])
+        out = (C.c_void_p * max(n, 1))()
+        check(self._L.sks_sets_from_device_keys(self.h, C.c_void_p(dptr), n, cnt, words_per_key, _w2(mask), window, out))
+        return [KmerSet(self, C.c_void_p(out[i])) for i in range(n)]
+
     # -- comparison
     def intersect(self, a: "KmerSet", b: "KmerSet") -> int:
         out = C.c_int64()

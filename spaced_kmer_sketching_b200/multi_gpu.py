@@ -96,11 +96,8 @@ def allgather_sets(ctx, local_sets: Sequence, mask: int, window: int, rank: int,
     all_keys = allgather_varlen(keys, world, dist)
     torch.cuda.current_stream().synchronize()   # the gathered buffers are read by libsks on the same stream
     out = []
-    for r in range(world):
-        base, off = all_keys[r].data_ptr(), 0
-        for c in all_counts[r].tolist():
-            out.append(ctx.set_from_device_keys(base + off * 8 * kw, int(c), kw, mask, window, True))
-            off += int(c)
+    for r in range(world):   # one device copy + one buffer per source rank
+        out.extend(ctx.sets_from_device_keys(all_keys[r].data_ptr(), all_counts[r].tolist(), kw, mask, window))
     return out
 
 

@@ -335,3 +335,29 @@ def test_c3_chromosome_scale(ctx):
     assert np.array_equal(sub[:64], port.gen(lo + 64, 7)[lo:])
     osub = port.sketch_set(sub, [len(sub)], mask, w, port.FMH, 1, 200, 181)
     assert len(osub) > 4000 and np.isin(osub[:, 0], keys[:, 0]).all()
+
+
+def test_c5_multi_seed_sweep_ani_error(ctx):
+    """BASELINE.json configs[4] in small: several (k+10, k) random seed masks over graded mutants of one base
+    genome; the sketches match the oracle and the estimated ANI tracks the true substitution rate."""
+    L, Ds = 1_000_000, [0, 1000, 200, 100, 50, 20, 1000, 200, 100, 50, 20, 500]
+    n = len(Ds)
+    batch = ctx.synth(L, [1000] * n, [2000 + g for g in range(n)], Ds)
+    base = port.gen(L, 1000)
+    for k in (12, 16, 20, 24, 28):
+        w = k + 10
+        mask = sks.generate_random_spaced_seed_mask(w, k)
+        assert mask == port.random_mask(w, k, 0)
+        pred = sks.frac_min_hash(1, 200)
+        sets = ctx.sketch(batch, mask, w, pred)
+        counts = ctx.intersect_all_pairs(sets)
+        sizes = np.array([s.kmer_set_size() for s in sets], dtype=np.int32)
+        ani = sks.ani_from_counts(counts.ravel(), np.repeat(sizes, n), k).reshape(n, n)
+        for g in (0, 3, 5):   # oracle parity on three of the genomes
+            codes = base if Ds[g] == 0 else port.mutate(base, 2000 + g, Ds[g])
+            assert np.array_equal(sets[g].keys(), port.sketch_set(codes, [L], mask, w, port.FMH, 1, 200, 181)), (k, g)
+        assert np.array_equal(counts, counts.T) and (np.diag(counts) == sizes).all()
+        for g in range(1, n):   # ANI(base, mutant) vs 1 - 1/D (substitution-only, SURVEY.md 4.2 generator)
+            true = 1.0 - 1.0 / Ds[g]
+            # weight 12 on 1 Mbp has ~6 % chance matches (4^12 = 16.7 M k-mers), which biases the estimate upwards
+            assert abs(ani[0, g] - true) < (0.008 if k == 12 else 0.004), (k, g, ani[0, g], true)
