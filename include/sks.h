@@ -203,6 +203,14 @@ int sks_set_from_host_keys(sks_ctx *ctx, const uint64_t *keys_lohi, int64_t n_ke
                            sks_set **out);
 void sks_set_destroy(sks_ctx *ctx, sks_set *s);
 
+/* ---- sketch files (not in the reference: it never persists a sketch) ---------- */
+/* Little-endian file: "SKSKETCH", u32 version (1), u32 window, u64 mask[2], u32 pred kind, i32 nonce,
+ * u64 modulus, u32 hash variant, u32 words per key (1 or 2), u64 n_keys, then the ascending distinct
+ * masked_bits.  A BITSET set is written as its keys.  `pred` may be NULL (recorded as kind 0xFFFFFFFF). */
+int sks_set_save(sks_ctx *ctx, sks_set *s, const sks_pred *pred, const char *path);
+/* Loads a file written by sks_set_save as a SORTED set; out_pred (may be NULL) receives the recorded condition. */
+int sks_set_load(sks_ctx *ctx, const char *path, sks_set **out, sks_pred *out_pred);
+
 /* ---- comparison ------------------------------------------------------------------------------ */
 /* kmer_set_intersection, src/kmer_set.cpp:23-41 */
 int sks_intersect(sks_ctx *ctx, sks_set *a, sks_set *b, int64_t *out);

@@ -90,6 +90,8 @@ PROTOTYPES = {
     "sks_set_from_unsorted_device_keys": (ci, [vp, vp, i64, ci, u64p, ci, C.POINTER(vp)]),
     "sks_set_from_host_keys": (ci, [vp, vp, i64, u64p, ci, C.POINTER(vp)]),
     "sks_set_destroy": (None, [vp, vp]),
+    "sks_set_save": (ci, [vp, vp, C.POINTER(SksPred), C.c_char_p]),
+    "sks_set_load": (ci, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(SksPred)]),
     "sks_intersect": (ci, [vp, vp, vp, i64p]),
     "sks_intersect_pairs": (ci, [vp, C.POINTER(vp), i64, C.POINTER(vp), i64, vp]),
     "sks_intersect_all_pairs": (ci, [vp, C.POINTER(vp), i64, i64, i64, vp]),

@@ -6,7 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <thread>
 #include <sstream>
 #include <string>
 
@@ -555,16 +557,33 @@ std::vector<kmer_set> kmer_sets_from_fasta_files(const int num_files, char *fast
     std::vector<const uint32_t *> pw((size_t)num_files);
     std::vector<const uint64_t *> ps((size_t)num_files);
     std::vector<uint64_t> nb((size_t)num_files), ns((size_t)num_files);
+    // files are parsed concurrently (the reference's cilk_for over files, src/kmer_set.cpp:124-131)
+    std::vector<int> status((size_t)num_files, SKS_OK);
+    {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const int n_threads = (int)std::min<unsigned>(hw, (unsigned)num_files);
+        std::atomic<int> next{0};
+        auto work = [&]() {
+            for (int i = next.fetch_add(1); i < num_files; i = next.fetch_add(1))
+            {
+                parsed &f = files[(size_t)i];
+                status[(size_t)i] = sks_fasta_parse_file(fasta_filenames[i], &f.n_bases, &f.n_segs, &f.words, &f.segs);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+        work();
+        for (std::thread &t : pool) t.join();
+    }
     for (int i = 0; i < num_files; ++i)
     {
         parsed &f = files[(size_t)i];
-        const int st = sks_fasta_parse_file(fasta_filenames[i], &f.n_bases, &f.n_segs, &f.words, &f.segs);
-        if (st == SKS_ERR_IO)
+        if (status[(size_t)i] == SKS_ERR_IO)
         {
             std::cerr << "Unable to open " << fasta_filenames[i] << ". \n Exiting..." << std::endl;
             exit(1);
         }
-        check(st, "sks_fasta_parse_file");
+        if (status[(size_t)i] != SKS_OK) throw std::runtime_error("sks_fasta_parse_file failed");
         pw[(size_t)i] = f.words;
         ps[(size_t)i] = f.segs;
         nb[(size_t)i] = f.n_bases;

@@ -2,6 +2,7 @@
 // intersections.  Host-only entry points live in sks_host.cpp.  See include/sks.h for the contract
 // and the reference interfaces each call replaces.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -157,23 +158,28 @@ int layout_batch(sks_batch *b, int n_genomes, const uint64_t *n_bases, const uin
 }
 
 int upload_tables(sks_ctx *ctx, sks_batch *b) {
+  // descriptor tables go through the pinned ring, so that nothing here waits for the stream
   const int G = b->n_genomes;
-  SKS_TRY(alloc_buffer(ctx, sizeof(GenomeDesc) * (size_t)std::max(G, 1), &b->genomes));
-  SKS_TRY(alloc_buffer(ctx, 4 * std::max<size_t>(b->h_seg_end.size(), 1), &b->seg_end));
-  if (G > 0)
-    SKS_CUDA_TRY(cudaMemcpyAsync(b->genomes->ptr, b->h_genomes.data(), sizeof(GenomeDesc) * G, cudaMemcpyHostToDevice,
-                                 ctx->stream));
-  if (!b->h_seg_end.empty())
-    SKS_CUDA_TRY(cudaMemcpyAsync(b->seg_end->ptr, b->h_seg_end.data(), 4 * b->h_seg_end.size(), cudaMemcpyHostToDevice,
-                                 ctx->stream));
-  if (G > 1 && b->n_tiles > 0) {
-    std::vector<uint32_t> tg(b->n_tiles);
+  const size_t sz_g = sizeof(GenomeDesc) * (size_t)G, sz_s = 4 * b->h_seg_end.size();
+  const size_t sz_t = (G > 1) ? 4 * (size_t)b->n_tiles : 0;
+  SKS_TRY(alloc_buffer(ctx, std::max<size_t>(sz_g, 16), &b->genomes));
+  SKS_TRY(alloc_buffer(ctx, std::max<size_t>(sz_s, 16), &b->seg_end));
+  char *stage = nullptr;
+  SKS_TRY(ctx_pinned(ctx, sz_g + sz_s + sz_t + 64, reinterpret_cast<void **>(&stage)));
+  if (G > 0) {
+    memcpy(stage, b->h_genomes.data(), sz_g);
+    SKS_CUDA_TRY(cudaMemcpyAsync(b->genomes->ptr, stage, sz_g, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (sz_s) {
+    memcpy(stage + sz_g, b->h_seg_end.data(), sz_s);
+    SKS_CUDA_TRY(cudaMemcpyAsync(b->seg_end->ptr, stage + sz_g, sz_s, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (sz_t) {
+    uint32_t *tg = reinterpret_cast<uint32_t *>(stage + sz_g + sz_s);
     for (int g = 0; g < G; ++g)
-      std::fill(tg.begin() + b->h_genomes[g].tile_first, tg.begin() + b->h_genomes[g].tile_first + b->h_genomes[g].n_tiles,
-                (uint32_t)g);
-    SKS_TRY(alloc_buffer(ctx, 4 * (size_t)b->n_tiles, &b->tile_genome));
-    SKS_CUDA_TRY(cudaMemcpyAsync(b->tile_genome->ptr, tg.data(), 4 * (size_t)b->n_tiles, cudaMemcpyHostToDevice, ctx->stream));
-    SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // tg is a local
+      std::fill(tg + b->h_genomes[g].tile_first, tg + b->h_genomes[g].tile_first + b->h_genomes[g].n_tiles, (uint32_t)g);
+    SKS_TRY(alloc_buffer(ctx, sz_t, &b->tile_genome));
+    SKS_CUDA_TRY(cudaMemcpyAsync(b->tile_genome->ptr, tg, sz_t, cudaMemcpyHostToDevice, ctx->stream));
   }
   return SKS_OK;
 }
@@ -882,6 +888,99 @@ int sks_set_from_host_keys(sks_ctx *ctx, const uint64_t *keys_lohi, int64_t n_ke
 void sks_set_destroy(sks_ctx *ctx, sks_set *s) {
   (void)ctx;
   delete s;
+}
+
+// ---- sketch files -----------------------------------------------------------------------------------
+namespace {
+struct SketchFileHeader {
+  char magic[8];
+  uint32_t version, window;
+  uint64_t mask[2];
+  uint32_t pred_kind;
+  int32_t nonce;
+  uint64_t modulus;
+  uint32_t hash_variant, key_words;
+  uint64_t n_keys;
+};
+static_assert(sizeof(SketchFileHeader) == 64, "sketch file header layout");
+}  // namespace
+
+int sks_set_save(sks_ctx *ctx, sks_set *s, const sks_pred *pred, const char *path) {
+  if (!ctx || !s || !path) return set_error(SKS_ERR_INVALID, "null argument");
+  int64_t n = 0;
+  SKS_TRY(sks_set_size(ctx, s, &n));
+  std::vector<uint64_t> keys((size_t)n * 2);
+  SKS_TRY(sks_set_keys(ctx, s, keys.data(), (uint64_t)n));
+  SketchFileHeader h;
+  memset(&h, 0, sizeof(h));
+  memcpy(h.magic, "SKSKETCH", 8);
+  h.version = 1;
+  h.window = (uint32_t)s->window;
+  h.mask[0] = s->mask[0];
+  h.mask[1] = s->mask[1];
+  h.pred_kind = pred ? (uint32_t)pred->kind : 0xFFFFFFFFu;
+  h.nonce = pred ? pred->nonce : 0;
+  h.modulus = pred ? pred->modulus : 0;
+  h.hash_variant = pred ? (uint32_t)(pred->hash_variant ? pred->hash_variant : SKS_HASH_BOOST_181) : 0;
+  h.key_words = s->window <= 32 ? 1 : 2;
+  h.n_keys = (uint64_t)n;
+  FILE *f = fopen(path, "wb");
+  if (!f) return set_error(SKS_ERR_IO, "Unable to open %s for writing", path);
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  if (h.key_words == 2) {
+    ok = ok && (n == 0 || fwrite(keys.data(), 16, (size_t)n, f) == (size_t)n);
+  } else {
+    std::vector<uint64_t> lo((size_t)n);
+    for (int64_t i = 0; i < n; ++i) lo[(size_t)i] = keys[(size_t)i * 2];
+    ok = ok && (n == 0 || fwrite(lo.data(), 8, (size_t)n, f) == (size_t)n);
+  }
+  ok = (fclose(f) == 0) && ok;
+  return ok ? SKS_OK : set_error(SKS_ERR_IO, "short write to %s", path);
+}
+
+int sks_set_load(sks_ctx *ctx, const char *path, sks_set **out, sks_pred *out_pred) {
+  if (!ctx || !path || !out) return set_error(SKS_ERR_INVALID, "null argument");
+  FILE *f = fopen(path, "rb");
+  if (!f) return set_error(SKS_ERR_IO, "Unable to open %s", path);
+  SketchFileHeader h;
+  int st = SKS_OK;
+  std::vector<uint64_t> keys;
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "SKSKETCH", 8) != 0 || h.version != 1 ||
+      (h.key_words != 1 && h.key_words != 2) || h.window < 1 || h.window > 64 || h.n_keys > (1ull << 40)) {
+    st = set_error(SKS_ERR_IO, "%s is not a version-1 sketch file", path);
+  } else {
+    keys.resize((size_t)h.n_keys * h.key_words);
+    if (h.n_keys && fread(keys.data(), 8 * h.key_words, (size_t)h.n_keys, f) != (size_t)h.n_keys)
+      st = set_error(SKS_ERR_IO, "%s is truncated", path);
+  }
+  fclose(f);
+  SKS_TRY(st);
+  for (uint64_t i = 1; i < h.n_keys; ++i) {  // the file must hold ascending distinct keys
+    const uint64_t *a = &keys[(size_t)(i - 1) * h.key_words], *b = &keys[(size_t)i * h.key_words];
+    const bool less = h.key_words == 1 ? a[0] < b[0] : (a[1] != b[1] ? a[1] < b[1] : a[0] < b[0]);
+    if (!less) return set_error(SKS_ERR_IO, "%s: keys are not ascending and distinct", path);
+  }
+  DeviceGuard guard(ctx->device);
+  BufferRef buf;
+  SKS_TRY(alloc_buffer(ctx, keys.size() * 8, &buf));
+  if (!keys.empty()) {
+    SKS_CUDA_TRY(cudaMemcpyAsync(buf->ptr, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
+  sks_set *s = new_set(ctx, SKS_REPR_SORTED, h.mask, (int)h.window, sks_mask_weight(h.mask));
+  if (!s) return set_error(SKS_ERR_INVALID, "out of host memory");
+  s->buf = buf;
+  s->key_words = (int)h.key_words;
+  s->count = (int64_t)h.n_keys;
+  *out = s;
+  if (out_pred) {
+    memset(out_pred, 0, sizeof(*out_pred));
+    out_pred->kind = (int32_t)h.pred_kind;
+    out_pred->nonce = h.nonce;
+    out_pred->modulus = h.modulus;
+    out_pred->hash_variant = (int32_t)h.hash_variant;
+  }
+  return SKS_OK;
 }
 
 // ---- comparison ----------------------------------------------------------------------------------

@@ -70,15 +70,13 @@ void modulus_magic(uint64_t modulus, uint64_t *minv, uint64_t *mbound, int *mshi
   *mshift = s;
 }
 
-// PEXT(masked_bits, mask) as a table of rotate-and-mask pieces, one list per 32-bit limb.
+// PEXT(masked_bits, mask) as a table of rotate-and-mask pieces, up to kPiecesPerLimb per 32-bit limb.
 int build_pext_table(const uint64_t mask[2], int n_limbs, PextTable *out, int *n_index_bits) {
   memset(out, 0, sizeof(*out));
-  int n_pieces = 0, dst = 0;
-  for (int k = 0; k < 4; ++k) {
-    out->piece_begin[k] = (uint8_t)n_pieces;
-    if (k >= n_limbs) continue;
+  int dst = 0;
+  for (int k = 0; k < n_limbs && k < 4; ++k) {
     const uint32_t limb = (uint32_t)(mask[k >> 1] >> (32 * (k & 1)));
-    int b = 0;
+    int b = 0, n = 0;
     while (b < 32) {
       if (!((limb >> b) & 1)) {
         ++b;
@@ -87,17 +85,16 @@ int build_pext_table(const uint64_t mask[2], int n_limbs, PextTable *out, int *n
       int e = b;
       while (e < 32 && ((limb >> e) & 1)) ++e;
       const int len = e - b;
-      if (n_pieces >= kMaxPieces) return set_error(SKS_ERR_INVALID, "mask has too many runs");
+      if (n >= kPiecesPerLimb) return set_error(SKS_ERR_INVALID, "mask has too many runs in one limb");
       if (dst + len > 32) return set_error(SKS_ERR_INVALID, "mask weight exceeds 16: no 32-bit bitset index");
-      out->rot[n_pieces] = (uint8_t)((b - dst) & 31);
-      out->dmask[n_pieces] = (len == 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << dst;
-      ++n_pieces;
+      out->rot[k][n] = (uint32_t)((b - dst) & 31);
+      out->dmask[k][n] = (len == 32 ? 0xFFFFFFFFu : ((1u << len) - 1u)) << dst;
+      ++n;
       dst += len;
       b = e;
     }
+    out->n_pieces[k] = (uint32_t)n;
   }
-  out->piece_begin[4] = (uint8_t)n_pieces;
-  for (int k = n_limbs; k < 4; ++k) out->piece_begin[k + 1] = (uint8_t)n_pieces;
   *n_index_bits = dst;
   return SKS_OK;
 }
@@ -316,23 +313,30 @@ int sks_fasta_parse(const char *text, size_t n, uint64_t *n_bases, uint64_t *n_s
 
 int sks_fasta_parse_file(const char *path, uint64_t *n_bases, uint64_t *n_segs, uint32_t **out_words,
                          uint64_t **out_seg_len) {
+  if (!path || !n_bases || !n_segs || !out_words || !out_seg_len) return set_error(SKS_ERR_INVALID, "null argument");
   FILE *f = fopen(path, "rb");
   if (!f) return set_error(SKS_ERR_IO, "Unable to open %s", path);
   std::string text;
+  if (fseek(f, 0, SEEK_END) == 0) {
+    const long sz = ftell(f);
+    if (sz > 0) text.reserve((size_t)sz);
+    rewind(f);
+  }
   char buf[1 << 16];
   size_t got;
   while ((got = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, got);
   fclose(f);
-  uint64_t nb = 0, ns = 0;
-  sks_fasta_parse(text.data(), text.size(), &nb, &ns, nullptr, nullptr);
-  uint32_t *words = static_cast<uint32_t *>(calloc(sks_packed_words(nb) + 1, sizeof(uint32_t)));
-  uint64_t *segs = static_cast<uint64_t *>(calloc(ns + 1, sizeof(uint64_t)));
+  // one pass: a file of n bytes holds at most n bases and n/2 + 1 segments (a run needs a separator)
+  uint32_t *words = static_cast<uint32_t *>(malloc((text.size() / 16 + 2) * sizeof(uint32_t)));
+  uint64_t *segs = static_cast<uint64_t *>(malloc((text.size() / 2 + 2) * sizeof(uint64_t)));
   if (!words || !segs) {
     free(words);
     free(segs);
     return set_error(SKS_ERR_INVALID, "out of host memory");
   }
+  uint64_t nb = 0, ns = 0;
   sks_fasta_parse(text.data(), text.size(), &nb, &ns, words, segs);
+  if (uint64_t *shrunk = static_cast<uint64_t *>(realloc(segs, (ns + 1) * sizeof(uint64_t)))) segs = shrunk;
   *n_bases = nb;
   *n_segs = ns;
   *out_words = words;

@@ -65,15 +65,16 @@ enum PredMode : int { PRED_ALL = 0, PRED_FMH181 = 1, PRED_FMH171 = 2 };
 constexpr int kSliceBits = 19;
 constexpr int kSliceWords = (1 << kSliceBits) / 32;  // 16384
 
-constexpr int kMaxPieces = 40;  // <= 32 runs, each split at most once per 32-bit limb boundary
-
-// One piece of the PEXT table: bits of limb `limb` selected by (rotr(x, rot) & dmask) land in the
-// compacted index.  Pieces are grouped by limb: limb k owns [piece_begin[k], piece_begin[k+1]).
+// PEXT(masked_bits, mask) as rotate-and-mask pieces: one piece per run of mask ones inside a 32-bit limb
+// (a limb holds 16 base positions, hence at most 8 runs).  The compacted index takes the bits selected
+// by (rotr(limb, rot) & dmask); unused slots have dmask == 0.  The table is indexed with compile-time
+// constants only, so every entry is a direct constant-bank operand (a dynamically indexed table went
+// through LDC and kept the ADU pipe 80 % busy).
+constexpr int kPiecesPerLimb = 8;
 struct PextTable {
-  uint32_t dmask[kMaxPieces];
-  uint8_t rot[kMaxPieces];
-  uint8_t piece_begin[5];
-  uint8_t pad[3];
+  uint32_t dmask[4][kPiecesPerLimb];
+  uint32_t rot[4][kPiecesPerLimb];
+  uint32_t n_pieces[4];
 };
 
 struct SketchParams {

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
   key_t *s_keys = reinterpret_cast<key_t *>(smem_raw + 2 * kStageWords * 4 + 2 * sizeof(TileMeta) + 64);
   uint32_t *s_pos = reinterpret_cast<uint32_t *>(s_keys + kStageSlots);
 
+  constexpr bool kSparse = PRED != PRED_ALL;  // few survivors per tile: stage across tiles (see the flush below)
   const int tid = threadIdx.x;
   const int w = P.window;
   const int d2 = 2 * (w & 15);  // alignment shift of the forward stream
@@ -173,6 +174,30 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
     fence_proxy_async();
     mbar_expect_tx(&s_bar[stage], copy_words * 4);
     bulk_g2s(s_words + stage * kStageWords, src, copy_words * 4, &s_bar[stage]);
+  };
+
+  // Copies the staged survivors of `genome` to its output region: one global reservation per flush.
+  // `staged` is the value of *s_count every thread read between two barriers (so it is uniform and nobody
+  // is staging any more).
+  auto flush = [&](uint32_t genome, uint32_t staged) {
+    const uint32_t n = staged < (uint32_t)kStageSlots ? staged : (uint32_t)kStageSlots;  // the rest was spilled
+    if (n > 0) {      // uniform
+      if (tid == 0) {
+        *s_base = atomicAdd(P.out_count + genome, (unsigned long long)n);
+        *s_count = 0;
+      }
+      __syncthreads();
+      const unsigned long long base = *s_base;
+      const unsigned long long cap = P.out_cap[genome], off = P.out_off[genome];
+      key_t *out = reinterpret_cast<key_t *>(P.out_keys);
+      for (uint32_t i = tid; i < n; i += kSketchThreads) {
+        if (base + i < cap) {
+          out[off + base + i] = s_keys[i];
+          if (OUT == OUT_LIST) P.out_pos[off + base + i] = s_pos[i];
+        }
+      }
+      __syncthreads();
+    }
   };
 
   if (tid == 0 && blockIdx.x < P.n_tiles) issue(blockIdx.x, 0);
@@ -283,49 +308,65 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
             if (OUT == OUT_BITSET || OUT == OUT_INDEX) {  // PEXT(masked, mask): rotate-and-mask pieces
 #pragma unroll
               for (int k = 0; k < NL; ++k) {
-                for (int p = P.pext.piece_begin[k]; p < P.pext.piece_begin[k + 1]; ++p)
-                  idx |= __funnelshift_r(c[k], c[k], P.pext.rot[p]) & P.pext.dmask[p];
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                  idx |= __funnelshift_r(c[k], c[k], P.pext.rot[k][p]) & P.pext.dmask[k][p];
+                if (P.pext.n_pieces[k] > 4) {  // uniform
+#pragma unroll
+                  for (int p = 4; p < kPiecesPerLimb; ++p)
+                    idx |= __funnelshift_r(c[k], c[k], P.pext.rot[k][p]) & P.pext.dmask[k][p];
+                }
               }
             }
             if (OUT == OUT_BITSET) {
               atomicOr(P.bitset + (uint64_t)tm.genome * P.bitset_words + (idx >> 5), 1u << (idx & 31));
             } else {
               const uint32_t slot = atomicAdd(s_count, 1u);
-              if (OUT == OUT_INDEX) {
+              if (kSparse && slot >= (uint32_t)kStageSlots) {
+                // the stage is full (dense survivors under a sparse-mode predicate): write this one directly
+                const unsigned long long gs = atomicAdd(P.out_count + tm.genome, 1ull);
+                if (gs < P.out_cap[tm.genome]) {
+                  const unsigned long long at = P.out_off[tm.genome] + gs;
+                  if (OUT == OUT_INDEX) {
+                    reinterpret_cast<uint32_t *>(P.out_keys)[at] = idx;
+                  } else if (NL <= 2) {
+                    reinterpret_cast<unsigned long long *>(P.out_keys)[at] = b0;
+                  } else {
+                    reinterpret_cast<ulonglong2 *>(P.out_keys)[at] = make_ulonglong2(b0, b1);
+                  }
+                  if (OUT == OUT_LIST) P.out_pos[at] = (p0 + j) | (lt ? 0u : 0x80000000u);
+                }
+              } else if (OUT == OUT_INDEX) {
                 reinterpret_cast<uint32_t *>(s_keys)[slot] = idx;
               } else if (NL <= 2) {
                 reinterpret_cast<unsigned long long *>(s_keys)[slot] = b0;
               } else {
                 reinterpret_cast<ulonglong2 *>(s_keys)[slot] = make_ulonglong2(b0, b1);
               }
-              if (OUT == OUT_LIST) s_pos[slot] = (p0 + j) | (lt ? 0u : 0x80000000u);
+              if (OUT == OUT_LIST && !(kSparse && slot >= (uint32_t)kStageSlots)) s_pos[slot] = (p0 + j) | (lt ? 0u : 0x80000000u);
             }
           }
         }
       }
 
-      // ---- flush the round's kept k-mers: one global reservation per CTA -------------------------
-      if (OUT != OUT_BITSET) {
+      // ---- dense mode: flush the round's kept k-mers (every window may survive) ---------------------
+      if (OUT != OUT_BITSET && !kSparse) {
         __syncthreads();
-        const uint32_t n = *s_count;
-        if (n > 0) {  // uniform
-          if (tid == 0) *s_base = atomicAdd(P.out_count + tm.genome, (unsigned long long)n);
-          __syncthreads();
-          const unsigned long long base = *s_base;
-          const unsigned long long cap = P.out_cap[tm.genome], off = P.out_off[tm.genome];
-          if (tid == 0) *s_count = 0;
-          key_t *out = reinterpret_cast<key_t *>(P.out_keys);
-          for (uint32_t i = tid; i < n; i += kSketchThreads) {
-            if (base + i < cap) {
-              out[off + base + i] = s_keys[i];
-              if (OUT == OUT_LIST) P.out_pos[off + base + i] = s_pos[i];
-            }
-          }
-          __syncthreads();
-        }
+        const uint32_t staged = *s_count;
+        __syncthreads();
+        flush(tm.genome, staged);
       }
     }
     __syncthreads();  // everyone is done with s_words[stage] / s_meta[stage] before it is refilled
+    // ---- sparse mode (a FracMinHash filter keeps ~1/c of the windows): survivors of many tiles share the
+    // stage; flush when it is half full, when the next tile belongs to another genome, or at the end
+    if (OUT != OUT_BITSET && kSparse) {
+      const uint32_t staged = *s_count;
+      const bool last = tile + gridDim.x >= P.n_tiles;
+      const bool do_flush = staged >= (uint32_t)kStageSlots / 2 || last || s_meta[stage ^ 1].genome != tm.genome;
+      __syncthreads();  // everyone has read s_count / s_meta before the next tile touches them
+      if (do_flush) flush(tm.genome, staged);
+    }
   }
 }
 

@@ -281,6 +281,12 @@ class Context:
         check(self._L.sks_sets_from_device_keys(self.h, C.c_void_p(dptr), n, cnt, words_per_key, _w2(mask), window, out))
         return [KmerSet(self, C.c_void_p(out[i])) for i in range(n)]
 
+    def load_set(self, path: str) -> Tuple["KmerSet", Predicate]:
+        """Reads a sketch file written by KmerSet.save."""
+        h, p = C.c_void_p(), SksPred()
+        check(self._L.sks_set_load(self.h, path.encode(), C.byref(h), C.byref(p)))
+        return KmerSet(self, h), Predicate(p.kind, p.nonce, p.modulus, p.hash_variant)
+
     # -- comparison
     def intersect(self, a: "KmerSet", b: "KmerSet") -> int:
         out = C.c_int64()
@@ -391,6 +397,11 @@ class KmerSet:
         check(self.ctx._L.sks_set_keys(self.ctx.h, self.h, out.ctypes.data, n))
         return out
 
+    def save(self, path: str, pred: Optional[Predicate] = None) -> None:
+        """Writes the set as a sketch file (include/sks.h: sks_set_save)."""
+        p = pred.c() if pred is not None else None
+        check(self.ctx._L.sks_set_save(self.ctx.h, self.h, C.byref(p) if p is not None else None, path.encode()))
+
     def device_keys(self) -> Tuple[int, int, int]:
         p, n, kw = C.c_void_p(), C.c_int64(), C.c_int()
         check(self.ctx._L.sks_set_device_keys(self.ctx.h, self.h, C.byref(p), C.byref(n), C.byref(kw)))
@@ -412,7 +423,13 @@ class KmerSet:
 def kmer_sets_from_fasta_files(ctx: Context, fasta_filenames: Sequence[str], mask: int, window_length: int,
                                sketching_cond: Predicate, repr_: int = REPR_AUTO) -> List[KmerSet]:
     """(parallel_)kmer_sets_from_fasta_files, src/kmer_set.cpp:81-133: one batched launch."""
-    genomes = [fasta_parse_file(f) for f in fasta_filenames]
+    if len(fasta_filenames) > 1:   # host parse + pack in parallel (ctypes releases the GIL), like the reference's cilk_for
+        from concurrent.futures import ThreadPoolExecutor
+        import os
+        with ThreadPoolExecutor(min(len(fasta_filenames), os.cpu_count() or 1)) as pool:
+            genomes = list(pool.map(fasta_parse_file, fasta_filenames))
+    else:
+        genomes = [fasta_parse_file(f) for f in fasta_filenames]
     batch = ctx.upload(genomes)
     try:
         return ctx.sketch(batch, mask, window_length, sketching_cond, repr_)

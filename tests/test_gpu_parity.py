@@ -361,3 +361,39 @@ def test_c5_multi_seed_sweep_ani_error(ctx):
             true = 1.0 - 1.0 / Ds[g]
             # weight 12 on 1 Mbp has ~6 % chance matches (4^12 = 16.7 M k-mers), which biases the estimate upwards
             assert abs(ani[0, g] - true) < (0.008 if k == 12 else 0.004), (k, g, ani[0, g], true)
+
+
+def test_output_capacity_retry_on_repetitive_genome(ctx):
+    """FMH output regions are sized from the expected survivor rate; a homopolymer whose single k-mer passes
+    the filter keeps EVERY window and must go through the exact-capacity retry."""
+    codes = np.zeros(200_000, dtype=np.uint8)
+    mask, w = sks.seed_to_mask("11001011")
+    nonce = next(n for n in range(1, 200) if port.fmh(0, mask, w, n, 181) % 3 == 0)   # poly-A -> canonical key 0
+    pred = sks.frac_min_hash(nonce, 3)
+    batch = ctx.upload_codes([codes, port.gen(50_000, 3)])
+    masked, bits = ctx.kmer_list(batch, 0, mask, w, pred)
+    om, ob = port.kmers(codes, [len(codes)], mask, w, port.FMH, nonce, 3, 181, want_bits=True)
+    assert len(masked) == len(codes) - w + 1 and np.array_equal(masked, om) and np.array_equal(bits, ob)
+    sets = ctx.sketch(batch, mask, w, pred, sks.REPR_SORTED)
+    assert sets[0].kmer_set_size() == 1 and sets[0].keys().tolist() == [[0, 0]]
+    assert np.array_equal(sets[1].keys(), port.sketch_set(port.gen(50_000, 3), [50_000], mask, w, port.FMH, nonce, 3, 181))
+
+
+def test_sketch_files_roundtrip(ctx, tmp_path):
+    A = port.gen(80_000, 21)
+    batch = ctx.upload_codes([A, port.mutate(A, 22, 30)])
+    for seed, pred, r in ((C3_SEED, sks.frac_min_hash(1, 20), sks.REPR_SORTED), ("1" * 40, sks.frac_min_hash(3, 9, 171), sks.REPR_SORTED),
+                          ("110101101", sks.all_kmers(), sks.REPR_BITSET)):
+        mask, w = sks.seed_to_mask(seed)
+        sa, sb = ctx.sketch(batch, mask, w, pred, r)
+        pa = str(tmp_path / "a.sks")
+        sa.save(pa, pred)
+        la, lp = ctx.load_set(pa)
+        assert (lp.kind, lp.nonce, lp.modulus) == (pred.kind, pred.nonce, pred.modulus)
+        assert la.window == w and la.weight == sks.mask_weight(mask) and np.array_equal(la.keys(), sa.keys())
+        if r == sks.REPR_SORTED:
+            assert ctx.intersect(la, sb) == ctx.intersect(sa, sb)
+    (tmp_path / "bad.sks").write_bytes(b"not a sketch")
+    with pytest.raises(sks.SksError) as e:
+        ctx.load_set(str(tmp_path / "bad.sks"))
+    assert e.value.code == 5
