@@ -92,7 +92,8 @@ int64_t sks_ctx_launch_count(const sks_ctx *ctx);
 #define SKS_KERNEL_SYNTH 6        /* synthetic genome generator                          */
 #define SKS_KERNEL_LIST 7         /* ordered-list finalisation                           */
 #define SKS_KERNEL_BITSET_BUILD 8 /* bucket sort + slice-wise bitset assembly (K4, bucketed) */
-#define SKS_KERNEL_KINDS 9
+#define SKS_KERNEL_FASTA 9        /* device-side FASTA parse + 2-bit pack                */
+#define SKS_KERNEL_KINDS 10
 int sks_ctx_profile(sks_ctx *ctx, int enable);
 int sks_ctx_kernel_stats(sks_ctx *ctx, int kind, int64_t *out_launches, double *out_total_ms);
 const char *sks_kernel_name(int kind);
@@ -142,6 +143,15 @@ void sks_free(void *p);
  * (src/kmer_set.cpp:54-68). */
 int sks_batch_upload(sks_ctx *ctx, int n_genomes, const uint32_t *const *packed, const uint64_t *n_bases,
                      const uint64_t *const *seg_len, const uint64_t *n_segs, sks_batch **out);
+/* FASTA ingest ON THE DEVICE: the raw bytes of n_files FASTA files (HOST buffers) are uploaded and parsed,
+ * split at non-ACGT bytes and 2-bit packed by kernels, with the reference's record rules
+ * (strings_from_fasta + cut_nucleotide_strings, src/fasta_processing.cpp:79-211).  Same result as
+ * sks_fasta_parse + sks_batch_upload; at most 2 GiB of text per call. */
+int sks_batch_from_fasta_text(sks_ctx *ctx, int n_files, const char *const *text, const uint64_t *n_bytes, sks_batch **out);
+/* Same, reading the files; an unreadable file returns SKS_ERR_IO. */
+int sks_batch_from_fasta_files(sks_ctx *ctx, int n_files, const char *const *paths, sks_batch **out);
+/* Segment (ACGT-run) lengths of one genome of a batch; out_seg_len NULL => only *n_segs. */
+int sks_batch_segments(const sks_batch *b, int genome, uint64_t *n_segs, uint64_t *out_seg_len);
 /* Synthetic genomes generated ON DEVICE (benchmark inputs, SURVEY.md 4.2 KAT-3 generator):
  * genome g = mutate(gen(n_bases, gen_seed[g]), mut_seed[g], mut_D[g]); mut_D[g]==0 => no mutation. */
 int sks_batch_synth(sks_ctx *ctx, int n_genomes, uint64_t n_bases, const uint64_t *gen_seed,

@@ -16,7 +16,7 @@ SKS_OK, SKS_ERR_INVALID, SKS_ERR_CUDA, SKS_ERR_CAPACITY, SKS_ERR_MISMATCH, SKS_E
 PRED_ALL, PRED_FMH = 0, 1
 HASH_BOOST_171, HASH_BOOST_181 = 171, 181
 REPR_AUTO, REPR_SORTED, REPR_BITSET = 0, 1, 2
-KERNEL_KINDS = 9
+KERNEL_KINDS = 10
 
 
 class SksPred(C.Structure):
@@ -70,6 +70,9 @@ PROTOTYPES = {
     "sks_fasta_parse_file": (ci, [C.c_char_p, u64p, u64p, C.POINTER(vp), C.POINTER(vp)]),
     "sks_free": (None, [vp]),
     "sks_batch_upload": (ci, [vp, ci, C.POINTER(vp), u64p, C.POINTER(vp), u64p, C.POINTER(vp)]),
+    "sks_batch_from_fasta_text": (ci, [vp, ci, C.POINTER(C.c_char_p), u64p, C.POINTER(vp)]),
+    "sks_batch_from_fasta_files": (ci, [vp, ci, C.POINTER(C.c_char_p), C.POINTER(vp)]),
+    "sks_batch_segments": (ci, [vp, ci, u64p, vp]),
     "sks_batch_synth": (ci, [vp, ci, u64, u64p, u64p, u64p, C.POINTER(vp)]),
     "sks_batch_synth_at": (ci, [vp, ci, u64, u64p, u64p, u64p, u64p, C.POINTER(vp)]),
     "sks_batch_slice": (ci, [vp, vp, ci, u64, u64, ci, C.POINTER(vp)]),

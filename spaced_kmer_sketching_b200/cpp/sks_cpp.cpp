@@ -541,24 +541,11 @@ std::vector<kmer_set> kmer_sets_from_fasta_files(const int num_files, char *fast
     uint64_t m[2];
     sks::mask_words(mask, m);
 
-    // host: parse + 2-bit pack + segment tables (the reference's exit(1) on an unreadable file is kept)
-    struct parsed
-    {
-        uint32_t *words = nullptr;
-        uint64_t *segs = nullptr;
-        uint64_t n_bases = 0, n_segs = 0;
-        ~parsed()
-        {
-            sks_free(words);
-            sks_free(segs);
-        }
-    };
-    std::vector<parsed> files((size_t)num_files);
-    std::vector<const uint32_t *> pw((size_t)num_files);
-    std::vector<const uint64_t *> ps((size_t)num_files);
-    std::vector<uint64_t> nb((size_t)num_files), ns((size_t)num_files);
-    // files are parsed concurrently (the reference's cilk_for over files, src/kmer_set.cpp:124-131)
-    std::vector<int> status((size_t)num_files, SKS_OK);
+    // host: read the files concurrently (the reference's cilk_for over files, src/kmer_set.cpp:124-131; its
+    // exit(1) on an unreadable file is kept).  Parsing, splitting at non-ACGT bytes and 2-bit packing happen
+    // on the device (sks_batch_from_fasta_text), at most 2 GiB of text per batch.
+    std::vector<std::string> texts((size_t)num_files);
+    std::vector<char> unreadable((size_t)num_files, 0);
     {
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         const int n_threads = (int)std::min<unsigned>(hw, (unsigned)num_files);
@@ -566,8 +553,23 @@ std::vector<kmer_set> kmer_sets_from_fasta_files(const int num_files, char *fast
         auto work = [&]() {
             for (int i = next.fetch_add(1); i < num_files; i = next.fetch_add(1))
             {
-                parsed &f = files[(size_t)i];
-                status[(size_t)i] = sks_fasta_parse_file(fasta_filenames[i], &f.n_bases, &f.n_segs, &f.words, &f.segs);
+                FILE *fp = fopen(fasta_filenames[i], "rb");
+                if (!fp)
+                {
+                    unreadable[(size_t)i] = 1;
+                    continue;
+                }
+                std::string &t = texts[(size_t)i];
+                if (fseek(fp, 0, SEEK_END) == 0)
+                {
+                    const long sz = ftell(fp);
+                    if (sz > 0) t.reserve((size_t)sz);
+                    rewind(fp);
+                }
+                char buf[1 << 16];
+                size_t got;
+                while ((got = fread(buf, 1, sizeof(buf), fp)) > 0) t.append(buf, got);
+                fclose(fp);
             }
         };
         std::vector<std::thread> pool;
@@ -576,44 +578,72 @@ std::vector<kmer_set> kmer_sets_from_fasta_files(const int num_files, char *fast
         for (std::thread &t : pool) t.join();
     }
     for (int i = 0; i < num_files; ++i)
-    {
-        parsed &f = files[(size_t)i];
-        if (status[(size_t)i] == SKS_ERR_IO)
+        if (unreadable[(size_t)i])
         {
             std::cerr << "Unable to open " << fasta_filenames[i] << ". \n Exiting..." << std::endl;
             exit(1);
         }
-        if (status[(size_t)i] != SKS_OK) throw std::runtime_error("sks_fasta_parse_file failed");
-        pw[(size_t)i] = f.words;
-        ps[(size_t)i] = f.segs;
-        nb[(size_t)i] = f.n_bases;
-        ns[(size_t)i] = f.n_segs;
-    }
-    sks::batch_guard bg;
-    check(sks_batch_upload(ctx(), num_files, pw.data(), nb.data(), ps.data(), ns.data(), &bg.b), "sks_batch_upload");
 
-    if (plan.kind == sks::pred_plan::DEVICE)
+    const uint64_t batch_limit = (1ull << 31) - (1ull << 20);
+    for (int first = 0; first < num_files;)
     {
-        std::vector<sks_set *> sets((size_t)num_files, nullptr);
-        check(sks_sketch(ctx(), bg.b, m, window_length, &plan.pred, sks::g_ts.repr, sets.data()), "sks_sketch");
-        for (int i = 0; i < num_files; ++i) sks::set_access::adopt(out[(size_t)i], sets[(size_t)i], window_length, mask);
-        return out;
-    }
-    // Opaque condition: the device slides, canonicalises and returns every k-mer; the callable runs here.
-    for (int i = 0; i < num_files; ++i)
-    {
-        std::vector<kmer> kept;
-        append_list(kept, bg.b, i, mask, window_length, plan, sketching_cond);
-        std::vector<uint64_t> keys;
-        keys.reserve(kept.size() * 2);
-        for (const kmer &k : kept)
+        int last = first;
+        uint64_t bytes = 0;
+        std::vector<const char *> ptr;
+        std::vector<uint64_t> len;
+        while (last < num_files && (last == first || bytes + texts[(size_t)last].size() <= batch_limit))
         {
-            keys.push_back(k.masked_bits.word(0));
-            keys.push_back(k.masked_bits.word(1));
+            ptr.push_back(texts[(size_t)last].data());
+            len.push_back(texts[(size_t)last].size());
+            bytes += texts[(size_t)last].size();
+            ++last;
         }
-        sks_set *h = nullptr;
-        check(sks_set_from_host_keys(ctx(), keys.data(), (int64_t)kept.size(), m, window_length, &h), "sks_set_from_host_keys");
-        sks::set_access::adopt(out[(size_t)i], h, window_length, mask);
+        const int n = last - first;
+        sks::batch_guard bg;
+        if (bytes <= batch_limit)
+        {
+            check(sks_batch_from_fasta_text(ctx(), n, ptr.data(), len.data(), &bg.b), "sks_batch_from_fasta_text");
+        }
+        else
+        { // a single file beyond the device parser's limit: parse and pack it on the host
+            uint64_t nb = 0, ns = 0;
+            check(sks_fasta_parse(ptr[0], (size_t)len[0], &nb, &ns, nullptr, nullptr), "sks_fasta_parse");
+            std::vector<uint32_t> words(sks_packed_words(nb) + 1);
+            std::vector<uint64_t> segs((size_t)ns + 1);
+            check(sks_fasta_parse(ptr[0], (size_t)len[0], &nb, &ns, words.data(), segs.data()), "sks_fasta_parse");
+            const uint32_t *pw = words.data();
+            const uint64_t *ps = segs.data();
+            check(sks_batch_upload(ctx(), 1, &pw, &nb, &ps, &ns, &bg.b), "sks_batch_upload");
+            check(sks_ctx_sync(ctx()), "sks_ctx_sync");
+        }
+        if (plan.kind == sks::pred_plan::DEVICE)
+        {
+            std::vector<sks_set *> sets((size_t)n, nullptr);
+            check(sks_sketch(ctx(), bg.b, m, window_length, &plan.pred, sks::g_ts.repr, sets.data()), "sks_sketch");
+            for (int i = 0; i < n; ++i) sks::set_access::adopt(out[(size_t)(first + i)], sets[(size_t)i], window_length, mask);
+        }
+        else
+        {
+            // Opaque condition: the device slides, canonicalises and returns every k-mer; the callable runs here.
+            for (int i = 0; i < n; ++i)
+            {
+                std::vector<kmer> kept;
+                append_list(kept, bg.b, i, mask, window_length, plan, sketching_cond);
+                std::vector<uint64_t> keys;
+                keys.reserve(kept.size() * 2);
+                for (const kmer &k : kept)
+                {
+                    keys.push_back(k.masked_bits.word(0));
+                    keys.push_back(k.masked_bits.word(1));
+                }
+                sks_set *h = nullptr;
+                check(sks_set_from_host_keys(ctx(), keys.data(), (int64_t)kept.size(), m, window_length, &h),
+                      "sks_set_from_host_keys");
+                sks::set_access::adopt(out[(size_t)(first + i)], h, window_length, mask);
+            }
+        }
+        check(sks_ctx_sync(ctx()), "sks_ctx_sync"); // the host text buffers of this batch may go away
+        first = last;
     }
     return out;
 }

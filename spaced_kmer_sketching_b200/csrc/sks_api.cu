@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 
 #include "sks_internal.cuh"
 
@@ -518,7 +519,7 @@ int sks_ctx_kernel_stats(sks_ctx *ctx, int kind, int64_t *out_launches, double *
 const char *sks_kernel_name(int kind) {
   static const char *names[SKS_KERNEL_KINDS] = {"sketch_kernel", "fill_zero_kernel", "bitset_pair_counts_kernel",
                                                 "bitset_popcount_kernel", "sort_unique", "sorted_intersect_kernel",
-                                                "synth_kernel", "list_finalize", "bitset_build"};
+                                                "synth_kernel", "list_finalize", "bitset_build", "fasta_parse"};
   return (kind >= 0 && kind < SKS_KERNEL_KINDS) ? names[kind] : "?";
 }
 
@@ -599,6 +600,89 @@ int sks_batch_synth_at(sks_ctx *ctx, int n_genomes, uint64_t n_bases, const uint
     return st;
   }
   *out = b;
+  return SKS_OK;
+}
+
+int sks_batch_from_fasta_text(sks_ctx *ctx, int n_files, const char *const *text, const uint64_t *n_bytes, sks_batch **out) {
+  if (!ctx || !out || n_files < 0 || (n_files > 0 && (!text || !n_bytes))) return set_error(SKS_ERR_INVALID, "bad argument");
+  DeviceGuard guard(ctx->device);
+  std::vector<uint64_t> file_off((size_t)n_files + 1, 0);
+  for (int f = 0; f < n_files; ++f) file_off[(size_t)f + 1] = file_off[(size_t)f] + n_bytes[f];
+  const uint64_t total = file_off.back();
+  BufferRef d_text;
+  SKS_TRY(alloc_buffer(ctx, (size_t)total + 16, &d_text));
+  for (int f = 0; f < n_files; ++f)
+    if (n_bytes[f])
+      SKS_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(d_text->ptr) + file_off[(size_t)f], text[f], (size_t)n_bytes[f],
+                                   cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<uint64_t> nb;
+  std::vector<std::vector<uint64_t>> segs;
+  BufferRef codes, gbase;
+  SKS_TRY(fasta_parse_device(ctx, static_cast<const unsigned char *>(d_text->ptr), file_off, &nb, &segs, &codes, &gbase));
+  sks_batch *b = new (std::nothrow) sks_batch();
+  if (!b) return set_error(SKS_ERR_INVALID, "out of host memory");
+  b->device = ctx->device;
+  std::vector<const uint64_t *> seg_ptr((size_t)n_files);
+  std::vector<uint64_t> n_segs((size_t)n_files);
+  for (int f = 0; f < n_files; ++f) {
+    seg_ptr[(size_t)f] = segs[(size_t)f].data();
+    n_segs[(size_t)f] = segs[(size_t)f].size();
+  }
+  uint64_t total_words = 0;
+  int st = layout_batch(b, n_files, nb.data(), seg_ptr.data(), n_segs.data(), &total_words);
+  if (st == SKS_OK) st = alloc_buffer(ctx, (size_t)total_words * 4, &b->words);
+  if (st == SKS_OK) st = launch_fill_zero(ctx, b->words->ptr, (size_t)total_words * 4);
+  if (st == SKS_OK) st = upload_tables(ctx, b);
+  if (st == SKS_OK && n_files > 0) {
+    uint32_t max_words = 0;
+    for (const GenomeDesc &gd : b->h_genomes) max_words = std::max(max_words, gd.n_words);
+    st = launch_pack_codes(ctx, static_cast<const uint8_t *>(codes->ptr), static_cast<const uint32_t *>(gbase->ptr),
+                           static_cast<const GenomeDesc *>(b->genomes->ptr), n_files, max_words,
+                           static_cast<uint32_t *>(b->words->ptr));
+  }
+  if (st != SKS_OK) {
+    delete b;
+    return st;
+  }
+  *out = b;
+  return SKS_OK;
+}
+
+int sks_batch_from_fasta_files(sks_ctx *ctx, int n_files, const char *const *paths, sks_batch **out) {
+  if (!ctx || !out || n_files < 0 || (n_files > 0 && !paths)) return set_error(SKS_ERR_INVALID, "bad argument");
+  std::vector<std::string> texts((size_t)n_files);
+  for (int f = 0; f < n_files; ++f) {
+    FILE *fp = fopen(paths[f], "rb");
+    if (!fp) return set_error(SKS_ERR_IO, "Unable to open %s", paths[f]);
+    char buf[1 << 16];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof(buf), fp)) > 0) texts[(size_t)f].append(buf, got);
+    fclose(fp);
+  }
+  std::vector<const char *> ptr((size_t)n_files);
+  std::vector<uint64_t> len((size_t)n_files);
+  for (int f = 0; f < n_files; ++f) {
+    ptr[(size_t)f] = texts[(size_t)f].data();
+    len[(size_t)f] = texts[(size_t)f].size();
+  }
+  const int st = sks_batch_from_fasta_text(ctx, n_files, ptr.data(), len.data(), out);
+  if (st == SKS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) return set_error(SKS_ERR_CUDA, "FASTA upload failed");
+  return st;
+}
+
+int sks_batch_segments(const sks_batch *b, int genome, uint64_t *n_segs, uint64_t *out_seg_len) {
+  if (!b || !n_segs || genome < 0 || genome >= b->n_genomes) return set_error(SKS_ERR_INVALID, "bad argument");
+  const GenomeDesc &gd = b->h_genomes[genome];
+  uint64_t prev = 0, n = 0;
+  for (uint32_t s = 0; s < gd.n_segs; ++s) {
+    const uint64_t e = b->h_seg_end[gd.seg_first + s];
+    if (e > prev) {
+      if (out_seg_len) out_seg_len[n] = e - prev;
+      ++n;
+    }
+    prev = e;
+  }
+  *n_segs = n;
   return SKS_OK;
 }
 

@@ -205,6 +205,12 @@ int launch_list_finalize(sks_ctx *ctx, const uint32_t *words, const uint32_t *se
                          int key_words, const void *raw_keys, const uint32_t *raw_pos, uint32_t n,
                          unsigned long long *out_masked, unsigned long long *out_bits);
 
+int fasta_parse_device(sks_ctx *ctx, const unsigned char *d_text, const std::vector<uint64_t> &h_file_off,
+                       std::vector<uint64_t> *n_bases, std::vector<std::vector<uint64_t>> *seg_len, BufferRef *codes_buf,
+                       BufferRef *genome_base_buf);
+int launch_pack_codes(sks_ctx *ctx, const uint8_t *d_codes, const uint32_t *d_genome_base, const GenomeDesc *d_genomes,
+                      int n_genomes, uint32_t max_words, uint32_t *d_words);
+
 // host-only helpers (sks_host.cpp)
 uint64_t boost_hash_bitset(uint64_t lo, uint64_t hi, int variant);
 void modulus_magic(uint64_t modulus, uint64_t *minv, uint64_t *mbound, int *mshift);

@@ -224,6 +224,22 @@ class Context:
         return self.upload([(pack_codes(s), len(s), None if seg_lens is None else seg_lens[i])
                             for i, s in enumerate(seqs)])
 
+    def batch_from_fasta_text(self, texts: Sequence[bytes]) -> "Batch":
+        """Device-side FASTA ingest: raw file bytes are uploaded and parsed / packed by kernels."""
+        n = len(texts)
+        ptr = (C.c_char_p * max(n, 1))(*texts)
+        ln = (C.c_uint64 * max(n, 1))(*[len(t) for t in texts])
+        h = C.c_void_p()
+        check(self._L.sks_batch_from_fasta_text(self.h, n, ptr, ln, C.byref(h)))
+        return Batch(self, h)
+
+    def batch_from_fasta_files(self, paths: Sequence[str]) -> "Batch":
+        n = len(paths)
+        ptr = (C.c_char_p * max(n, 1))(*[p.encode() for p in paths])
+        h = C.c_void_p()
+        check(self._L.sks_batch_from_fasta_files(self.h, n, ptr, C.byref(h)))
+        return Batch(self, h)
+
     def synth(self, n_bases: int, gen_seed: Sequence[int], mut_seed: Sequence[int], mut_D: Sequence[int]) -> "Batch":
         n = len(gen_seed)
         a = (C.c_uint64 * max(n, 1))(*gen_seed)
@@ -345,6 +361,14 @@ class Batch:
     def n_bases(self, genome: int) -> int:
         return int(self.ctx._L.sks_batch_n_bases(self.h, genome))
 
+    def segments(self, genome: int) -> np.ndarray:
+        """Lengths of the ACGT runs of one genome."""
+        n = C.c_uint64()
+        check(self.ctx._L.sks_batch_segments(self.h, genome, C.byref(n), None))
+        out = np.zeros(max(n.value, 1), dtype=np.uint64)
+        check(self.ctx._L.sks_batch_segments(self.h, genome, C.byref(n), out.ctypes.data))
+        return out[:n.value]
+
     def download(self, genome: int) -> np.ndarray:
         out = np.zeros(self.ctx._L.sks_packed_words(self.n_bases(genome)), dtype=np.uint32)
         check(self.ctx._L.sks_batch_download(self.ctx.h, self.h, genome, out.ctypes.data))
@@ -423,14 +447,7 @@ class KmerSet:
 def kmer_sets_from_fasta_files(ctx: Context, fasta_filenames: Sequence[str], mask: int, window_length: int,
                                sketching_cond: Predicate, repr_: int = REPR_AUTO) -> List[KmerSet]:
     """(parallel_)kmer_sets_from_fasta_files, src/kmer_set.cpp:81-133: one batched launch."""
-    if len(fasta_filenames) > 1:   # host parse + pack in parallel (ctypes releases the GIL), like the reference's cilk_for
-        from concurrent.futures import ThreadPoolExecutor
-        import os
-        with ThreadPoolExecutor(min(len(fasta_filenames), os.cpu_count() or 1)) as pool:
-            genomes = list(pool.map(fasta_parse_file, fasta_filenames))
-    else:
-        genomes = [fasta_parse_file(f) for f in fasta_filenames]
-    batch = ctx.upload(genomes)
+    batch = ctx.batch_from_fasta_files(list(fasta_filenames))   # raw bytes up, parse + split + pack on the device
     try:
         return ctx.sketch(batch, mask, window_length, sketching_cond, repr_)
     finally:

@@ -397,3 +397,57 @@ def test_sketch_files_roundtrip(ctx, tmp_path):
     with pytest.raises(sks.SksError) as e:
         ctx.load_set(str(tmp_path / "bad.sks"))
     assert e.value.code == 5
+
+
+def _check_device_fasta(ctx, texts):
+    batch = ctx.batch_from_fasta_text(texts)
+    assert batch.n_genomes == len(texts)
+    for g, t in enumerate(texts):
+        words, nb, segs = sks.fasta_parse(t)                    # host parser of libsks
+        oc, osegs = port.fasta_parse(t)                         # the oracle
+        assert nb == len(oc) and list(segs) == list(osegs)
+        assert batch.n_bases(g) == nb, (g, t[:80])
+        assert list(batch.segments(g)) == list(osegs), (g, t[:80])
+        assert np.array_equal(sks.unpack_codes(batch.download(g), nb), oc), (g, t[:80])
+    return batch
+
+
+def test_device_fasta_parser_matches_reference_rules(ctx):
+    """Device-side FASTA ingest against the oracle on every record / split quirk."""
+    g = load_golden("fasta.json")
+    texts = [case["text"].encode("latin1") for case in g.values()]
+    texts += [b">r1\nACGTAC\nGTNNAC\n\nGGGG\n>r2\nacgtRYac\n", b">r1\r\nACGT\r\nACGT\r\n", b">\nACGT\n>ok\nAC GT\nAAAA\n>ok2\nTTTT\n",
+              b"ACGT\n>x\n\nCCCC\n", b"", b"\n", b">", b">x", b">x\nACGT", b"AC GT\n>y\nAC\n\n\nGT\nA C\nTT\n>z\nGG", b">a b c\nACGT\n",
+              b">x\nAAAA\nCC CC\n", b">x\nAAAA\n\nCC CC\nGG\n>y\nTT\n"]
+    _check_device_fasta(ctx, texts)            # all in one batch: file boundaries must not leak state
+    for t in texts:
+        _check_device_fasta(ctx, [t])          # and alone
+    rng = np.random.default_rng(5)
+    pieces = [b"ACGT", b"acgt", b"N", b"NNNN", b" ", b"\n", b"\n\n", b"\r\n", b">", b">name\n", b">n m\n", b"R", b"GATTACA", b"\n>\n"]
+    for trial in range(60):
+        n_files = int(rng.integers(1, 5))
+        files = []
+        for _ in range(n_files):
+            k = int(rng.integers(0, 60))
+            files.append(b"".join(pieces[int(i)] if rng.random() < 0.5 else port.codes_to_text(rng.integers(0, 4, int(rng.integers(1, 90)), dtype=np.uint8))
+                                  for i in rng.integers(0, len(pieces), k)))
+        _check_device_fasta(ctx, files)
+
+
+def test_device_fasta_parser_genome_sized(ctx, tmp_path):
+    A = port.gen(5_000_000, 42)
+    text = port.codes_to_text(A)
+    fa = tmp_path / "a.fna"
+    port.write_fasta(str(fa), A)
+    single_line = b">one line\n" + text + b"\n"
+    messy = b">m\n" + text[:1_000_000] + b"\r\n" + text[1_000_000:2_000_000].lower() + b"NNNNNNNNNN" + text[2_000_000:] + b"\n"
+    batch = _check_device_fasta(ctx, [fa.read_bytes(), single_line, messy])
+    fb = ctx.batch_from_fasta_files([str(fa)])
+    assert fb.n_bases(0) == 5_000_000 and np.array_equal(fb.download(0), batch.download(0))
+    mask, w = sks.seed_to_mask(C3_SEED)
+    sets = ctx.sketch(batch, mask, w, sks.frac_min_hash(1, 200))
+    want = port.sketch_set(A, [len(A)], mask, w, port.FMH, 1, 200, 181)
+    assert np.array_equal(sets[0].keys(), want) and np.array_equal(sets[1].keys(), want)
+    with pytest.raises(sks.SksError) as e:
+        ctx.batch_from_fasta_files([str(tmp_path / "missing.fna")])
+    assert e.value.code == 5
