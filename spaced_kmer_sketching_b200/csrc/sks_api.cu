@@ -269,16 +269,52 @@ int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
   const uint32_t *tg = batch->tile_genome ? static_cast<const uint32_t *>(batch->tile_genome->ptr) : nullptr;
   const bool bucketed = index_bits > kSliceBits && index_bits >= ctx->bucket_min_bits;
   if (bucketed) {
-    // K2/K3 emit 32-bit PEXT indices; K4 = bucket by slice + assemble every 64 KB slice in smem
-    BufferRef raw, pos, sorted;
-    std::vector<uint64_t> off, count;
-    uint64_t span = 0;
-    SKS_TRY(sketch_raw_keys(ctx, batch, plan, pred, window, OUT_INDEX, &raw, &pos, &off, &count, &span));
-    SKS_TRY(alloc_buffer(ctx, (size_t)span * 4, &sorted));
     SKS_TRY(alloc_buffer(ctx, sizeof(unsigned long long) * (size_t)G, &count_buf));
-    SKS_TRY(launch_bitset_build(ctx, static_cast<const uint32_t *>(raw->ptr), static_cast<uint32_t *>(sorted->ptr),
-                                off.data(), count.data(), G, index_bits, static_cast<uint32_t *>(buf->ptr), words,
-                                static_cast<unsigned long long *>(count_buf->ptr)));
+    unsigned long long *d_set_count = static_cast<unsigned long long *>(count_buf->ptr);
+    // Fast path: the sketch kernel scatters the PEXT indices straight into fixed per-(genome, bucket) regions
+    // sized at 4x the mean bucket load (K2/K3/K4a fused), then the slices are assembled (K4b).  A genome whose
+    // index distribution overflows a region (heavy skew) is detected by a flag and redone through the exact
+    // counting partition below.
+    const PartGeometry geo = part_geometry(index_bits);
+    uint64_t max_windows = 0;
+    for (int g = 0; g < G; ++g) max_windows = std::max(max_windows, genome_windows(batch, g, window));
+    const uint64_t cap = 4 * ((max_windows + geo.n_parts - 1) / geo.n_parts) + 1024;
+    const uint64_t slots = cap * geo.n_parts * (uint64_t)G;
+    bool done = false;
+    if (!ctx->exact_partition && slots < (1ull << 32) && slots * 4 <= (8ull << 30)) {
+      BufferRef regions, tabs;
+      SKS_TRY(alloc_buffer(ctx, (size_t)slots * 4, &regions));
+      SKS_TRY(alloc_buffer(ctx, 4 * (size_t)geo.n_parts * G + 64, &tabs));
+      uint32_t *d_cursor = static_cast<uint32_t *>(tabs->ptr);
+      uint32_t *d_overflow = d_cursor + (size_t)geo.n_parts * G;
+      SKS_TRY(launch_region_starts(ctx, d_cursor, geo.n_parts * (uint32_t)G, (uint32_t)cap));
+      SKS_CUDA_TRY(cudaMemsetAsync(d_overflow, 0, 4, ctx->stream));
+      plan.p.out_keys = regions->ptr;
+      plan.p.part_cursor = d_cursor;
+      plan.p.part_overflow = d_overflow;
+      plan.p.n_parts = geo.n_parts;
+      plan.p.part_cap = (uint32_t)cap;
+      plan.p.part_shift = geo.part_shift;
+      SKS_TRY(launch_sketch(ctx, plan.p, tg, plan.n_limbs, plan.pred_mode, OUT_PART));
+      SKS_TRY(launch_bitset_assemble(ctx, static_cast<const uint32_t *>(regions->ptr), d_cursor, (uint32_t)cap, G, index_bits,
+                                     static_cast<uint32_t *>(buf->ptr), words, d_set_count));
+      uint32_t *h_flag = nullptr;
+      SKS_TRY(ctx_pinned(ctx, 64, reinterpret_cast<void **>(&h_flag)));
+      SKS_CUDA_TRY(cudaMemcpyAsync(h_flag, d_overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+      SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      done = *h_flag == 0;
+    }
+    if (!done) {
+      // Exact path: K2/K3 emit the indices, a counting partition orders them by bucket, K4b assembles.
+      BufferRef raw, pos, sorted;
+      std::vector<uint64_t> off, count;
+      uint64_t span = 0;
+      SKS_TRY(sketch_raw_keys(ctx, batch, plan, pred, window, OUT_INDEX, &raw, &pos, &off, &count, &span));
+      SKS_TRY(alloc_buffer(ctx, (size_t)span * 4, &sorted));
+      SKS_TRY(launch_bitset_build(ctx, static_cast<const uint32_t *>(raw->ptr), static_cast<uint32_t *>(sorted->ptr),
+                                  off.data(), count.data(), G, index_bits, static_cast<uint32_t *>(buf->ptr), words,
+                                  d_set_count));
+    }
   } else {
     SKS_TRY(launch_fill_zero(ctx, buf->ptr, (size_t)words * 4 * G));
     plan.p.bitset = static_cast<uint32_t *>(buf->ptr);
@@ -434,6 +470,7 @@ int sks_ctx_create(int device, sks_ctx **out) {
   uint64_t threshold = UINT64_MAX;
   SKS_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
   if (const char *e = getenv("SKS_BUCKET_MIN_BITS")) ctx->bucket_min_bits = atoi(e);
+  if (const char *e = getenv("SKS_EXACT_PARTITION")) ctx->exact_partition = atoi(e) != 0;
   *out = ctx;
   return SKS_OK;
 }

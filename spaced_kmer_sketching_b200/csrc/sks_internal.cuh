@@ -57,13 +57,30 @@ struct GenomeDesc {
   uint32_t n_tiles;
 };
 
-enum OutMode : int { OUT_KEYS = 0, OUT_BITSET = 1, OUT_LIST = 2, OUT_INDEX = 3 };
+enum OutMode : int { OUT_KEYS = 0, OUT_BITSET = 1, OUT_LIST = 2, OUT_INDEX = 3, OUT_PART = 4 };
 enum PredMode : int { PRED_ALL = 0, PRED_FMH181 = 1, PRED_FMH171 = 2 };
 
 // Bucketed bitset build: the 4^weight-bit bitset is cut into slices of 2^kSliceBits bits (64 KB) that
 // are assembled in shared memory and streamed out once (sks_sets.cu, bitset_build_kernel).
 constexpr int kSliceBits = 19;
 constexpr int kSliceWords = (1 << kSliceBits) / 32;  // 16384
+constexpr int kGroupSliceBits = 3;                   // 8 slices (512 KB of bitset) per partition bucket
+constexpr int kMaxPartBits = 32 - kSliceBits - kGroupSliceBits;  // <= 1024 buckets
+constexpr int kMaxParts = 1 << kMaxPartBits;
+// Partition geometry of the bucketed bitset build for a given index width.
+struct PartGeometry {
+  int part_shift;         // bucket = index >> part_shift
+  uint32_t n_parts;       // buckets per genome
+  uint32_t group_slices;  // slices per bucket
+};
+inline PartGeometry part_geometry(int index_bits) {
+  const int group_bits = index_bits - kSliceBits < kGroupSliceBits ? index_bits - kSliceBits : kGroupSliceBits;
+  PartGeometry g;
+  g.part_shift = kSliceBits + group_bits;
+  g.n_parts = 1u << (index_bits - g.part_shift);
+  g.group_slices = 1u << group_bits;
+  return g;
+}
 
 // PEXT(masked_bits, mask) as rotate-and-mask pieces: one piece per run of mask ones inside a 32-bit limb
 // (a limb holds 16 base positions, hence at most 8 runs).  The compacted index takes the bits selected
@@ -96,6 +113,13 @@ struct SketchParams {
   const uint64_t *out_off;              // [n_genomes] first slot of the genome's region
   const uint64_t *out_cap;              // [n_genomes] slots in the region
   unsigned long long *out_count;        // [n_genomes] kept k-mers (keeps counting past out_cap)
+  // OUT_PART: PEXT indices scattered straight into per-(genome, bucket) regions of part_cap slots each
+  // (out_keys = region buffer); part_cursor[genome * n_parts + bucket] starts at the region's first slot
+  uint32_t *part_cursor;
+  uint32_t *part_overflow;     // set to 1 when a region was too small (the caller then takes the exact path)
+  uint32_t n_parts;            // <= kMaxParts
+  uint32_t part_cap;
+  int part_shift;              // bucket = index >> part_shift
   // OUT_BITSET
   uint32_t *bitset;            // n_genomes consecutive bitsets
   uint64_t bitset_words;       // words per genome
@@ -127,6 +151,7 @@ struct sks_ctx {
   // reusable scratch (grown on demand)
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
+  bool exact_partition = false;  // SKS_EXACT_PARTITION=1: always take the counting partition of the bucketed build
   int bucket_min_bits = 26;  // bitsets of >= 2^this bits are built by the bucketed path (SKS_BUCKET_MIN_BITS)
   // pinned staging for small D2H/H2D traffic
   void *pinned = nullptr;
@@ -194,6 +219,9 @@ int launch_bitset_pair_counts(sks_ctx *ctx, const uint32_t *a, const uint32_t *b
 int launch_bitset_build(sks_ctx *ctx, const uint32_t *raw_idx, uint32_t *sorted_idx, const uint64_t *h_off,
                         const uint64_t *h_count, int n_genomes, int index_bits, uint32_t *bitset, uint64_t bitset_words,
                         unsigned long long *d_set_count);
+int launch_region_starts(sks_ctx *ctx, uint32_t *d_cursor, uint32_t n, uint32_t cap);
+int launch_bitset_assemble(sks_ctx *ctx, const uint32_t *regions, const uint32_t *d_cursor, uint32_t part_cap, int n_genomes,
+                           int index_bits, uint32_t *bitset, uint64_t bitset_words, unsigned long long *d_set_count);
 int launch_bitset_popcount(sks_ctx *ctx, const uint32_t *a, uint64_t n_words, unsigned long long *out1);
 int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t *h_off, const uint64_t *h_count,
                         int n_regions, uint64_t span, BufferRef *out_buf, std::vector<uint64_t> *out_off,

@@ -142,9 +142,6 @@ int stream_grid(const sks_ctx *ctx, size_t n16) {
 // kmer_set_size() for free.  (Measured alternatives: radix sort by slice with cub, 205 us of sort; one
 // bucket per slice with a per-index global cursor bump, 276 us of scatter; 256 coarse buckets with the
 // group's indices filtered out of the bucket by every CTA, 265 us of build of which ~60 us was the filter.)
-constexpr int kGroupSliceBits = 3;                   // 8 slices (512 KB of bitset) per bucket
-constexpr int kMaxPartBits = 32 - kSliceBits - kGroupSliceBits;  // <= 1024 buckets
-constexpr int kMaxParts = 1 << kMaxPartBits;
 constexpr int kBuildThreads = 512;
 constexpr int kKeyCap = 11264;                       // indices of one bucket kept in shared memory (44 KB)
 
@@ -156,7 +153,7 @@ struct BuildGenome {
   uint32_t *bitset;
   unsigned long long *set_count;
   uint32_t n;               // number of indices
-  uint32_t pad;
+  uint32_t cap;             // > 0: the buckets are fixed regions of `cap` slots (filled by the sketch kernel)
 };
 
 __global__ void __launch_bounds__(256)
@@ -288,7 +285,9 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
       cur_genome = genome;
     }
     const BuildGenome g = genomes[genome];
-    const uint32_t lo = __ldg(g.starts + part), hi = __ldg(g.cursor + part);  // cursor = bucket end after the scatter
+    const uint32_t lo = __ldg(g.starts + part);
+    uint32_t hi = __ldg(g.cursor + part);  // cursor = bucket end after the scatter
+    if (g.cap && hi > lo + g.cap) hi = lo + g.cap;  // an overflowed region (the caller redoes the genome exactly)
     const uint32_t n = hi - lo;
     const uint32_t *__restrict__ bk = g.bucketed + lo;
     const bool direct = n > kKeyCap;  // more indices than shared memory holds (heavily skewed genome)
@@ -565,10 +564,9 @@ int launch_bitset_build(sks_ctx *ctx, const uint32_t *raw_idx, uint32_t *buckete
   if (n_genomes == 0) return SKS_OK;
   if (index_bits <= kSliceBits || index_bits > 32)
     return set_error(SKS_ERR_INVALID, "bucketed bitset build handles 20..32 index bits, not %d", index_bits);
-  const int group_bits = std::min(kGroupSliceBits, index_bits - kSliceBits);
-  const int part_shift = kSliceBits + group_bits;  // bucket = idx >> part_shift
-  const uint32_t n_parts = 1u << (index_bits - part_shift);
-  const uint32_t group_slices = 1u << group_bits;
+  const PartGeometry geo = part_geometry(index_bits);
+  const int part_shift = geo.part_shift;
+  const uint32_t n_parts = geo.n_parts, group_slices = geo.group_slices;
   uint64_t max_n = 0;
   for (int g = 0; g < n_genomes; ++g) max_n = std::max(max_n, h_count[g]);
   if (max_n >= (1ull << 32)) return set_error(SKS_ERR_CAPACITY, "too many k-mers in one genome for the bucketed build");
@@ -592,7 +590,7 @@ int launch_bitset_build(sks_ctx *ctx, const uint32_t *raw_idx, uint32_t *buckete
     h_desc[g].bitset = bitset + (size_t)g * bitset_words;
     h_desc[g].set_count = d_set_count + g;
     h_desc[g].n = (uint32_t)h_count[g];
-    h_desc[g].pad = 0;
+    h_desc[g].cap = 0;
   }
 
   KernelTimer timer(ctx, SKS_KERNEL_BITSET_BUILD);
@@ -618,6 +616,64 @@ int launch_bitset_build(sks_ctx *ctx, const uint32_t *raw_idx, uint32_t *buckete
   if (n_items >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "too many bitset slices in one batch");
   const unsigned gx = (unsigned)std::min<uint64_t>(n_items, (uint64_t)ctx->sm_count * 2);  // two ~108 KB CTAs per SM
   bitset_build_kernel<<<gx, kBuildThreads, smem, ctx->stream>>>(d_desc, (uint32_t)n_genomes, n_parts, group_slices,
+                                                               d_counter);
+  SKS_CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  return SKS_OK;
+}
+
+namespace {
+__global__ void region_starts_kernel(uint32_t *__restrict__ starts, uint32_t n, uint32_t cap) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) starts[i] = i * cap;
+}
+}  // namespace
+
+// Fills `cursor[0..n)` with the first slot of every (genome, bucket) region: region i = [i * cap, (i+1) * cap).
+int launch_region_starts(sks_ctx *ctx, uint32_t *d_cursor, uint32_t n, uint32_t cap) {
+  region_starts_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_cursor, n, cap);
+  SKS_CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  return SKS_OK;
+}
+
+// The assemble half of the bucketed build when the sketch kernel (OUT_PART) has already scattered the PEXT
+// indices into fixed regions: region (g, b) = regions[(g * n_parts + b) * part_cap ...), filled up to
+// d_cursor[g * n_parts + b] (absolute slot).
+int launch_bitset_assemble(sks_ctx *ctx, const uint32_t *regions, const uint32_t *d_cursor, uint32_t part_cap, int n_genomes,
+                           int index_bits, uint32_t *bitset, uint64_t bitset_words, unsigned long long *d_set_count) {
+  if (n_genomes == 0) return SKS_OK;
+  const PartGeometry geo = part_geometry(index_bits);
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t sz_desc = align(sizeof(BuildGenome) * n_genomes);
+  const size_t sz_starts = align((size_t)geo.n_parts * n_genomes * 4);
+  char *base = nullptr;
+  SKS_TRY(ctx_scratch(ctx, sz_desc + sz_starts + 256, reinterpret_cast<void **>(&base)));
+  BuildGenome *d_desc = reinterpret_cast<BuildGenome *>(base);
+  uint32_t *d_starts = reinterpret_cast<uint32_t *>(base + sz_desc);
+  unsigned int *d_counter = reinterpret_cast<unsigned int *>(base + sz_desc + sz_starts);
+  BuildGenome *h_desc = nullptr;
+  SKS_TRY(ctx_pinned(ctx, sizeof(BuildGenome) * n_genomes, reinterpret_cast<void **>(&h_desc)));
+  for (int g = 0; g < n_genomes; ++g) {
+    h_desc[g].raw = nullptr;
+    h_desc[g].bucketed = const_cast<uint32_t *>(regions);
+    h_desc[g].starts = d_starts + (size_t)g * geo.n_parts;
+    h_desc[g].cursor = const_cast<uint32_t *>(d_cursor) + (size_t)g * geo.n_parts;
+    h_desc[g].bitset = bitset + (size_t)g * bitset_words;
+    h_desc[g].set_count = d_set_count + g;
+    h_desc[g].n = 0;
+    h_desc[g].cap = part_cap;
+  }
+  KernelTimer timer(ctx, SKS_KERNEL_BITSET_BUILD);
+  SKS_CUDA_TRY(cudaMemsetAsync(d_set_count, 0, sizeof(unsigned long long) * n_genomes, ctx->stream));
+  SKS_CUDA_TRY(cudaMemsetAsync(d_counter, 0, 256, ctx->stream));
+  SKS_CUDA_TRY(cudaMemcpyAsync(d_desc, h_desc, sizeof(BuildGenome) * n_genomes, cudaMemcpyHostToDevice, ctx->stream));
+  SKS_TRY(launch_region_starts(ctx, d_starts, geo.n_parts * (uint32_t)n_genomes, part_cap));
+  constexpr int smem = (kSliceWords + kKeyCap) * 4;
+  SKS_CUDA_TRY(cudaFuncSetAttribute(bitset_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const uint64_t n_items = (uint64_t)n_genomes * geo.n_parts;
+  const unsigned gx = (unsigned)std::min<uint64_t>(n_items, (uint64_t)ctx->sm_count * 2);
+  bitset_build_kernel<<<gx, kBuildThreads, smem, ctx->stream>>>(d_desc, (uint32_t)n_genomes, geo.n_parts, geo.group_slices,
                                                                d_counter);
   SKS_CUDA_TRY(cudaGetLastError());
   ctx->launches++;

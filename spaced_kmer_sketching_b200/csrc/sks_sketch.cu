@@ -103,6 +103,22 @@ struct KeyType<4, OUT> {
   using type = ulonglong2;
 };
 template <>
+struct KeyType<1, OUT_PART> {
+  using type = uint32_t;
+};
+template <>
+struct KeyType<2, OUT_PART> {
+  using type = uint32_t;
+};
+template <>
+struct KeyType<3, OUT_PART> {
+  using type = uint32_t;
+};
+template <>
+struct KeyType<4, OUT_PART> {
+  using type = uint32_t;
+};
+template <>
 struct KeyType<1, OUT_INDEX> {
   using type = uint32_t;
 };
@@ -126,6 +142,7 @@ constexpr size_t sketch_smem_bytes() {
   size_t b = 2 * kStageWords * 4 + 2 * sizeof(TileMeta) + 64;
   if (OUT != OUT_BITSET) b += kStageSlots * sizeof(typename KeyType<NL, OUT>::type);
   if (OUT == OUT_LIST) b += kStageSlots * 4;
+  if (OUT == OUT_PART) b += kStageSlots * 2 + 2 * kMaxParts * 4;  // ranks, bucket histogram, bucket bases
   return b;
 }
 
@@ -141,8 +158,13 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
   unsigned long long *s_base = reinterpret_cast<unsigned long long *>(s_bar + 3);
   key_t *s_keys = reinterpret_cast<key_t *>(smem_raw + 2 * kStageWords * 4 + 2 * sizeof(TileMeta) + 64);
   uint32_t *s_pos = reinterpret_cast<uint32_t *>(s_keys + kStageSlots);
+  // OUT_PART: slot = j * 256 + tid is fixed; s_rank = rank of the index inside its bucket this round
+  uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_keys + kStageSlots);  // [kMaxParts]
+  uint32_t *s_pbase = s_hist + kMaxParts;                                 // [kMaxParts]
+  uint16_t *s_rank = reinterpret_cast<uint16_t *>(s_pbase + kMaxParts);   // [kStageSlots]
 
-  constexpr bool kSparse = PRED != PRED_ALL;  // few survivors per tile: stage across tiles (see the flush below)
+  // few survivors per tile: stage across tiles (see the flush below); OUT_PART always works round by round
+  constexpr bool kSparse = PRED != PRED_ALL && OUT != OUT_PART;
   const int tid = threadIdx.x;
   const int w = P.window;
   const int d2 = 2 * (w & 15);  // alignment shift of the forward stream
@@ -154,6 +176,8 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
     *s_count = 0;
     fence_barrier_init();
   }
+  if (OUT == OUT_PART)
+    for (uint32_t b = tid; b < P.n_parts; b += kSketchThreads) s_hist[b] = 0;
   __syncthreads();
 
   // Producer: describe tile `tile` in s_meta[stage] and start its bulk copy into s_words[stage].
@@ -303,9 +327,10 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
           }
 
           // ---- K3/K4: emit ---------------------------------------------------------------------
+          if (OUT == OUT_PART && !pass) s_rank[j * kSketchThreads + tid] = 0xFFFFu;
           if (pass) {
             uint32_t idx = 0;
-            if (OUT == OUT_BITSET || OUT == OUT_INDEX) {  // PEXT(masked, mask): rotate-and-mask pieces
+            if (OUT == OUT_BITSET || OUT == OUT_INDEX || OUT == OUT_PART) {  // PEXT(masked, mask): rotate-and-mask pieces
 #pragma unroll
               for (int k = 0; k < NL; ++k) {
 #pragma unroll
@@ -320,6 +345,9 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
             }
             if (OUT == OUT_BITSET) {
               atomicOr(P.bitset + (uint64_t)tm.genome * P.bitset_words + (idx >> 5), 1u << (idx & 31));
+            } else if (OUT == OUT_PART) {
+              reinterpret_cast<uint32_t *>(s_keys)[j * kSketchThreads + tid] = idx;
+              s_rank[j * kSketchThreads + tid] = (uint16_t)atomicAdd(&s_hist[idx >> P.part_shift], 1u);
             } else {
               const uint32_t slot = atomicAdd(s_count, 1u);
               if (kSparse && slot >= (uint32_t)kStageSlots) {
@@ -349,8 +377,37 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
         }
       }
 
+      if (OUT == OUT_PART) {
+        // ---- K4a fused: scatter the round's indices into their (genome, bucket) regions -----------------
+        if (vmask == 0) {
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j) s_rank[j * kSketchThreads + tid] = 0xFFFFu;
+        }
+        __syncthreads();
+        uint32_t *cursor = P.part_cursor + (size_t)tm.genome * P.n_parts;
+        for (uint32_t b = tid; b < P.n_parts; b += kSketchThreads) {
+          const uint32_t h = s_hist[b];
+          s_pbase[b] = h ? atomicAdd(cursor + b, h) : 0u;  // one reservation per non-empty bucket per round
+          s_hist[b] = 0;
+        }
+        __syncthreads();
+        uint32_t *out = reinterpret_cast<uint32_t *>(P.out_keys);
+        const uint32_t region0 = tm.genome * P.n_parts;
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+          const uint32_t r = s_rank[j * kSketchThreads + tid];
+          if (r != 0xFFFFu) {
+            const uint32_t idx = reinterpret_cast<uint32_t *>(s_keys)[j * kSketchThreads + tid];
+            const uint32_t b = idx >> P.part_shift;
+            const uint32_t at = s_pbase[b] + r;
+            if (at < (region0 + b + 1) * P.part_cap) out[at] = idx;
+            else *P.part_overflow = 1u;
+          }
+        }
+        __syncthreads();
+      }
       // ---- dense mode: flush the round's kept k-mers (every window may survive) ---------------------
-      if (OUT != OUT_BITSET && !kSparse) {
+      if (OUT != OUT_BITSET && OUT != OUT_PART && !kSparse) {
         __syncthreads();
         const uint32_t staged = *s_count;
         __syncthreads();
@@ -360,7 +417,7 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
     __syncthreads();  // everyone is done with s_words[stage] / s_meta[stage] before it is refilled
     // ---- sparse mode (a FracMinHash filter keeps ~1/c of the windows): survivors of many tiles share the
     // stage; flush when it is half full, when the next tile belongs to another genome, or at the end
-    if (OUT != OUT_BITSET && kSparse) {
+    if (OUT != OUT_BITSET && OUT != OUT_PART && kSparse) {
       const uint32_t staged = *s_count;
       const bool last = tile + gridDim.x >= P.n_tiles;
       const bool do_flush = staged >= (uint32_t)kStageSlots / 2 || last || s_meta[stage ^ 1].genome != tm.genome;
@@ -399,6 +456,7 @@ int launch_out(sks_ctx *ctx, const SketchParams &p, const uint32_t *tg, int out_
     case OUT_BITSET: return launch_one<NL, PRED, OUT_BITSET>(ctx, p, tg);
     case OUT_LIST: return launch_one<NL, PRED, OUT_LIST>(ctx, p, tg);
     case OUT_INDEX: return launch_one<NL, PRED, OUT_INDEX>(ctx, p, tg);
+    case OUT_PART: return launch_one<NL, PRED, OUT_PART>(ctx, p, tg);
   }
   return set_error(SKS_ERR_INVALID, "bad output mode %d", out_mode);
 }

@@ -53,6 +53,18 @@ def ctx_bucket():
     c.close()
 
 
+@pytest.fixture(scope="module")
+def ctx_exact():
+    """Bucketed build through the exact counting partition only (the fused fast path switched off)."""
+    import os
+    os.environ["SKS_BUCKET_MIN_BITS"] = "20"
+    os.environ["SKS_EXACT_PARTITION"] = "1"
+    c = sks.Context(0)
+    del os.environ["SKS_BUCKET_MIN_BITS"], os.environ["SKS_EXACT_PARTITION"]
+    yield c
+    c.close()
+
+
 def opred(pred):
     if pred.kind == sks.PRED_ALL:
         return (port.ALL,)
@@ -134,7 +146,7 @@ def test_fuzz_lists_and_sets_vs_oracle(ctx, ctx_bucket, block):
         batch.close()
 
 
-def test_bitset_paths_agree_multi_genome(ctx, ctx_bucket):
+def test_bitset_paths_agree_multi_genome(ctx, ctx_bucket, ctx_exact):
     """Atomic-insert and bucketed bitset builds give identical bitsets (sizes, members, intersections)."""
     rng = np.random.default_rng(11)
     genomes = [rng.integers(0, 4, n, dtype=np.uint8) for n in (70000, 5, 8192, 33333)]
@@ -150,7 +162,7 @@ def test_bitset_paths_agree_multi_genome(ctx, ctx_bucket):
         mask, w = sks.seed_to_mask(seed)
         osets = [port.sketch_set(g, [len(g)] if s is None else list(s), mask, w, *opred(pred))
                  for g, s in zip(genomes, segl)]
-        for c in (ctx, ctx_bucket):
+        for c in (ctx, ctx_bucket, ctx_exact):
             sets = c.sketch(c.upload_codes(genomes, segl), mask, w, pred, sks.REPR_BITSET)
             assert [s.kmer_set_size() for s in sets] == [len(o) for o in osets]
             for s, o in zip(sets, osets):
