@@ -265,7 +265,8 @@ def run_b200(args):
         peak, peak_src = measured_peak()
         bitset_bytes = (1 << (2 * weight)) // 8
         algo = {   # algorithmic bytes per launch, DESIGN.md "Kernels"
-            "sketch_kernel": 2 * L * (0.25 + 8.0),        # 2-bit bases + 4 B read + 4 B write of a bitset word per k-mer
+            "sketch_kernel": 2 * L * (0.25 + 4.0),         # 2-bit bases read + one 4-byte PEXT index written per k-mer
+            "bitset_pair_build_kernel": 2 * L * 4.0 + 2 * bitset_bytes,  # indices read + both bitsets written once
             "fill_zero_kernel": 2 * bitset_bytes,          # both bitsets cleared by one launch
             "bitset_pair_counts_kernel": 2 * bitset_bytes,  # both bitsets read once (|A|, |B|, |A n B| in one pass)
         }
@@ -293,15 +294,19 @@ def run_b200(args):
         # ---- cpu baseline (rank 0, N = 1 only): the reference on a bounded sample ------------------------
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            Ls = 1_000_000
+            Ls = args.cpu_sample_bases
             with tempfile.TemporaryDirectory() as d:
                 dt, kind, cores, counts = cpu_c2_step(Ls, d)
+            if Ls == L and tuple(counts[:3]) != (r.size_a, r.size_b, r.intersection):
+                raise SystemExit("CPU reference counts %r differ from the GPU's" % (counts[:3],))
             cpu = {"value": 2 * (Ls - w + 1) / dt, "unit": UNIT, "cores": cores, "kind": kind,
-                   "sample": "one C2 pass on a %d-base pair (full workload %d), %.1f s" % (Ls, L, dt)}
+                   "sample": "one C2 pass on a %d-base pair (full workload %d), %.1f s of wall time; the reference "
+                             "parallelises over files only, so a pair uses 2 threads" % (Ls, L, dt)}
 
         extra = {}
         if not args.no_extra:
-            extra = extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ranks, peak)
+            extra = c2_variants(ctx, sks, torch, batch, mask, w, stream, barrier, max_over_ranks, peak, flush)
+            extra.update(extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ranks, peak))
 
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
@@ -320,6 +325,54 @@ def run_b200(args):
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+def c2_variants(ctx, sks, torch, batch, mask, w, stream, barrier, max_over_ranks, peak, flush):
+    """The C2 pair through the other two routes of the library: (a) the general API -- sks_sketch builds the two
+    bitset sets, sks_intersect re-reads them (bitset_pair_counts_kernel, K5 on its own) -- and (b) the pair pipeline
+    with the bitsets kept on chip (SKS_REPR_BITSET_ONCHIP)."""
+    out = {}
+    pred = sks.all_kmers()
+    bitset_bytes = (1 << (2 * sks.mask_weight(mask))) // 8
+
+    def separate():
+        sa, sb = ctx.sketch(batch, mask, w, pred, sks.REPR_BITSET)
+        n = ctx.intersect(sa, sb)
+        sa.close()
+        sb.close()
+        return n
+
+    def onchip():
+        return ctx.pair_ani_resident(batch, mask, w, pred, sks.REPR_BITSET_ONCHIP).intersection
+
+    for name, fn in (("separate_build_then_intersect", separate), ("pair_pipeline_onchip", onchip)):
+        for _ in range(3):
+            fn()
+            flush.zero_()
+        barrier()
+        ctx.profile(True)
+        ctx.kernel_stats()
+        evs = []
+        reps = 10
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            n = fn()
+            e1.record(stream)
+            evs.append((e0, e1))
+            flush.zero_()
+        barrier()
+        ks = ctx.kernel_stats()
+        ctx.profile(False)
+        ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)) / reps
+        ent = {"ms_per_step": ms, "intersection": int(n),
+               "kernels_ms": {k: v[1] / v[0] for k, v in ks.items()}}
+        if "bitset_pair_counts_kernel" in ks:
+            per = ks["bitset_pair_counts_kernel"][1] / ks["bitset_pair_counts_kernel"][0]
+            ent["pair_counts_gbs"] = 2 * bitset_bytes / (per * 1e-3) / 1e9
+            ent["pair_counts_frac_of_hbm"] = ent["pair_counts_gbs"] / peak
+        out[name] = ent
+    return {"c2_variants": out}
 
 
 def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ranks, peak):
@@ -420,6 +473,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extra", action="store_true", help="skip the C3 / C4 legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-bases", type=int, default=C2_L, help="genome length of the cpu_baseline sample")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

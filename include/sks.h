@@ -50,6 +50,9 @@ extern "C" {
 #define SKS_REPR_AUTO 0   /* SORTED for FMH, BITSET for ALL when weight <= 16, else SORTED      */
 #define SKS_REPR_SORTED 1 /* ascending distinct masked_bits, 8 B (window <= 32) or 16 B per key  */
 #define SKS_REPR_BITSET 2 /* 4^weight-bit presence bitset indexed by PEXT(masked_bits, mask)     */
+/* sks_pair_ani* only: the two presence bitsets are assembled and compared slice by slice in shared memory
+ * and are never written to HBM (sks_sketch rejects it: there would be no set to return). */
+#define SKS_REPR_BITSET_ONCHIP 3
 
 typedef struct sks_pred {
   int32_t kind;         /* SKS_PRED_*                                   */
@@ -93,7 +96,8 @@ int64_t sks_ctx_launch_count(const sks_ctx *ctx);
 #define SKS_KERNEL_LIST 7         /* ordered-list finalisation                           */
 #define SKS_KERNEL_BITSET_BUILD 8 /* bucket sort + slice-wise bitset assembly (K4, bucketed) */
 #define SKS_KERNEL_FASTA 9        /* device-side FASTA parse + 2-bit pack                */
-#define SKS_KERNEL_KINDS 10
+#define SKS_KERNEL_PAIR_BUILD 10  /* fused slice assembly + AND/popcount of a genome pair (K4b + K5) */
+#define SKS_KERNEL_KINDS 11
 int sks_ctx_profile(sks_ctx *ctx, int enable);
 int sks_ctx_kernel_stats(sks_ctx *ctx, int kind, int64_t *out_launches, double *out_total_ms);
 const char *sks_kernel_name(int kind);
@@ -242,7 +246,11 @@ typedef struct sks_pair_result {
   int64_t size_a, size_b, intersection;
   double ani_ab, ani_ba; /* binomial_estimator(containment(I, |A|), weight), and with |B| */
 } sks_pair_result;
-/* HOST packed genomes in, counts + ANI out: upload, sketch both, intersect, sizes, ANI. */
+/* HOST packed genomes in, counts + ANI out: upload, sketch both, intersect, sizes, ANI.
+ * = kmer_sets_from_fasta_files on two genomes + kmer_set_intersection + containment / binomial_estimator
+ * (src/kmer-sketching.cpp:168-200 for n = 2).  With SKS_REPR_BITSET both 4^weight-bit sets are materialised in
+ * HBM and |A|, |B|, |A n B| are counted while their slices stream out (one fused kernel instead of a build
+ * and a re-read); SKS_REPR_BITSET_ONCHIP skips the HBM copy of the sets. */
 int sks_pair_ani(sks_ctx *ctx, const uint32_t *packed_a, uint64_t n_bases_a, const uint32_t *packed_b,
                  uint64_t n_bases_b, const uint64_t mask[2], int window, const sks_pred *pred, int repr,
                  sks_pair_result *out);

@@ -1,7 +1,7 @@
 """B200-native spaced k-mer sketching + ANI engine (drop-in for the sketch-and-compare path of
 bensonlzl/spaced-kmer-sketching).  CUDA kernels and the C ABI live in csrc/ -> libsks.so; the
 reference-shaped C++ API is in include/; this package is the Python host mirror."""
-from ._lib import (HASH_BOOST_171, HASH_BOOST_181, LIB_PATH, PRED_ALL, PRED_FMH, PROTOTYPES, REPR_AUTO, REPR_BITSET,
+from ._lib import (HASH_BOOST_171, HASH_BOOST_181, LIB_PATH, PRED_ALL, PRED_FMH, PROTOTYPES, REPR_AUTO, REPR_BITSET, REPR_BITSET_ONCHIP,
                    REPR_SORTED, SksError, load)
 from .engine import (Batch, Context, KmerSet, Predicate, all_kmers, ani_from_counts, binomial_estimator,
                      compute_pairwise_kmer_set_intersections, containment, contiguous_kmer, fasta_parse,

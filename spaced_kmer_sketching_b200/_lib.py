@@ -15,8 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libsks.so")
 SKS_OK, SKS_ERR_INVALID, SKS_ERR_CUDA, SKS_ERR_CAPACITY, SKS_ERR_MISMATCH, SKS_ERR_IO = range(6)
 PRED_ALL, PRED_FMH = 0, 1
 HASH_BOOST_171, HASH_BOOST_181 = 171, 181
-REPR_AUTO, REPR_SORTED, REPR_BITSET = 0, 1, 2
-KERNEL_KINDS = 10
+REPR_AUTO, REPR_SORTED, REPR_BITSET, REPR_BITSET_ONCHIP = 0, 1, 2, 3
+KERNEL_KINDS = 11
 
 
 class SksPred(C.Structure):

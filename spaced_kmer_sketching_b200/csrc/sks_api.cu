@@ -257,19 +257,29 @@ int sketch_raw_keys(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, cons
                     int out_mode, BufferRef *keys, BufferRef *pos, std::vector<uint64_t> *off,
                     std::vector<uint64_t> *count, uint64_t *span);
 
+// Request of the one-call pair pipeline: count |A|, |B|, |A n B| inside the bitset build of a 2-genome batch.
+struct PairFuse {
+  bool store = true;   // materialise both bitsets in HBM (false: the slices never leave shared memory)
+  bool done = false;   // the fused kernel ran and counts[] is valid
+  int64_t counts[3] = {0, 0, 0};
+};
+
 int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const sks_pred *pred, const uint64_t mask[2],
-                  int window, sks_set **out_sets) {
+                  int window, sks_set **out_sets, PairFuse *fuse = nullptr) {
   int index_bits = 0;
   SKS_TRY(build_pext_table(mask, plan.n_limbs, &plan.p.pext, &index_bits));
   const int G = batch->n_genomes;
   const uint64_t bits = 1ull << index_bits;           // 4^weight
   const uint64_t words = bits < 32 ? 1 : bits / 32;   // per genome
   BufferRef buf, count_buf;
-  SKS_TRY(alloc_buffer(ctx, (size_t)words * 4 * G, &buf));
   const uint32_t *tg = batch->tile_genome ? static_cast<const uint32_t *>(batch->tile_genome->ptr) : nullptr;
   const bool bucketed = index_bits > kSliceBits && index_bits >= ctx->bucket_min_bits;
+  if (fuse && G != 2) fuse = nullptr;
+  int64_t known_count[2] = {-1, -1};
   if (bucketed) {
-    SKS_TRY(alloc_buffer(ctx, sizeof(unsigned long long) * (size_t)G, &count_buf));
+    // per-genome popcounts; the pair pipeline appends |A n B| and the overflow flag so that one 32-byte copy
+    // brings everything back
+    SKS_TRY(alloc_buffer(ctx, sizeof(unsigned long long) * ((size_t)G + 2), &count_buf));
     unsigned long long *d_set_count = static_cast<unsigned long long *>(count_buf->ptr);
     // Fast path: the sketch kernel scatters the PEXT indices straight into fixed per-(genome, bucket) regions
     // sized at 4x the mean bucket load (K2/K3/K4a fused), then the slices are assembled (K4b).  A genome whose
@@ -286,9 +296,9 @@ int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
       SKS_TRY(alloc_buffer(ctx, (size_t)slots * 4, &regions));
       SKS_TRY(alloc_buffer(ctx, 4 * (size_t)geo.n_parts * G + 64, &tabs));
       uint32_t *d_cursor = static_cast<uint32_t *>(tabs->ptr);
-      uint32_t *d_overflow = d_cursor + (size_t)geo.n_parts * G;
+      uint32_t *d_overflow = reinterpret_cast<uint32_t *>(d_set_count + G + 1);
       SKS_TRY(launch_region_starts(ctx, d_cursor, geo.n_parts * (uint32_t)G, (uint32_t)cap));
-      SKS_CUDA_TRY(cudaMemsetAsync(d_overflow, 0, 4, ctx->stream));
+      SKS_CUDA_TRY(cudaMemsetAsync(d_overflow, 0, 8, ctx->stream));
       plan.p.out_keys = regions->ptr;
       plan.p.part_cursor = d_cursor;
       plan.p.part_overflow = d_overflow;
@@ -296,19 +306,43 @@ int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
       plan.p.part_cap = (uint32_t)cap;
       plan.p.part_shift = geo.part_shift;
       SKS_TRY(launch_sketch(ctx, plan.p, tg, plan.n_limbs, plan.pred_mode, OUT_PART));
-      SKS_TRY(launch_bitset_assemble(ctx, static_cast<const uint32_t *>(regions->ptr), d_cursor, (uint32_t)cap, G, index_bits,
-                                     static_cast<uint32_t *>(buf->ptr), words, d_set_count));
-      uint32_t *h_flag = nullptr;
-      SKS_TRY(ctx_pinned(ctx, 64, reinterpret_cast<void **>(&h_flag)));
-      SKS_CUDA_TRY(cudaMemcpyAsync(h_flag, d_overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
-      SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-      done = *h_flag == 0;
+      unsigned long long *h_back = nullptr;
+      SKS_TRY(ctx_pinned(ctx, 64, reinterpret_cast<void **>(&h_back)));
+      if (fuse) {
+        // K4b + K5 fused: both genomes' slices side by side in shared memory, counted while they stream out
+        uint32_t *ba = nullptr, *bb = nullptr;
+        if (fuse->store) {
+          SKS_TRY(alloc_buffer(ctx, (size_t)words * 4 * G, &buf));
+          ba = static_cast<uint32_t *>(buf->ptr);
+          bb = ba + words;
+        }
+        SKS_TRY(launch_bitset_pair_build(ctx, static_cast<const uint32_t *>(regions->ptr), d_cursor, (uint32_t)cap, index_bits,
+                                         ba, bb, d_set_count));
+        SKS_CUDA_TRY(cudaMemcpyAsync(h_back, d_set_count, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        done = (uint32_t)h_back[3] == 0;
+        if (done) {
+          fuse->done = true;
+          for (int k = 0; k < 3; ++k) fuse->counts[k] = (int64_t)h_back[k];
+          known_count[0] = fuse->counts[0];
+          known_count[1] = fuse->counts[1];
+          if (!fuse->store) return SKS_OK;  // nothing was materialised: there are no sets to hand out
+        }
+      } else {
+        SKS_TRY(alloc_buffer(ctx, (size_t)words * 4 * G, &buf));
+        SKS_TRY(launch_bitset_assemble(ctx, static_cast<const uint32_t *>(regions->ptr), d_cursor, (uint32_t)cap, G, index_bits,
+                                       static_cast<uint32_t *>(buf->ptr), words, d_set_count));
+        SKS_CUDA_TRY(cudaMemcpyAsync(h_back, d_overflow, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        done = (uint32_t)h_back[0] == 0;
+      }
     }
     if (!done) {
       // Exact path: K2/K3 emit the indices, a counting partition orders them by bucket, K4b assembles.
       BufferRef raw, pos, sorted;
       std::vector<uint64_t> off, count;
       uint64_t span = 0;
+      if (!buf) SKS_TRY(alloc_buffer(ctx, (size_t)words * 4 * G, &buf));
       SKS_TRY(sketch_raw_keys(ctx, batch, plan, pred, window, OUT_INDEX, &raw, &pos, &off, &count, &span));
       SKS_TRY(alloc_buffer(ctx, (size_t)span * 4, &sorted));
       SKS_TRY(launch_bitset_build(ctx, static_cast<const uint32_t *>(raw->ptr), static_cast<uint32_t *>(sorted->ptr),
@@ -316,6 +350,7 @@ int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
                                   d_set_count));
     }
   } else {
+    SKS_TRY(alloc_buffer(ctx, (size_t)words * 4 * G, &buf));
     SKS_TRY(launch_fill_zero(ctx, buf->ptr, (size_t)words * 4 * G));
     plan.p.bitset = static_cast<uint32_t *>(buf->ptr);
     plan.p.bitset_words = words;
@@ -327,7 +362,7 @@ int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
     s->buf = buf;
     s->byte_off = (size_t)g * words * 4;
     s->bitset_words = words;
-    s->count = -1;
+    s->count = (fuse && fuse->done) ? known_count[g] : -1;
     s->count_buf = count_buf;
     s->count_off = (size_t)g * sizeof(unsigned long long);
     out_sets[g] = s;
@@ -556,7 +591,8 @@ int sks_ctx_kernel_stats(sks_ctx *ctx, int kind, int64_t *out_launches, double *
 const char *sks_kernel_name(int kind) {
   static const char *names[SKS_KERNEL_KINDS] = {"sketch_kernel", "fill_zero_kernel", "bitset_pair_counts_kernel",
                                                 "bitset_popcount_kernel", "sort_unique", "sorted_intersect_kernel",
-                                                "synth_kernel", "list_finalize", "bitset_build", "fasta_parse"};
+                                                "synth_kernel", "list_finalize", "bitset_build", "fasta_parse",
+                                                "bitset_pair_build_kernel"};
   return (kind >= 0 && kind < SKS_KERNEL_KINDS) ? names[kind] : "?";
 }
 
@@ -1206,15 +1242,39 @@ int sks_pair_ani_resident(sks_ctx *ctx, const sks_batch *batch, const uint64_t m
                           int repr, sks_pair_result *out) {
   if (!ctx || !batch || !out) return set_error(SKS_ERR_INVALID, "null argument");
   if (batch->n_genomes != 2) return set_error(SKS_ERR_INVALID, "pair pipeline needs a 2-genome batch");
+  if (batch->device != ctx->device) return set_error(SKS_ERR_INVALID, "batch lives on another device");
+  DeviceGuard guard(ctx->device);
+  SketchPlan plan;
+  SKS_TRY(make_plan(batch, mask, window, pred, &plan));
+  if (repr == SKS_REPR_AUTO)
+    repr = (pred->kind == SKS_PRED_ALL && plan.weight <= 16) ? SKS_REPR_BITSET : SKS_REPR_SORTED;
   sks_set *sets[2] = {nullptr, nullptr};
-  SKS_TRY(sks_sketch(ctx, batch, mask, window, pred, repr, sets));
   int64_t inter = 0, sa = 0, sb = 0;
-  int st = sks_intersect(ctx, sets[0], sets[1], &inter);
-  if (st == SKS_OK) st = sks_set_size(ctx, sets[0], &sa);
-  if (st == SKS_OK) st = sks_set_size(ctx, sets[1], &sb);
-  const int weight = sets[0]->weight;
-  sks_set_destroy(ctx, sets[0]);
-  sks_set_destroy(ctx, sets[1]);
+  int st = SKS_OK;
+  PairFuse fuse;
+  if (repr == SKS_REPR_BITSET || repr == SKS_REPR_BITSET_ONCHIP) {
+    if (plan.weight > 16)
+      return set_error(SKS_ERR_INVALID, "bitset representation needs weight <= 16 (4^%d bits do not fit)", plan.weight);
+    // large bitsets: the fused build counts |A|, |B|, |A n B| while the slices are still in shared memory
+    fuse.store = repr == SKS_REPR_BITSET;
+    st = sketch_bitset(ctx, batch, plan, pred, mask, window, sets, &fuse);
+  } else {
+    st = sks_sketch(ctx, batch, mask, window, pred, repr, sets);
+  }
+  if (st == SKS_OK) {
+    if (fuse.done) {
+      sa = fuse.counts[0];
+      sb = fuse.counts[1];
+      inter = fuse.counts[2];
+    } else {
+      st = sks_intersect(ctx, sets[0], sets[1], &inter);
+      if (st == SKS_OK) st = sks_set_size(ctx, sets[0], &sa);
+      if (st == SKS_OK) st = sks_set_size(ctx, sets[1], &sb);
+    }
+  }
+  const int weight = plan.weight;
+  if (sets[0]) sks_set_destroy(ctx, sets[0]);
+  if (sets[1]) sks_set_destroy(ctx, sets[1]);
   if (st != SKS_OK) return st;
   out->size_a = sa;
   out->size_b = sb;

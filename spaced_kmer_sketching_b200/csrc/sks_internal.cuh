@@ -222,6 +222,8 @@ int launch_bitset_build(sks_ctx *ctx, const uint32_t *raw_idx, uint32_t *sorted_
 int launch_region_starts(sks_ctx *ctx, uint32_t *d_cursor, uint32_t n, uint32_t cap);
 int launch_bitset_assemble(sks_ctx *ctx, const uint32_t *regions, const uint32_t *d_cursor, uint32_t part_cap, int n_genomes,
                            int index_bits, uint32_t *bitset, uint64_t bitset_words, unsigned long long *d_set_count);
+int launch_bitset_pair_build(sks_ctx *ctx, const uint32_t *regions, const uint32_t *d_cursor, uint32_t part_cap, int index_bits,
+                             uint32_t *bitset_a, uint32_t *bitset_b, unsigned long long *d_out3);
 int launch_bitset_popcount(sks_ctx *ctx, const uint32_t *a, uint64_t n_words, unsigned long long *out1);
 int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t *h_off, const uint64_t *h_count,
                         int n_regions, uint64_t span, BufferRef *out_buf, std::vector<uint64_t> *out_off,

@@ -335,6 +335,123 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
   if (cur_genome != 0xFFFFFFFFu) flush_total(cur_genome);
 }
 
+// ---- fused pair build: K4b + K5 in one pass ---------------------------------------------------------
+// The one-call pair pipeline (sks_pair_ani*) needs |A|, |B| and |A n B| of two genomes sketched in the same
+// launch.  A CTA takes one bucket of BOTH genomes, assembles slice s of A and slice s of B side by side in
+// shared memory, counts popc(a), popc(b), popc(a & b) while the two slices stream out, and so the 1 GiB
+// re-read of bitset_pair_counts_kernel disappears.  kStore = false keeps the bitsets on chip altogether
+// (nothing but the three counts leaves the SM).  One 1024-thread CTA per SM (216 KB of shared memory).
+constexpr int kPairThreads = 1024;
+constexpr int kPairSmemBytes = (2 * kSliceWords + 2 * kKeyCap) * 4;
+
+struct PairBuild {
+  const uint32_t *regions;  // (genome, bucket) regions of `cap` slots, genome-major
+  const uint32_t *cursor;   // [2 * n_parts] absolute end slot of every region (may exceed the region: overflow)
+  uint32_t cap;
+  uint32_t n_parts;
+  uint32_t group_slices;
+  uint32_t *bitset[2];               // kStore only
+  unsigned long long *out3;          // |A|, |B|, |A n B|
+  unsigned int *work_counter;
+};
+
+template <bool kStore>
+__global__ void __launch_bounds__(kPairThreads, 1) bitset_pair_build_kernel(const __grid_constant__ PairBuild P) {
+  extern __shared__ __align__(128) uint32_t s_dyn[];
+  uint32_t *s_slice[2] = {s_dyn, s_dyn + kSliceWords};
+  uint32_t *s_keys[2] = {s_dyn + 2 * kSliceWords, s_dyn + 2 * kSliceWords + kKeyCap};
+  __shared__ uint32_t s_item;
+  __shared__ unsigned long long s_tot[3][kPairThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t slice_mask = P.group_slices - 1;
+  uint32_t ca = 0, cb = 0, ci = 0;  // < 2^32 bits per genome
+  uint4 *a4 = reinterpret_cast<uint4 *>(s_slice[0]);
+  uint4 *b4 = reinterpret_cast<uint4 *>(s_slice[1]);
+  for (int i = tid; i < kSliceWords / 2; i += kPairThreads) a4[i] = make_uint4(0, 0, 0, 0);  // both slices (contiguous)
+
+  for (;;) {
+    __syncthreads();  // everyone is done with s_item / s_keys of the previous bucket
+    if (tid == 0) s_item = atomicAdd(P.work_counter, 1u);
+    __syncthreads();
+    const uint32_t part = s_item;
+    if (part >= P.n_parts) break;
+    const uint32_t *bk[2];
+    uint32_t n[2], n4[2];
+    bool direct[2];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const uint32_t region = g * P.n_parts + part;
+      const uint32_t lo = region * P.cap;
+      uint32_t hi = __ldg(P.cursor + region);
+      if (hi > lo + P.cap) hi = lo + P.cap;  // overflowed region: the caller redoes the pair exactly
+      n[g] = hi - lo;
+      bk[g] = P.regions + lo;
+      direct[g] = n[g] > (uint32_t)kKeyCap;
+      n4[g] = 0;
+      if (!direct[g] && n[g] > 0) {
+        n4[g] = (n[g] + 3) / 4;  // tail padded with copies of the last index (OR is idempotent)
+        for (uint32_t i = tid; i < n4[g] * 4; i += kPairThreads) s_keys[g][i] = __ldg(bk[g] + (i < n[g] ? i : n[g] - 1));
+      }
+    }
+    __syncthreads();
+    for (uint32_t slice = 0; slice < P.group_slices; ++slice) {
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        uint32_t *dst = s_slice[g];
+        auto put = [&](uint32_t key) {
+          if (((key >> kSliceBits) & slice_mask) == slice) {
+            const uint32_t bit = key & ((1u << kSliceBits) - 1);
+            atomicOr(&dst[bit >> 5], 1u << (bit & 31));
+          }
+        };
+        if (!direct[g]) {
+          const uint4 *k4 = reinterpret_cast<const uint4 *>(s_keys[g]);
+          for (uint32_t i = tid; i < n4[g]; i += kPairThreads) {
+            const uint4 v = k4[i];
+            put(v.x);
+            put(v.y);
+            put(v.z);
+            put(v.w);
+          }
+        } else {
+          for (uint32_t i = tid; i < n[g]; i += kPairThreads) put(__ldg(bk[g] + i));
+        }
+      }
+      __syncthreads();
+      const size_t slice_off = ((size_t)part * P.group_slices + slice) * (kSliceWords / 4);
+      uint4 *da = kStore ? reinterpret_cast<uint4 *>(P.bitset[0]) + slice_off : nullptr;
+      uint4 *db = kStore ? reinterpret_cast<uint4 *>(P.bitset[1]) + slice_off : nullptr;
+#pragma unroll
+      for (int i = tid; i < kSliceWords / 4; i += kPairThreads) {
+        const uint4 va = a4[i], vb = b4[i];
+        a4[i] = make_uint4(0, 0, 0, 0);
+        b4[i] = make_uint4(0, 0, 0, 0);
+        ca += popc4(va);
+        cb += popc4(vb);
+        ci += popc4(make_uint4(va.x & vb.x, va.y & vb.y, va.z & vb.z, va.w & vb.w));
+        if (kStore) {
+          __stcs(da + i, va);
+          __stcs(db + i, vb);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  unsigned long long t[3] = {ca, cb, ci};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t[k] += __shfl_down_sync(0xffffffffu, t[k], o);
+    if (lane == 0) s_tot[k][tid >> 5] = t[k];
+  }
+  __syncthreads();
+  if (tid < 3) {
+    unsigned long long sum = 0;
+    for (int i = 0; i < kPairThreads / 32; ++i) sum += s_tot[tid][i];
+    if (sum) atomicAdd(P.out3 + tid, sum);
+  }
+}
+
 // ---- sort + unique --------------------------------------------------------------------------------
 struct Region {
   unsigned long long begin, end;  // slots
@@ -675,6 +792,40 @@ int launch_bitset_assemble(sks_ctx *ctx, const uint32_t *regions, const uint32_t
   const unsigned gx = (unsigned)std::min<uint64_t>(n_items, (uint64_t)ctx->sm_count * 2);
   bitset_build_kernel<<<gx, kBuildThreads, smem, ctx->stream>>>(d_desc, (uint32_t)n_genomes, geo.n_parts, geo.group_slices,
                                                                d_counter);
+  SKS_CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  return SKS_OK;
+}
+
+// Fused K4b + K5 for a 2-genome batch whose indices the sketch kernel (OUT_PART) scattered into fixed regions.
+// bitset_a / bitset_b may both be NULL: the bitsets then never leave shared memory.  d_out3 = |A|, |B|, |A n B|.
+int launch_bitset_pair_build(sks_ctx *ctx, const uint32_t *regions, const uint32_t *d_cursor, uint32_t part_cap, int index_bits,
+                             uint32_t *bitset_a, uint32_t *bitset_b, unsigned long long *d_out3) {
+  const PartGeometry geo = part_geometry(index_bits);
+  unsigned int *d_counter = nullptr;
+  SKS_TRY(ctx_scratch(ctx, 256, reinterpret_cast<void **>(&d_counter)));
+  PairBuild p;
+  p.regions = regions;
+  p.cursor = d_cursor;
+  p.cap = part_cap;
+  p.n_parts = geo.n_parts;
+  p.group_slices = geo.group_slices;
+  p.bitset[0] = bitset_a;
+  p.bitset[1] = bitset_b;
+  p.out3 = d_out3;
+  p.work_counter = d_counter;
+  const bool store = bitset_a != nullptr;
+  KernelTimer timer(ctx, SKS_KERNEL_PAIR_BUILD);
+  SKS_CUDA_TRY(cudaMemsetAsync(d_out3, 0, 3 * sizeof(unsigned long long), ctx->stream));
+  SKS_CUDA_TRY(cudaMemsetAsync(d_counter, 0, 256, ctx->stream));
+  const unsigned gx = std::min<unsigned>(geo.n_parts, (unsigned)ctx->sm_count);
+  if (store) {
+    SKS_CUDA_TRY(cudaFuncSetAttribute(bitset_pair_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    bitset_pair_build_kernel<true><<<gx, kPairThreads, kPairSmemBytes, ctx->stream>>>(p);
+  } else {
+    SKS_CUDA_TRY(cudaFuncSetAttribute(bitset_pair_build_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    bitset_pair_build_kernel<false><<<gx, kPairThreads, kPairSmemBytes, ctx->stream>>>(p);
+  }
   SKS_CUDA_TRY(cudaGetLastError());
   ctx->launches++;
   return SKS_OK;

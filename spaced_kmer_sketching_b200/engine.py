@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _lib
-from ._lib import (HASH_BOOST_171, HASH_BOOST_181, PRED_ALL, PRED_FMH, REPR_AUTO, REPR_BITSET, REPR_SORTED, SksError,
+from ._lib import (HASH_BOOST_171, HASH_BOOST_181, PRED_ALL, PRED_FMH, REPR_AUTO, REPR_BITSET, REPR_BITSET_ONCHIP, REPR_SORTED, SksError,
                    SksPairResult, SksPred, check)
 
 M64 = (1 << 64) - 1

@@ -261,9 +261,55 @@ def test_sets_golden(ctx, name):
     r = ctx.pair_ani_resident(batch, mask, w, sks.all_kmers(), sks.REPR_BITSET)
     assert (r.size_a, r.size_b, r.intersection) == (case["size_a"], case["size_b"], case["intersection"])
     assert abs(r.ani_ab - float(case["ani_ab"])) <= 1e-12 and abs(r.ani_ba - float(case["ani_ba"])) <= 1e-12
+    r3 = ctx.pair_ani_resident(batch, mask, w, sks.all_kmers(), sks.REPR_BITSET_ONCHIP)
+    assert (r3.size_a, r3.size_b, r3.intersection, r3.ani_ab, r3.ani_ba) == (r.size_a, r.size_b, r.intersection, r.ani_ab, r.ani_ba)
     wa, wb = batch.download(0), batch.download(1)
     r2 = ctx.pair_ani(wa, g["L"], wb, g["L"], mask, w, sks.all_kmers())
     assert (r2.size_a, r2.size_b, r2.intersection, r2.ani_ab) == (r.size_a, r.size_b, r.intersection, r.ani_ab)
+
+
+def test_pair_pipeline_fused_build_and_onchip(ctx, ctx_bucket, ctx_exact):
+    """sks_pair_ani*: the fused slice-assembly + AND/popcount kernel (bitsets stored, and kept on chip) gives
+    the counts of the separate build + intersection, on random, segmented, skewed and tiny genomes."""
+    rng = np.random.default_rng(5)
+    polya = np.zeros(60000, dtype=np.uint8)
+    polya[rng.integers(0, 60000, 300)] = rng.integers(0, 4, 300)
+    at_rich = rng.choice(np.array([0, 3], dtype=np.uint8), 50000, p=[0.5, 0.5])
+    cases = [
+        (rng.integers(0, 4, 80000, dtype=np.uint8), None),
+        (polya, None),                                   # one bucket holds nearly everything (region overflow)
+        (at_rich, None),
+        (rng.integers(0, 4, 30011, dtype=np.uint8), [11, 5000, 3, 25, 24972]),
+        (rng.integers(0, 4, 9, dtype=np.uint8), None),   # shorter than the window: empty set
+    ]
+    for seed in ("011101110010111110011011", "1101100111011", "1111111111111111"):
+        mask, w = sks.seed_to_mask(seed)
+        weight = sks.mask_weight(mask)
+        for ia in range(len(cases)):
+            ib = (ia + 1) % len(cases)
+            A, sA = cases[ia]
+            Bm = A.copy() if ia % 2 == 0 else cases[ib][0]
+            sB = sA if ia % 2 == 0 else cases[ib][1]
+            if ia % 2 == 0 and len(Bm) > 100:
+                idx = rng.integers(0, len(Bm), len(Bm) // 50)
+                Bm[idx] = (Bm[idx] + 1) & 3
+            oa = port.sketch_set(A, [len(A)] if sA is None else list(sA), mask, w, port.ALL)
+            ob = port.sketch_set(Bm, [len(Bm)] if sB is None else list(sB), mask, w, port.ALL)
+            want = (len(oa), len(ob), port.intersection(oa, ob))
+            for c in (ctx, ctx_bucket, ctx_exact):
+                batch = c.upload_codes([A, Bm], [sA, sB])
+                for r in (sks.REPR_BITSET, sks.REPR_BITSET_ONCHIP, sks.REPR_SORTED, sks.REPR_AUTO):
+                    res = c.pair_ani_resident(batch, mask, w, sks.all_kmers(), r)
+                    assert (res.size_a, res.size_b, res.intersection) == want, (seed, ia, r)
+                    assert abs(res.ani_ab - port.ani(want[2], want[0], weight)) <= 1e-12
+                    assert abs(res.ani_ba - port.ani(want[2], want[1], weight)) <= 1e-12
+                batch.close()
+    # the on-chip representation has no set to hand out
+    batch = ctx.upload_codes([cases[0][0]])
+    mask, w = sks.seed_to_mask("1101100111011")
+    with pytest.raises(sks.SksError):
+        ctx.sketch(batch, mask, w, sks.all_kmers(), sks.REPR_BITSET_ONCHIP)
+    batch.close()
 
 
 def test_fasta_files_to_sets(ctx, tmp_path):
