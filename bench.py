@@ -365,7 +365,9 @@ def c2_variants(ctx, sks, torch, batch, mask, w, stream, barrier, max_over_ranks
         ks = ctx.kernel_stats()
         ctx.profile(False)
         ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in evs)) / reps
-        ent = {"ms_per_step": ms, "intersection": int(n),
+        per_rep = [a.elapsed_time(b) for a, b in evs]
+        ent = {"ms_per_step": ms, "ms_per_step_median": sorted(per_rep)[len(per_rep) // 2], "ms_per_rep": [round(x, 3) for x in per_rep],
+               "intersection": int(n),
                "kernels_ms": {k: v[1] / v[0] for k, v in ks.items()}}
         if "bitset_pair_counts_kernel" in ks:
             per = ks["bitset_pair_counts_kernel"][1] / ks["bitset_pair_counts_kernel"][0]

@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 
@@ -12,8 +14,74 @@
 
 namespace sks {
 
+// Large blocks (bitsets, index regions, key buffers) are recycled by exact size per (device, stream) instead
+// of going back to the stream-ordered pool: after a mix of small and large requests the pool satisfies a
+// 1 GiB cudaMallocAsync by remapping physical chunks, which was measured at 2-85 ms per call.  Reuse on the
+// same stream is safe by stream order.  The cache of a stream is dropped when its context goes away.
+namespace {
+constexpr size_t kCacheMinBytes = (size_t)1 << 20;
+constexpr size_t kCacheMaxBytes = (size_t)12 << 30;
+struct BlockKey {
+  int device;
+  cudaStream_t stream;
+  size_t bytes;
+  bool operator<(const BlockKey &o) const {
+    if (device != o.device) return device < o.device;
+    if (stream != o.stream) return stream < o.stream;
+    return bytes < o.bytes;
+  }
+};
+struct BlockCache {
+  std::mutex mu;
+  std::multimap<BlockKey, void *> blocks;
+  size_t cached = 0;
+};
+BlockCache &block_cache() {
+  static BlockCache *c = new BlockCache();  // never destroyed: the CUDA runtime may be gone at exit
+  return *c;
+}
+void *cache_take(int device, cudaStream_t stream, size_t bytes) {
+  BlockCache &c = block_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto it = c.blocks.find(BlockKey{device, stream, bytes});
+  if (it == c.blocks.end()) return nullptr;
+  void *p = it->second;
+  c.blocks.erase(it);
+  c.cached -= bytes;
+  return p;
+}
+bool cache_put(int device, cudaStream_t stream, size_t bytes, void *p) {
+  if (bytes < kCacheMinBytes) return false;
+  BlockCache &c = block_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (c.cached + bytes > kCacheMaxBytes) return false;
+  c.blocks.emplace(BlockKey{device, stream, bytes}, p);
+  c.cached += bytes;
+  return true;
+}
+}  // namespace
+
+// Frees the cached blocks of one stream (all streams of the device when `stream_only` is false).
+void cache_release(int device, cudaStream_t stream, bool stream_only) {
+  BlockCache &c = block_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  for (auto it = c.blocks.begin(); it != c.blocks.end();) {
+    if (it->first.device == device && (!stream_only || it->first.stream == stream)) {
+      if (cudaFreeAsync(it->second, it->first.stream) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(it->second);
+      }
+      c.cached -= it->first.bytes;
+      it = c.blocks.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
 DeviceBuffer::~DeviceBuffer() {
   if (ptr) {
+    if (cache_put(device, stream, bytes, ptr)) return;
     int cur = 0;
     cudaGetDevice(&cur);
     if (cur != device) cudaSetDevice(device);
@@ -28,7 +96,20 @@ DeviceBuffer::~DeviceBuffer() {
 int alloc_buffer(sks_ctx *ctx, size_t bytes, BufferRef *out) {
   auto buf = std::make_shared<DeviceBuffer>();
   if (bytes == 0) bytes = 16;
-  SKS_CUDA_TRY(cudaMallocAsync(&buf->ptr, bytes, ctx->stream));
+  if (bytes >= kCacheMinBytes) buf->ptr = cache_take(ctx->device, ctx->stream, bytes);
+  if (!buf->ptr) {
+    cudaError_t e = cudaMallocAsync(&buf->ptr, bytes, ctx->stream);
+    if (e == cudaErrorMemoryAllocation) {  // give the recycled blocks back and try once more
+      cudaGetLastError();
+      cache_release(ctx->device, nullptr, false);
+      cudaStreamSynchronize(ctx->stream);
+      e = cudaMallocAsync(&buf->ptr, bytes, ctx->stream);
+    }
+    if (e != cudaSuccess) {
+      buf->ptr = nullptr;
+      return set_error(SKS_ERR_CUDA, "cudaMallocAsync of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+  }
   buf->bytes = bytes;
   buf->device = ctx->device;
   buf->stream = ctx->stream;
@@ -515,6 +596,7 @@ void sks_ctx_destroy(sks_ctx *ctx) {
   DeviceGuard guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch) cudaFreeAsync(ctx->scratch, ctx->stream);
+  cache_release(ctx->device, ctx->stream, true);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -533,6 +615,7 @@ int sks_ctx_set_stream(sks_ctx *ctx, void *cuda_stream) {
   if (!ctx) return set_error(SKS_ERR_INVALID, "null context");
   DeviceGuard guard(ctx->device);
   SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  cache_release(ctx->device, ctx->stream, true);
   if (ctx->scratch) {
     SKS_CUDA_TRY(cudaFreeAsync(ctx->scratch, ctx->stream));
     SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));

@@ -138,6 +138,7 @@ struct DeviceBuffer {  // ref-counted cudaMalloc block shared by the sets of one
 };
 using BufferRef = std::shared_ptr<DeviceBuffer>;
 int alloc_buffer(sks_ctx *ctx, size_t bytes, BufferRef *out);
+void cache_release(int device, cudaStream_t stream, bool stream_only);
 
 }  // namespace sks
 

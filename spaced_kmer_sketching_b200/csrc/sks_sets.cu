@@ -300,14 +300,19 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
     }
     __syncthreads();
     const uint4 *k4 = reinterpret_cast<const uint4 *>(s_keys);
+    // kmer_set_size() comes from the atomics themselves: an index is new iff its bit was still clear.  (A POPC
+    // per streamed word costs more than the atomics: POPC issues at a quarter of the ALU rate through the same
+    // queue as the shared-memory traffic -- ncu: every POPC of the old stream loop stalled on mio_throttle.)
+    uint32_t fresh = 0;
     auto put = [&](uint32_t key, uint32_t slice) {
       if (((key >> kSliceBits) & slice_mask) == slice) {
-        const uint32_t bit = key & ((1u << kSliceBits) - 1);
-        atomicOr(&s_slice[bit >> 5], 1u << (bit & 31));
+        const uint32_t bit = key & ((1u << kSliceBits) - 1), m = 1u << (bit & 31);
+        fresh += (atomicOr(&s_slice[bit >> 5], m) & m) == 0;
       }
     };
     for (uint32_t slice = 0; slice < group_slices; ++slice) {
       if (!direct) {
+        // the padding copies of the last index find their bit already set: they never count
         for (uint32_t i = tid; i < n4; i += kBuildThreads) {
           const uint4 v = k4[i];
           put(v.x, slice);
@@ -320,17 +325,15 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
       }
       __syncthreads();
       uint4 *dst = reinterpret_cast<uint4 *>(g.bitset + ((size_t)part * group_slices + slice) * kSliceWords);
-      uint32_t c = 0;
 #pragma unroll
       for (int i = tid; i < kSliceWords / 4; i += kBuildThreads) {
         const uint4 v = b4[i];
         b4[i] = make_uint4(0, 0, 0, 0);
-        c += popc4(v);
         __stcs(dst + i, v);
       }
-      total += c;
       __syncthreads();
     }
+    total += fresh;
   }
   if (cur_genome != 0xFFFFFFFFu) flush_total(cur_genome);
 }
@@ -338,9 +341,16 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
 // ---- fused pair build: K4b + K5 in one pass ---------------------------------------------------------
 // The one-call pair pipeline (sks_pair_ani*) needs |A|, |B| and |A n B| of two genomes sketched in the same
 // launch.  A CTA takes one bucket of BOTH genomes, assembles slice s of A and slice s of B side by side in
-// shared memory, counts popc(a), popc(b), popc(a & b) while the two slices stream out, and so the 1 GiB
-// re-read of bitset_pair_counts_kernel disappears.  kStore = false keeps the bitsets on chip altogether
-// (nothing but the three counts leaves the SM).  One 1024-thread CTA per SM (216 KB of shared memory).
+// shared memory with atomicOr, takes |A|, |B|, |A n B| from the atomics' return values, and streams the two
+// slices out: the 1 GiB re-read of bitset_pair_counts_kernel disappears.  kStore = false keeps the bitsets on
+// chip altogether (nothing but the three counts leaves the SM).  One 1024-thread CTA per SM (216 KB of shared
+// memory).  The kernel is bound by the shared-memory pipe, not by HBM: ~2 cycles per shared atomic plus the
+// LDS/STS/STG of the stream phase, in lock-step phases (ncu: mio_throttle).  Measured and rejected (the git
+// history and DESIGN.md have the numbers): 32 KB sub-slices double-buffered through TMA bulk stores (same
+// time: the store pattern alone needs 0.19 ms, the phases do not overlap it), a counting sort of the bucket by
+// sub-slice (the sort costs what the scans cost), independent warp groups on named barriers (sparse-lane
+// atomics), and zero-fill + global atomics on L2-resident lines (the lines are evicted first: 0.6 GB of DRAM
+// reads).
 constexpr int kPairThreads = 1024;
 constexpr int kPairSmemBytes = (2 * kSliceWords + 2 * kKeyCap) * 4;
 
@@ -394,45 +404,55 @@ __global__ void __launch_bounds__(kPairThreads, 1) bitset_pair_build_kernel(cons
       }
     }
     __syncthreads();
-    for (uint32_t slice = 0; slice < P.group_slices; ++slice) {
+    // |A|, |B|, |A n B| come from the atomics: an index is new iff its bit was still clear, and a new index of B
+    // is shared iff A's finished slice has the bit (no POPC over the streamed words, see bitset_build_kernel).
+    auto scan = [&](int g, uint32_t slice, auto &&visit) {
+      if (!direct[g]) {
+        const uint4 *k4 = reinterpret_cast<const uint4 *>(s_keys[g]);
+        for (uint32_t i = tid; i < n4[g]; i += kPairThreads) {
+          const uint4 v = k4[i];
+          const uint32_t k[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        uint32_t *dst = s_slice[g];
-        auto put = [&](uint32_t key) {
-          if (((key >> kSliceBits) & slice_mask) == slice) {
-            const uint32_t bit = key & ((1u << kSliceBits) - 1);
-            atomicOr(&dst[bit >> 5], 1u << (bit & 31));
-          }
-        };
-        if (!direct[g]) {
-          const uint4 *k4 = reinterpret_cast<const uint4 *>(s_keys[g]);
-          for (uint32_t i = tid; i < n4[g]; i += kPairThreads) {
-            const uint4 v = k4[i];
-            put(v.x);
-            put(v.y);
-            put(v.z);
-            put(v.w);
-          }
-        } else {
-          for (uint32_t i = tid; i < n[g]; i += kPairThreads) put(__ldg(bk[g] + i));
+          for (int u = 0; u < 4; ++u)
+            if (((k[u] >> kSliceBits) & slice_mask) == slice) visit(k[u] & ((1u << kSliceBits) - 1));
+        }
+      } else {
+        for (uint32_t i = tid; i < n[g]; i += kPairThreads) {
+          const uint32_t k = __ldg(bk[g] + i);
+          if (((k >> kSliceBits) & slice_mask) == slice) visit(k & ((1u << kSliceBits) - 1));
         }
       }
+    };
+    for (uint32_t slice = 0; slice < P.group_slices; ++slice) {
+      scan(0, slice, [&](uint32_t bit) {
+        const uint32_t m = 1u << (bit & 31);
+        ca += (atomicOr(&s_slice[0][bit >> 5], m) & m) == 0;
+      });
       __syncthreads();
-      const size_t slice_off = ((size_t)part * P.group_slices + slice) * (kSliceWords / 4);
-      uint4 *da = kStore ? reinterpret_cast<uint4 *>(P.bitset[0]) + slice_off : nullptr;
-      uint4 *db = kStore ? reinterpret_cast<uint4 *>(P.bitset[1]) + slice_off : nullptr;
+      scan(1, slice, [&](uint32_t bit) {
+        const uint32_t m = 1u << (bit & 31);
+        if ((atomicOr(&s_slice[1][bit >> 5], m) & m) == 0) {
+          ++cb;
+          ci += (s_slice[0][bit >> 5] & m) != 0;
+        }
+      });
+      __syncthreads();
+      if (kStore) {
+        const size_t slice_off = ((size_t)part * P.group_slices + slice) * (kSliceWords / 4);
+        uint4 *da = reinterpret_cast<uint4 *>(P.bitset[0]) + slice_off;
+        uint4 *db = reinterpret_cast<uint4 *>(P.bitset[1]) + slice_off;
 #pragma unroll
-      for (int i = tid; i < kSliceWords / 4; i += kPairThreads) {
-        const uint4 va = a4[i], vb = b4[i];
-        a4[i] = make_uint4(0, 0, 0, 0);
-        b4[i] = make_uint4(0, 0, 0, 0);
-        ca += popc4(va);
-        cb += popc4(vb);
-        ci += popc4(make_uint4(va.x & vb.x, va.y & vb.y, va.z & vb.z, va.w & vb.w));
-        if (kStore) {
+        for (int i = tid; i < kSliceWords / 4; i += kPairThreads) {
+          const uint4 va = a4[i], vb = b4[i];
+          a4[i] = make_uint4(0, 0, 0, 0);
+          b4[i] = make_uint4(0, 0, 0, 0);
           __stcs(da + i, va);
           __stcs(db + i, vb);
         }
+      } else {
+        // nothing leaves the SM: clear only the words that were touched
+        scan(0, slice, [&](uint32_t bit) { s_slice[0][bit >> 5] = 0; });
+        scan(1, slice, [&](uint32_t bit) { s_slice[1][bit >> 5] = 0; });
       }
       __syncthreads();
     }

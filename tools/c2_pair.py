@@ -11,7 +11,7 @@ ctx = sks.Context(0)
 mask, w = sks.seed_to_mask("011101110010111110011011")
 batch = ctx.synth(L, [42, 42], [0, 43], [0, 100])
 ctx.profile(True)
-for repr_ in (sks.REPR_BITSET, sks.REPR_BITSET_ONCHIP):
+for repr_ in (sks.REPR_BITSET, sks.REPR_BITSET_ONCHIP):  # 2 = stored, 3 = on chip
     for i in range(reps):
         r = ctx.pair_ani_resident(batch, mask, w, sks.all_kmers(), repr_)
     print(repr_, (r.size_a, r.size_b, r.intersection), {k: (v[0], round(v[1] / v[0], 4)) for k, v in ctx.kernel_stats().items()})
