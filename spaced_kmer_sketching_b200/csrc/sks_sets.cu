@@ -145,6 +145,19 @@ int stream_grid(const sks_ctx *ctx, size_t n16) {
 constexpr int kBuildThreads = 512;
 constexpr int kKeyCap = 11264;                       // indices of one bucket kept in shared memory (44 KB)
 
+// 1-D bulk store shared -> global (TMA engine), tracked by the issuing thread's bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 struct BuildGenome {
   const uint32_t *raw;      // PEXT indices as emitted by the sketch kernel
   uint32_t *bucketed;       // the same, grouped by bucket
@@ -310,6 +323,9 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
         fresh += (atomicOr(&s_slice[bit >> 5], m) & m) == 0;
       }
     };
+    auto clear = [&](uint32_t key, uint32_t slice) {
+      if (((key >> kSliceBits) & slice_mask) == slice) s_slice[(key & ((1u << kSliceBits) - 1)) >> 5] = 0;
+    };
     for (uint32_t slice = 0; slice < group_slices; ++slice) {
       if (!direct) {
         // the padding copies of the last index find their bit already set: they never count
@@ -323,18 +339,32 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
       } else {
         for (uint32_t i = tid; i < n; i += kBuildThreads) put(__ldg(bk + i), slice);
       }
+      // the slice leaves through one bulk store (TMA engine, SASS UBLKCP); once the engine has read it, the
+      // words that were touched are cleared by a re-visit.  The other CTA of the SM assembles meanwhile.
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();
-      uint4 *dst = reinterpret_cast<uint4 *>(g.bitset + ((size_t)part * group_slices + slice) * kSliceWords);
-#pragma unroll
-      for (int i = tid; i < kSliceWords / 4; i += kBuildThreads) {
-        const uint4 v = b4[i];
-        b4[i] = make_uint4(0, 0, 0, 0);
-        __stcs(dst + i, v);
+      if (tid == 0) {
+        bulk_s2g(g.bitset + ((size_t)part * group_slices + slice) * kSliceWords, s_slice, kSliceWords * 4);
+        bulk_commit();
+        bulk_wait_read<0>();
+      }
+      __syncthreads();
+      if (!direct) {
+        for (uint32_t i = tid; i < n4; i += kBuildThreads) {
+          const uint4 v = k4[i];
+          clear(v.x, slice);
+          clear(v.y, slice);
+          clear(v.z, slice);
+          clear(v.w, slice);
+        }
+      } else {
+        for (uint32_t i = tid; i < n; i += kBuildThreads) clear(__ldg(bk + i), slice);
       }
       __syncthreads();
     }
     total += fresh;
   }
+  if (tid == 0) bulk_wait_all();
   if (cur_genome != 0xFFFFFFFFu) flush_total(cur_genome);
 }
 
@@ -344,13 +374,12 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
 // shared memory with atomicOr, takes |A|, |B|, |A n B| from the atomics' return values, and streams the two
 // slices out: the 1 GiB re-read of bitset_pair_counts_kernel disappears.  kStore = false keeps the bitsets on
 // chip altogether (nothing but the three counts leaves the SM).  One 1024-thread CTA per SM (216 KB of shared
-// memory).  The kernel is bound by the shared-memory pipe, not by HBM: ~2 cycles per shared atomic plus the
-// LDS/STS/STG of the stream phase, in lock-step phases (ncu: mio_throttle).  Measured and rejected (the git
-// history and DESIGN.md have the numbers): 32 KB sub-slices double-buffered through TMA bulk stores (same
-// time: the store pattern alone needs 0.19 ms, the phases do not overlap it), a counting sort of the bucket by
-// sub-slice (the sort costs what the scans cost), independent warp groups on named barriers (sparse-lane
-// atomics), and zero-fill + global atomics on L2-resident lines (the lines are evicted first: 0.6 GB of DRAM
-// reads).
+// memory).  The slices leave through TMA bulk stores, A's while B's is assembled and vice versa.  The kernel
+// is bound by the latency of its lock-step phases (a phase is one barrier-to-barrier LDS -> ATOMS chain over
+// ~600 indices), not by HBM.  Measured and rejected (DESIGN.md has the numbers): register-staged LDS/STG
+// stream-out, 32 KB sub-slices double-buffered through TMA, a counting sort of the bucket by sub-slice,
+// 2-4 smaller CTAs per SM, independent warp groups on named barriers, per-lane match queues, and
+// zero-fill + global atomics on L2-resident lines (the lines are evicted first: 0.6 GB of DRAM reads).
 constexpr int kPairThreads = 1024;
 constexpr int kPairSmemBytes = (2 * kSliceWords + 2 * kKeyCap) * 4;
 
@@ -375,8 +404,8 @@ __global__ void __launch_bounds__(kPairThreads, 1) bitset_pair_build_kernel(cons
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t slice_mask = P.group_slices - 1;
   uint32_t ca = 0, cb = 0, ci = 0;  // < 2^32 bits per genome
+  uint32_t n_stored = 0;            // kStore: slices stored so far by this CTA (0 or 1 is all that matters)
   uint4 *a4 = reinterpret_cast<uint4 *>(s_slice[0]);
-  uint4 *b4 = reinterpret_cast<uint4 *>(s_slice[1]);
   for (int i = tid; i < kSliceWords / 2; i += kPairThreads) a4[i] = make_uint4(0, 0, 0, 0);  // both slices (contiguous)
 
   for (;;) {
@@ -423,40 +452,75 @@ __global__ void __launch_bounds__(kPairThreads, 1) bitset_pair_build_kernel(cons
         }
       }
     };
-    for (uint32_t slice = 0; slice < P.group_slices; ++slice) {
-      scan(0, slice, [&](uint32_t bit) {
-        const uint32_t m = 1u << (bit & 31);
-        ca += (atomicOr(&s_slice[0][bit >> 5], m) & m) == 0;
-      });
-      __syncthreads();
-      scan(1, slice, [&](uint32_t bit) {
-        const uint32_t m = 1u << (bit & 31);
-        if ((atomicOr(&s_slice[1][bit >> 5], m) & m) == 0) {
-          ++cb;
-          ci += (s_slice[0][bit >> 5] & m) != 0;
-        }
-      });
-      __syncthreads();
-      if (kStore) {
-        const size_t slice_off = ((size_t)part * P.group_slices + slice) * (kSliceWords / 4);
-        uint4 *da = reinterpret_cast<uint4 *>(P.bitset[0]) + slice_off;
-        uint4 *db = reinterpret_cast<uint4 *>(P.bitset[1]) + slice_off;
+    if (kStore) {
+      // The two slice buffers double-buffer each other: A's slice leaves through a bulk store (TMA engine, SASS
+      // UBLKCP) while B's is being assembled and vice versa, so the LSU/MIO queue carries only the atomics.
+      // Before a buffer is reused its last store must have read it (wait_group.read 1: only the other buffer's
+      // store may still be pending); it is then cleared by re-visiting the indices of the slice it held (by
+      // 128-bit zero stores at the first slice of a bucket, whose predecessor's indices are gone).
+      for (uint32_t slice = 0; slice < P.group_slices; ++slice) {
+        const size_t slice_off = ((size_t)part * P.group_slices + slice) * kSliceWords;
 #pragma unroll
-        for (int i = tid; i < kSliceWords / 4; i += kPairThreads) {
-          const uint4 va = a4[i], vb = b4[i];
-          a4[i] = make_uint4(0, 0, 0, 0);
-          b4[i] = make_uint4(0, 0, 0, 0);
-          __stcs(da + i, va);
-          __stcs(db + i, vb);
+        for (int g = 0; g < 2; ++g) {
+          uint32_t *buf = s_slice[g];
+          if (n_stored) {  // CTA-uniform: this buffer has been stored before
+            if (tid == 0) bulk_wait_read<1>();
+            __syncthreads();
+            if (slice == 0) {
+              uint4 *z = reinterpret_cast<uint4 *>(buf);
+#pragma unroll
+              for (int i = tid; i < kSliceWords / 4; i += kPairThreads) z[i] = make_uint4(0, 0, 0, 0);
+            } else {
+              scan(g, slice - 1, [&](uint32_t bit) { buf[bit >> 5] = 0; });
+            }
+            __syncthreads();
+          }
+          if (g == 0) {
+            scan(0, slice, [&](uint32_t bit) {
+              const uint32_t m = 1u << (bit & 31);
+              ca += (atomicOr(&buf[bit >> 5], m) & m) == 0;
+            });
+          } else {
+            scan(1, slice, [&](uint32_t bit) {
+              const uint32_t m = 1u << (bit & 31);
+              if ((atomicOr(&buf[bit >> 5], m) & m) == 0) {
+                ++cb;
+                ci += (s_slice[0][bit >> 5] & m) != 0;
+              }
+            });
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
+          __syncthreads();
+          if (tid == 0) {
+            bulk_s2g(P.bitset[g] + slice_off, buf, kSliceWords * 4);
+            bulk_commit();
+          }
         }
-      } else {
+        n_stored = 1;
+      }
+    } else {
+      for (uint32_t slice = 0; slice < P.group_slices; ++slice) {
+        scan(0, slice, [&](uint32_t bit) {
+          const uint32_t m = 1u << (bit & 31);
+          ca += (atomicOr(&s_slice[0][bit >> 5], m) & m) == 0;
+        });
+        __syncthreads();
+        scan(1, slice, [&](uint32_t bit) {
+          const uint32_t m = 1u << (bit & 31);
+          if ((atomicOr(&s_slice[1][bit >> 5], m) & m) == 0) {
+            ++cb;
+            ci += (s_slice[0][bit >> 5] & m) != 0;
+          }
+        });
+        __syncthreads();
         // nothing leaves the SM: clear only the words that were touched
         scan(0, slice, [&](uint32_t bit) { s_slice[0][bit >> 5] = 0; });
         scan(1, slice, [&](uint32_t bit) { s_slice[1][bit >> 5] = 0; });
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
+  if (kStore && tid == 0) bulk_wait_all();
   unsigned long long t[3] = {ca, cb, ci};
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
