@@ -236,6 +236,11 @@ int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *co
  * entries are left untouched. */
 int sks_intersect_all_pairs(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end,
                             int32_t *out);
+/* Same for the block rows [row_begin, row_end) x columns [col_begin, col_end) of that matrix: the unit of the
+ * multi-GPU tiling (every unordered block pair is evaluated by exactly one rank and mirrored after the gather,
+ * since |A n B| = |B n A|). */
+int sks_intersect_block(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end,
+                        int64_t col_begin, int64_t col_end, int32_t *out);
 /* ANI matrix from counts, src/kmer-sketching.cpp:196-200: containment on the FIRST set of the
  * ordered pair, then ^(1/weight).  Host double arithmetic. */
 void sks_ani_from_counts(const int32_t *intersections, const int32_t *first_set_sizes, int64_t n_pairs,

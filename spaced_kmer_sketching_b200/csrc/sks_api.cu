@@ -1290,17 +1290,20 @@ int sks_intersect(sks_ctx *ctx, sks_set *a, sks_set *b, int64_t *out) {
   return SKS_OK;
 }
 
-int sks_intersect_all_pairs(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end,
-                            int32_t *out) {
+int sks_intersect_block(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end,
+                        int64_t col_begin, int64_t col_end, int32_t *out) {
   if (!ctx || (n > 0 && (!sets || !out))) return set_error(SKS_ERR_INVALID, "null argument");
   if (row_begin < 0 || row_end > n || row_begin > row_end) return set_error(SKS_ERR_INVALID, "bad row range");
-  // |A n B| is symmetric: evaluate each unordered pair touching the row range once, mirror inside it.
+  if (col_begin < 0 || col_end > n || col_begin > col_end) return set_error(SKS_ERR_INVALID, "bad column range");
+  // |A n B| is symmetric: an unordered pair that lies in the block with both orientations is evaluated once
+  // and mirrored inside the block.
+  auto in_block = [&](int64_t i, int64_t j) { return i >= row_begin && i < row_end && j >= col_begin && j < col_end; };
   std::vector<sks_set *> pa, pb;
   std::vector<std::pair<int64_t, int64_t>> ij;
   for (int64_t i = row_begin; i < row_end; ++i)
-    for (int64_t j = 0; j < n; ++j) {
+    for (int64_t j = col_begin; j < col_end; ++j) {
       if (j == i) continue;
-      if (j >= row_begin && j < row_end && j < i) continue;
+      if (j < i && in_block(j, i)) continue;  // (j, i) is in the block too and comes first
       pa.push_back(sets[i]);
       pb.push_back(sets[j]);
       ij.emplace_back(i, j);
@@ -1310,14 +1313,19 @@ int sks_intersect_all_pairs(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64
   for (size_t k = 0; k < ij.size(); ++k) {
     const int64_t i = ij[k].first, j = ij[k].second;
     out[i * n + j] = r[k];
-    if (j >= row_begin && j < row_end) out[j * n + i] = r[k];
+    if (in_block(j, i)) out[j * n + i] = r[k];
   }
-  for (int64_t i = row_begin; i < row_end; ++i) {  // |A n A| = |A|
+  for (int64_t i = std::max(row_begin, col_begin); i < std::min(row_end, col_end); ++i) {  // |A n A| = |A|
     int64_t sz = 0;
     SKS_TRY(sks_set_size(ctx, sets[i], &sz));
     out[i * n + i] = (int32_t)sz;
   }
   return SKS_OK;
+}
+
+int sks_intersect_all_pairs(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end,
+                            int32_t *out) {
+  return sks_intersect_block(ctx, sets, n, row_begin, row_end, 0, n, out);
 }
 
 // ---- one-call pair pipeline ----------------------------------------------------------------------

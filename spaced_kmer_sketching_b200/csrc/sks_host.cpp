@@ -10,6 +10,7 @@
 #include <numeric>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sks.h"
@@ -186,8 +187,22 @@ double sks_binomial_estimator(double containment, int kmer_num_ones) {  // src/a
 }
 void sks_ani_from_counts(const int32_t *intersections, const int32_t *first_set_sizes, int64_t n_pairs, int weight,
                          double *out_ani) {  // src/kmer-sketching.cpp:196-200
-  for (int64_t i = 0; i < n_pairs; ++i)
-    out_ani[i] = sks_binomial_estimator(sks_containment(intersections[i], first_set_sizes[i]), weight);
+  auto span = [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i)
+      out_ani[i] = sks_binomial_estimator(sks_containment(intersections[i], first_set_sizes[i]), weight);
+  };
+  // a plain loop in the reference; a large matrix (10^6 pairs at C4) is split over host threads here, the
+  // arithmetic per pair is unchanged (host double division + std::pow)
+  const unsigned hw = std::thread::hardware_concurrency();
+  const int64_t n_threads = std::min<int64_t>(std::min<int64_t>(hw ? hw : 1, 16), n_pairs / 16384);
+  if (n_threads <= 1) {
+    span(0, n_pairs);
+    return;
+  }
+  std::vector<std::thread> pool;
+  const int64_t per = (n_pairs + n_threads - 1) / n_threads;
+  for (int64_t t = 0; t < n_threads; ++t) pool.emplace_back(span, t * per, std::min(n_pairs, (t + 1) * per));
+  for (auto &th : pool) th.join();
 }
 
 size_t sks_packed_words(uint64_t n_bases) { return (size_t)((n_bases + 15) / 16); }

@@ -326,6 +326,14 @@ class Context:
         check(self._L.sks_intersect_all_pairs(self.h, ps, n, row_begin, row_end, out.ctypes.data))
         return out
 
+    def intersect_block(self, sets: Sequence["KmerSet"], rows: Tuple[int, int], cols: Tuple[int, int],
+                        out: np.ndarray) -> np.ndarray:
+        """out[i, j] = |sets[i] n sets[j]| for i in rows, j in cols (half-open ranges); other entries untouched."""
+        n = len(sets)
+        ps = (C.c_void_p * max(n, 1))(*[s.h for s in sets])
+        check(self._L.sks_intersect_block(self.h, ps, n, rows[0], rows[1], cols[0], cols[1], out.ctypes.data))
+        return out
+
     def pair_ani(self, packed_a: np.ndarray, n_a: int, packed_b: np.ndarray, n_b: int, mask: int, window: int,
                  pred: Predicate, repr_: int = REPR_AUTO) -> SksPairResult:
         r, p = SksPairResult(), pred.c()

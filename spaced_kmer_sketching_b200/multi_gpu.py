@@ -42,23 +42,78 @@ def row_tile(n_sets: int, rank: int, world: int) -> Tuple[int, int]:
     return genome_shard(n_sets, rank, world)
 
 
-def allgather_varlen(local, world: int, dist=None):
-    """All-gather of 1-D tensors of different lengths: returns the list of every rank's tensor.
-    One small all-gather of lengths, one padded all-gather of payload."""
+def _all_gather_flat(dist, out, inp, world: int):
+    """out[world * n] <- every rank's inp[n]; NCCL takes the fused form, gloo the list form."""
+    if inp.is_cuda and hasattr(dist, "all_gather_into_tensor"):
+        dist.all_gather_into_tensor(out, inp)
+    else:
+        dist.all_gather(list(out.view(world, -1).unbind(0)), inp)
+
+
+def block_rects(n_sets: int, rank: int, world: int):
+    """Rectangles ((row_begin, row_end), (col_begin, col_end)) of the n x n pair matrix that `rank` evaluates, all
+    inside its own block row: the cyclic half of the column blocks r, r+1, ..., so that every unordered pair
+    of blocks {r, c} is evaluated exactly once (|A n B| is symmetric; the mirror entries are filled in after
+    the gather).  For an even world the opposite block {r, r + world/2} is split between its two ranks: the
+    lower one takes the first half of its own rows against the whole block, the upper one the other half of
+    those rows as columns."""
+    rows = row_tile(n_sets, rank, world)
+    half = world // 2
+    rects = [(rows, row_tile(n_sets, (rank + k) % world, world)) for k in range(half + (world % 2))]
+    if world % 2 == 0 and world > 1:
+        if rank < half:
+            mid = rows[0] + (rows[1] - rows[0] + 1) // 2
+            rects.append(((rows[0], mid), row_tile(n_sets, rank + half, world)))
+        else:
+            other = row_tile(n_sets, rank - half, world)
+            mid = other[0] + (other[1] - other[0] + 1) // 2
+            rects.append((rows, (mid, other[1])))
+    return [r for r in rects if r[0][1] > r[0][0] and r[1][1] > r[1][0]]
+
+
+def tiled_counts(ctx, sets: Sequence, rank: int, world: int) -> np.ndarray:
+    """This rank's share of the n x n intersection counts (entries not evaluated here are -1)."""
+    n = len(sets)
+    counts = np.full((n, n), -1, dtype=np.int32)
+    for rows, cols in block_rects(n, rank, world):
+        ctx.intersect_block(sets, rows, cols, counts)
+    return counts
+
+
+def mirror_counts(counts: np.ndarray) -> np.ndarray:
+    """Fills the entries no rank evaluated (-1) from their transposes."""
+    return np.where(counts < 0, counts.T, counts)
+
+
+def allgather_varlen_many(locals_, world: int, dist=None):
+    """All-gather of several 1-D tensors of rank-dependent lengths with ONE host synchronisation: a small
+    all-gather of all the lengths, then one padded all-gather per tensor.  Returns, per input tensor, the list
+    of every rank's contribution."""
     import torch
     if world == 1:
-        return [local]
-    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
-    lens = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(lens, n)
-    lens = [int(x.item()) for x in lens]
-    cap = max(max(lens), 1)
-    padded = torch.zeros(cap, dtype=local.dtype, device=local.device)
-    padded[: local.numel()] = local
-    out = torch.empty(world * cap, dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, padded) if hasattr(dist, "all_gather_into_tensor") and local.is_cuda else \
-        dist.all_gather(list(out.view(world, cap).unbind(0)), padded)
-    return [out.view(world, cap)[r, : lens[r]] for r in range(world)]
+        return [[t] for t in locals_]
+    dev = locals_[0].device
+    n = torch.tensor([t.numel() for t in locals_], dtype=torch.int64, device=dev)
+    lens = torch.empty(world * len(locals_), dtype=torch.int64, device=dev)
+    _all_gather_flat(dist, lens, n, world)
+    lens = lens.view(world, len(locals_)).cpu()      # the one sync
+    out = []
+    for k, local in enumerate(locals_):
+        cap = max(int(lens[:, k].max()), 1)
+        if local.numel() == cap:
+            padded = local.contiguous()
+        else:
+            padded = torch.zeros(cap, dtype=local.dtype, device=dev)
+            padded[: local.numel()] = local
+        buf = torch.empty(world * cap, dtype=local.dtype, device=dev)
+        _all_gather_flat(dist, buf, padded, world)
+        out.append([buf.view(world, cap)[r, : int(lens[r, k])] for r in range(world)])
+    return out
+
+
+def allgather_varlen(local, world: int, dist=None):
+    """All-gather of 1-D tensors of different lengths: returns the list of every rank's tensor."""
+    return allgather_varlen_many([local], world, dist)[0]
 
 
 class _DevPtr:
@@ -92,12 +147,13 @@ def allgather_sets(ctx, local_sets: Sequence, mask: int, window: int, rank: int,
     import torch.distributed as dist
     keys, counts, kw = keys_as_tensor(local_sets, torch)
     cnt = torch.tensor(counts, dtype=torch.int64, device="cuda")
-    all_counts = allgather_varlen(cnt, world, dist)
-    all_keys = allgather_varlen(keys, world, dist)
-    torch.cuda.current_stream().synchronize()   # the gathered buffers are read by libsks on the same stream
-    out = []
+    all_counts, all_keys = allgather_varlen_many([cnt, keys], world, dist)   # one length sync, two NCCL all-gathers
+    counts_host = torch.cat(all_counts).cpu()    # syncs the stream: the gathered buffers are complete
+    out, at = [], 0
     for r in range(world):   # one device copy + one buffer per source rank
-        out.extend(ctx.sets_from_device_keys(all_keys[r].data_ptr(), all_counts[r].tolist(), kw, mask, window))
+        n_r = all_counts[r].numel()
+        out.extend(ctx.sets_from_device_keys(all_keys[r].data_ptr(), counts_host[at:at + n_r].tolist(), kw, mask, window))
+        at += n_r
     return out
 
 
@@ -130,9 +186,7 @@ def all_vs_all(ctx, local_batch, mask: int, window: int, pred, rank: int, world:
     sets = allgather_sets(ctx, local_sets, mask, window, rank, world)
     n = len(sets)
     rows = row_tile(n, rank, world)
-    counts = np.zeros((n, n), dtype=np.int32)
-    ctx.intersect_all_pairs(sets, rows[0], rows[1], counts)
-    counts = gather_rows(counts, rows, world)
+    counts = mirror_counts(gather_rows(tiled_counts(ctx, sets, rank, world), rows, world))
     sizes = np.array([s.kmer_set_size() for s in sets], dtype=np.int32)
     ani = engine.ani_from_counts(counts.ravel(), np.repeat(sizes, n), engine.mask_weight(mask)).reshape(n, n)
     return counts, sizes, ani

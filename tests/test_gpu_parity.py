@@ -223,6 +223,14 @@ def test_multi_golden(ctx):
         sizes = np.repeat(np.array(case["sizes"], dtype=np.int32), n)
         ani = sks.ani_from_counts(ints.ravel(), sizes, sks.mask_weight(mask))
         assert np.max(np.abs(ani - np.array([float(x) for x in case["ani"]]))) <= 1e-12
+        # the multi-GPU tiling on one device: every rank's block pairs, row blocks stacked, mirrored
+        from spaced_kmer_sketching_b200 import multi_gpu
+        for world in (1, 2, 3, 4, 6):
+            full = np.full((n, n), -1, dtype=np.int32)
+            for r in range(world):
+                rows = multi_gpu.row_tile(n, r, world)
+                full[rows[0]:rows[1]] = multi_gpu.tiled_counts(ctx, sets, r, world)[rows[0]:rows[1]]
+            assert np.array_equal(multi_gpu.mirror_counts(full), ints), world
 
 
 def test_synth_matches_oracle_generator(ctx):

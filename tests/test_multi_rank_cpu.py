@@ -38,6 +38,37 @@ def test_genome_and_row_tiles_partition():
         assert spans == [multi_gpu.row_tile(n, r, world) for r in range(world)]
 
 
+def test_block_rects_cover_every_unordered_pair_once():
+    for world in range(1, 10):
+        for n in (0, 1, 5, 16, 37):
+            seen = np.zeros((n, n), dtype=np.int32)
+            work = []
+            for r in range(world):
+                rows = multi_gpu.row_tile(n, r, world)
+                cells = 0
+                for (r0, r1), (c0, c1) in multi_gpu.block_rects(n, r, world):
+                    assert rows[0] <= r0 and r1 <= rows[1]       # results stay in the rank's own block row
+                    seen[r0:r1, c0:c1] += 1
+                    cells += (r1 - r0) * (c1 - c0)
+                work.append(cells)
+            both = seen + seen.T - np.diag(np.diag(seen))
+            off = ~np.eye(n, dtype=bool)
+            # every unordered pair once; within a diagonal block both orientations appear (one is evaluated, the
+            # C side mirrors it), so count those through `both` = 2
+            for i in range(n):
+                for j in range(i + 1, n):
+                    same_block = any(multi_gpu.row_tile(n, r, world)[0] <= i < multi_gpu.row_tile(n, r, world)[1] and
+                                     multi_gpu.row_tile(n, r, world)[0] <= j < multi_gpu.row_tile(n, r, world)[1]
+                                     for r in range(world))
+                    assert both[i, j] == (2 if same_block else 1), (world, n, i, j)
+            assert (np.diag(seen) == 1).all()
+            if n >= 4 * world:
+                assert max(work) <= 1.35 * (sum(work) / world) + n, (world, n, work)
+    # mirror: entries no rank evaluated come from the transpose
+    m = np.array([[5, -1, 2], [1, 6, -1], [-1, 3, 7]], dtype=np.int32)
+    assert multi_gpu.mirror_counts(m).tolist() == [[5, 1, 2], [1, 6, 3], [2, 3, 7]]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
