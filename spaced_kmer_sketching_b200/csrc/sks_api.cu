@@ -1255,11 +1255,54 @@ int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *co
     return SKS_OK;
   }
 
-  // SORTED: one launch over the whole pair list
-  const size_t tab_bytes = (size_t)na * 32, out_bytes = (size_t)na * 4;
+  // SORTED.  Runs of pairs that share their first set (the rows of an all-vs-all block) go to the kernel that
+  // keeps that set resident in shared memory; everything else to the merge kernel.  One pass over the pair
+  // tables either way.
+  const int kw = a[0]->key_words;
+  static const bool row_enabled = getenv("SKS_ROW_INTERSECT") ? atoi(getenv("SKS_ROW_INTERSECT")) != 0 : true;
+  bool one_mask = na < (int64_t)1 << 31;
+  for (int64_t i = 1; i < na && one_mask; ++i)
+    one_mask = a[i]->mask[0] == a[0]->mask[0] && a[i]->mask[1] == a[0]->mask[1];
+  int shift = 0;  // bucket of a key = its top 12 bits below the mask's highest bit
+  {
+    const uint64_t m0 = a[0]->mask[0], m1 = a[0]->mask[1];
+    const int top = m1 ? 127 - __builtin_clzll(m1) : (m0 ? 63 - __builtin_clzll(m0) : 0);
+    shift = std::max(top + 1 - 12, 0);
+  }
+  const int64_t row_cap = row_intersect_capacity(kw);
+  std::vector<RowTaskHost> tasks;
+  std::vector<uint32_t> rest;
+  {
+    int64_t row_pairs = 0;
+    std::vector<std::pair<int64_t, int64_t>> runs;
+    for (int64_t i = 0; i < na;) {
+      int64_t j = i + 1;
+      while (j < na && a[j] == a[i]) ++j;
+      if (row_enabled && one_mask && j - i >= 4 && a[i]->count > 0 && a[i]->count <= row_cap) {
+        runs.emplace_back(i, j);
+        row_pairs += j - i;
+      } else {
+        for (int64_t k = i; k < j; ++k) rest.push_back((uint32_t)k);
+      }
+      i = j;
+    }
+    const int64_t per_task = row_pairs > (int64_t)ctx->sm_count * 32 * 4 ? 32 : 16;  // columns per CTA
+    for (auto &run : runs)
+      for (int64_t c = run.first; c < run.second; c += per_task) {
+        RowTaskHost t;
+        t.a = static_cast<const char *>(a[run.first]->buf->ptr) + a[run.first]->byte_off;
+        t.n_a = (uint32_t)a[run.first]->count;
+        t.first = (uint32_t)c;
+        t.n_cols = (uint32_t)std::min<int64_t>(per_task, run.second - c);
+        t.pad = 0;
+        tasks.push_back(t);
+      }
+  }
+  const size_t tab_bytes = (size_t)na * 32, out_bytes = ((size_t)na * 4 + 15) & ~(size_t)15;
+  const size_t task_bytes = tasks.size() * sizeof(RowTaskHost), rest_bytes = rest.size() * 4;
   char *d_tab = nullptr, *h_tab = nullptr;
-  SKS_TRY(ctx_scratch(ctx, tab_bytes + out_bytes, reinterpret_cast<void **>(&d_tab)));
-  SKS_TRY(ctx_pinned(ctx, tab_bytes + out_bytes, reinterpret_cast<void **>(&h_tab)));
+  SKS_TRY(ctx_scratch(ctx, tab_bytes + out_bytes + task_bytes + rest_bytes, reinterpret_cast<void **>(&d_tab)));
+  SKS_TRY(ctx_pinned(ctx, tab_bytes + out_bytes + task_bytes + rest_bytes, reinterpret_cast<void **>(&h_tab)));
   const void **h_pa = reinterpret_cast<const void **>(h_tab);
   const void **h_pb = h_pa + na;
   int64_t *h_na = reinterpret_cast<int64_t *>(h_pb + na), *h_nb = h_na + na;
@@ -1269,15 +1312,29 @@ int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *co
     h_na[i] = a[i]->count;
     h_nb[i] = b[i]->count;
   }
+  // layout (host and device): tables | out | tasks | rest
+  if (task_bytes) memcpy(h_tab + tab_bytes + out_bytes, tasks.data(), task_bytes);
+  if (rest_bytes) memcpy(h_tab + tab_bytes + out_bytes + task_bytes, rest.data(), rest_bytes);
   SKS_CUDA_TRY(cudaMemcpyAsync(d_tab, h_tab, tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (task_bytes + rest_bytes)
+    SKS_CUDA_TRY(cudaMemcpyAsync(d_tab + tab_bytes + out_bytes, h_tab + tab_bytes + out_bytes, task_bytes + rest_bytes,
+                                 cudaMemcpyHostToDevice, ctx->stream));
   const void **d_pa = reinterpret_cast<const void **>(d_tab);
   const void **d_pb = d_pa + na;
   int64_t *d_na = reinterpret_cast<int64_t *>(d_pb + na), *d_nb = d_na + na;
   int32_t *d_out = reinterpret_cast<int32_t *>(d_tab + tab_bytes);
-  SKS_TRY(launch_sorted_intersect_pairs(ctx, a[0]->key_words, d_pa, d_na, d_pb, d_nb, na, d_out));
-  SKS_CUDA_TRY(cudaMemcpyAsync(h_tab + tab_bytes, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!tasks.empty()) {
+    SKS_CUDA_TRY(cudaMemsetAsync(d_out, 0, out_bytes, ctx->stream));  // the row kernel adds partial counts
+    SKS_TRY(launch_row_intersect(ctx, kw, d_tab + tab_bytes + out_bytes, (int64_t)tasks.size(), d_pb, d_nb, d_out, shift));
+  }
+  if (rest.size() == (size_t)na)
+    SKS_TRY(launch_sorted_intersect_pairs(ctx, kw, d_pa, d_na, d_pb, d_nb, na, d_out));
+  else if (!rest.empty())
+    SKS_TRY(launch_sorted_intersect_pairs(ctx, kw, d_pa, d_na, d_pb, d_nb, (int64_t)rest.size(), d_out,
+                                          reinterpret_cast<const uint32_t *>(d_tab + tab_bytes + out_bytes + task_bytes)));
+  SKS_CUDA_TRY(cudaMemcpyAsync(h_tab + tab_bytes, d_out, (size_t)na * 4, cudaMemcpyDeviceToHost, ctx->stream));
   SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  memcpy(out, h_tab + tab_bytes, out_bytes);
+  memcpy(out, h_tab + tab_bytes, (size_t)na * 4);
   return SKS_OK;
 }
 

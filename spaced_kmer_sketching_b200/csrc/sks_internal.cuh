@@ -230,7 +230,16 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
                         int n_regions, uint64_t span, BufferRef *out_buf, std::vector<uint64_t> *out_off,
                         std::vector<uint64_t> *out_count);
 int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const *d_a, const int64_t *d_na,
-                                  const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out);
+                                  const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out,
+                                  const uint32_t *d_pair_idx = nullptr);
+// Row-resident variant: tasks (RowTask, 24 bytes: a, n_a, first, n_cols, pad) over the same pair tables.
+struct RowTaskHost {
+  const void *a;
+  uint32_t n_a, first, n_cols, pad;
+};
+int64_t row_intersect_capacity(int key_words);
+int launch_row_intersect(sks_ctx *ctx, int key_words, const void *d_tasks, int64_t n_tasks, const void *const *d_b,
+                         const int64_t *d_nb, int32_t *d_out, int shift);
 
 int launch_list_finalize(sks_ctx *ctx, const uint32_t *words, const uint32_t *seg_end, uint32_t n_segs, int window,
                          int key_words, const void *raw_keys, const uint32_t *raw_pos, uint32_t n,

@@ -655,9 +655,9 @@ template <int KW>
 __global__ void __launch_bounds__(kIntersectThreads)
     sorted_intersect_kernel(const void *const *__restrict__ pa, const long long *__restrict__ na,
                             const void *const *__restrict__ pb, const long long *__restrict__ nb,
-                            int32_t *__restrict__ out) {
+                            int32_t *__restrict__ out, const uint32_t *__restrict__ pair_idx) {
   using K = WarpKey<KW>;
-  const long long pair = blockIdx.x;
+  const long long pair = pair_idx ? (long long)pair_idx[blockIdx.x] : (long long)blockIdx.x;
   const unsigned long long *A = static_cast<const unsigned long long *>(pa[pair]);
   const unsigned long long *B = static_cast<const unsigned long long *>(pb[pair]);
   long long nA = na[pair], nB = nb[pair];
@@ -1065,23 +1065,237 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
 }
 
 int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const *d_a, const int64_t *d_na,
-                                  const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out) {
+                                  const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out,
+                                  const uint32_t *d_pair_idx) {
   if (n_pairs == 0) return SKS_OK;
   KernelTimer timer(ctx, SKS_KERNEL_INTERSECT);
   for (int64_t done = 0; done < n_pairs;) {
     const int64_t chunk = std::min<int64_t>(n_pairs - done, 1 << 30);
+    const uint32_t *idx = d_pair_idx ? d_pair_idx + done : nullptr;
+    const int64_t base = d_pair_idx ? 0 : done;  // with an index list the tables are addressed through it
     if (key_words == 1)
       sorted_intersect_kernel<1><<<(unsigned)chunk, kIntersectThreads, 0, ctx->stream>>>(
-          d_a + done, reinterpret_cast<const long long *>(d_na + done), d_b + done,
-          reinterpret_cast<const long long *>(d_nb + done), d_out + done);
+          d_a + base, reinterpret_cast<const long long *>(d_na + base), d_b + base,
+          reinterpret_cast<const long long *>(d_nb + base), d_out + base, idx);
     else
       sorted_intersect_kernel<2><<<(unsigned)chunk, kIntersectThreads, 0, ctx->stream>>>(
-          d_a + done, reinterpret_cast<const long long *>(d_na + done), d_b + done,
-          reinterpret_cast<const long long *>(d_nb + done), d_out + done);
+          d_a + base, reinterpret_cast<const long long *>(d_na + base), d_b + base,
+          reinterpret_cast<const long long *>(d_nb + base), d_out + base, idx);
     SKS_CUDA_TRY(cudaGetLastError());
     ctx->launches++;
     done += chunk;
   }
+  return SKS_OK;
+}
+
+// ---- sorted-set intersection with the row set resident in shared memory ------------------------------
+// All-vs-all compares one set against many.  A 1024-thread CTA loads the row set A (up to ~26 k 8-byte keys)
+// into shared memory once, indexes it by the top 12 bits of the key (bucket starts), and then every warp
+// takes one column set B at a time: its lanes stream B's keys from L2 (8 independent loads in flight per lane)
+// and look each one up in A's bucket (a handful of LDS.64 instead of a merge step).  |A n B| is the number of
+// hits.  Pairs whose row set does not fit, or rows with too few columns to pay for the load, go through
+// sorted_intersect_kernel.
+constexpr int kRowThreads = 1024;
+constexpr int kRowWarps = kRowThreads / 32;
+constexpr int kRowTableBits = 12;
+constexpr int kRowBuckets = 1 << kRowTableBits;
+constexpr int kRowSmemBytes = 225 * 1024;
+constexpr int kRowUnroll = 8;
+
+template <int KW>
+struct RowKey;
+template <>
+struct RowKey<1> {
+  unsigned long long v;
+  __device__ __forceinline__ static RowKey load(const unsigned long long *p, uint32_t i) { return {p[i]}; }
+  __device__ __forceinline__ uint32_t bucket(int shift) const {
+    const unsigned long long b = v >> shift;
+    return b < (unsigned long long)kRowBuckets ? (uint32_t)b : (uint32_t)kRowBuckets - 1;
+  }
+  __device__ __forceinline__ bool eq(const RowKey &o) const { return v == o.v; }
+  __device__ __forceinline__ bool lt(const RowKey &o) const { return v < o.v; }
+};
+template <>
+struct RowKey<2> {
+  unsigned long long lo, hi;
+  __device__ __forceinline__ static RowKey load(const unsigned long long *p, uint32_t i) { return {p[2 * i], p[2 * i + 1]}; }
+  __device__ __forceinline__ uint32_t bucket(int shift) const {
+    unsigned long long b;
+    if (shift >= 64) b = hi >> (shift - 64);
+    else if (shift == 0) b = hi ? ~0ull : lo;
+    else b = (hi >> shift) ? ~0ull : ((hi << (64 - shift)) | (lo >> shift));
+    return b < (unsigned long long)kRowBuckets ? (uint32_t)b : (uint32_t)kRowBuckets - 1;
+  }
+  __device__ __forceinline__ bool eq(const RowKey &o) const { return lo == o.lo && hi == o.hi; }
+  __device__ __forceinline__ bool lt(const RowKey &o) const { return hi != o.hi ? hi < o.hi : lo < o.lo; }
+};
+
+struct RowTask {
+  const void *a;
+  uint32_t n_a;
+  uint32_t first;   // the task's columns are the pairs [first, first + n_cols) of the pair tables
+  uint32_t n_cols;
+  uint32_t pad;
+};
+
+template <int KW>
+__global__ void __launch_bounds__(kRowThreads, 1)
+    row_intersect_wide_kernel(const RowTask *__restrict__ tasks, const void *const *__restrict__ pb,
+                         const long long *__restrict__ nb, int32_t *__restrict__ out, int shift) {
+  using K = RowKey<KW>;
+  extern __shared__ __align__(16) unsigned long long s_row[];
+  const RowTask t = tasks[blockIdx.x];
+  uint32_t *s_start = reinterpret_cast<uint32_t *>(s_row + (size_t)t.n_a * KW);  // [kRowBuckets + 1]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    const unsigned long long *A = static_cast<const unsigned long long *>(t.a);
+    for (uint32_t i = tid; i < t.n_a * KW; i += kRowThreads) s_row[i] = __ldg(A + i);
+  }
+  __syncthreads();
+  // bucket starts: s_start[b] = first index whose bucket is >= b
+  for (uint32_t i = tid; i <= t.n_a; i += kRowThreads) {
+    const uint32_t bi = i < t.n_a ? K::load(s_row, i).bucket(shift) : (uint32_t)kRowBuckets;
+    const uint32_t bp = i > 0 ? K::load(s_row, i - 1).bucket(shift) + 1 : 0u;
+    for (uint32_t b = bp; b <= bi; ++b) s_start[b] = i;
+  }
+  __syncthreads();
+
+  auto hit = [&](const K &k) -> uint32_t {
+    const uint32_t b = k.bucket(shift);
+    uint32_t lo = s_start[b], hi = s_start[b + 1];
+    while (hi - lo > 4) {  // a crowded bucket: halve [lo, hi), which keeps containing k's position if k is in A
+      const uint32_t mid = (lo + hi) >> 1;
+      if (K::load(s_row, mid).lt(k)) lo = mid + 1; else hi = mid + 1;
+    }
+    uint32_t f = 0;
+    for (uint32_t p = lo; p < hi; ++p) f |= K::load(s_row, p).eq(k) ? 1u : 0u;
+    return f;
+  };
+
+  // a unit = (column, part of its keys); with fewer than 32 columns several warps share one
+  const uint32_t parts = t.n_cols >= (uint32_t)kRowWarps ? 1u : (uint32_t)kRowWarps / t.n_cols;
+  for (uint32_t unit = warp; unit < t.n_cols * parts; unit += kRowWarps) {
+    const uint32_t col = unit % t.n_cols, part = unit / t.n_cols;
+    const unsigned long long *B = static_cast<const unsigned long long *>(pb[t.first + col]);
+    const uint32_t n_b = (uint32_t)nb[t.first + col];
+    const uint32_t per = ((n_b + parts - 1) / parts + 31) & ~31u;
+    const uint32_t begin = part * per, end = begin + per < n_b ? begin + per : n_b;
+    uint32_t cnt = 0;
+    uint32_t i = begin + lane;
+    for (; i + 32 * (kRowUnroll - 1) < end; i += 32 * kRowUnroll) {
+      K k[kRowUnroll];
+#pragma unroll
+      for (int u = 0; u < kRowUnroll; ++u) k[u] = K::load(B, i + 32 * u);
+#pragma unroll
+      for (int u = 0; u < kRowUnroll; ++u) cnt += hit(k[u]);
+    }
+    for (; i < end; i += 32) cnt += hit(K::load(B, i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if (lane == 0 && cnt) atomicAdd(out + t.first + col, (int32_t)cnt);
+  }
+}
+
+// 8-byte keys: the row set is stored as two 32-bit planes -- the 32 bits right below the bucket bits (sorted
+// inside a bucket, so it can be binary searched) and the remaining low bits (compared on a match).  Random 4-byte
+// shared-memory reads collide in the banks about half as often as 8-byte ones, the bucket entry is one word
+// (start | length << 16), and a lookup costs ~6 LDS.32 instead of a divergent scan of ~10 LDS.64.
+__global__ void __launch_bounds__(kRowThreads, 1)
+    row_intersect_kernel(const RowTask *__restrict__ tasks, const void *const *__restrict__ pb,
+                         const long long *__restrict__ nb, int32_t *__restrict__ out, int shift) {
+  extern __shared__ __align__(16) uint32_t s_u32[];
+  const RowTask t = tasks[blockIdx.x];
+  uint32_t *s_hi = s_u32;                // [n_a] bits [shift-1 .. pshift] of the key
+  uint32_t *s_lo = s_u32 + t.n_a;        // [n_a] bits [pshift-1 .. 0]
+  uint32_t *s_tab = s_lo + t.n_a;        // [kRowBuckets] start | length << 16
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int pshift = shift > 32 ? shift - 32 : 0;
+  const unsigned long long rem_mask = shift >= 64 ? ~0ull : ((1ull << shift) - 1);
+  const uint32_t lo_mask = pshift ? (1u << pshift) - 1 : 0u;  // pshift <= 20
+  auto bucket_of = [&](unsigned long long k) -> uint32_t {
+    const unsigned long long b = shift >= 64 ? 0ull : k >> shift;
+    return b < (unsigned long long)kRowBuckets ? (uint32_t)b : (uint32_t)kRowBuckets - 1;
+  };
+  const unsigned long long *A = static_cast<const unsigned long long *>(t.a);
+  for (uint32_t i = tid; i < (uint32_t)kRowBuckets; i += kRowThreads) s_tab[i] = 0;
+  __syncthreads();
+  for (uint32_t i = tid; i < t.n_a; i += kRowThreads) {
+    const unsigned long long k = __ldg(A + i);
+    const unsigned long long rem = k & rem_mask;
+    s_hi[i] = (uint32_t)(rem >> pshift);
+    s_lo[i] = (uint32_t)rem & lo_mask;
+    // bucket entry: the first key of the bucket writes the start, every key adds 1 to the length
+    const uint32_t b = bucket_of(k);
+    const bool first = i == 0 || bucket_of(__ldg(A + i - 1)) != b;
+    atomicAdd(&s_tab[b], (1u << 16) | (first ? i : 0u));
+  }
+  __syncthreads();
+
+  auto hit = [&](unsigned long long k) -> uint32_t {
+    const uint32_t e = s_tab[bucket_of(k)];
+    uint32_t lo = e & 0xFFFFu, n = e >> 16;
+    const unsigned long long rem = k & rem_mask;
+    const uint32_t kh = (uint32_t)(rem >> pshift), kl = (uint32_t)rem & lo_mask;
+    while (n > 0) {  // lower bound of kh in the bucket's s_hi range
+      const uint32_t half = n >> 1;
+      if (s_hi[lo + half] < kh) {
+        lo += half + 1;
+        n -= half + 1;
+      } else {
+        n = half;
+      }
+    }
+    const uint32_t end = (e & 0xFFFFu) + (e >> 16);
+    uint32_t f = 0;
+    for (; lo < end && s_hi[lo] == kh; ++lo) f |= s_lo[lo] == kl ? 1u : 0u;
+    return f;
+  };
+
+  const uint32_t parts = t.n_cols >= (uint32_t)kRowWarps ? 1u : (uint32_t)kRowWarps / t.n_cols;
+  for (uint32_t unit = warp; unit < t.n_cols * parts; unit += kRowWarps) {
+    const uint32_t col = unit % t.n_cols, part = unit / t.n_cols;
+    const unsigned long long *B = static_cast<const unsigned long long *>(pb[t.first + col]);
+    const uint32_t n_b = (uint32_t)nb[t.first + col];
+    const uint32_t per = ((n_b + parts - 1) / parts + 31) & ~31u;
+    const uint32_t begin = part * per, end = begin + per < n_b ? begin + per : n_b;
+    uint32_t cnt = 0;
+    uint32_t i = begin + lane;
+    for (; i + 32 * (kRowUnroll - 1) < end; i += 32 * kRowUnroll) {
+      unsigned long long k[kRowUnroll];
+#pragma unroll
+      for (int u = 0; u < kRowUnroll; ++u) k[u] = __ldg(B + i + 32 * u);
+#pragma unroll
+      for (int u = 0; u < kRowUnroll; ++u) cnt += hit(k[u]);
+    }
+    for (; i < end; i += 32) cnt += hit(__ldg(B + i));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if (lane == 0 && cnt) atomicAdd(out + t.first + col, (int32_t)cnt);
+  }
+}
+
+// Largest row set (in keys) the resident kernel takes.
+int64_t row_intersect_capacity(int key_words) {
+  const int64_t cap = ((int64_t)kRowSmemBytes - (kRowBuckets + 1) * 4 - 64) / (8 * key_words);
+  return key_words == 1 ? std::min<int64_t>(cap, 65535) : cap;  // 16-bit starts and lengths in the bucket entries
+}
+
+int launch_row_intersect(sks_ctx *ctx, int key_words, const void *d_tasks, int64_t n_tasks, const void *const *d_b,
+                         const int64_t *d_nb, int32_t *d_out, int shift) {
+  if (n_tasks == 0) return SKS_OK;
+  KernelTimer timer(ctx, SKS_KERNEL_INTERSECT);
+  const RowTask *tasks = static_cast<const RowTask *>(d_tasks);
+  if (key_words == 1) {
+    SKS_CUDA_TRY(cudaFuncSetAttribute(row_intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
+    row_intersect_kernel<<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(
+        tasks, d_b, reinterpret_cast<const long long *>(d_nb), d_out, shift);
+  } else {
+    SKS_CUDA_TRY(cudaFuncSetAttribute(row_intersect_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
+    row_intersect_wide_kernel<2><<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(
+        tasks, d_b, reinterpret_cast<const long long *>(d_nb), d_out, shift);
+  }
+  SKS_CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
   return SKS_OK;
 }
 

@@ -233,6 +233,44 @@ def test_multi_golden(ctx):
             assert np.array_equal(multi_gpu.mirror_counts(full), ints), world
 
 
+def test_all_pairs_row_resident_and_merge_paths(ctx):
+    """All-vs-all through the row-resident intersection kernel (row set in shared memory, bucket index on the top
+    key bits), incl. 16-byte keys, a row too large to be resident (merge kernel), empty sets, tiny key ranges."""
+    rng = np.random.default_rng(21)
+    base = rng.integers(0, 4, 20000, dtype=np.uint8)
+    genomes = [base]
+    for d in (500, 100, 40, 15, 7, 3):
+        g = base.copy()
+        idx = rng.integers(0, len(g), len(g) // d)
+        g[idx] = (g[idx] + rng.integers(1, 4, len(idx))) & 3
+        genomes.append(g)
+    genomes.append(rng.integers(0, 4, 45000, dtype=np.uint8))      # more keys than the resident kernel holds
+    genomes.append(rng.integers(0, 4, 12, dtype=np.uint8))         # shorter than most windows: empty set
+    genomes.append(np.zeros(5000, dtype=np.uint8))                 # poly-A: one key
+    batch = ctx.upload_codes(genomes)
+    n = len(genomes)
+    for seed, pred in (("0011111011010111111011001011101", sks.all_kmers()),
+                       ("0011111011010111111011001011101", sks.frac_min_hash(1, 3)),
+                       ("1110110111011011101101110110111011011101", sks.all_kmers()),     # window 40: 16-byte keys
+                       ("11001011", sks.all_kmers()),                                      # 16-bit keys
+                       ("1", sks.all_kmers())):
+        mask, w = sks.seed_to_mask(seed)
+        sets = ctx.sketch(batch, mask, w, pred, sks.REPR_SORTED)
+        osets = [port.sketch_set(g, [len(g)], mask, w, *opred(pred)) for g in genomes]
+        want = np.array([[port.intersection(a, b) for b in osets] for a in osets], dtype=np.int32)
+        got = ctx.intersect_all_pairs(sets)
+        assert np.array_equal(got, want), seed
+        # rectangles, as the multi-GPU tiling issues them
+        part = np.full((n, n), -1, dtype=np.int32)
+        ctx.intersect_block(sets, (2, 7), (0, n), part)
+        ctx.intersect_block(sets, (7, n), (1, 6), part)
+        assert np.array_equal(part[2:7], want[2:7]) and np.array_equal(part[7:, 1:6], want[7:, 1:6])
+        assert (part[:2] == -1).all() and (part[7:, 6:] == -1).all()
+        for x in sets:
+            x.close()
+    batch.close()
+
+
 def test_synth_matches_oracle_generator(ctx):
     batch = ctx.synth(100_003, [42, 42, 9], [0, 43, 5], [0, 100, 3])
     A = port.gen(100_003, 42)
