@@ -85,6 +85,12 @@ def mirror_counts(counts: np.ndarray) -> np.ndarray:
     return np.where(counts < 0, counts.T, counts)
 
 
+def mirror_rows(counts: np.ndarray, rows: Tuple[int, int]) -> np.ndarray:
+    """The block rows [rows) of the mirrored matrix only (what one rank needs for the ANI of its own rows)."""
+    block = counts[rows[0]:rows[1]]
+    return np.where(block < 0, counts[:, rows[0]:rows[1]].T, block)
+
+
 def allgather_varlen_many(locals_, world: int, dist=None):
     """All-gather of several 1-D tensors of rank-dependent lengths with ONE host synchronisation: a small
     all-gather of all the lengths, then one padded all-gather per tensor.  Returns, per input tensor, the list
