@@ -14,12 +14,12 @@
 
 namespace sks {
 
-// Large blocks (bitsets, index regions, key buffers) are recycled by exact size per (device, stream) instead
+// Device blocks (bitsets, index regions, key buffers, control blocks) are recycled by exact size per (device, stream) instead
 // of going back to the stream-ordered pool: after a mix of small and large requests the pool satisfies a
 // 1 GiB cudaMallocAsync by remapping physical chunks, which was measured at 2-85 ms per call.  Reuse on the
 // same stream is safe by stream order.  The cache of a stream is dropped when its context goes away.
 namespace {
-constexpr size_t kCacheMinBytes = (size_t)1 << 20;
+constexpr size_t kCacheMinBytes = 0;  // every size: the same few sizes recur call after call
 constexpr size_t kCacheMaxBytes = (size_t)12 << 30;
 struct BlockKey {
   int device;
@@ -358,28 +358,30 @@ int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
   if (fuse && G != 2) fuse = nullptr;
   int64_t known_count[2] = {-1, -1};
   if (bucketed) {
-    // per-genome popcounts; the pair pipeline appends |A n B| and the overflow flag so that one 32-byte copy
-    // brings everything back
-    SKS_TRY(alloc_buffer(ctx, sizeof(unsigned long long) * ((size_t)G + 2), &count_buf));
+    // One control block, zeroed by one memset: per-genome popcounts | |A n B| (pair pipeline) | overflow flag |
+    // work-queue counter | per-(genome, bucket) cursors.  The sets keep it alive for their sizes; one 32-byte
+    // copy brings counts and flag back.
+    const PartGeometry geo = part_geometry(index_bits);
+    const size_t ctl_head = (sizeof(unsigned long long) * ((size_t)G + 2) + 63) & ~(size_t)63;
+    const size_t ctl_bytes = ctl_head + 64 + 4 * (size_t)geo.n_parts * G;
+    SKS_TRY(alloc_buffer(ctx, ctl_bytes, &count_buf));
     unsigned long long *d_set_count = static_cast<unsigned long long *>(count_buf->ptr);
+    uint32_t *d_overflow = reinterpret_cast<uint32_t *>(d_set_count + G + 1);
+    unsigned int *d_work = reinterpret_cast<unsigned int *>(static_cast<char *>(count_buf->ptr) + ctl_head);
+    uint32_t *d_cursor = reinterpret_cast<uint32_t *>(static_cast<char *>(count_buf->ptr) + ctl_head + 64);
     // Fast path: the sketch kernel scatters the PEXT indices straight into fixed per-(genome, bucket) regions
     // sized at 4x the mean bucket load (K2/K3/K4a fused), then the slices are assembled (K4b).  A genome whose
     // index distribution overflows a region (heavy skew) is detected by a flag and redone through the exact
     // counting partition below.
-    const PartGeometry geo = part_geometry(index_bits);
     uint64_t max_windows = 0;
     for (int g = 0; g < G; ++g) max_windows = std::max(max_windows, genome_windows(batch, g, window));
     const uint64_t cap = 4 * ((max_windows + geo.n_parts - 1) / geo.n_parts) + 1024;
     const uint64_t slots = cap * geo.n_parts * (uint64_t)G;
     bool done = false;
-    if (!ctx->exact_partition && slots < (1ull << 32) && slots * 4 <= (8ull << 30)) {
-      BufferRef regions, tabs;
+    if (!ctx->exact_partition && cap < (1ull << 32) && slots * 4 <= (16ull << 30)) {
+      BufferRef regions;
       SKS_TRY(alloc_buffer(ctx, (size_t)slots * 4, &regions));
-      SKS_TRY(alloc_buffer(ctx, 4 * (size_t)geo.n_parts * G + 64, &tabs));
-      uint32_t *d_cursor = static_cast<uint32_t *>(tabs->ptr);
-      uint32_t *d_overflow = reinterpret_cast<uint32_t *>(d_set_count + G + 1);
-      SKS_TRY(launch_region_starts(ctx, d_cursor, geo.n_parts * (uint32_t)G, (uint32_t)cap));
-      SKS_CUDA_TRY(cudaMemsetAsync(d_overflow, 0, 8, ctx->stream));
+      SKS_CUDA_TRY(cudaMemsetAsync(count_buf->ptr, 0, ctl_bytes, ctx->stream));
       plan.p.out_keys = regions->ptr;
       plan.p.part_cursor = d_cursor;
       plan.p.part_overflow = d_overflow;
@@ -390,7 +392,7 @@ int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
       unsigned long long *h_back = nullptr;
       SKS_TRY(ctx_pinned(ctx, 64, reinterpret_cast<void **>(&h_back)));
       if (fuse) {
-        // K4b + K5 fused: both genomes' slices side by side in shared memory, counted while they stream out
+        // K4b + K5 fused: both genomes' slices side by side in shared memory, counted while they are assembled
         uint32_t *ba = nullptr, *bb = nullptr;
         if (fuse->store) {
           SKS_TRY(alloc_buffer(ctx, (size_t)words * 4 * G, &buf));
@@ -398,7 +400,7 @@ int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
           bb = ba + words;
         }
         SKS_TRY(launch_bitset_pair_build(ctx, static_cast<const uint32_t *>(regions->ptr), d_cursor, (uint32_t)cap, index_bits,
-                                         ba, bb, d_set_count));
+                                         ba, bb, d_set_count, d_work));
         SKS_CUDA_TRY(cudaMemcpyAsync(h_back, d_set_count, 32, cudaMemcpyDeviceToHost, ctx->stream));
         SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         done = (uint32_t)h_back[3] == 0;
@@ -412,7 +414,7 @@ int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
       } else {
         SKS_TRY(alloc_buffer(ctx, (size_t)words * 4 * G, &buf));
         SKS_TRY(launch_bitset_assemble(ctx, static_cast<const uint32_t *>(regions->ptr), d_cursor, (uint32_t)cap, G, index_bits,
-                                       static_cast<uint32_t *>(buf->ptr), words, d_set_count));
+                                       static_cast<uint32_t *>(buf->ptr), words, d_set_count, d_work));
         SKS_CUDA_TRY(cudaMemcpyAsync(h_back, d_overflow, 8, cudaMemcpyDeviceToHost, ctx->stream));
         SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         done = (uint32_t)h_back[0] == 0;

@@ -114,7 +114,7 @@ struct SketchParams {
   const uint64_t *out_cap;              // [n_genomes] slots in the region
   unsigned long long *out_count;        // [n_genomes] kept k-mers (keeps counting past out_cap)
   // OUT_PART: PEXT indices scattered straight into per-(genome, bucket) regions of part_cap slots each
-  // (out_keys = region buffer); part_cursor[genome * n_parts + bucket] starts at the region's first slot
+  // (out_keys = region buffer); part_cursor[genome * n_parts + bucket] = slots used in the region, starts at 0
   uint32_t *part_cursor;
   uint32_t *part_overflow;     // set to 1 when a region was too small (the caller then takes the exact path)
   uint32_t n_parts;            // <= kMaxParts
@@ -220,11 +220,11 @@ int launch_bitset_pair_counts(sks_ctx *ctx, const uint32_t *a, const uint32_t *b
 int launch_bitset_build(sks_ctx *ctx, const uint32_t *raw_idx, uint32_t *sorted_idx, const uint64_t *h_off,
                         const uint64_t *h_count, int n_genomes, int index_bits, uint32_t *bitset, uint64_t bitset_words,
                         unsigned long long *d_set_count);
-int launch_region_starts(sks_ctx *ctx, uint32_t *d_cursor, uint32_t n, uint32_t cap);
 int launch_bitset_assemble(sks_ctx *ctx, const uint32_t *regions, const uint32_t *d_cursor, uint32_t part_cap, int n_genomes,
-                           int index_bits, uint32_t *bitset, uint64_t bitset_words, unsigned long long *d_set_count);
+                           int index_bits, uint32_t *bitset, uint64_t bitset_words, unsigned long long *d_set_count,
+                           unsigned int *d_work_counter);
 int launch_bitset_pair_build(sks_ctx *ctx, const uint32_t *regions, const uint32_t *d_cursor, uint32_t part_cap, int index_bits,
-                             uint32_t *bitset_a, uint32_t *bitset_b, unsigned long long *d_out3);
+                             uint32_t *bitset_a, uint32_t *bitset_b, unsigned long long *d_out3, unsigned int *d_work_counter);
 int launch_bitset_popcount(sks_ctx *ctx, const uint32_t *a, uint64_t n_words, unsigned long long *out1);
 int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t *h_off, const uint64_t *h_count,
                         int n_regions, uint64_t span, BufferRef *out_buf, std::vector<uint64_t> *out_off,

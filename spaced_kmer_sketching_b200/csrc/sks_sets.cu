@@ -298,10 +298,17 @@ __global__ void __launch_bounds__(kBuildThreads, 2)
       cur_genome = genome;
     }
     const BuildGenome g = genomes[genome];
-    const uint32_t lo = __ldg(g.starts + part);
-    uint32_t hi = __ldg(g.cursor + part);  // cursor = bucket end after the scatter
-    if (g.cap && hi > lo + g.cap) hi = lo + g.cap;  // an overflowed region (the caller redoes the genome exactly)
-    const uint32_t n = hi - lo;
+    size_t lo;
+    uint32_t n;
+    if (g.cap) {  // fixed regions filled by the sketch kernel: cursor = slots used (may exceed the region: overflow,
+                  // the caller then redoes the genome exactly)
+      lo = (size_t)part * g.cap;
+      n = __ldg(g.cursor + part);
+      if (n > g.cap) n = g.cap;
+    } else {      // counting partition: cursor = bucket end after the scatter
+      lo = __ldg(g.starts + part);
+      n = __ldg(g.cursor + part) - lo;
+    }
     const uint32_t *__restrict__ bk = g.bucketed + lo;
     const bool direct = n > kKeyCap;  // more indices than shared memory holds (heavily skewed genome)
     uint32_t n4 = 0;
@@ -420,11 +427,9 @@ __global__ void __launch_bounds__(kPairThreads, 1) bitset_pair_build_kernel(cons
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
       const uint32_t region = g * P.n_parts + part;
-      const uint32_t lo = region * P.cap;
-      uint32_t hi = __ldg(P.cursor + region);
-      if (hi > lo + P.cap) hi = lo + P.cap;  // overflowed region: the caller redoes the pair exactly
-      n[g] = hi - lo;
-      bk[g] = P.regions + lo;
+      n[g] = __ldg(P.cursor + region);        // slots used in the region
+      if (n[g] > P.cap) n[g] = P.cap;          // overflowed region: the caller redoes the pair exactly
+      bk[g] = P.regions + (size_t)region * P.cap;
       direct[g] = n[g] > (uint32_t)kKeyCap;
       n4[g] = 0;
       if (!direct[g] && n[g] > 0) {
@@ -823,59 +828,36 @@ int launch_bitset_build(sks_ctx *ctx, const uint32_t *raw_idx, uint32_t *buckete
   return SKS_OK;
 }
 
-namespace {
-__global__ void region_starts_kernel(uint32_t *__restrict__ starts, uint32_t n, uint32_t cap) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) starts[i] = i * cap;
-}
-}  // namespace
-
-// Fills `cursor[0..n)` with the first slot of every (genome, bucket) region: region i = [i * cap, (i+1) * cap).
-int launch_region_starts(sks_ctx *ctx, uint32_t *d_cursor, uint32_t n, uint32_t cap) {
-  region_starts_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_cursor, n, cap);
-  SKS_CUDA_TRY(cudaGetLastError());
-  ctx->launches++;
-  return SKS_OK;
-}
-
 // The assemble half of the bucketed build when the sketch kernel (OUT_PART) has already scattered the PEXT
 // indices into fixed regions: region (g, b) = regions[(g * n_parts + b) * part_cap ...), filled up to
 // d_cursor[g * n_parts + b] (absolute slot).
 int launch_bitset_assemble(sks_ctx *ctx, const uint32_t *regions, const uint32_t *d_cursor, uint32_t part_cap, int n_genomes,
-                           int index_bits, uint32_t *bitset, uint64_t bitset_words, unsigned long long *d_set_count) {
+                           int index_bits, uint32_t *bitset, uint64_t bitset_words, unsigned long long *d_set_count,
+                           unsigned int *d_work_counter) {
   if (n_genomes == 0) return SKS_OK;
   const PartGeometry geo = part_geometry(index_bits);
-  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t sz_desc = align(sizeof(BuildGenome) * n_genomes);
-  const size_t sz_starts = align((size_t)geo.n_parts * n_genomes * 4);
-  char *base = nullptr;
-  SKS_TRY(ctx_scratch(ctx, sz_desc + sz_starts + 256, reinterpret_cast<void **>(&base)));
-  BuildGenome *d_desc = reinterpret_cast<BuildGenome *>(base);
-  uint32_t *d_starts = reinterpret_cast<uint32_t *>(base + sz_desc);
-  unsigned int *d_counter = reinterpret_cast<unsigned int *>(base + sz_desc + sz_starts);
-  BuildGenome *h_desc = nullptr;
+  BuildGenome *d_desc = nullptr, *h_desc = nullptr;
+  SKS_TRY(ctx_scratch(ctx, sizeof(BuildGenome) * n_genomes, reinterpret_cast<void **>(&d_desc)));
   SKS_TRY(ctx_pinned(ctx, sizeof(BuildGenome) * n_genomes, reinterpret_cast<void **>(&h_desc)));
   for (int g = 0; g < n_genomes; ++g) {
     h_desc[g].raw = nullptr;
-    h_desc[g].bucketed = const_cast<uint32_t *>(regions);
-    h_desc[g].starts = d_starts + (size_t)g * geo.n_parts;
+    h_desc[g].bucketed = const_cast<uint32_t *>(regions) + (size_t)g * geo.n_parts * part_cap;
+    h_desc[g].starts = nullptr;
     h_desc[g].cursor = const_cast<uint32_t *>(d_cursor) + (size_t)g * geo.n_parts;
     h_desc[g].bitset = bitset + (size_t)g * bitset_words;
     h_desc[g].set_count = d_set_count + g;
     h_desc[g].n = 0;
     h_desc[g].cap = part_cap;
   }
+  // d_set_count and d_work_counter were zeroed by the caller together with the cursors
   KernelTimer timer(ctx, SKS_KERNEL_BITSET_BUILD);
-  SKS_CUDA_TRY(cudaMemsetAsync(d_set_count, 0, sizeof(unsigned long long) * n_genomes, ctx->stream));
-  SKS_CUDA_TRY(cudaMemsetAsync(d_counter, 0, 256, ctx->stream));
   SKS_CUDA_TRY(cudaMemcpyAsync(d_desc, h_desc, sizeof(BuildGenome) * n_genomes, cudaMemcpyHostToDevice, ctx->stream));
-  SKS_TRY(launch_region_starts(ctx, d_starts, geo.n_parts * (uint32_t)n_genomes, part_cap));
   constexpr int smem = (kSliceWords + kKeyCap) * 4;
   SKS_CUDA_TRY(cudaFuncSetAttribute(bitset_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint64_t n_items = (uint64_t)n_genomes * geo.n_parts;
   const unsigned gx = (unsigned)std::min<uint64_t>(n_items, (uint64_t)ctx->sm_count * 2);
   bitset_build_kernel<<<gx, kBuildThreads, smem, ctx->stream>>>(d_desc, (uint32_t)n_genomes, geo.n_parts, geo.group_slices,
-                                                               d_counter);
+                                                               d_work_counter);
   SKS_CUDA_TRY(cudaGetLastError());
   ctx->launches++;
   return SKS_OK;
@@ -884,10 +866,8 @@ int launch_bitset_assemble(sks_ctx *ctx, const uint32_t *regions, const uint32_t
 // Fused K4b + K5 for a 2-genome batch whose indices the sketch kernel (OUT_PART) scattered into fixed regions.
 // bitset_a / bitset_b may both be NULL: the bitsets then never leave shared memory.  d_out3 = |A|, |B|, |A n B|.
 int launch_bitset_pair_build(sks_ctx *ctx, const uint32_t *regions, const uint32_t *d_cursor, uint32_t part_cap, int index_bits,
-                             uint32_t *bitset_a, uint32_t *bitset_b, unsigned long long *d_out3) {
+                             uint32_t *bitset_a, uint32_t *bitset_b, unsigned long long *d_out3, unsigned int *d_work_counter) {
   const PartGeometry geo = part_geometry(index_bits);
-  unsigned int *d_counter = nullptr;
-  SKS_TRY(ctx_scratch(ctx, 256, reinterpret_cast<void **>(&d_counter)));
   PairBuild p;
   p.regions = regions;
   p.cursor = d_cursor;
@@ -897,11 +877,9 @@ int launch_bitset_pair_build(sks_ctx *ctx, const uint32_t *regions, const uint32
   p.bitset[0] = bitset_a;
   p.bitset[1] = bitset_b;
   p.out3 = d_out3;
-  p.work_counter = d_counter;
+  p.work_counter = d_work_counter;  // zeroed by the caller together with d_out3 and the cursors
   const bool store = bitset_a != nullptr;
   KernelTimer timer(ctx, SKS_KERNEL_PAIR_BUILD);
-  SKS_CUDA_TRY(cudaMemsetAsync(d_out3, 0, 3 * sizeof(unsigned long long), ctx->stream));
-  SKS_CUDA_TRY(cudaMemsetAsync(d_counter, 0, 256, ctx->stream));
   const unsigned gx = std::min<unsigned>(geo.n_parts, (unsigned)ctx->sm_count);
   if (store) {
     SKS_CUDA_TRY(cudaFuncSetAttribute(bitset_pair_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));

@@ -399,8 +399,8 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
           if (r != 0xFFFFu) {
             const uint32_t idx = reinterpret_cast<uint32_t *>(s_keys)[j * kSketchThreads + tid];
             const uint32_t b = idx >> P.part_shift;
-            const uint32_t at = s_pbase[b] + r;
-            if (at < (region0 + b + 1) * P.part_cap) out[at] = idx;
+            const uint32_t at = s_pbase[b] + r;  // slot inside the (genome, bucket) region
+            if (at < P.part_cap) out[(size_t)(region0 + b) * P.part_cap + at] = idx;
             else *P.part_overflow = 1u;
           }
         }
