@@ -391,9 +391,24 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
     L3 = 250_000_000
     shard = multi_gpu.position_shard(L3, w3, rank, world)
     b3 = multi_gpu.synth_slice(ctx, L3, 7, shard, w3)
+    def c3_step():
+        """Local sketch of the rank's slice; for N > 1 the global set on every rank: all-gather of the partial
+        sketches' keys, sort + unique of the union (slices overlap by the halo only, duplicates are k-mers that
+        occur in two slices)."""
+        (loc,) = ctx.sketch(b3, mask3, w3, pred)
+        if world == 1:
+            return loc, loc
+        keys, _, kw = multi_gpu.keys_as_tensor([loc], torch)
+        parts = multi_gpu.allgather_varlen(keys, world, dist)
+        allk = torch.cat(parts)
+        glob = ctx.set_from_device_keys(allk.data_ptr(), allk.numel() // kw, kw, mask3, w3, sorted_unique=False)
+        return loc, glob
+
     for _ in range(2):
-        (s,) = ctx.sketch(b3, mask3, w3, pred)
-        s.close()
+        loc, glob = c3_step()
+        glob.close()
+        if world > 1:
+            loc.close()
     flush.zero_()
     barrier()
     ctx.profile(True)
@@ -402,7 +417,10 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
     reps = 5
     e0.record(stream)
     for _ in range(reps):
-        (s,) = ctx.sketch(b3, mask3, w3, pred)
+        s, glob = c3_step()
+        n_global = glob.kmer_set_size()
+        if world > 1:
+            glob.close()
         if _ != reps - 1:
             s.close()
     e1.record(stream)
@@ -413,13 +431,14 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
     n_local = s.kmer_set_size()
     sk_ms = ks["sketch_kernel"][1] / ks["sketch_kernel"][0]
     bases_local = shard[1] + w3 - 1
-    out["c3_sketch"] = {"workload": "250 Mbp sequence, seed " + C3_SEED + ", FMH(200, nonce 1, Boost>=1.81), position-sharded",
+    out["c3_sketch"] = {"workload": "250 Mbp sequence, seed " + C3_SEED + ", FMH(200, nonce 1, Boost>=1.81), position-sharded, global set on every rank",
                         "bases_per_s": L3 / (ms / 1e3), "ms": ms, "scaling": "strong",
                         "sketch_kernel_ms": sk_ms,
                         "sketch_kernel_gbs": bases_local * (0.25 + 8.0 / 200) / (sk_ms * 1e-3) / 1e9,
                         "sketch_kernel_frac_of_hbm": bases_local * (0.25 + 8.0 / 200) / (sk_ms * 1e-3) / 1e9 / peak,
                         "sketch_kernel_bases_per_s": bases_local / (sk_ms * 1e-3),
-                        "local_sketch_size": int(n_local)}
+                        "local_sketch_size": int(n_local), "global_sketch_size": int(n_global),
+                        "includes": "local sketch" + (" + NCCL all-gather of the partial sketches + sort-unique of the union on every rank" if world > 1 else "")}
     s.close()
     b3.close()
 
