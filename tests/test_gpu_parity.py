@@ -441,6 +441,41 @@ def test_c3_chromosome_scale(ctx):
     assert len(osub) > 4000 and np.isin(osub[:, 0], keys[:, 0]).all()
 
 
+def test_c4_all_vs_all_at_genome_size(ctx):
+    """BASELINE.json configs[3] in small: 24 graded mutants of one 5 Mbp genome, weight-21 span-31 seed, FMH(200):
+    the n^2 intersection counts (row-resident and merge kernels) against numpy set intersections of the key
+    arrays, two sketches against the oracle, and the rank tiling of the multi-GPU path."""
+    from spaced_kmer_sketching_b200 import multi_gpu
+    L, n = 5_000_000, 24
+    Ds = [[0, 1000, 200, 100, 50, 20][g % 6] for g in range(n)]
+    batch = ctx.synth(L, [1000] * n, [2000 + g for g in range(n)], Ds)
+    mask, w = sks.seed_to_mask(C3_SEED)
+    pred = sks.frac_min_hash(1, 200)
+    sets = ctx.sketch(batch, mask, w, pred)
+    keys = [s.keys()[:, 0] for s in sets]
+    assert all(abs(len(k) - L / 200) < 1500 and (k[1:] > k[:-1]).all() for k in keys)
+    base = port.gen(L, 1000)
+    for g in (0, 5):
+        codes = base if Ds[g] == 0 else port.mutate(base, 2000 + g, Ds[g])
+        assert np.array_equal(keys[g], port.sketch_set(codes, [L], mask, w, port.FMH, 1, 200, 181)[:, 0]), g
+    want = np.array([[len(np.intersect1d(a, b, assume_unique=True)) for b in keys] for a in keys], dtype=np.int32)
+    assert np.array_equal(ctx.intersect_all_pairs(sets), want)
+    full = np.full((n, n), -1, dtype=np.int32)
+    for r in range(4):
+        rows = multi_gpu.row_tile(n, r, 4)
+        full[rows[0]:rows[1]] = multi_gpu.tiled_counts(ctx, sets, r, 4)[rows[0]:rows[1]]
+    assert np.array_equal(multi_gpu.mirror_counts(full), want)
+    # containment on the FIRST set of the ordered pair (src/kmer-sketching.cpp:198): the matrix is not symmetric
+    sizes = np.array([len(k) for k in keys], dtype=np.int32)
+    ani = sks.ani_from_counts(want.ravel(), np.repeat(sizes, n), sks.mask_weight(mask)).reshape(n, n)
+    for g in range(1, n):
+        if Ds[g]:
+            assert abs(ani[0, g] - (1.0 - 1.0 / Ds[g])) < 0.002, (g, ani[0, g])
+    for x in sets:
+        x.close()
+    batch.close()
+
+
 def test_c5_multi_seed_sweep_ani_error(ctx):
     """BASELINE.json configs[4] in small: several (k+10, k) random seed masks over graded mutants of one base
     genome; the sketches match the oracle and the estimated ANI tracks the true substitution rate."""
