@@ -1271,22 +1271,17 @@ int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *co
   bool one_mask = na < (int64_t)1 << 31;
   for (int64_t i = 1; i < na && one_mask; ++i)
     one_mask = a[i]->mask[0] == a[0]->mask[0] && a[i]->mask[1] == a[0]->mask[1];
-  int shift = 0;  // bucket of a key = its top 12 bits below the mask's highest bit
-  {
-    const uint64_t m0 = a[0]->mask[0], m1 = a[0]->mask[1];
-    const int top = m1 ? 127 - __builtin_clzll(m1) : (m0 ? 63 - __builtin_clzll(m0) : 0);
-    shift = std::max(top + 1 - 12, 0);
-  }
-  const int64_t row_cap = row_intersect_capacity(kw);
   std::vector<RowTaskHost> tasks;
   std::vector<uint32_t> rest;
+  int64_t max_row = 0;
   {
     int64_t row_pairs = 0;
     std::vector<std::pair<int64_t, int64_t>> runs;
     for (int64_t i = 0; i < na;) {
       int64_t j = i + 1;
       while (j < na && a[j] == a[i]) ++j;
-      if (row_enabled && one_mask && j - i >= 4 && a[i]->count > 0 && a[i]->count <= row_cap) {
+      if (row_enabled && one_mask && j - i >= 4 && a[i]->count > 0 && row_intersect_fits(kw, a[0]->mask, a[i]->count)) {
+        max_row = std::max<int64_t>(max_row, a[i]->count);
         runs.emplace_back(i, j);
         row_pairs += j - i;
       } else {
@@ -1333,7 +1328,8 @@ int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *co
   int32_t *d_out = reinterpret_cast<int32_t *>(d_tab + tab_bytes);
   if (!tasks.empty()) {
     SKS_CUDA_TRY(cudaMemsetAsync(d_out, 0, out_bytes, ctx->stream));  // the row kernel adds partial counts
-    SKS_TRY(launch_row_intersect(ctx, kw, d_tab + tab_bytes + out_bytes, (int64_t)tasks.size(), d_pb, d_nb, d_out, shift));
+    SKS_TRY(launch_row_intersect(ctx, kw, d_tab + tab_bytes + out_bytes, (int64_t)tasks.size(), d_pb, d_nb, d_out, a[0]->mask,
+                                 max_row));
   }
   if (rest.size() == (size_t)na)
     SKS_TRY(launch_sorted_intersect_pairs(ctx, kw, d_pa, d_na, d_pb, d_nb, na, d_out));

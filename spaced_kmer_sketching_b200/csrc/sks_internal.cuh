@@ -237,9 +237,9 @@ struct RowTaskHost {
   const void *a;
   uint32_t n_a, first, n_cols, pad;
 };
-int64_t row_intersect_capacity(int key_words);
+bool row_intersect_fits(int key_words, const uint64_t mask[2], int64_t n_a);
 int launch_row_intersect(sks_ctx *ctx, int key_words, const void *d_tasks, int64_t n_tasks, const void *const *d_b,
-                         const int64_t *d_nb, int32_t *d_out, int shift);
+                         const int64_t *d_nb, int32_t *d_out, const uint64_t mask[2], int64_t max_n_a);
 
 int launch_list_finalize(sks_ctx *ctx, const uint32_t *words, const uint32_t *seg_end, uint32_t n_segs, int window,
                          int key_words, const void *raw_keys, const uint32_t *raw_pos, uint32_t n,

@@ -1483,72 +1483,89 @@ __global__ void __launch_bounds__(kRowThreads, 1)
   }
 }
 
-// 8-byte keys: the row set is stored as two 32-bit planes -- the 32 bits right below the bucket bits (sorted
-// inside a bucket, so it can be binary searched) and the remaining low bits (compared on a match).  Random 4-byte
-// shared-memory reads collide in the banks about half as often as 8-byte ones, the bucket entry is one word
-// (start | length << 16), and a lookup costs ~6 LDS.32 instead of a divergent scan of ~10 LDS.64.
+// 8-byte keys: the row set is stored as two planes -- the 32 bits right below the bucket bits and the remaining
+// low bits (16-bit when they fit) -- which leaves room for a bucket index on the top 13-15 key bits (16-bit
+// starts, built from the sorted order without atomics).  A bucket then holds ~1 key: a lookup is two 16-bit
+// table reads and one or two (hi, lo) compares, ~25 instructions instead of the ~65 of a merge step per key.
+// All bit surgery is on 32-bit halves with launch-uniform shift amounts -- variable 64-bit shifts and masks made
+// an earlier version of this kernel spend ~175 warp instructions per 32 lookups.  The bucket index is built
+// from mask-SELECTED bits only (up to four runs of the mask's top set bits, concatenated): the positions a spaced
+// seed skips are always zero in a key and would leave most buckets of a contiguous bit field empty.  Keys are
+// subsets of the mask, so nothing lies above its highest bit.
+struct RowPlan {
+  int n_pieces;        // runs of mask bits that form the bucket index, all inside the key's upper half
+  int s[4];            // piece i = ((khi >> s[i]) & m[i]) << o[i]
+  uint32_t m[4];
+  int o[4];
+  int tb;              // bucket bits
+  int shift_low;       // lowest bucket bit (>= 32): the bits below it go to the two planes
+};
+
+template <typename LoT>
 __global__ void __launch_bounds__(kRowThreads, 1)
     row_intersect_kernel(const RowTask *__restrict__ tasks, const void *const *__restrict__ pb,
-                         const long long *__restrict__ nb, int32_t *__restrict__ out, int shift) {
+                         const long long *__restrict__ nb, int32_t *__restrict__ out, const __grid_constant__ RowPlan R) {
   extern __shared__ __align__(16) uint32_t s_u32[];
   const RowTask t = tasks[blockIdx.x];
-  uint32_t *s_hi = s_u32;                // [n_a] bits [shift-1 .. pshift] of the key
-  uint32_t *s_lo = s_u32 + t.n_a;        // [n_a] bits [pshift-1 .. 0]
-  uint32_t *s_tab = s_lo + t.n_a;        // [kRowBuckets] start | length << 16
+  uint32_t *s_hi = s_u32;                                                    // [n_a] bits [shift_low-1 .. pshift]
+  LoT *s_lo = reinterpret_cast<LoT *>(s_u32 + t.n_a);                        // [n_a] bits [pshift-1 .. 0]
+  uint16_t *s_tab = reinterpret_cast<uint16_t *>(s_u32 + t.n_a + (t.n_a * sizeof(LoT) + 3) / 4);  // [2^tb + 1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int pshift = shift > 32 ? shift - 32 : 0;
-  const unsigned long long rem_mask = shift >= 64 ? ~0ull : ((1ull << shift) - 1);
-  const uint32_t lo_mask = pshift ? (1u << pshift) - 1 : 0u;  // pshift <= 20
-  auto bucket_of = [&](unsigned long long k) -> uint32_t {
-    const unsigned long long b = shift >= 64 ? 0ull : k >> shift;
-    return b < (unsigned long long)kRowBuckets ? (uint32_t)b : (uint32_t)kRowBuckets - 1;
+  const int pshift = R.shift_low - 32;  // 0 <= pshift <= 24
+  const uint32_t n_buckets = 1u << R.tb;
+  const uint32_t lo_mask = pshift ? (1u << pshift) - 1 : 0u;
+  // (bucket, the 32 bits below the bucket bits, the rest) of a key given as two halves
+  auto split = [&](uint32_t klo, uint32_t khi, uint32_t &b, uint32_t &h, uint32_t &l) {
+    b = ((khi >> R.s[0]) & R.m[0]) << R.o[0];
+    if (R.n_pieces > 1) b |= ((khi >> R.s[1]) & R.m[1]) << R.o[1];
+    if (R.n_pieces > 2) b |= ((khi >> R.s[2]) & R.m[2]) << R.o[2];
+    if (R.n_pieces > 3) b |= ((khi >> R.s[3]) & R.m[3]) << R.o[3];
+    h = __funnelshift_r(klo, khi, pshift);
+    l = klo & lo_mask;
   };
-  const unsigned long long *A = static_cast<const unsigned long long *>(t.a);
-  for (uint32_t i = tid; i < (uint32_t)kRowBuckets; i += kRowThreads) s_tab[i] = 0;
-  __syncthreads();
-  for (uint32_t i = tid; i < t.n_a; i += kRowThreads) {
-    const unsigned long long k = __ldg(A + i);
-    const unsigned long long rem = k & rem_mask;
-    s_hi[i] = (uint32_t)(rem >> pshift);
-    s_lo[i] = (uint32_t)rem & lo_mask;
-    // bucket entry: the first key of the bucket writes the start, every key adds 1 to the length
-    const uint32_t b = bucket_of(k);
-    const bool first = i == 0 || bucket_of(__ldg(A + i - 1)) != b;
-    atomicAdd(&s_tab[b], (1u << 16) | (first ? i : 0u));
+  const uint2 *A = static_cast<const uint2 *>(t.a);
+  for (uint32_t i = tid; i <= t.n_a; i += kRowThreads) {
+    uint32_t bi = n_buckets, h, l;
+    if (i < t.n_a) {
+      const uint2 k = __ldg(A + i);
+      split(k.x, k.y, bi, h, l);
+      s_hi[i] = h;
+      s_lo[i] = (LoT)l;
+    }
+    // s_tab[b] = first index whose bucket is >= b: this key owns the entries (bucket of its predecessor, bi]
+    // (the bucket index is monotonic in the key: it concatenates the key's top mask bits in order)
+    uint32_t bp = 0;
+    if (i > 0) {
+      const uint2 k = __ldg(A + i - 1);
+      split(k.x, k.y, bp, h, l);
+      ++bp;
+    }
+    for (uint32_t b = bp; b <= bi; ++b) s_tab[b] = (uint16_t)i;
   }
   __syncthreads();
 
-  auto hit = [&](unsigned long long k) -> uint32_t {
-    const uint32_t e = s_tab[bucket_of(k)];
-    uint32_t lo = e & 0xFFFFu, n = e >> 16;
-    const unsigned long long rem = k & rem_mask;
-    const uint32_t kh = (uint32_t)(rem >> pshift), kl = (uint32_t)rem & lo_mask;
-    while (n > 0) {  // lower bound of kh in the bucket's s_hi range
-      const uint32_t half = n >> 1;
-      if (s_hi[lo + half] < kh) {
-        lo += half + 1;
-        n -= half + 1;
-      } else {
-        n = half;
-      }
-    }
-    const uint32_t end = (e & 0xFFFFu) + (e >> 16);
+  auto hit = [&](uint2 k) -> uint32_t {
+    uint32_t b, kh, kl;
+    split(k.x, k.y, b, kh, kl);
+    uint32_t p = s_tab[b];
+    const uint32_t end = s_tab[b + 1];
     uint32_t f = 0;
-    for (; lo < end && s_hi[lo] == kh; ++lo) f |= s_lo[lo] == kl ? 1u : 0u;
+#pragma unroll 1  // a bucket holds ~1 key: an unrolled probe loop (the compiler's choice: by 8) is all overhead
+    for (; p < end; ++p) f |= (s_hi[p] == kh && s_lo[p] == (LoT)kl) ? 1u : 0u;
     return f;
   };
 
   const uint32_t parts = t.n_cols >= (uint32_t)kRowWarps ? 1u : (uint32_t)kRowWarps / t.n_cols;
   for (uint32_t unit = warp; unit < t.n_cols * parts; unit += kRowWarps) {
     const uint32_t col = unit % t.n_cols, part = unit / t.n_cols;
-    const unsigned long long *B = static_cast<const unsigned long long *>(pb[t.first + col]);
+    const uint2 *B = static_cast<const uint2 *>(pb[t.first + col]);
     const uint32_t n_b = (uint32_t)nb[t.first + col];
     const uint32_t per = ((n_b + parts - 1) / parts + 31) & ~31u;
     const uint32_t begin = part * per, end = begin + per < n_b ? begin + per : n_b;
     uint32_t cnt = 0;
     uint32_t i = begin + lane;
     for (; i + 32 * (kRowUnroll - 1) < end; i += 32 * kRowUnroll) {
-      unsigned long long k[kRowUnroll];
+      uint2 k[kRowUnroll];
 #pragma unroll
       for (int u = 0; u < kRowUnroll; ++u) k[u] = __ldg(B + i + 32 * u);
 #pragma unroll
@@ -1561,25 +1578,74 @@ __global__ void __launch_bounds__(kRowThreads, 1)
   }
 }
 
-// Largest row set (in keys) the resident kernel takes.
-int64_t row_intersect_capacity(int key_words) {
-  const int64_t cap = ((int64_t)kRowSmemBytes - (kRowBuckets + 1) * 4 - 64) / (8 * key_words);
-  return key_words == 1 ? std::min<int64_t>(cap, 65535) : cap;  // 16-bit starts and lengths in the bucket entries
+// Bucket plan of the resident kernel for 8-byte keys under `mask`, for rows of up to n_a keys: the top mask bits
+// (at most 15, in at most four runs, all at or above bit 32) index the buckets.  Returns false when a row does
+// not fit shared memory or the mask's top bits lie too low / are too fragmented to be worth it.
+bool row_plan(uint64_t mask, int64_t n_a, RowPlan *plan, bool *lo16) {
+  if (n_a > 65535 || mask == 0) return false;
+  for (int want = 15; want >= 10; --want) {
+    RowPlan p = {};
+    int bit = 63, got = 0;
+    while (got < want && p.n_pieces < 4 && bit >= 32) {
+      while (bit >= 32 && !((mask >> bit) & 1)) --bit;   // next run of set bits, from the top
+      if (bit < 32) break;
+      int hi = bit;
+      while (bit >= 32 && ((mask >> bit) & 1) && hi - bit + 1 <= want - got) --bit;
+      const int len = hi - bit;  // bits (bit, hi]
+      p.s[p.n_pieces] = bit + 1 - 32;
+      p.m[p.n_pieces] = (1u << len) - 1;
+      got += len;
+      p.o[p.n_pieces] = want - got;  // filled from the top of the index downwards
+      ++p.n_pieces;
+      p.shift_low = bit + 1;
+    }
+    if (got != want) continue;  // not enough mask bits in the upper half within four runs
+    p.tb = want;
+    const int lo_bits = p.shift_low - 32;
+    if (lo_bits > 24) continue;
+    const bool l16 = lo_bits <= 16;
+    const int64_t bytes = n_a * 4 + ((n_a * (l16 ? 2 : 4) + 3) & ~(int64_t)3) + 2 * (((int64_t)1 << want) + 1) + 16;
+    if (bytes > kRowSmemBytes) continue;
+    *plan = p;
+    *lo16 = l16;
+    return true;
+  }
+  return false;
 }
 
+// Can a row of n_a keys be made resident (8-byte keys: depends on the mask too)?
+bool row_intersect_fits(int key_words, const uint64_t mask[2], int64_t n_a) {
+  if (key_words == 1) {
+    RowPlan p;
+    bool lo16;
+    return row_plan(mask[0], n_a, &p, &lo16);
+  }
+  return n_a <= ((int64_t)kRowSmemBytes - (kRowBuckets + 1) * 4 - 64) / (8 * key_words);
+}
+
+// All tasks of one launch share the plan of the largest row (`max_n_a`).
 int launch_row_intersect(sks_ctx *ctx, int key_words, const void *d_tasks, int64_t n_tasks, const void *const *d_b,
-                         const int64_t *d_nb, int32_t *d_out, int shift) {
+                         const int64_t *d_nb, int32_t *d_out, const uint64_t mask[2], int64_t max_n_a) {
   if (n_tasks == 0) return SKS_OK;
   KernelTimer timer(ctx, SKS_KERNEL_INTERSECT);
   const RowTask *tasks = static_cast<const RowTask *>(d_tasks);
+  const long long *nb = reinterpret_cast<const long long *>(d_nb);
   if (key_words == 1) {
-    SKS_CUDA_TRY(cudaFuncSetAttribute(row_intersect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
-    row_intersect_kernel<<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(
-        tasks, d_b, reinterpret_cast<const long long *>(d_nb), d_out, shift);
+    RowPlan plan;
+    bool lo16 = true;
+    if (!row_plan(mask[0], max_n_a, &plan, &lo16)) return set_error(SKS_ERR_INVALID, "row set does not fit the resident kernel");
+    if (lo16) {
+      SKS_CUDA_TRY(cudaFuncSetAttribute(row_intersect_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
+      row_intersect_kernel<uint16_t><<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(tasks, d_b, nb, d_out, plan);
+    } else {
+      SKS_CUDA_TRY(cudaFuncSetAttribute(row_intersect_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
+      row_intersect_kernel<uint32_t><<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(tasks, d_b, nb, d_out, plan);
+    }
   } else {
+    const int top_bit = mask[1] ? 127 - __builtin_clzll(mask[1]) : (mask[0] ? 63 - __builtin_clzll(mask[0]) : 0);
+    const int shift = std::max(top_bit + 1 - kRowTableBits, 0);
     SKS_CUDA_TRY(cudaFuncSetAttribute(row_intersect_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
-    row_intersect_wide_kernel<2><<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(
-        tasks, d_b, reinterpret_cast<const long long *>(d_nb), d_out, shift);
+    row_intersect_wide_kernel<2><<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(tasks, d_b, nb, d_out, shift);
   }
   SKS_CUDA_TRY(cudaGetLastError());
   ctx->launches++;
