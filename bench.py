@@ -127,6 +127,40 @@ def cpu_c2_step(L, workdir):
     return dt, "port", 1, (len(sa), len(sb), inter, ani)
 
 
+def cpu_fmh_rates():
+    """Per-unit rates of the reference's CPU path on the C3 / C4 kind of work (FracMinHash sketches, sketch-sized
+    intersections), on a small sample: `parallel_kmer_sets_from_fasta_files` over 8 x 1 Mbp genomes (one thread
+    per file, as its cilk_for does) and `parallel_compute_pairwise_kmer_set_intersections` over all 64 ordered
+    pairs.  Context for the extra legs, not a target."""
+    from oracle import port, ref
+    if not ref.available():
+        return {"unavailable": "oracle/_ref/libref.so was not built"}
+    L, n = 1_000_000, 8
+    mask, w = port.seed_to_mask(C3_SEED)
+    base = port.gen(L, 1000)
+    with tempfile.TemporaryDirectory() as d:
+        paths = []
+        for g in range(n):
+            codes = base if g == 0 else port.mutate(base, 2000 + g, [1000, 200, 100, 50, 20][g % 5])
+            paths.append(os.path.join(d, "g%d.fna" % g))
+            port.write_fasta(paths[-1], codes, "g%d" % g)
+        t0 = time.perf_counter()
+        sets = ref.sets_from_fasta_files(paths, mask, w, ref.FMH, 1, 200, parallel=True)
+        t1 = time.perf_counter()
+        first = [a for a in sets for _ in sets]
+        second = [b for _ in sets for b in sets]
+        reps = 20
+        for _ in range(reps):
+            ref.pairwise_intersections(first, second, parallel=True)
+        t2 = time.perf_counter()
+    threads = min(n, os.cpu_count() or 1)
+    return {"sample": "%d x %d-base genomes, seed %s, FMH(200): sketch through parallel_kmer_sets_from_fasta_files, "
+                      "all %d ordered pairs x %d through parallel_compute_pairwise_kmer_set_intersections "
+                      "(sketches of ~%d k-mers)" % (n, L, C3_SEED, n * n, reps, sets[0].size()),
+            "threads": threads, "sketch_bases_per_s": n * L / (t1 - t0),
+            "intersect_pairs_per_s": n * n * reps / (t2 - t1)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -304,6 +338,8 @@ def run_b200(args):
                              "parallelises over files only, so a pair uses 2 threads" % (Ls, L, dt)}
 
         extra = {}
+        if cpu is not None and not args.no_extra:
+            extra["reference_cpu_rates"] = cpu_fmh_rates()
         if not args.no_extra:
             extra = c2_variants(ctx, sks, torch, batch, mask, w, stream, barrier, max_over_ranks, peak, flush)
             extra.update(extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ranks, peak))
