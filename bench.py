@@ -522,6 +522,38 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
             for x in local_sets:
                 x.close()
     ctx.profile(False)
+    bg.close()
+
+    # C5 (rank 0 of a 1-GPU run only): several random spaced seeds of weight 12..28 over 100 graded mutants of one
+    # genome -- per seed: sketch, all-vs-all, and the error of the ANI estimate against the true substitution rate
+    if world == 1:
+        n5, L5 = 100, 5_000_000
+        D5 = [[0, 1000, 200, 100, 50, 20][g % 6] for g in range(n5)]
+        b5 = ctx.synth(L5, [1000] * n5, [2000 + g for g in range(n5)], D5)
+        rows5 = []
+        for k in (12, 16, 20, 24, 28):
+            w5 = k + 10
+            m5 = sks.generate_random_spaced_seed_mask(w5, k)      # the reference's (k+10, k, seed 0) masks
+            for rep in range(2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                sets5 = ctx.sketch(b5, m5, w5, pred)
+                cnt5 = ctx.intersect_all_pairs(sets5)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ms5 = e0.elapsed_time(e1)
+                sizes5 = np.diag(cnt5).astype(np.int32)
+                for x in sets5:
+                    x.close()
+            ani5 = sks.ani_from_counts(cnt5.ravel(), np.repeat(sizes5, n5), k).reshape(n5, n5)
+            err = [abs(ani5[0, g] - (1.0 - 1.0 / D5[g])) for g in range(1, n5) if D5[g]]
+            rows5.append({"weight": k, "window": w5, "ms_sketch_plus_all_pairs": ms5,
+                          "mean_abs_ani_error_vs_true": float(np.mean(err)), "max_abs_ani_error": float(np.max(err)),
+                          "mean_sketch_size": float(np.mean(sizes5))})
+        b5.close()
+        out["c5_multi_seed"] = {"workload": "%d synthetic 5 Mbp genomes (graded mutants of one base), random spaced seeds "
+                                            "(k+10, k, seed 0) for k = 12..28, FMH(200); ANI(base, mutant) against 1 - 1/D" % n5,
+                                "per_seed": rows5}
     total = sum(res)
     out["c4_all_vs_all"] = {"kernels": c4_kernels,"workload": "%d synthetic 5 Mbp genomes (%d per GPU) at graded mutation rates, seed %s, "
                                         "FMH(200), all n^2 ordered pairs; every unordered block pair on one rank" % (n_total, G, C3_SEED),
