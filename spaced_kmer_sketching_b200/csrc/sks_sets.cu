@@ -922,7 +922,6 @@ int launch_bitset_popcount(sks_ctx *ctx, const uint32_t *a, uint64_t n_words, un
 // CTA holds (skewed keys) raise a flag and the call falls back to the device-wide radix sort.
 constexpr int kSortCap = 4096;          // keys per bucket (32 KB of shared memory)
 constexpr int kSortMaxBucketBits = 12;
-constexpr int kSortThreads = 256;
 
 __device__ __forceinline__ uint32_t sort_bucket(unsigned long long key, int shift, uint32_t mask) {
   return shift >= 64 ? 0u : (uint32_t)(key >> shift) & mask;
@@ -1036,6 +1035,7 @@ __global__ void __launch_bounds__(256)
 // size (the partition aims at ~300 keys per bucket: the network costs log^2 per key), then the distinct keys go to
 // tmp2 at the bucket's place and their number to ucount.  (cub::BlockRadixSort over the full 4096-key capacity
 // was measured too: 0.21 ms at C3 and 0.59 ms at C4 against 0.19 / 0.33 ms for a 2048-key network.)
+template <int kSortThreads>
 __global__ void __launch_bounds__(kSortThreads)
     sortp_bucket_kernel(const unsigned long long *__restrict__ tmp, const Region *__restrict__ regions,
                         const uint32_t *__restrict__ boff, const uint32_t *__restrict__ hist,
@@ -1190,7 +1190,10 @@ int sort_unique_buckets(sks_ctx *ctx, unsigned long long *keys, const uint64_t *
   sortp_hist_kernel<<<grid, 256, 0, ctx->stream>>>(keys, d_regions, d_hist, bb, shift);
   sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_hist, d_boff, d_cursor, nb, nullptr, kSortCap, d_flag);
   sortp_scatter_kernel<<<grid, 256, 0, ctx->stream>>>(keys, d_regions, d_cursor, d_tmp, bb, shift);
-  sortp_bucket_kernel<<<(unsigned)n_b, kSortThreads, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2, d_ucount, bb);
+  if ((max_count >> bb) > 600)  // 2048-key networks: more threads per bucket
+    sortp_bucket_kernel<512><<<(unsigned)n_b, 512, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2, d_ucount, bb);
+  else
+    sortp_bucket_kernel<256><<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2, d_ucount, bb);
   sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_ucount, d_uboff, nullptr, nb, d_utot, 0xFFFFFFFFu, d_flag);
   sortp_region_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(d_utot, d_uoff, n_regions);
   sortp_copy_kernel<<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp2, d_regions, d_boff, d_uboff, d_ucount, d_uoff, d_out, bb);
