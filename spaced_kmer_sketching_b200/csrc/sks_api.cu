@@ -1263,9 +1263,9 @@ int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *co
     return SKS_OK;
   }
 
-  // SORTED.  Runs of pairs that share their first set (the rows of an all-vs-all block) go to the kernel that
-  // keeps that set resident in shared memory; everything else to the merge kernel.  One pass over the pair
-  // tables either way.
+  // SORTED.  Runs of pairs that share their first set (the rows of an all-vs-all block; a single pair is a run of
+  // one) go to the kernel that keeps that set resident in shared memory; pairs whose first set does not fit go to
+  // the merge kernel.  One pass over the pair tables either way.
   const int kw = a[0]->key_words;
   static const bool row_enabled = getenv("SKS_ROW_INTERSECT") ? atoi(getenv("SKS_ROW_INTERSECT")) != 0 : true;
   bool one_mask = na < (int64_t)1 << 31;
@@ -1280,7 +1280,7 @@ int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *co
     for (int64_t i = 0; i < na;) {
       int64_t j = i + 1;
       while (j < na && a[j] == a[i]) ++j;
-      if (row_enabled && one_mask && j - i >= 4 && a[i]->count > 0 && row_intersect_fits(kw, a[0]->mask, a[i]->count)) {
+      if (row_enabled && one_mask && a[i]->count > 0 && row_intersect_fits(kw, a[0]->mask, a[i]->count)) {
         max_row = std::max<int64_t>(max_row, a[i]->count);
         runs.emplace_back(i, j);
         row_pairs += j - i;

@@ -1035,16 +1035,20 @@ __global__ void __launch_bounds__(256)
 // size (the partition aims at ~300 keys per bucket: the network costs log^2 per key), then the distinct keys go to
 // tmp2 at the bucket's place and their number to ucount.  (cub::BlockRadixSort over the full 4096-key capacity
 // was measured too: 0.21 ms at C3 and 0.59 ms at C4 against 0.19 / 0.33 ms for a 2048-key network.)
-template <int kSortThreads>
+template <int kSortThreads, int kCap>
 __global__ void __launch_bounds__(kSortThreads)
     sortp_bucket_kernel(const unsigned long long *__restrict__ tmp, const Region *__restrict__ regions,
                         const uint32_t *__restrict__ boff, const uint32_t *__restrict__ hist,
-                        unsigned long long *__restrict__ tmp2, uint32_t *__restrict__ ucount, int bb) {
-  __shared__ unsigned long long s[kSortCap];
+                        unsigned long long *__restrict__ tmp2, uint32_t *__restrict__ ucount, int bb,
+                        uint32_t *__restrict__ flag) {
+  __shared__ unsigned long long s[kCap];
   __shared__ uint32_t s_warp[kSortThreads / 32];
   const uint32_t n = hist[blockIdx.x];
-  if (n == 0 || n > (uint32_t)kSortCap) {  // uniform; an oversized bucket was flagged by the scan
-    if (threadIdx.x == 0) ucount[blockIdx.x] = 0;
+  if (n == 0 || n > (uint32_t)kCap) {  // uniform; an oversized bucket sends the whole call to the library sort
+    if (threadIdx.x == 0) {
+      ucount[blockIdx.x] = 0;
+      if (n) *flag = 1u;
+    }
     return;
   }
   const Region r = regions[blockIdx.x >> bb];
@@ -1070,12 +1074,11 @@ __global__ void __launch_bounds__(kSortThreads)
       __syncthreads();
     }
   }
-  // distinct keys: heads, block-wide exclusive scan, compact
-  constexpr int PER = kSortCap / kSortThreads;  // consecutive elements per thread
+  // distinct keys: heads, block-wide exclusive scan, compact (per = consecutive elements per thread, <= 16)
+  const uint32_t per = (P + kSortThreads - 1) / kSortThreads;
   uint32_t head = 0, cnt = 0;
-#pragma unroll
-  for (int e = 0; e < PER; ++e) {
-    const uint32_t i = tid * PER + e;
+  for (uint32_t e = 0; e < per; ++e) {
+    const uint32_t i = tid * per + e;
     if (i < n && (i == 0 || s[i] != s[i - 1])) {
       head |= 1u << e;
       ++cnt;
@@ -1092,9 +1095,8 @@ __global__ void __launch_bounds__(kSortThreads)
   __syncthreads();
   uint32_t before = incl - cnt;
   for (uint32_t w = 0; w < (tid >> 5); ++w) before += s_warp[w];
-#pragma unroll
-  for (int e = 0; e < PER; ++e)
-    if (head & (1u << e)) tmp2[lo + before++] = s[tid * PER + e];
+  for (uint32_t e = 0; e < per; ++e)
+    if (head & (1u << e)) tmp2[lo + before++] = s[tid * per + e];
   if (tid == kSortThreads - 1) ucount[blockIdx.x] = before;
 }
 
@@ -1191,9 +1193,11 @@ int sort_unique_buckets(sks_ctx *ctx, unsigned long long *keys, const uint64_t *
   sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_hist, d_boff, d_cursor, nb, nullptr, kSortCap, d_flag);
   sortp_scatter_kernel<<<grid, 256, 0, ctx->stream>>>(keys, d_regions, d_cursor, d_tmp, bb, shift);
   if ((max_count >> bb) > 600)  // 2048-key networks: more threads per bucket
-    sortp_bucket_kernel<512><<<(unsigned)n_b, 512, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2, d_ucount, bb);
-  else
-    sortp_bucket_kernel<256><<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2, d_ucount, bb);
+    sortp_bucket_kernel<512, kSortCap><<<(unsigned)n_b, 512, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2,
+                                                                             d_ucount, bb, d_flag);
+  else  // ~300 keys per bucket on average: 8 KB of shared memory per CTA keeps more buckets in flight per SM
+    sortp_bucket_kernel<256, 1024><<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2, d_ucount,
+                                                                         bb, d_flag);
   sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_ucount, d_uboff, nullptr, nb, d_utot, 0xFFFFFFFFu, d_flag);
   sortp_region_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(d_utot, d_uoff, n_regions);
   sortp_copy_kernel<<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp2, d_regions, d_boff, d_uboff, d_ucount, d_uoff, d_out, bb);
