@@ -1326,16 +1326,25 @@ int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *co
   const void **d_pb = d_pa + na;
   int64_t *d_na = reinterpret_cast<int64_t *>(d_pb + na), *d_nb = d_na + na;
   int32_t *d_out = reinterpret_cast<int32_t *>(d_tab + tab_bytes);
-  if (!tasks.empty()) {
-    SKS_CUDA_TRY(cudaMemsetAsync(d_out, 0, out_bytes, ctx->stream));  // the row kernel adds partial counts
+  // merge kernel: few pairs of large sets are cut into slices so that the whole GPU works on them
+  int slices = 1;
+  if (!rest.empty()) {
+    int64_t max_small = 0;
+    for (uint32_t k : rest) max_small = std::max<int64_t>(max_small, std::min(a[k]->count, b[k]->count));
+    const int64_t by_size = max_small / 16384;                                    // >= 2048 keys per warp
+    const int64_t by_fill = (int64_t)ctx->sm_count * 8 / (int64_t)rest.size();     // enough CTAs to fill the GPU
+    slices = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(by_size, by_fill), 1024));
+  }
+  if (!tasks.empty() || slices > 1) {
+    SKS_CUDA_TRY(cudaMemsetAsync(d_out, 0, out_bytes, ctx->stream));  // both kernels add partial counts
     SKS_TRY(launch_row_intersect(ctx, kw, d_tab + tab_bytes + out_bytes, (int64_t)tasks.size(), d_pb, d_nb, d_out, a[0]->mask,
                                  max_row));
   }
   if (rest.size() == (size_t)na)
-    SKS_TRY(launch_sorted_intersect_pairs(ctx, kw, d_pa, d_na, d_pb, d_nb, na, d_out));
+    SKS_TRY(launch_sorted_intersect_pairs(ctx, kw, d_pa, d_na, d_pb, d_nb, na, d_out, nullptr, slices));
   else if (!rest.empty())
     SKS_TRY(launch_sorted_intersect_pairs(ctx, kw, d_pa, d_na, d_pb, d_nb, (int64_t)rest.size(), d_out,
-                                          reinterpret_cast<const uint32_t *>(d_tab + tab_bytes + out_bytes + task_bytes)));
+                                          reinterpret_cast<const uint32_t *>(d_tab + tab_bytes + out_bytes + task_bytes), slices));
   SKS_CUDA_TRY(cudaMemcpyAsync(h_tab + tab_bytes, d_out, (size_t)na * 4, cudaMemcpyDeviceToHost, ctx->stream));
   SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   memcpy(out, h_tab + tab_bytes, (size_t)na * 4);

@@ -231,7 +231,7 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
                         std::vector<uint64_t> *out_count, int top_bit = -1);  // top_bit: highest set bit of the mask
 int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const *d_a, const int64_t *d_na,
                                   const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out,
-                                  const uint32_t *d_pair_idx = nullptr);
+                                  const uint32_t *d_pair_idx = nullptr, int slices = 1);
 // Row-resident variant: tasks (RowTask, 24 bytes: a, n_a, first, n_cols, pad) over the same pair tables.
 struct RowTaskHost {
   const void *a;

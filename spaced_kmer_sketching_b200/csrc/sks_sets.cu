@@ -674,8 +674,10 @@ __global__ void __launch_bounds__(kIntersectThreads)
   constexpr int kWarps = kIntersectThreads / 32;
   uint32_t cnt = 0;
   if (nA > 0 && nB > 0) {
-    const long long per = ((nA + kWarps - 1) / kWarps + 31) & ~31ll;
-    long long ai = (long long)warp * per;
+    // gridDim.y CTAs share one pair (large sets): every warp of every CTA takes its own slice of A
+    const long long n_slices = (long long)kWarps * gridDim.y;
+    const long long per = ((nA + n_slices - 1) / n_slices + 31) & ~31ll;
+    long long ai = ((long long)blockIdx.y * kWarps + warp) * per;
     const long long a_end = ai + per < nA ? ai + per : nA;
     if (ai < a_end) {
       // bi = lower_bound(B, A[ai]) by a 32-ary search: every lane probes one splitter
@@ -725,7 +727,8 @@ __global__ void __launch_bounds__(kIntersectThreads)
   if (threadIdx.x == 0) {
     uint32_t t = 0;
     for (int k = 0; k < kWarps; ++k) t += s[k];
-    out[pair] = (int32_t)t;
+    if (gridDim.y == 1) out[pair] = (int32_t)t;
+    else if (t) atomicAdd(out + pair, (int32_t)t);  // the launcher zeroed out[]
   }
 }
 
@@ -1358,21 +1361,24 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
   return SKS_OK;
 }
 
+// `slices` > 1: that many CTAs share every pair and add their partial counts (d_out must be zero on entry).
 int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const *d_a, const int64_t *d_na,
                                   const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out,
-                                  const uint32_t *d_pair_idx) {
+                                  const uint32_t *d_pair_idx, int slices) {
   if (n_pairs == 0) return SKS_OK;
   KernelTimer timer(ctx, SKS_KERNEL_INTERSECT);
+  if (slices < 1) slices = 1;
   for (int64_t done = 0; done < n_pairs;) {
     const int64_t chunk = std::min<int64_t>(n_pairs - done, 1 << 30);
     const uint32_t *idx = d_pair_idx ? d_pair_idx + done : nullptr;
     const int64_t base = d_pair_idx ? 0 : done;  // with an index list the tables are addressed through it
+    const dim3 grid((unsigned)chunk, (unsigned)slices);
     if (key_words == 1)
-      sorted_intersect_kernel<1><<<(unsigned)chunk, kIntersectThreads, 0, ctx->stream>>>(
+      sorted_intersect_kernel<1><<<grid, kIntersectThreads, 0, ctx->stream>>>(
           d_a + base, reinterpret_cast<const long long *>(d_na + base), d_b + base,
           reinterpret_cast<const long long *>(d_nb + base), d_out + base, idx);
     else
-      sorted_intersect_kernel<2><<<(unsigned)chunk, kIntersectThreads, 0, ctx->stream>>>(
+      sorted_intersect_kernel<2><<<grid, kIntersectThreads, 0, ctx->stream>>>(
           d_a + base, reinterpret_cast<const long long *>(d_na + base), d_b + base,
           reinterpret_cast<const long long *>(d_nb + base), d_out + base, idx);
     SKS_CUDA_TRY(cudaGetLastError());
