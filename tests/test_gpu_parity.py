@@ -271,6 +271,44 @@ def test_all_pairs_row_resident_and_merge_paths(ctx):
     batch.close()
 
 
+def test_fuzz_all_pairs_random_masks(ctx):
+    """Random spaced seeds of every span (bucket plans of 1..4 mask runs, masks below bit 32, 16-byte keys), random
+    FracMinHash moduli: the all-pairs counts equal numpy intersections of the key arrays, which equal the oracle's
+    sets for a sample of genomes."""
+    rng = np.random.default_rng(77)
+    base = rng.integers(0, 4, 60000, dtype=np.uint8)
+    genomes = [base]
+    for d in (300, 60, 25, 9, 4):
+        g = base.copy()
+        idx = rng.integers(0, len(g), len(g) // d)
+        g[idx] = (g[idx] + rng.integers(1, 4, len(idx))) & 3
+        genomes.append(g)
+    genomes.append(rng.integers(0, 4, 20000, dtype=np.uint8))
+    batch = ctx.upload_codes(genomes)
+    n = len(genomes)
+    for trial in range(28):
+        w = int(rng.integers(6, 65))
+        k = int(rng.integers(max(3, w // 3), w + 1))
+        mask = sks.generate_random_spaced_seed_mask(w, k, int(rng.integers(0, 1000)))
+        pred = sks.all_kmers() if trial % 4 == 0 else sks.frac_min_hash(int(rng.integers(0, 5)), int(rng.integers(2, 40)))
+        sets = ctx.sketch(batch, mask, w, pred, sks.REPR_SORTED)
+        keys = [s.keys() for s in sets]
+        as_set = [set(map(tuple, kk.tolist())) for kk in keys]
+        want = np.array([[len(a & b) for b in as_set] for a in as_set], dtype=np.int32)
+        got = ctx.intersect_all_pairs(sets)
+        assert np.array_equal(got, want), (trial, w, k, hex(mask))
+        g = int(rng.integers(0, n))
+        assert np.array_equal(keys[g], port.sketch_set(genomes[g], [len(genomes[g])], mask, w, *opred(pred))), (trial, g)
+        # single pairs and the ring (src/generators.hpp:20-31) go through the same tables
+        a, b = int(rng.integers(0, n)), int(rng.integers(0, n))
+        assert ctx.intersect(sets[a], sets[b]) == want[a, b]
+        ring = ctx.intersect_pairs(sets, sets[1:] + sets[:1])
+        assert ring.tolist() == [int(want[i, (i + 1) % n]) for i in range(n)]
+        for x in sets:
+            x.close()
+    batch.close()
+
+
 def test_synth_matches_oracle_generator(ctx):
     batch = ctx.synth(100_003, [42, 42, 9], [0, 43, 5], [0, 100, 3])
     A = port.gen(100_003, 42)
