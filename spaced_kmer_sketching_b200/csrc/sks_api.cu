@@ -320,7 +320,10 @@ int make_plan(const sks_batch *batch, const uint64_t mask[2], int window, const 
     plan->pred_mode = variant == SKS_HASH_BOOST_171 ? PRED_FMH171 : PRED_FMH181;
     // frac_min_hash::operator(), src/kmer.hpp:146: everything but H(masked_bits) is constant per launch
     p.hconst = boost_hash_bitset(mask[0], mask[1], variant) ^ (uint64_t)(int64_t)window ^ (uint64_t)(int64_t)pred->nonce;
-    modulus_magic(pred->modulus, &p.minv, &p.mbound, &p.mshift);
+    int mshift = 0;
+    modulus_magic(pred->modulus, &p.minv, &p.mbound, &mshift);
+    p.mbound <<= mshift;  // floor((2^64-1) / modulus) < 2^(64-s): no overflow
+    p.mlow = (1ull << mshift) - 1;  // a non-zero modulus has s <= 63
   } else {
     return set_error(SKS_ERR_INVALID, "unknown predicate kind %d", pred->kind);
   }

@@ -102,11 +102,12 @@ struct SketchParams {
   uint32_t n_tiles;            // over the whole batch
   int window;                  // w, 1..64
   uint32_t mask[4];            // 128-bit mask as four 32-bit limbs
-  // predicate (FMH): pass <=> ror((H(masked) ^ hconst) * minv, mshift) <= mbound
+  // predicate (FMH), modulus = 2^s * d with d odd: pass <=> t = (H(masked) ^ hconst) * minv has (t & mlow) == 0
+  // and t <= mbound
   uint64_t hconst;             // H(mask) ^ window ^ (int64)nonce
-  uint64_t minv;               // inverse of the odd part of the modulus mod 2^64
-  uint64_t mbound;             // floor((2^64-1) / modulus)
-  int mshift;                  // log2 of the power-of-two part of the modulus
+  uint64_t minv;               // inverse of d mod 2^64
+  uint64_t mbound;             // floor((2^64-1) / modulus) << s
+  uint64_t mlow;               // 2^s - 1
   // OUT_KEYS / OUT_LIST: per-genome output regions
   void *out_keys;                       // uint64 (NL<=2) / ulonglong2 (NL>2) slots; uint32 for OUT_INDEX
   uint32_t *out_pos;                    // OUT_LIST only: (strand<<31 | start position) per slot

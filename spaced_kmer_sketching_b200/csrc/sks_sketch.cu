@@ -53,13 +53,32 @@ __device__ __forceinline__ uint32_t rev_groups(uint32_t x) {
 }
 
 // ---- Boost hash restatement (src/kmer.hpp:137-148 call sites; see oracle/oracle.c header) --------
+// x * m mod 2^64 in three instructions (IMAD.WIDE + two IMADs that accumulate into the upper half); the compiler's
+// own schedule for `x * m` spends a fourth on a separate add, and the sketch kernel is bound by exactly these.
+__device__ __forceinline__ uint64_t mul64(uint64_t x, uint64_t m) {
+  uint64_t r;
+  asm("{\n"
+      " .reg .u32 xl, xh, ml, mh, pl, ph;\n"
+      " .reg .u64 p;\n"
+      " mov.b64 {xl, xh}, %1;\n"
+      " mov.b64 {ml, mh}, %2;\n"
+      " mul.wide.u32 p, xl, ml;\n"
+      " mov.b64 {pl, ph}, p;\n"
+      " mad.lo.u32 ph, xl, mh, ph;\n"
+      " mad.lo.u32 ph, xh, ml, ph;\n"
+      " mov.b64 %0, {pl, ph};\n"
+      "}"
+      : "=l"(r)
+      : "l"(x), "l"(m));
+  return r;
+}
 __device__ __forceinline__ uint64_t hc181(uint64_t h, uint64_t k) {
   const uint64_t M = 0x0e9846af9b1a615dULL;
   uint64_t x = h + 0x9e3779b9ULL + k;
   x ^= x >> 32;
-  x *= M;
+  x = mul64(x, M);
   x ^= x >> 32;
-  x *= M;
+  x = mul64(x, M);
   x ^= x >> 28;
   return x;
 }
@@ -321,9 +340,10 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
           bool pass = (vmask >> j) & 1u;
           if (PRED != PRED_ALL) {
             const uint64_t h = bitset_hash<PRED>(b0, b1) ^ P.hconst;
-            uint64_t t = h * P.minv;
-            t = (t >> P.mshift) | (t << ((64 - P.mshift) & 63));
-            pass = pass && (t <= P.mbound);
+            // h % c == 0 with c = 2^s * d, d odd:  t = h * d^-1 (mod 2^64) has its low s bits clear and
+            // t >> s <= floor((2^64 - 1) / c), i.e. t <= mbound << s
+            const uint64_t t = mul64(h, P.minv);
+            pass = pass && ((t & P.mlow) == 0) && (t <= P.mbound);
           }
 
           // ---- K3/K4: emit ---------------------------------------------------------------------
