@@ -293,7 +293,7 @@ def run_b200(args):
         assert (r2.size_a, r2.size_b, r2.intersection) == (r.size_a, r.size_b, r.intersection)
         e2e_value = world * kmers_per_step * args.steps / (e2e_ms / 1e3)
         h2d = int(wa.numel() * 4 + wb.numel() * 4 + 2 * 32 + 8)    # packed bases + genome descriptors + segment ends
-        d2h = 24                                                  # |A|, |B|, |A n B| as three uint64
+        d2h = 32                                                  # |A|, |B|, |A n B| and the region-overflow flag, four uint64
 
         # ---- roofline of the dominant kernel (per-launch CUDA-event times over the timed region) ----------
         peak, peak_src = measured_peak()
