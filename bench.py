@@ -209,6 +209,9 @@ def run_b200(args):
         raise SystemExit("bench.py needs a CUDA device: libsks has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # one rank per GPU shares the host's few cores with the other ranks: no intra-op thread pools
+        torch.set_num_threads(1)
+    if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
