@@ -505,13 +505,12 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
         torch.cuda.synchronize()
         t_host = time.perf_counter()
         rows = multi_gpu.row_tile(len(all_sets), rank, world)
-        gathered = multi_gpu.gather_rows(counts, rows, world)
-        mine = multi_gpu.mirror_rows(gathered, rows)
-        first_sizes = np.repeat(np.diag(gathered)[rows[0]:rows[1]], len(all_sets)).astype(np.int32)
+        mine = multi_gpu.exchange_blocks(counts, rank, world)   # this rank's complete rows: blocks swapped point to point
+        first_sizes = np.repeat(np.diagonal(mine[:, rows[0]:rows[1]]), len(all_sets)).astype(np.int32)
         ani = sks.ani_from_counts(np.ascontiguousarray(mine).ravel(), first_sizes, sks.mask_weight(mask3))
         t_host = (time.perf_counter() - t_host) * 1e3
         if it == 0:   # the whole matrix is consistent: every entry evaluated exactly once, symmetric counts
-            full = multi_gpu.mirror_counts(gathered)
+            full = multi_gpu.mirror_counts(multi_gpu.gather_rows(counts, rows, world))
             assert (full >= 0).all() and (full == full.T).all() and np.array_equal(full[rows[0]:rows[1]], mine)
         assert ani.shape[0] == (rows[1] - rows[0]) * len(all_sets)
         barrier()
@@ -563,7 +562,7 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
                             "ani_pairs_per_s": n_total * n_total / (total / 1e3),
                             "ani_pairs_per_s_compare_only": n_total * n_total / (res[2] / 1e3),
                             "sketch_bases_per_s": n_total * Lg / (res[0] / 1e3),
-                            "ms": {"sketch": res[0], "allgather": res[1], "intersect": res[2], "gather_counts_and_ani": res[3]},
+                            "ms": {"sketch": res[0], "allgather": res[1], "intersect": res[2], "exchange_counts_and_ani": res[3]},
                             "mean_sketch_size": float(np.mean(sizes)), "scaling": "weak"}
     return out
 

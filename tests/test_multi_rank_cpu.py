@@ -113,6 +113,16 @@ def _worker(rank, world, port_no, q):
             for j in range(n_genomes):
                 mat[i, j] = port.intersection(sets[i], sets[j])
         full = multi_gpu.gather_rows(mat, rows, world)
+        # the block exchange of the tiled evaluation: keep only what block_rects assigns to this rank, swap blocks
+        # point to point, and the rank's rows must come out complete
+        share = np.full((n_genomes, n_genomes), -1, dtype=np.int32)
+        for (r0, r1), (c0, c1) in multi_gpu.block_rects(n_genomes, rank, world):
+            share[r0:r1, c0:c1] = mat[r0:r1, c0:c1]
+        for i in range(rows[0], rows[1]):      # a diagonal block is mirrored inside by sks_intersect_block
+            for j in range(rows[0], rows[1]):
+                share[i, j] = mat[i, j]
+        got = multi_gpu.exchange_blocks(share, rank, world)
+        assert np.array_equal(got, full[rows[0]:rows[1]]), (rank, got.tolist())
         q.put((rank, full.tolist()))
     finally:
         dist.destroy_process_group()
