@@ -998,9 +998,11 @@ constexpr int kSortChunk = 4096;  // keys per CTA pass of the scatter
 
 __global__ void __launch_bounds__(256)
     sortp_scatter_kernel(const unsigned long long *__restrict__ keys, const Region *__restrict__ regions,
-                         uint32_t *__restrict__ cursor, unsigned long long *__restrict__ tmp, int bb, int shift) {
+                         uint32_t *__restrict__ cursor, unsigned long long *__restrict__ tmp, int bb, int shift,
+                         const uint32_t *__restrict__ flag) {
   __shared__ uint32_t s_hist[1 << kSortMaxBucketBits];
   __shared__ uint32_t s_base[1 << kSortMaxBucketBits];
+  if (*flag) return;  // the scan found an oversized bucket: the call is going to the library sort anyway
   const Region r = regions[blockIdx.y];
   const uint32_t nb = 1u << bb, bmask = nb - 1;
   uint32_t *cur = cursor + ((size_t)blockIdx.y << bb);
@@ -1046,6 +1048,7 @@ __global__ void __launch_bounds__(kSortThreads)
                         uint32_t *__restrict__ flag) {
   __shared__ unsigned long long s[kCap];
   __shared__ uint32_t s_warp[kSortThreads / 32];
+  if (*flag) return;
   const uint32_t n = hist[blockIdx.x];
   if (n == 0 || n > (uint32_t)kCap) {  // uniform; an oversized bucket sends the whole call to the library sort
     if (threadIdx.x == 0) {
@@ -1134,7 +1137,9 @@ __global__ void __launch_bounds__(1024)
 __global__ void __launch_bounds__(256)
     sortp_copy_kernel(const unsigned long long *__restrict__ tmp2, const Region *__restrict__ regions,
                       const uint32_t *__restrict__ boff, const uint32_t *__restrict__ uboff, const uint32_t *__restrict__ ucount,
-                      const unsigned long long *__restrict__ uoff, unsigned long long *__restrict__ out, int bb) {
+                      const unsigned long long *__restrict__ uoff, unsigned long long *__restrict__ out, int bb,
+                      const uint32_t *__restrict__ flag) {
+  if (*flag) return;
   const uint32_t n = ucount[blockIdx.x];
   const uint32_t region = blockIdx.x >> bb;
   const unsigned long long src = regions[region].begin + boff[blockIdx.x];
@@ -1157,6 +1162,8 @@ int sort_unique_buckets(sks_ctx *ctx, unsigned long long *keys, const uint64_t *
   if ((max_count >> bb) > 2048 || ((uint64_t)n_regions << bb) > (1u << 22)) return SKS_OK;  // too large for this scheme
   const int shift = top_bit + 1 - bb;  // bucket = the bb bits below the mask's highest bit
   if (shift < 0) return SKS_OK;
+  // fewer possible keys than 4 per raw key: the input is mostly duplicates and the partition would be all contention
+  if (top_bit + 1 < 62 && ((uint64_t)1 << (top_bit + 1)) < 4 * max_count) return SKS_OK;
   const size_t n_b = (size_t)n_regions << bb;
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t sz_regions = align(sizeof(Region) * n_regions), sz_tab = align(4 * n_b), sz_plane = align(8 * span);
@@ -1194,7 +1201,7 @@ int sort_unique_buckets(sks_ctx *ctx, unsigned long long *keys, const uint64_t *
   const uint32_t nb = 1u << bb;
   sortp_hist_kernel<<<grid, 256, 0, ctx->stream>>>(keys, d_regions, d_hist, bb, shift);
   sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_hist, d_boff, d_cursor, nb, nullptr, kSortCap, d_flag);
-  sortp_scatter_kernel<<<grid, 256, 0, ctx->stream>>>(keys, d_regions, d_cursor, d_tmp, bb, shift);
+  sortp_scatter_kernel<<<grid, 256, 0, ctx->stream>>>(keys, d_regions, d_cursor, d_tmp, bb, shift, d_flag);
   if ((max_count >> bb) > 600)  // 2048-key networks: more threads per bucket
     sortp_bucket_kernel<512, kSortCap><<<(unsigned)n_b, 512, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2,
                                                                              d_ucount, bb, d_flag);
@@ -1203,7 +1210,8 @@ int sort_unique_buckets(sks_ctx *ctx, unsigned long long *keys, const uint64_t *
                                                                          bb, d_flag);
   sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_ucount, d_uboff, nullptr, nb, d_utot, 0xFFFFFFFFu, d_flag);
   sortp_region_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(d_utot, d_uoff, n_regions);
-  sortp_copy_kernel<<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp2, d_regions, d_boff, d_uboff, d_ucount, d_uoff, d_out, bb);
+  sortp_copy_kernel<<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp2, d_regions, d_boff, d_uboff, d_ucount, d_uoff, d_out, bb,
+                                                            d_flag);
   SKS_CUDA_TRY(cudaGetLastError());
   ctx->launches += 7;
 
@@ -1246,6 +1254,9 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
   }
 
   const size_t kb = (size_t)key_words * 8;
+  uint64_t largest = 0;
+  for (int g = 0; g < n_regions; ++g) largest = std::max(largest, h_count[g]);
+  const bool per_region = n_regions == 1 || (n_regions <= 64 && largest >= 65536);
   // scratch: regions | begin/end offsets | alt keys (| lo/hi planes) | flags | pos | uoff | ucount | cub temp
   std::vector<Region> h_regions(n_regions);
   std::vector<long long> h_begin(n_regions), h_end(n_regions);
@@ -1260,7 +1271,7 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
     unsigned long long *kp = nullptr;
     long long *op = nullptr;
     uint32_t *fp = nullptr;
-    if (n_regions == 1) {
+    if (per_region) {
       cub::DeviceRadixSort::SortPairs(nullptr, t, kp, kp, kp, kp, (int)span, 0, 64, ctx->stream);
     } else {
       cub::DeviceSegmentedRadixSort::SortPairs(nullptr, t, kp, kp, kp, kp, (int)span, n_regions, op, op, 0, 64,
@@ -1299,8 +1310,12 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
   const int nblk = (int)((span + 255) / 256);
   if (key_words == 1) {
     size_t tb = cub_bytes;
-    if (n_regions == 1) {
-      cub::DeviceRadixSort::SortKeys(d_cub, tb, d_keys + h_off[0], plane[0] + h_off[0], (int)h_count[0], 0, 64, ctx->stream);
+    if (per_region) {  // few large regions: a device-wide sort each (the segmented sort gives a segment to ONE CTA)
+      for (int g = 0; g < n_regions; ++g) {
+        tb = cub_bytes;
+        if (h_count[g])
+          cub::DeviceRadixSort::SortKeys(d_cub, tb, d_keys + h_off[g], plane[0] + h_off[g], (int)h_count[g], 0, 64, ctx->stream);
+      }
     } else {
       cub::DeviceSegmentedRadixSort::SortKeys(d_cub, tb, d_keys, plane[0], (int)span, n_regions, d_begin, d_end, 0, 64,
                                               ctx->stream);
@@ -1310,12 +1325,16 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
   } else {
     split_keys_kernel<<<nblk, 256, 0, ctx->stream>>>(static_cast<const ulonglong2 *>(keys), plane[0], plane[1], span);
     size_t tb = cub_bytes;
-    if (n_regions == 1) {
-      const uint64_t b = h_off[0];
-      const int n = (int)h_count[0];
-      cub::DeviceRadixSort::SortPairs(d_cub, tb, plane[0] + b, plane[2] + b, plane[1] + b, plane[3] + b, n, 0, 64, ctx->stream);
-      tb = cub_bytes;
-      cub::DeviceRadixSort::SortPairs(d_cub, tb, plane[3] + b, plane[1] + b, plane[2] + b, plane[0] + b, n, 0, 64, ctx->stream);
+    if (per_region) {
+      for (int g = 0; g < n_regions; ++g) {
+        const uint64_t b = h_off[g];
+        const int n = (int)h_count[g];
+        if (!n) continue;
+        tb = cub_bytes;
+        cub::DeviceRadixSort::SortPairs(d_cub, tb, plane[0] + b, plane[2] + b, plane[1] + b, plane[3] + b, n, 0, 64, ctx->stream);
+        tb = cub_bytes;
+        cub::DeviceRadixSort::SortPairs(d_cub, tb, plane[3] + b, plane[1] + b, plane[2] + b, plane[0] + b, n, 0, 64, ctx->stream);
+      }
     } else {
       cub::DeviceSegmentedRadixSort::SortPairs(d_cub, tb, plane[0], plane[2], plane[1], plane[3], (int)span, n_regions,
                                                d_begin, d_end, 0, 64, ctx->stream);

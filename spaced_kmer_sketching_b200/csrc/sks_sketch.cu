@@ -155,11 +155,16 @@ struct KeyType<4, OUT_INDEX> {
 };
 
 constexpr int kStageSlots = kSketchThreads * kGroup;  // kept k-mers staged per round (4096)
+// OUT_BITSET: presence bitsets of up to 2^18 bits (weight <= 9) are accumulated per CTA in shared memory and OR-ed
+// into HBM when the CTA moves on to another genome: millions of windows hammering a few thousand words with global
+// atomics took 1.96 ms at C1 (weight 5: a 1024-bit bitset).
+constexpr int kSmallBitsetWords = 8192;
 
 template <int NL, int OUT>
 constexpr size_t sketch_smem_bytes() {
   size_t b = 2 * kStageWords * 4 + 2 * sizeof(TileMeta) + 64;
   if (OUT != OUT_BITSET) b += kStageSlots * sizeof(typename KeyType<NL, OUT>::type);
+  if (OUT == OUT_BITSET) b += kSmallBitsetWords * 4;  // CTA-private copy of a small presence bitset
   if (OUT == OUT_LIST) b += kStageSlots * 4;
   if (OUT == OUT_PART) b += kStageSlots * 2 + 2 * kMaxParts * 4;  // ranks, bucket histogram, bucket bases
   return b;
@@ -182,6 +187,22 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
   uint32_t *s_pbase = s_hist + kMaxParts;                                 // [kMaxParts]
   uint16_t *s_rank = reinterpret_cast<uint16_t *>(s_pbase + kMaxParts);   // [kStageSlots]
 
+  // OUT_BITSET with a small bitset: CTA-private accumulation (the stage area of the other modes is unused here)
+  uint32_t *s_bits = reinterpret_cast<uint32_t *>(s_keys);
+  const bool small_bitset = OUT == OUT_BITSET && P.bitset_words <= (uint64_t)kSmallBitsetWords;
+  uint32_t bits_genome = 0xFFFFFFFFu;  // genome whose bits s_bits holds
+  auto flush_bits = [&](uint32_t genome) {  // uniform call; OR the CTA's bits into the genome's bitset, clear the copy
+    __syncthreads();
+    uint32_t *dst = P.bitset + (uint64_t)genome * P.bitset_words;
+    for (uint32_t i = threadIdx.x; i < (uint32_t)P.bitset_words; i += kSketchThreads) {
+      const uint32_t v = s_bits[i];
+      if (v) {
+        atomicOr(dst + i, v);
+        s_bits[i] = 0;
+      }
+    }
+    __syncthreads();
+  };
   // few survivors per tile: stage across tiles (see the flush below); OUT_PART always works round by round
   constexpr bool kSparse = PRED != PRED_ALL && OUT != OUT_PART;
   const int tid = threadIdx.x;
@@ -197,6 +218,8 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
   }
   if (OUT == OUT_PART)
     for (uint32_t b = tid; b < P.n_parts; b += kSketchThreads) s_hist[b] = 0;
+  if (small_bitset)
+    for (uint32_t i = tid; i < (uint32_t)P.bitset_words; i += kSketchThreads) s_bits[i] = 0;
   __syncthreads();
 
   // Producer: describe tile `tile` in s_meta[stage] and start its bulk copy into s_words[stage].
@@ -253,6 +276,10 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
     mbar_wait(&s_bar[stage], (it >> 1) & 1);
 
     const TileMeta tm = s_meta[stage];
+    if (small_bitset && tm.genome != bits_genome) {  // uniform: the tile belongs to another genome
+      if (bits_genome != 0xFFFFFFFFu) flush_bits(bits_genome);
+      bits_genome = tm.genome;
+    }
     const uint32_t *sm = s_words + stage * kStageWords;
     const uint32_t n_bases = tm.n_bases;
 
@@ -364,7 +391,12 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
               }
             }
             if (OUT == OUT_BITSET) {
-              atomicOr(P.bitset + (uint64_t)tm.genome * P.bitset_words + (idx >> 5), 1u << (idx & 31));
+              const uint32_t bit = 1u << (idx & 31);
+              if (small_bitset) {
+                if (!(s_bits[idx >> 5] & bit)) atomicOr(&s_bits[idx >> 5], bit);  // mostly set already
+              } else {
+                atomicOr(P.bitset + (uint64_t)tm.genome * P.bitset_words + (idx >> 5), bit);
+              }
             } else if (OUT == OUT_PART) {
               reinterpret_cast<uint32_t *>(s_keys)[j * kSketchThreads + tid] = idx;
               s_rank[j * kSketchThreads + tid] = (uint16_t)atomicAdd(&s_hist[idx >> P.part_shift], 1u);
@@ -445,6 +477,7 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
       if (do_flush) flush(tm.genome, staged);
     }
   }
+  if (small_bitset && bits_genome != 0xFFFFFFFFu) flush_bits(bits_genome);
 }
 
 template <int NL, int PRED, int OUT>
