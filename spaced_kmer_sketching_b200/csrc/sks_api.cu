@@ -445,6 +445,7 @@ int sketch_bitset(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
     SKS_TRY(launch_fill_zero(ctx, buf->ptr, (size_t)words * 4 * G));
     plan.p.bitset = static_cast<uint32_t *>(buf->ptr);
     plan.p.bitset_words = words;
+
     SKS_TRY(launch_sketch(ctx, plan.p, tg, plan.n_limbs, plan.pred_mode, OUT_BITSET));
   }
   for (int g = 0; g < G; ++g) {

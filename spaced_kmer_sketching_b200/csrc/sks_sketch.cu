@@ -395,6 +395,8 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
               if (small_bitset) {
                 if (!(s_bits[idx >> 5] & bit)) atomicOr(&s_bits[idx >> 5], bit);  // mostly set already
               } else {
+                // fire-and-forget RED into the L2-resident bitset (looking at the word first was measured: the
+                // load's latency costs 2-4x more than the redundant atomics it saves)
                 atomicOr(P.bitset + (uint64_t)tm.genome * P.bitset_words + (idx >> 5), bit);
               }
             } else if (OUT == OUT_PART) {
