@@ -74,7 +74,9 @@ struct PartGeometry {
   uint32_t group_slices;  // slices per bucket
 };
 inline PartGeometry part_geometry(int index_bits) {
-  const int group_bits = index_bits - kSliceBits < kGroupSliceBits ? index_bits - kSliceBits : kGroupSliceBits;
+  // as many buckets as the sketch kernel's tables hold (kMaxParts): a bucket's indices have to fit shared memory
+  // in the build kernels, and at 2^30 bits 256 buckets of 8 slices were twice too full for that
+  const int group_bits = index_bits - kSliceBits - kMaxPartBits > 0 ? index_bits - kSliceBits - kMaxPartBits : 0;
   PartGeometry g;
   g.part_shift = kSliceBits + group_bits;
   g.n_parts = 1u << (index_bits - g.part_shift);
