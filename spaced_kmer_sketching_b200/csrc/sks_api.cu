@@ -533,7 +533,7 @@ int sketch_sorted(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
   uint64_t span = 0;
   SKS_TRY(sketch_raw_keys(ctx, batch, plan, pred, window, OUT_KEYS, &raw, &pos, &off, &count, &span));
   SKS_TRY(sort_unique_regions(ctx, key_words, raw->ptr, off.data(), count.data(), G, span, &uniq, &uoff, &ucount,
-                              mask_top_bit(mask)));
+                              mask));
   for (int g = 0; g < G; ++g) {
     sks_set *s = new_set(ctx, SKS_REPR_SORTED, mask, window, plan.weight);
     if (!s) return set_error(SKS_ERR_INVALID, "out of host memory");
@@ -1102,7 +1102,7 @@ int sks_set_from_unsorted_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_
     SKS_CUDA_TRY(cudaMemcpyAsync(raw->ptr, dptr, (size_t)n_keys * 8 * words_per_key, cudaMemcpyDeviceToDevice, ctx->stream));
   const uint64_t off = 0, cnt = (uint64_t)n_keys;
   std::vector<uint64_t> uoff, ucount;
-  SKS_TRY(sort_unique_regions(ctx, words_per_key, raw->ptr, &off, &cnt, 1, cnt, &uniq, &uoff, &ucount, mask_top_bit(mask)));
+  SKS_TRY(sort_unique_regions(ctx, words_per_key, raw->ptr, &off, &cnt, 1, cnt, &uniq, &uoff, &ucount, mask));
   sks_set *s = new_set(ctx, SKS_REPR_SORTED, mask, window, sks_mask_weight(mask));
   if (!s) return set_error(SKS_ERR_INVALID, "out of host memory");
   s->buf = uniq;

@@ -926,21 +926,85 @@ int launch_bitset_popcount(sks_ctx *ctx, const uint32_t *a, uint64_t n_words, un
 constexpr int kSortCap = 4096;          // keys per bucket (32 KB of shared memory)
 constexpr int kSortMaxBucketBits = 12;
 
-__device__ __forceinline__ uint32_t sort_bucket(unsigned long long key, int shift, uint32_t mask) {
-  return shift >= 64 ? 0u : (uint32_t)(key >> shift) & mask;
+// Bucket index of the bucket sort: the top `bb` MASK-SELECTED bits of the key (up to six runs of the mask,
+// concatenated from the top, so the index is monotone in the key).  A plain bit field below the mask's highest bit
+// would include the positions a spaced seed skips, which are zero in every key: a quarter of the buckets would
+// get all the keys.
+struct SortPlan {
+  int n_pieces;
+  int word[6];       // 0: low 64 bits of the key, 1: high 64 bits
+  int s[6];          // piece i = ((word >> s[i]) & m[i]) << o[i]
+  uint32_t m[6];
+  int o[6];
+};
+// Key of the bucket sort: 8 bytes (windows <= 32) or 16 bytes as {lo, hi}.
+template <int KW>
+struct SortKey;
+template <>
+struct SortKey<1> {
+  using T = unsigned long long;
+  __device__ __forceinline__ static T pad() { return ~0ull; }
+  __device__ __forceinline__ static bool gt(T a, T b) { return a > b; }
+  __device__ __forceinline__ static bool ne(T a, T b) { return a != b; }
+  __device__ __forceinline__ static uint32_t bucket(T k, const SortPlan &p) {
+    uint32_t b = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (i < p.n_pieces) b |= ((uint32_t)(k >> p.s[i]) & p.m[i]) << p.o[i];
+    return b;
+  }
+};
+template <>
+struct SortKey<2> {
+  using T = ulonglong2;  // x = low word, y = high word
+  __device__ __forceinline__ static T pad() { return make_ulonglong2(~0ull, ~0ull); }
+  __device__ __forceinline__ static bool gt(T a, T b) { return a.y != b.y ? a.y > b.y : a.x > b.x; }
+  __device__ __forceinline__ static bool ne(T a, T b) { return a.x != b.x || a.y != b.y; }
+  __device__ __forceinline__ static uint32_t bucket(T k, const SortPlan &p) {
+    uint32_t b = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (i < p.n_pieces) b |= ((uint32_t)((p.word[i] ? k.y : k.x) >> p.s[i]) & p.m[i]) << p.o[i];
+    return b;
+  }
+};
+
+// Plan for `bb` bucket bits under `mask`; false when the mask has fewer set bits than that or needs more than six
+// pieces.
+inline bool sort_plan(const uint64_t mask[2], int bb, SortPlan *out) {
+  SortPlan p = {};
+  int got = 0, bit = 127;
+  auto set = [&](int b) { return b >= 0 && ((mask[b >> 6] >> (b & 63)) & 1); };
+  while (got < bb) {
+    while (bit >= 0 && !set(bit)) --bit;
+    if (bit < 0 || p.n_pieces == 6) return false;
+    const int hi = bit;
+    // a piece stays inside one 64-bit word and takes at most what is still missing
+    while (bit >= 0 && set(bit) && (bit >> 6) == (hi >> 6) && hi - bit + 1 <= bb - got) --bit;
+    const int len = hi - bit;
+    p.word[p.n_pieces] = hi >> 6;
+    p.s[p.n_pieces] = (bit + 1) & 63;
+    p.m[p.n_pieces] = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1);
+    got += len;
+    p.o[p.n_pieces] = bb - got;
+    ++p.n_pieces;
+  }
+  *out = p;
+  return true;
 }
 
+template <int KW>
 __global__ void __launch_bounds__(256)
-    sortp_hist_kernel(const unsigned long long *__restrict__ keys, const Region *__restrict__ regions,
-                      uint32_t *__restrict__ hist, int bb, int shift) {
+    sortp_hist_kernel(const typename SortKey<KW>::T *__restrict__ keys, const Region *__restrict__ regions,
+                      uint32_t *__restrict__ hist, int bb, const __grid_constant__ SortPlan plan) {
   __shared__ uint32_t s_hist[1 << kSortMaxBucketBits];
   const Region r = regions[blockIdx.y];
-  const uint32_t nb = 1u << bb, bmask = nb - 1;
+  const uint32_t nb = 1u << bb;
   for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = r.begin + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < r.end; i += stride)
-    atomicAdd(&s_hist[sort_bucket(__ldg(keys + i), shift, bmask)], 1u);
+    atomicAdd(&s_hist[SortKey<KW>::bucket(keys[i], plan)], 1u);
   __syncthreads();
   uint32_t *h = hist + ((size_t)blockIdx.y << bb);
   for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x)
@@ -996,33 +1060,34 @@ __global__ void __launch_bounds__(1024)
 
 constexpr int kSortChunk = 4096;  // keys per CTA pass of the scatter
 
+template <int KW>
 __global__ void __launch_bounds__(256)
-    sortp_scatter_kernel(const unsigned long long *__restrict__ keys, const Region *__restrict__ regions,
-                         uint32_t *__restrict__ cursor, unsigned long long *__restrict__ tmp, int bb, int shift,
-                         const uint32_t *__restrict__ flag) {
+    sortp_scatter_kernel(const typename SortKey<KW>::T *__restrict__ keys, const Region *__restrict__ regions,
+                         uint32_t *__restrict__ cursor, typename SortKey<KW>::T *__restrict__ tmp, int bb,
+                         const __grid_constant__ SortPlan plan, const uint32_t *__restrict__ flag) {
   __shared__ uint32_t s_hist[1 << kSortMaxBucketBits];
   __shared__ uint32_t s_base[1 << kSortMaxBucketBits];
   if (*flag) return;  // the scan found an oversized bucket: the call is going to the library sort anyway
   const Region r = regions[blockIdx.y];
-  const uint32_t nb = 1u << bb, bmask = nb - 1;
+  const uint32_t nb = 1u << bb;
   uint32_t *cur = cursor + ((size_t)blockIdx.y << bb);
   const unsigned long long n = r.end - r.begin;
   const unsigned long long n_chunks = (n + kSortChunk - 1) / kSortChunk;
   for (unsigned long long chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) s_hist[i] = 0;
     __syncthreads();
-    unsigned long long key[kSortChunk / 256];
+    typename SortKey<KW>::T key[kSortChunk / 256];
     uint32_t rank[kSortChunk / 256];
     const unsigned long long base = r.begin + chunk * kSortChunk;
 #pragma unroll
     for (int u = 0; u < kSortChunk / 256; ++u) {
       const unsigned long long i = base + u * 256 + threadIdx.x;
-      if (i < r.end) key[u] = __ldg(keys + i);
+      if (i < r.end) key[u] = keys[i];
     }
 #pragma unroll
     for (int u = 0; u < kSortChunk / 256; ++u) {
       const unsigned long long i = base + u * 256 + threadIdx.x;
-      if (i < r.end) rank[u] = atomicAdd(&s_hist[sort_bucket(key[u], shift, bmask)], 1u);
+      if (i < r.end) rank[u] = atomicAdd(&s_hist[SortKey<KW>::bucket(key[u], plan)], 1u);
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) s_base[i] = s_hist[i] ? atomicAdd(cur + i, s_hist[i]) : 0u;
@@ -1030,7 +1095,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
     for (int u = 0; u < kSortChunk / 256; ++u) {
       const unsigned long long i = base + u * 256 + threadIdx.x;
-      if (i < r.end) tmp[r.begin + s_base[sort_bucket(key[u], shift, bmask)] + rank[u]] = key[u];
+      if (i < r.end) tmp[r.begin + s_base[SortKey<KW>::bucket(key[u], plan)] + rank[u]] = key[u];
     }
     __syncthreads();
   }
@@ -1040,13 +1105,14 @@ __global__ void __launch_bounds__(256)
 // size (the partition aims at ~300 keys per bucket: the network costs log^2 per key), then the distinct keys go to
 // tmp2 at the bucket's place and their number to ucount.  (cub::BlockRadixSort over the full 4096-key capacity
 // was measured too: 0.21 ms at C3 and 0.59 ms at C4 against 0.19 / 0.33 ms for a 2048-key network.)
-template <int kSortThreads, int kCap>
+template <int KW, int kSortThreads, int kCap>
 __global__ void __launch_bounds__(kSortThreads)
-    sortp_bucket_kernel(const unsigned long long *__restrict__ tmp, const Region *__restrict__ regions,
+    sortp_bucket_kernel(const typename SortKey<KW>::T *__restrict__ tmp, const Region *__restrict__ regions,
                         const uint32_t *__restrict__ boff, const uint32_t *__restrict__ hist,
-                        unsigned long long *__restrict__ tmp2, uint32_t *__restrict__ ucount, int bb,
+                        typename SortKey<KW>::T *__restrict__ tmp2, uint32_t *__restrict__ ucount, int bb,
                         uint32_t *__restrict__ flag) {
-  __shared__ unsigned long long s[kCap];
+  using K = SortKey<KW>;
+  __shared__ typename K::T s[kCap];
   __shared__ uint32_t s_warp[kSortThreads / 32];
   if (*flag) return;
   const uint32_t n = hist[blockIdx.x];
@@ -1063,16 +1129,16 @@ __global__ void __launch_bounds__(kSortThreads)
   while (P < n) P <<= 1;
   const uint32_t tid = threadIdx.x;
   // the tail is padded with copies of the largest possible key; index < n decides what is real afterwards
-  for (uint32_t i = tid; i < P; i += kSortThreads) s[i] = i < n ? tmp[lo + i] : ~0ull;
+  for (uint32_t i = tid; i < P; i += kSortThreads) s[i] = i < n ? tmp[lo + i] : K::pad();
   __syncthreads();
   for (uint32_t k = 2; k <= P; k <<= 1) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
       for (uint32_t t = tid; t < P / 2; t += kSortThreads) {
         const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
         const uint32_t l = i | j;
-        const unsigned long long a = s[i], b = s[l];
+        const typename K::T a = s[i], b = s[l];
         const bool up = (i & k) == 0;
-        if ((a > b) == up) {
+        if (K::gt(a, b) == up) {
           s[i] = b;
           s[l] = a;
         }
@@ -1085,7 +1151,7 @@ __global__ void __launch_bounds__(kSortThreads)
   uint32_t head = 0, cnt = 0;
   for (uint32_t e = 0; e < per; ++e) {
     const uint32_t i = tid * per + e;
-    if (i < n && (i == 0 || s[i] != s[i - 1])) {
+    if (i < n && (i == 0 || K::ne(s[i], s[i - 1]))) {
       head |= 1u << e;
       ++cnt;
     }
@@ -1134,10 +1200,11 @@ __global__ void __launch_bounds__(1024)
   }
 }
 
+template <int KW>
 __global__ void __launch_bounds__(256)
-    sortp_copy_kernel(const unsigned long long *__restrict__ tmp2, const Region *__restrict__ regions,
+    sortp_copy_kernel(const typename SortKey<KW>::T *__restrict__ tmp2, const Region *__restrict__ regions,
                       const uint32_t *__restrict__ boff, const uint32_t *__restrict__ uboff, const uint32_t *__restrict__ ucount,
-                      const unsigned long long *__restrict__ uoff, unsigned long long *__restrict__ out, int bb,
+                      const unsigned long long *__restrict__ uoff, typename SortKey<KW>::T *__restrict__ out, int bb,
                       const uint32_t *__restrict__ flag) {
   if (*flag) return;
   const uint32_t n = ucount[blockIdx.x];
@@ -1148,9 +1215,10 @@ __global__ void __launch_bounds__(256)
 }
 
 // Returns SKS_OK with *handled = false when the keys are too skewed (or too many) for the bucket sort.
-int sort_unique_buckets(sks_ctx *ctx, unsigned long long *keys, const uint64_t *h_off, const uint64_t *h_count, int n_regions,
-                        uint64_t span, uint64_t total, int top_bit, BufferRef *out_buf, std::vector<uint64_t> *out_off,
-                        std::vector<uint64_t> *out_count, bool *handled) {
+template <int KW>
+int sort_unique_buckets(sks_ctx *ctx, typename SortKey<KW>::T *keys, const uint64_t *h_off, const uint64_t *h_count, int n_regions,
+                        uint64_t span, uint64_t total, const uint64_t mask[2], BufferRef *out_buf,
+                        std::vector<uint64_t> *out_off, std::vector<uint64_t> *out_count, bool *handled) {
   *handled = false;
   uint64_t max_count = 0;
   for (int g = 0; g < n_regions; ++g) max_count = std::max(max_count, h_count[g]);
@@ -1159,14 +1227,21 @@ int sort_unique_buckets(sks_ctx *ctx, unsigned long long *keys, const uint64_t *
   // (>= 4 keys per bucket and 4096-key chunk); beyond 1024 buckets only as far as the network's capacity demands
   while (bb < 10 && (max_count >> bb) > 320) ++bb;
   while (bb < kSortMaxBucketBits && (max_count >> bb) > 1536) ++bb;
-  if ((max_count >> bb) > 2048 || ((uint64_t)n_regions << bb) > (1u << 22)) return SKS_OK;  // too large for this scheme
-  const int shift = top_bit + 1 - bb;  // bucket = the bb bits below the mask's highest bit
-  if (shift < 0) return SKS_OK;
+  // 16-byte keys: half as many fit a CTA
+  const uint64_t big_cap = KW == 1 ? kSortCap : kSortCap / 2;
+  if (KW == 2)
+    while (bb < kSortMaxBucketBits && (max_count >> bb) > 768) ++bb;
+  if ((max_count >> bb) > big_cap / 2 || ((uint64_t)n_regions << bb) > (1u << 22)) return SKS_OK;  // too large for this scheme
+  const int mask_bits = __builtin_popcountll(mask[0]) + __builtin_popcountll(mask[1]);
   // fewer possible keys than 4 per raw key: the input is mostly duplicates and the partition would be all contention
-  if (top_bit + 1 < 62 && ((uint64_t)1 << (top_bit + 1)) < 4 * max_count) return SKS_OK;
+  if (mask_bits < 62 && ((uint64_t)1 << mask_bits) < 4 * max_count) return SKS_OK;
+  SortPlan plan;
+  if (!sort_plan(mask, bb, &plan)) return SKS_OK;
+  using KT = typename SortKey<KW>::T;
+  constexpr size_t kb = sizeof(KT);
   const size_t n_b = (size_t)n_regions << bb;
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
-  const size_t sz_regions = align(sizeof(Region) * n_regions), sz_tab = align(4 * n_b), sz_plane = align(8 * span);
+  const size_t sz_regions = align(sizeof(Region) * n_regions), sz_tab = align(4 * n_b), sz_plane = align(kb * span);
   const size_t sz_u64 = align(8 * (size_t)n_regions);
   // scratch: regions | hist | boff | cursor | ucount | uboff | flag | utot | uoff | ucnt64 | tmp | tmp2
   char *base = nullptr;
@@ -1182,15 +1257,15 @@ int sort_unique_buckets(sks_ctx *ctx, unsigned long long *keys, const uint64_t *
   unsigned long long *d_utot = reinterpret_cast<unsigned long long *>(base + o); o += sz_u64;
   unsigned long long *d_uoff = reinterpret_cast<unsigned long long *>(base + o); o += sz_u64;
   o += sz_u64;
-  unsigned long long *d_tmp = reinterpret_cast<unsigned long long *>(base + o); o += sz_plane;
-  unsigned long long *d_tmp2 = reinterpret_cast<unsigned long long *>(base + o);
+  KT *d_tmp = reinterpret_cast<KT *>(base + o); o += sz_plane;
+  KT *d_tmp2 = reinterpret_cast<KT *>(base + o);
 
   Region *h_regions = nullptr;
   SKS_TRY(ctx_pinned(ctx, sizeof(Region) * n_regions, reinterpret_cast<void **>(&h_regions)));
   for (int g = 0; g < n_regions; ++g) h_regions[g] = {h_off[g], h_off[g] + h_count[g]};
   SKS_CUDA_TRY(cudaMemcpyAsync(d_regions, h_regions, sizeof(Region) * n_regions, cudaMemcpyHostToDevice, ctx->stream));
-  SKS_TRY(alloc_buffer(ctx, 8 * total, out_buf));
-  unsigned long long *d_out = static_cast<unsigned long long *>((*out_buf)->ptr);
+  SKS_TRY(alloc_buffer(ctx, kb * total, out_buf));
+  KT *d_out = static_cast<KT *>((*out_buf)->ptr);
 
   KernelTimer timer(ctx, SKS_KERNEL_SORT_UNIQUE);
   SKS_CUDA_TRY(cudaMemsetAsync(d_hist, 0, sz_tab, ctx->stream));
@@ -1199,18 +1274,18 @@ int sort_unique_buckets(sks_ctx *ctx, unsigned long long *keys, const uint64_t *
                                                                                (uint64_t)ctx->sm_count * 8));
   dim3 grid(per_region, (unsigned)n_regions);
   const uint32_t nb = 1u << bb;
-  sortp_hist_kernel<<<grid, 256, 0, ctx->stream>>>(keys, d_regions, d_hist, bb, shift);
-  sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_hist, d_boff, d_cursor, nb, nullptr, kSortCap, d_flag);
-  sortp_scatter_kernel<<<grid, 256, 0, ctx->stream>>>(keys, d_regions, d_cursor, d_tmp, bb, shift, d_flag);
+  sortp_hist_kernel<KW><<<grid, 256, 0, ctx->stream>>>(keys, d_regions, d_hist, bb, plan);
+  sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_hist, d_boff, d_cursor, nb, nullptr, (uint32_t)big_cap, d_flag);
+  sortp_scatter_kernel<KW><<<grid, 256, 0, ctx->stream>>>(keys, d_regions, d_cursor, d_tmp, bb, plan, d_flag);
   if ((max_count >> bb) > 600)  // 2048-key networks: more threads per bucket
-    sortp_bucket_kernel<512, kSortCap><<<(unsigned)n_b, 512, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2,
+    sortp_bucket_kernel<KW, 512, kSortCap / KW><<<(unsigned)n_b, 512, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2,
                                                                              d_ucount, bb, d_flag);
   else  // ~300 keys per bucket on average: 8 KB of shared memory per CTA keeps more buckets in flight per SM
-    sortp_bucket_kernel<256, 1024><<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2, d_ucount,
+    sortp_bucket_kernel<KW, 256, 1024><<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2, d_ucount,
                                                                          bb, d_flag);
   sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_ucount, d_uboff, nullptr, nb, d_utot, 0xFFFFFFFFu, d_flag);
   sortp_region_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(d_utot, d_uoff, n_regions);
-  sortp_copy_kernel<<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp2, d_regions, d_boff, d_uboff, d_ucount, d_uoff, d_out, bb,
+  sortp_copy_kernel<KW><<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp2, d_regions, d_boff, d_uboff, d_ucount, d_uoff, d_out, bb,
                                                             d_flag);
   SKS_CUDA_TRY(cudaGetLastError());
   ctx->launches += 7;
@@ -1235,7 +1310,7 @@ int sort_unique_buckets(sks_ctx *ctx, unsigned long long *keys, const uint64_t *
 
 int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t *h_off, const uint64_t *h_count,
                         int n_regions, uint64_t span, BufferRef *out_buf, std::vector<uint64_t> *out_off,
-                        std::vector<uint64_t> *out_count, int top_bit) {
+                        std::vector<uint64_t> *out_count, const uint64_t *mask) {
   out_off->assign(n_regions, 0);
   out_count->assign(n_regions, 0);
   uint64_t total = 0;
@@ -1246,10 +1321,14 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
   }
   if (span >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "sort span of %llu slots exceeds 2^31", (unsigned long long)span);
   static const bool bucket_sort = getenv("SKS_BUCKET_SORT") ? atoi(getenv("SKS_BUCKET_SORT")) != 0 : true;
-  if (bucket_sort && key_words == 1 && top_bit >= 0 && top_bit < 64) {
+  if (bucket_sort && mask) {
     bool handled = false;
-    SKS_TRY(sort_unique_buckets(ctx, static_cast<unsigned long long *>(keys), h_off, h_count, n_regions, span, total, top_bit,
-                                out_buf, out_off, out_count, &handled));
+    if (key_words == 1)
+      SKS_TRY(sort_unique_buckets<1>(ctx, static_cast<unsigned long long *>(keys), h_off, h_count, n_regions, span, total,
+                                     mask, out_buf, out_off, out_count, &handled));
+    else
+      SKS_TRY(sort_unique_buckets<2>(ctx, static_cast<ulonglong2 *>(keys), h_off, h_count, n_regions, span, total, mask,
+                                     out_buf, out_off, out_count, &handled));
     if (handled) return SKS_OK;
   }
 
