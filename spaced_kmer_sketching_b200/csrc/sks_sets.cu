@@ -1506,10 +1506,7 @@ template <>
 struct RowKey<1> {
   unsigned long long v;
   __device__ __forceinline__ static RowKey load(const unsigned long long *p, uint32_t i) { return {p[i]}; }
-  __device__ __forceinline__ uint32_t bucket(int shift) const {
-    const unsigned long long b = v >> shift;
-    return b < (unsigned long long)kRowBuckets ? (uint32_t)b : (uint32_t)kRowBuckets - 1;
-  }
+  __device__ __forceinline__ uint32_t bucket(const SortPlan &p) const { return SortKey<1>::bucket(v, p); }
   __device__ __forceinline__ bool eq(const RowKey &o) const { return v == o.v; }
   __device__ __forceinline__ bool lt(const RowKey &o) const { return v < o.v; }
 };
@@ -1517,13 +1514,7 @@ template <>
 struct RowKey<2> {
   unsigned long long lo, hi;
   __device__ __forceinline__ static RowKey load(const unsigned long long *p, uint32_t i) { return {p[2 * i], p[2 * i + 1]}; }
-  __device__ __forceinline__ uint32_t bucket(int shift) const {
-    unsigned long long b;
-    if (shift >= 64) b = hi >> (shift - 64);
-    else if (shift == 0) b = hi ? ~0ull : lo;
-    else b = (hi >> shift) ? ~0ull : ((hi << (64 - shift)) | (lo >> shift));
-    return b < (unsigned long long)kRowBuckets ? (uint32_t)b : (uint32_t)kRowBuckets - 1;
-  }
+  __device__ __forceinline__ uint32_t bucket(const SortPlan &p) const { return SortKey<2>::bucket(make_ulonglong2(lo, hi), p); }
   __device__ __forceinline__ bool eq(const RowKey &o) const { return lo == o.lo && hi == o.hi; }
   __device__ __forceinline__ bool lt(const RowKey &o) const { return hi != o.hi ? hi < o.hi : lo < o.lo; }
 };
@@ -1539,7 +1530,8 @@ struct RowTask {
 template <int KW>
 __global__ void __launch_bounds__(kRowThreads, 1)
     row_intersect_wide_kernel(const RowTask *__restrict__ tasks, const void *const *__restrict__ pb,
-                         const long long *__restrict__ nb, int32_t *__restrict__ out, int shift) {
+                         const long long *__restrict__ nb, int32_t *__restrict__ out, const __grid_constant__ SortPlan plan,
+                         int tb) {
   using K = RowKey<KW>;
   extern __shared__ __align__(16) unsigned long long s_row[];
   const RowTask t = tasks[blockIdx.x];
@@ -1552,14 +1544,14 @@ __global__ void __launch_bounds__(kRowThreads, 1)
   __syncthreads();
   // bucket starts: s_start[b] = first index whose bucket is >= b
   for (uint32_t i = tid; i <= t.n_a; i += kRowThreads) {
-    const uint32_t bi = i < t.n_a ? K::load(s_row, i).bucket(shift) : (uint32_t)kRowBuckets;
-    const uint32_t bp = i > 0 ? K::load(s_row, i - 1).bucket(shift) + 1 : 0u;
+    const uint32_t bi = i < t.n_a ? K::load(s_row, i).bucket(plan) : 1u << tb;
+    const uint32_t bp = i > 0 ? K::load(s_row, i - 1).bucket(plan) + 1 : 0u;
     for (uint32_t b = bp; b <= bi; ++b) s_start[b] = i;
   }
   __syncthreads();
 
   auto hit = [&](const K &k) -> uint32_t {
-    const uint32_t b = k.bucket(shift);
+    const uint32_t b = k.bucket(plan);
     uint32_t lo = s_start[b], hi = s_start[b + 1];
     while (hi - lo > 4) {  // a crowded bucket: halve [lo, hi), which keeps containing k's position if k is in A
       const uint32_t mid = (lo + hi) >> 1;
@@ -1753,10 +1745,13 @@ int launch_row_intersect(sks_ctx *ctx, int key_words, const void *d_tasks, int64
       row_intersect_kernel<uint32_t><<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(tasks, d_b, nb, d_out, plan);
     }
   } else {
-    const int top_bit = mask[1] ? 127 - __builtin_clzll(mask[1]) : (mask[0] ? 63 - __builtin_clzll(mask[0]) : 0);
-    const int shift = std::max(top_bit + 1 - kRowTableBits, 0);
+    // bucket index: the top (up to 12) mask-selected key bits
+    int tb = std::min(kRowTableBits, __builtin_popcountll(mask[0]) + __builtin_popcountll(mask[1]));
+    SortPlan plan = {};
+    while (tb > 0 && !sort_plan(mask, tb, &plan)) --tb;
+    if (tb == 0) plan = SortPlan{};
     SKS_CUDA_TRY(cudaFuncSetAttribute(row_intersect_wide_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
-    row_intersect_wide_kernel<2><<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(tasks, d_b, nb, d_out, shift);
+    row_intersect_wide_kernel<2><<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(tasks, d_b, nb, d_out, plan, tb);
   }
   SKS_CUDA_TRY(cudaGetLastError());
   ctx->launches++;
