@@ -344,7 +344,7 @@ def run_b200(args):
         if cpu is not None and not args.no_extra:
             extra["reference_cpu_rates"] = cpu_fmh_rates()
         if not args.no_extra:
-            extra = c2_variants(ctx, sks, torch, batch, mask, w, stream, barrier, max_over_ranks, peak, flush)
+            extra.update(c2_variants(ctx, sks, torch, batch, mask, w, stream, barrier, max_over_ranks, peak, flush))
             extra.update(extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ranks, peak))
 
     clocks = sampler.stop() if rank == 0 else None
