@@ -1652,9 +1652,20 @@ __global__ void __launch_bounds__(kRowThreads, 1)
     split(k.x, k.y, b, kh, kl);
     uint32_t p = s_tab[b];
     const uint32_t end = s_tab[b + 1];
+    // probe the first plane only (a bucket holds ~1 key; the warp runs the longest lane's bucket); the second
+    // plane is compared once afterwards.  Two keys of one bucket that agree in the first plane are rare but
+    // possible: then the bucket is walked again with both planes.
+    uint32_t cand = 0, n_match = 0;
+#pragma unroll 1  // an unrolled probe loop (the compiler's choice: by 8) is all overhead
+    for (; p < end; ++p) {
+      const bool m = s_hi[p] == kh;
+      cand = m ? p : cand;
+      n_match += m ? 1u : 0u;
+    }
+    if (n_match == 0) return 0u;
+    if (n_match == 1) return s_lo[cand] == (LoT)kl ? 1u : 0u;
     uint32_t f = 0;
-#pragma unroll 1  // a bucket holds ~1 key: an unrolled probe loop (the compiler's choice: by 8) is all overhead
-    for (; p < end; ++p) f |= (s_hi[p] == kh && s_lo[p] == (LoT)kl) ? 1u : 0u;
+    for (p = s_tab[b]; p < end; ++p) f |= (s_hi[p] == kh && s_lo[p] == (LoT)kl) ? 1u : 0u;
     return f;
   };
 
