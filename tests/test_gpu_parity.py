@@ -628,3 +628,18 @@ def test_device_fasta_parser_genome_sized(ctx, tmp_path):
     with pytest.raises(sks.SksError) as e:
         ctx.batch_from_fasta_files([str(tmp_path / "missing.fna")])
     assert e.value.code == 5
+
+
+def test_alternative_routes_in_a_subprocess():
+    """The merge-only intersection and the library-sort-only routes (process-wide switches, read once) against the
+    same oracle results: the sorted-set tests again, in a child process with the switches set."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("SKS_ROW_INTERSECT") == "0":
+        pytest.skip("already inside the child process")
+    env = dict(os.environ, SKS_ROW_INTERSECT="0", SKS_BUCKET_SORT="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                        "fuzz_all_pairs or all_pairs_row or multi_golden or fuzz_lists or sets_golden"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
