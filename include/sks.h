@@ -241,6 +241,9 @@ int sks_intersect_all_pairs(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64
  * since |A n B| = |B n A|). */
 int sks_intersect_block(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end,
                         int64_t col_begin, int64_t col_end, int32_t *out);
+/* Several such rectangles (rects[4*q .. 4*q+3] = row_begin, row_end, col_begin, col_end) in one pass over one pair
+ * table: what a rank of the multi-GPU tiling evaluates. */
+int sks_intersect_rects(sks_ctx *ctx, sks_set *const *sets, int64_t n, const int64_t *rects, int64_t n_rects, int32_t *out);
 /* ANI matrix from counts, src/kmer-sketching.cpp:196-200: containment on the FIRST set of the
  * ordered pair, then ^(1/weight).  Host double arithmetic. */
 void sks_ani_from_counts(const int32_t *intersections, const int32_t *first_set_sizes, int64_t n_pairs,

@@ -99,6 +99,7 @@ PROTOTYPES = {
     "sks_intersect_pairs": (ci, [vp, C.POINTER(vp), i64, C.POINTER(vp), i64, vp]),
     "sks_intersect_all_pairs": (ci, [vp, C.POINTER(vp), i64, i64, i64, vp]),
     "sks_intersect_block": (ci, [vp, C.POINTER(vp), i64, i64, i64, i64, i64, vp]),
+    "sks_intersect_rects": (ci, [vp, C.POINTER(vp), i64, vp, i64, vp]),
     "sks_ani_from_counts": (None, [vp, vp, i64, ci, vp]),
     "sks_pair_ani": (ci, [vp, vp, u64, vp, u64, u64p, ci, C.POINTER(SksPred), ci, C.POINTER(SksPairResult)]),
     "sks_pair_ani_resident": (ci, [vp, vp, u64p, ci, C.POINTER(SksPred), ci, C.POINTER(SksPairResult)]),

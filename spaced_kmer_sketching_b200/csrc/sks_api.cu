@@ -1364,37 +1364,51 @@ int sks_intersect(sks_ctx *ctx, sks_set *a, sks_set *b, int64_t *out) {
   return SKS_OK;
 }
 
-int sks_intersect_block(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end,
-                        int64_t col_begin, int64_t col_end, int32_t *out) {
-  if (!ctx || (n > 0 && (!sets || !out))) return set_error(SKS_ERR_INVALID, "null argument");
-  if (row_begin < 0 || row_end > n || row_begin > row_end) return set_error(SKS_ERR_INVALID, "bad row range");
-  if (col_begin < 0 || col_end > n || col_begin > col_end) return set_error(SKS_ERR_INVALID, "bad column range");
-  // |A n B| is symmetric: an unordered pair that lies in the block with both orientations is evaluated once
-  // and mirrored inside the block.
-  auto in_block = [&](int64_t i, int64_t j) { return i >= row_begin && i < row_end && j >= col_begin && j < col_end; };
+int sks_intersect_rects(sks_ctx *ctx, sks_set *const *sets, int64_t n, const int64_t *rects, int64_t n_rects, int32_t *out) {
+  if (!ctx || (n > 0 && (!sets || !out)) || (n_rects > 0 && !rects)) return set_error(SKS_ERR_INVALID, "null argument");
   std::vector<sks_set *> pa, pb;
   std::vector<std::pair<int64_t, int64_t>> ij;
-  for (int64_t i = row_begin; i < row_end; ++i)
-    for (int64_t j = col_begin; j < col_end; ++j) {
-      if (j == i) continue;
-      if (j < i && in_block(j, i)) continue;  // (j, i) is in the block too and comes first
-      pa.push_back(sets[i]);
-      pb.push_back(sets[j]);
-      ij.emplace_back(i, j);
-    }
+  std::vector<char> mirrored;
+  for (int64_t q = 0; q < n_rects; ++q) {
+    const int64_t row_begin = rects[4 * q], row_end = rects[4 * q + 1], col_begin = rects[4 * q + 2], col_end = rects[4 * q + 3];
+    if (row_begin < 0 || row_end > n || row_begin > row_end) return set_error(SKS_ERR_INVALID, "bad row range");
+    if (col_begin < 0 || col_end > n || col_begin > col_end) return set_error(SKS_ERR_INVALID, "bad column range");
+    // |A n B| is symmetric: an unordered pair that lies in the rectangle with both orientations is evaluated once
+    // and mirrored inside it.
+    auto in_rect = [&](int64_t i, int64_t j) { return i >= row_begin && i < row_end && j >= col_begin && j < col_end; };
+    for (int64_t i = row_begin; i < row_end; ++i)
+      for (int64_t j = col_begin; j < col_end; ++j) {
+        if (j == i) continue;
+        const bool both = in_rect(j, i);
+        if (j < i && both) continue;  // (j, i) is in the rectangle too and comes first
+        pa.push_back(sets[i]);
+        pb.push_back(sets[j]);
+        ij.emplace_back(i, j);
+        mirrored.push_back(both ? 1 : 0);
+      }
+  }
   std::vector<int32_t> r(pa.size());
   SKS_TRY(sks_intersect_pairs(ctx, pa.data(), (int64_t)pa.size(), pb.data(), (int64_t)pb.size(), r.data()));
   for (size_t k = 0; k < ij.size(); ++k) {
     const int64_t i = ij[k].first, j = ij[k].second;
     out[i * n + j] = r[k];
-    if (in_block(j, i)) out[j * n + i] = r[k];
+    if (mirrored[k]) out[j * n + i] = r[k];
   }
-  for (int64_t i = std::max(row_begin, col_begin); i < std::min(row_end, col_end); ++i) {  // |A n A| = |A|
-    int64_t sz = 0;
-    SKS_TRY(sks_set_size(ctx, sets[i], &sz));
-    out[i * n + i] = (int32_t)sz;
+  for (int64_t q = 0; q < n_rects; ++q) {  // |A n A| = |A|
+    const int64_t lo = std::max(rects[4 * q], rects[4 * q + 2]), hi = std::min(rects[4 * q + 1], rects[4 * q + 3]);
+    for (int64_t i = lo; i < hi; ++i) {
+      int64_t sz = 0;
+      SKS_TRY(sks_set_size(ctx, sets[i], &sz));
+      out[i * n + i] = (int32_t)sz;
+    }
   }
   return SKS_OK;
+}
+
+int sks_intersect_block(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end,
+                        int64_t col_begin, int64_t col_end, int32_t *out) {
+  const int64_t rect[4] = {row_begin, row_end, col_begin, col_end};
+  return sks_intersect_rects(ctx, sets, n, rect, 1, out);
 }
 
 int sks_intersect_all_pairs(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end,

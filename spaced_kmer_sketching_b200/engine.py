@@ -334,6 +334,15 @@ class Context:
         check(self._L.sks_intersect_block(self.h, ps, n, rows[0], rows[1], cols[0], cols[1], out.ctypes.data))
         return out
 
+    def intersect_rects(self, sets: Sequence["KmerSet"], rects: Sequence[Tuple[Tuple[int, int], Tuple[int, int]]],
+                        out: np.ndarray) -> np.ndarray:
+        """Several (rows, cols) rectangles of the all-pairs matrix in one pass (one pair table, one launch)."""
+        n = len(sets)
+        ps = (C.c_void_p * max(n, 1))(*[s.h for s in sets])
+        flat = np.array([[r[0][0], r[0][1], r[1][0], r[1][1]] for r in rects], dtype=np.int64).reshape(-1)
+        check(self._L.sks_intersect_rects(self.h, ps, n, flat.ctypes.data, len(rects), out.ctypes.data))
+        return out
+
     def pair_ani(self, packed_a: np.ndarray, n_a: int, packed_b: np.ndarray, n_b: int, mask: int, window: int,
                  pred: Predicate, repr_: int = REPR_AUTO) -> SksPairResult:
         r, p = SksPairResult(), pred.c()

@@ -75,8 +75,7 @@ def tiled_counts(ctx, sets: Sequence, rank: int, world: int) -> np.ndarray:
     """This rank's share of the n x n intersection counts (entries not evaluated here are -1)."""
     n = len(sets)
     counts = np.full((n, n), -1, dtype=np.int32)
-    for rows, cols in block_rects(n, rank, world):
-        ctx.intersect_block(sets, rows, cols, counts)
+    ctx.intersect_rects(sets, block_rects(n, rank, world), counts)   # one pair table, one launch
     return counts
 
 
