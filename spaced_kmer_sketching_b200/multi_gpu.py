@@ -91,30 +91,37 @@ def exchange_blocks(counts: np.ndarray, rank: int, world: int) -> np.ndarray:
     (batch_isend_irecv): world - 1 blocks of n^2 / world^2 int32 per rank instead of an all-gather of n^2."""
     n = counts.shape[0]
     rows = row_tile(n, rank, world)
-    mine = np.ascontiguousarray(counts[rows[0]:rows[1]])
+    mine = counts[rows[0]:rows[1]].copy()
     if world == 1:
         return mirror_rows(counts, rows)
     import torch
     import torch.distributed as dist
     on_gpu = dist.get_backend() == "nccl"
-    ops, recv, keep = [], {}, []
-    for c in range(world):
+    # one host<->device copy each way: the rank's rows go up once, the received blocks come back in one buffer
+    src = torch.from_numpy(mine)
+    if on_gpu:
+        src = src.cuda()
+    peers = [c for c in range(world) if c != rank and row_tile(n, c, world)[1] > row_tile(n, c, world)[0]]
+    if rows[1] == rows[0]:
+        peers = []
+    n_rows = rows[1] - rows[0]
+    sizes = [(row_tile(n, c, world)[1] - row_tile(n, c, world)[0]) * n_rows for c in peers]
+    inbox = torch.empty(sum(sizes), dtype=torch.int32, device=src.device)
+    ops, keep, at = [], [], 0
+    for c, size in zip(peers, sizes):
         cols = row_tile(n, c, world)
-        if c == rank or cols[1] == cols[0] or rows[1] == rows[0]:
-            continue
-        send = torch.from_numpy(np.ascontiguousarray(mine[:, cols[0]:cols[1]]))
-        buf = torch.empty((cols[1] - cols[0], rows[1] - rows[0]), dtype=torch.int32)
-        if on_gpu:
-            send, buf = send.cuda(), buf.cuda()
+        send = src[:, cols[0]:cols[1]].contiguous()
         keep.append(send)
-        recv[c] = buf
-        ops += [dist.P2POp(dist.isend, send, c), dist.P2POp(dist.irecv, buf, c)]
+        ops += [dist.P2POp(dist.isend, send, c), dist.P2POp(dist.irecv, inbox[at:at + size], c)]
+        at += size
     if ops:
         for work in dist.batch_isend_irecv(ops):
             work.wait()
-    for c, buf in recv.items():
+    got, at = inbox.cpu().numpy(), 0
+    for c, size in zip(peers, sizes):
         cols = row_tile(n, c, world)
-        theirs = buf.cpu().numpy().T
+        theirs = got[at:at + size].reshape(cols[1] - cols[0], n_rows).T
+        at += size
         block = mine[:, cols[0]:cols[1]]
         mine[:, cols[0]:cols[1]] = np.where(block < 0, theirs, block)
     return mine
