@@ -1604,7 +1604,7 @@ struct RowPlan {
   int shift_low;       // lowest bucket bit (>= 32): the bits below it go to the two planes
 };
 
-template <typename LoT>
+template <typename LoT, int NP>  // NP = number of pieces of the bucket index (compile time: no selects)
 __global__ void __launch_bounds__(kRowThreads, 1)
     row_intersect_kernel(const RowTask *__restrict__ tasks, const void *const *__restrict__ pb,
                          const long long *__restrict__ nb, int32_t *__restrict__ out, const __grid_constant__ RowPlan R) {
@@ -1620,9 +1620,9 @@ __global__ void __launch_bounds__(kRowThreads, 1)
   // (bucket, the 32 bits below the bucket bits, the rest) of a key given as two halves
   auto split = [&](uint32_t klo, uint32_t khi, uint32_t &b, uint32_t &h, uint32_t &l) {
     b = ((khi >> R.s[0]) & R.m[0]) << R.o[0];
-    if (R.n_pieces > 1) b |= ((khi >> R.s[1]) & R.m[1]) << R.o[1];
-    if (R.n_pieces > 2) b |= ((khi >> R.s[2]) & R.m[2]) << R.o[2];
-    if (R.n_pieces > 3) b |= ((khi >> R.s[3]) & R.m[3]) << R.o[3];
+    if (NP > 1) b |= ((khi >> R.s[1]) & R.m[1]) << R.o[1];
+    if (NP > 2) b |= ((khi >> R.s[2]) & R.m[2]) << R.o[2];
+    if (NP > 3) b |= ((khi >> R.s[3]) & R.m[3]) << R.o[3];
     h = __funnelshift_r(klo, khi, pshift);
     l = klo & lo_mask;
   };
@@ -1748,13 +1748,24 @@ int launch_row_intersect(sks_ctx *ctx, int key_words, const void *d_tasks, int64
     RowPlan plan;
     bool lo16 = true;
     if (!row_plan(mask[0], max_n_a, &plan, &lo16)) return set_error(SKS_ERR_INVALID, "row set does not fit the resident kernel");
-    if (lo16) {
-      SKS_CUDA_TRY(cudaFuncSetAttribute(row_intersect_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
-      row_intersect_kernel<uint16_t><<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(tasks, d_b, nb, d_out, plan);
-    } else {
-      SKS_CUDA_TRY(cudaFuncSetAttribute(row_intersect_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
-      row_intersect_kernel<uint32_t><<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(tasks, d_b, nb, d_out, plan);
+    auto go = [&](auto kernel) -> int {
+      SKS_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmemBytes));
+      kernel<<<(unsigned)n_tasks, kRowThreads, kRowSmemBytes, ctx->stream>>>(tasks, d_b, nb, d_out, plan);
+      return SKS_OK;
+    };
+#define SKS_ROW_GO(NP)                                                    \
+  case NP:                                                                \
+    if (lo16) SKS_TRY(go(row_intersect_kernel<uint16_t, NP>));            \
+    else SKS_TRY(go(row_intersect_kernel<uint32_t, NP>));                 \
+    break;
+    switch (plan.n_pieces) {
+      SKS_ROW_GO(1)
+      SKS_ROW_GO(2)
+      SKS_ROW_GO(3)
+      default:
+        SKS_ROW_GO(4)
     }
+#undef SKS_ROW_GO
   } else {
     // bucket index: the top (up to 12) mask-selected key bits
     int tb = std::min(kRowTableBits, __builtin_popcountll(mask[0]) + __builtin_popcountll(mask[1]));
