@@ -1280,8 +1280,9 @@ int sort_unique_buckets(sks_ctx *ctx, typename SortKey<KW>::T *keys, const uint6
   if ((max_count >> bb) > 600)  // 2048-key networks: more threads per bucket
     sortp_bucket_kernel<KW, 512, kSortCap / KW><<<(unsigned)n_b, 512, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2,
                                                                              d_ucount, bb, d_flag);
-  else  // ~300 keys per bucket on average: 8 KB of shared memory per CTA keeps more buckets in flight per SM
-    sortp_bucket_kernel<KW, 256, 1024><<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2, d_ucount,
+  else  // ~300 keys per bucket on average: a 256/512-key network keeps 128 threads busy (half of 256 would idle);
+        // 8 KB of shared memory per CTA keeps many buckets in flight per SM
+    sortp_bucket_kernel<KW, 128, 1024><<<(unsigned)n_b, 128, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2, d_ucount,
                                                                          bb, d_flag);
   sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_ucount, d_uboff, nullptr, nb, d_utot, 0xFFFFFFFFu, d_flag);
   sortp_region_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(d_utot, d_uoff, n_regions);
