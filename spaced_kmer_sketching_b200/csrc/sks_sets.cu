@@ -1598,9 +1598,11 @@ __global__ void __launch_bounds__(kRowThreads, 1)
 // subsets of the mask, so nothing lies above its highest bit.
 struct RowPlan {
   int n_pieces;        // runs of mask bits that form the bucket index, all inside the key's upper half
-  int s[4];            // piece i = ((khi >> s[i]) & m[i]) << o[i]
+  int s[4];            // piece i = ((khi >> s[i]) & m[i]) << o[i]  ==  (khi >> rs[i]) & pm[i]
   uint32_t m[4];
   int o[4];
+  int rs[4];           // s[i] - o[i] (never negative: the index only closes gaps)
+  uint32_t pm[4];      // m[i] << o[i]
   int tb;              // bucket bits
   int shift_low;       // lowest bucket bit (>= 32): the bits below it go to the two planes
 };
@@ -1620,10 +1622,10 @@ __global__ void __launch_bounds__(kRowThreads, 1)
   const uint32_t lo_mask = pshift ? (1u << pshift) - 1 : 0u;
   // (bucket, the 32 bits below the bucket bits, the rest) of a key given as two halves
   auto split = [&](uint32_t klo, uint32_t khi, uint32_t &b, uint32_t &h, uint32_t &l) {
-    b = ((khi >> R.s[0]) & R.m[0]) << R.o[0];
-    if (NP > 1) b |= ((khi >> R.s[1]) & R.m[1]) << R.o[1];
-    if (NP > 2) b |= ((khi >> R.s[2]) & R.m[2]) << R.o[2];
-    if (NP > 3) b |= ((khi >> R.s[3]) & R.m[3]) << R.o[3];
+    b = (khi >> R.rs[0]) & R.pm[0];
+    if (NP > 1) b |= (khi >> R.rs[1]) & R.pm[1];
+    if (NP > 2) b |= (khi >> R.rs[2]) & R.pm[2];
+    if (NP > 3) b |= (khi >> R.rs[3]) & R.pm[3];
     h = __funnelshift_r(klo, khi, pshift);
     l = klo & lo_mask;
   };
@@ -1711,6 +1713,9 @@ bool row_plan(uint64_t mask, int64_t n_a, RowPlan *plan, bool *lo16) {
       p.m[p.n_pieces] = (1u << len) - 1;
       got += len;
       p.o[p.n_pieces] = want - got;  // filled from the top of the index downwards
+      p.rs[p.n_pieces] = p.s[p.n_pieces] - p.o[p.n_pieces];
+      p.pm[p.n_pieces] = p.m[p.n_pieces] << p.o[p.n_pieces];
+      if (p.rs[p.n_pieces] < 0) { got = -1; break; }  // cannot happen (see RowPlan); refuse the plan if it does
       ++p.n_pieces;
       p.shift_low = bit + 1;
     }
