@@ -1650,25 +1650,33 @@ __global__ void __launch_bounds__(kRowThreads, 1)
   }
   __syncthreads();
 
-  auto hit = [&](uint2 k) -> uint32_t {
-    uint32_t b, kh, kl;
-    split(k.x, k.y, b, kh, kl);
-    uint32_t p = s_tab[b];
-    const uint32_t end = s_tab[b + 1];
+  // a lookup in two steps, so that the table reads of a group of keys are in flight together
+  struct Probe {
+    uint32_t p, end, kh, kl;
+  };
+  auto prep = [&](uint2 k) -> Probe {
+    uint32_t b;
+    Probe q;
+    split(k.x, k.y, b, q.kh, q.kl);
+    q.p = s_tab[b];
+    q.end = s_tab[b + 1];
+    return q;
+  };
+  auto probe = [&](const Probe &q) -> uint32_t {
     // probe the first plane only (a bucket holds ~1 key; the warp runs the longest lane's bucket); the second
     // plane is compared once afterwards.  Two keys of one bucket that agree in the first plane are rare but
     // possible: then the bucket is walked again with both planes.
     uint32_t cand = 0, n_match = 0;
 #pragma unroll 1  // an unrolled probe loop (the compiler's choice: by 8) is all overhead
-    for (; p < end; ++p) {
-      const bool m = s_hi[p] == kh;
+    for (uint32_t p = q.p; p < q.end; ++p) {
+      const bool m = s_hi[p] == q.kh;
       cand = m ? p : cand;
       n_match += m ? 1u : 0u;
     }
     if (n_match == 0) return 0u;
-    if (n_match == 1) return s_lo[cand] == (LoT)kl ? 1u : 0u;
+    if (n_match == 1) return s_lo[cand] == (LoT)q.kl ? 1u : 0u;
     uint32_t f = 0;
-    for (p = s_tab[b]; p < end; ++p) f |= (s_hi[p] == kh && s_lo[p] == (LoT)kl) ? 1u : 0u;
+    for (uint32_t p = q.p; p < q.end; ++p) f |= (s_hi[p] == q.kh && s_lo[p] == (LoT)q.kl) ? 1u : 0u;
     return f;
   };
 
@@ -1686,9 +1694,15 @@ __global__ void __launch_bounds__(kRowThreads, 1)
 #pragma unroll
       for (int u = 0; u < kRowUnroll; ++u) k[u] = __ldg(B + i + 32 * u);
 #pragma unroll
-      for (int u = 0; u < kRowUnroll; ++u) cnt += hit(k[u]);
+      for (int h = 0; h < kRowUnroll; h += 4) {
+        Probe q[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) q[u] = prep(k[h + u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cnt += probe(q[u]);
+      }
     }
-    for (; i < end; i += 32) cnt += hit(__ldg(B + i));
+    for (; i < end; i += 32) cnt += probe(prep(__ldg(B + i)));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
     if (lane == 0 && cnt) atomicAdd(out + t.first + col, (int32_t)cnt);
