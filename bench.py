@@ -518,6 +518,19 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
         c4_kernels = {k: {"launches": v[0], "ms": v[1]} for k, v in ctx.kernel_stats().items()}
         n_total = len(all_sets)
         sizes = [x.kmer_set_size() for x in all_sets]
+        # algorithmic bytes of this rank's intersections: (|A| + |B|) * key_bytes per unordered pair it
+        # evaluated; a diagonal block is evaluated above the diagonal only (|A n A| = |A| costs nothing)
+        sz = np.asarray(sizes, dtype=np.int64)
+        key_bytes = 8 * (2 if w3 > 32 else 1)
+        c4_pairs, c4_bytes = 0, 0
+        for (r0, r1), (c0, c1) in multi_gpu.block_rects(n_total, rank, world):
+            nr, nc = r1 - r0, c1 - c0
+            if (r0, r1) == (c0, c1):
+                c4_pairs += nr * (nr - 1) // 2
+                c4_bytes += int(sz[r0:r1].sum()) * (nr - 1) * key_bytes
+            else:
+                c4_pairs += nr * nc
+                c4_bytes += (int(sz[r0:r1].sum()) * nc + int(sz[c0:c1].sum()) * nr) * key_bytes
         for x in all_sets:
             x.close()
         if world > 1:
@@ -564,6 +577,15 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
                             "sketch_bases_per_s": n_total * Lg / (res[0] / 1e3),
                             "ms": {"sketch": res[0], "allgather": res[1], "intersect": res[2], "exchange_counts_and_ani": res[3]},
                             "mean_sketch_size": float(np.mean(sizes)), "scaling": "weak"}
+    ik = c4_kernels.get("sorted_intersect_kernel")
+    if ik and ik["ms"] > 0:
+        gbs = c4_bytes / (ik["ms"] * 1e-3) / 1e9
+        out["c4_all_vs_all"]["intersect_roofline"] = {
+            "kernel": "row_intersect_kernel (+ sorted_intersect_kernel for rows that do not fit shared memory)",
+            "unordered_pairs_on_rank0": c4_pairs, "algorithmic_bytes": c4_bytes, "ms": ik["ms"],
+            "achieved_gbs": gbs, "frac_of_hbm": gbs / peak,
+            "note": "(|A|+|B|) * key_bytes per unordered pair / kernel time; the sets are L2-resident, so this is "
+                    "algorithmic bytes per second against the HBM peak, not DRAM traffic"}
     return out
 
 

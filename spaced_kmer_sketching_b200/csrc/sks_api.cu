@@ -35,6 +35,10 @@ struct BlockCache {
   std::mutex mu;
   std::multimap<BlockKey, void *> blocks;
   size_t cached = 0;
+  // streams that belong to a live context (with the number of contexts using them).  A block can outlive the
+  // context whose stream it was allocated on (a kmer_set sketched by a worker thread that has exited): such a
+  // block must neither be cached under nor freed in the order of a stream that no longer exists.
+  std::map<std::pair<int, cudaStream_t>, int> live;
 };
 BlockCache &block_cache() {
   static BlockCache *c = new BlockCache();  // never destroyed: the CUDA runtime may be gone at exit
@@ -54,10 +58,27 @@ bool cache_put(int device, cudaStream_t stream, size_t bytes, void *p) {
   if (bytes < kCacheMinBytes) return false;
   BlockCache &c = block_cache();
   std::lock_guard<std::mutex> lock(c.mu);
+  if (c.live.find({device, stream}) == c.live.end()) return false;
   if (c.cached + bytes > kCacheMaxBytes) return false;
   c.blocks.emplace(BlockKey{device, stream, bytes}, p);
   c.cached += bytes;
   return true;
+}
+bool stream_is_live(int device, cudaStream_t stream) {
+  BlockCache &c = block_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  return c.live.find({device, stream}) != c.live.end();
+}
+void stream_attach(int device, cudaStream_t stream) {
+  BlockCache &c = block_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  ++c.live[{device, stream}];
+}
+void stream_detach(int device, cudaStream_t stream) {
+  BlockCache &c = block_cache();
+  std::lock_guard<std::mutex> lock(c.mu);
+  auto it = c.live.find({device, stream});
+  if (it != c.live.end() && --it->second <= 0) c.live.erase(it);
 }
 }  // namespace
 
@@ -85,7 +106,8 @@ DeviceBuffer::~DeviceBuffer() {
     int cur = 0;
     cudaGetDevice(&cur);
     if (cur != device) cudaSetDevice(device);
-    if (cudaFreeAsync(ptr, stream) != cudaSuccess) {
+    // the owning context (and with it the stream) may be gone: cudaFree waits for the device and is always valid
+    if (!stream_is_live(device, stream) || cudaFreeAsync(ptr, stream) != cudaSuccess) {
       cudaGetLastError();
       cudaFree(ptr);
     }
@@ -590,6 +612,7 @@ int sks_ctx_create(int device, sks_ctx **out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   SKS_CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  stream_attach(device, ctx->stream);
   SKS_CUDA_TRY(cudaEventCreate(&ctx->ev0));
   SKS_CUDA_TRY(cudaEventCreate(&ctx->ev1));
   // keep freed blocks cached in the stream-ordered pool: steady-state calls allocate nothing
@@ -608,7 +631,8 @@ void sks_ctx_destroy(sks_ctx *ctx) {
   DeviceGuard guard(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->scratch) cudaFreeAsync(ctx->scratch, ctx->stream);
-  cache_release(ctx->device, ctx->stream, true);
+  stream_detach(ctx->device, ctx->stream);
+  if (!stream_is_live(ctx->device, ctx->stream)) cache_release(ctx->device, ctx->stream, true);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -627,7 +651,8 @@ int sks_ctx_set_stream(sks_ctx *ctx, void *cuda_stream) {
   if (!ctx) return set_error(SKS_ERR_INVALID, "null context");
   DeviceGuard guard(ctx->device);
   SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  cache_release(ctx->device, ctx->stream, true);
+  stream_detach(ctx->device, ctx->stream);
+  if (!stream_is_live(ctx->device, ctx->stream)) cache_release(ctx->device, ctx->stream, true);
   if (ctx->scratch) {
     SKS_CUDA_TRY(cudaFreeAsync(ctx->scratch, ctx->stream));
     SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -637,6 +662,7 @@ int sks_ctx_set_stream(sks_ctx *ctx, void *cuda_stream) {
   if (ctx->owns_stream && ctx->stream) SKS_CUDA_TRY(cudaStreamDestroy(ctx->stream));
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   ctx->owns_stream = false;
+  stream_attach(ctx->device, ctx->stream);
   return SKS_OK;
 }
 

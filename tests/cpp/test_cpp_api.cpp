@@ -4,6 +4,7 @@
 #include <iomanip>
 #include <iostream>
 #include <sstream>
+#include <thread>
 
 #include "ani_estimator.hpp"
 #include "fasta_processing.hpp"
@@ -102,6 +103,29 @@ int main(int argc, char *argv[])
         std::cout << "\"different_mask_inter\":" << kmer_set_intersection(dev_set, other) << ",";
         kmer_set empty;
         std::cout << "\"empty_inter\":" << kmer_set_intersection(empty, dev_set) << ",\"empty_size\":" << empty.kmer_set_size() << ",";
+    }
+    // Concurrent callers on distinct outputs, as the reference's Cilk workers are (src/kmer_set.cpp:124-131,179-182):
+    // every worker thread sketches into its own kmer_set and exits; the sets outlive the workers' implicit
+    // contexts and are then intersected from other threads.
+    {
+        std::vector<kmer_set> sets(8);
+        std::vector<std::thread> pool;
+        for (int t = 0; t < 8; ++t)
+            pool.emplace_back([&, t]() {
+                if (t < 4) sets[(size_t)t] = kmer_set_from_fasta_file(files[t % 2], mask, 24, sks::all_kmers());
+                else sets[(size_t)t] = kmer_set_from_fasta_file(files[t % 2], mask, 24, sks::fmh_condition(1, 50));
+            });
+        for (std::thread &t : pool) t.join();
+        pool.clear();
+        std::vector<int> inter(8, -1);
+        for (int t = 0; t < 8; ++t)
+            pool.emplace_back([&, t]() { inter[(size_t)t] = kmer_set_intersection(sets[(size_t)t], sets[(size_t)(t ^ 1)]); });
+        for (std::thread &t : pool) t.join();
+        std::cout << "\"threads\":{\"sizes\":[";
+        for (int t = 0; t < 8; ++t) std::cout << (t ? "," : "") << sets[(size_t)t].kmer_set_size();
+        std::cout << "],\"inter\":[";
+        for (int t = 0; t < 8; ++t) std::cout << (t ? "," : "") << inter[(size_t)t];
+        std::cout << "]},";
     }
     bool mismatch_threw = false;
     try

@@ -84,6 +84,13 @@ def test_cpp_api_against_oracle(tmp_path):
         ani = [port.ani(want[2 * i + j], len(sets[i]), 16) for i in (0, 1) for j in (0, 1)]
         assert max(abs(a - b) for a, b in zip(got["ani"], ani)) <= 1e-12, name
 
+    # eight worker threads, each with its own implicit context, then intersections from other threads
+    th = r["threads"]
+    for base, name in ((0, "all"), (4, "fmh_struct")):
+        sets = expect[name][1]
+        assert th["sizes"][base:base + 4] == [len(sets[0]), len(sets[1])] * 2, name
+        assert th["inter"][base:base + 4] == [port.intersection(sets[0], sets[1])] * 4, name
+
     m9, _ = port.seed_to_mask("110101101")
     ca, sa = port.fasta_parse(open(fa, "rb").read())
     lst = port.kmers(ca, list(sa), m9, 9)
