@@ -81,6 +81,9 @@ int sks_timer_begin(sks_ctx *ctx);
 int sks_timer_end(sks_ctx *ctx, float *out_ms);
 /* Number of kernels launched by this context so far (bench.py's gpu_launches). */
 int64_t sks_ctx_launch_count(const sks_ctx *ctx);
+/* Number of sks_pair_ani calls of this context that read the genomes in place from the caller's pinned host
+ * buffers (no host-to-device copy; see sks_pair_ani). */
+int64_t sks_ctx_in_place_count(const sks_ctx *ctx);
 
 /* Per-kernel CUDA-event timing (bench.py's roofline numbers).  While enabled, every kernel launch of
  * the context is bracketed by a pair of events on the context's stream; sks_ctx_kernel_stats
@@ -258,7 +261,11 @@ typedef struct sks_pair_result {
  * = kmer_sets_from_fasta_files on two genomes + kmer_set_intersection + containment / binomial_estimator
  * (src/kmer-sketching.cpp:168-200 for n = 2).  With SKS_REPR_BITSET both 4^weight-bit sets are materialised in
  * HBM and |A|, |B|, |A n B| are counted while their slices stream out (one fused kernel instead of a build
- * and a re-read); SKS_REPR_BITSET_ONCHIP skips the HBM copy of the sets. */
+ * and a re-read); SKS_REPR_BITSET_ONCHIP skips the HBM copy of the sets.
+ * Genomes in pinned (page-locked, device-mapped) host memory at 16-byte aligned addresses are not copied at all:
+ * the sketch kernel's bulk copies read them in place, tile by tile, while it computes (sks_ctx_in_place_count
+ * counts such calls; SKS_ZERO_COPY=0 turns it off).  Any other host memory is copied to the device first.  The call
+ * returns after the device has finished with the buffers either way. */
 int sks_pair_ani(sks_ctx *ctx, const uint32_t *packed_a, uint64_t n_bases_a, const uint32_t *packed_b,
                  uint64_t n_bases_b, const uint64_t mask[2], int window, const sks_pred *pred, int repr,
                  sks_pair_result *out);

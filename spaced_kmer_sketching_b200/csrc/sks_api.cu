@@ -322,7 +322,8 @@ int make_plan(const sks_batch *batch, const uint64_t mask[2], int window, const 
   SketchParams &p = plan->p;
   plan->n_limbs = (2 * window + 31) / 32;
   plan->weight = sks_mask_weight(mask);
-  p.words = static_cast<const uint32_t *>(batch->words->ptr);
+  p.words = batch->host_words ? nullptr : static_cast<const uint32_t *>(batch->words->ptr);
+  p.host_words = batch->host_words ? 1u : 0u;
   p.genomes = static_cast<const GenomeDesc *>(batch->genomes->ptr);
   p.seg_end = static_cast<const uint32_t *>(batch->seg_end->ptr);
   p.n_genomes = batch->n_genomes;
@@ -686,6 +687,7 @@ int sks_timer_end(sks_ctx *ctx, float *out_ms) {
   return SKS_OK;
 }
 int64_t sks_ctx_launch_count(const sks_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t sks_ctx_in_place_count(const sks_ctx *ctx) { return ctx ? ctx->in_place_calls : 0; }
 
 int sks_ctx_profile(sks_ctx *ctx, int enable) {
   if (!ctx) return set_error(SKS_ERR_INVALID, "null context");
@@ -745,6 +747,50 @@ int sks_batch_upload(sks_ctx *ctx, int n_genomes, const uint32_t *const *packed,
     if (st == SKS_OK) st = fail(cudaMemsetAsync(d + prev_end, 0, (total_words - prev_end) * 4, ctx->stream));
   }
   if (st == SKS_OK) st = upload_tables(ctx, b);
+  if (st != SKS_OK) {
+    delete b;
+    return st;
+  }
+  *out = b;
+  return SKS_OK;
+}
+
+// A batch whose genomes stay where the caller has them: pinned (page-locked, device-mapped) host buffers, 16-byte
+// aligned.  The sketch kernel's bulk copies then read the 2-bit words over PCIe tile by tile while it computes, and the
+// separate host-to-device copy (63 us for a 5 Mbp pair) disappears from the call.  Only for calls that hold the batch
+// themselves and return after the stream has drained (sks_pair_ani); fails without side effects when a buffer does
+// not qualify.  SKS_ZERO_COPY=0 turns it off.
+static int batch_in_place(sks_ctx *ctx, int n_genomes, const uint32_t *const *packed, const uint64_t *n_bases,
+                          sks_batch **out) {
+  static const bool enabled = [] { const char *e = getenv("SKS_ZERO_COPY"); return !e || atoi(e) != 0; }();
+  if (!enabled || n_genomes <= 0) return SKS_ERR_INVALID;
+  DeviceGuard guard(ctx->device);
+  std::vector<uint64_t> dev_word(n_genomes);
+  for (int g = 0; g < n_genomes; ++g) {
+    if (!packed[g] || n_bases[g] == 0) return SKS_ERR_INVALID;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, packed[g]) != cudaSuccess) {
+      cudaGetLastError();
+      return SKS_ERR_INVALID;
+    }
+    if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return SKS_ERR_INVALID;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(attr.devicePointer);
+    if (a & 15) return SKS_ERR_INVALID;
+    dev_word[g] = (uint64_t)(a >> 2);
+  }
+  sks_batch *b = new (std::nothrow) sks_batch();
+  if (!b) return SKS_ERR_INVALID;
+  b->device = ctx->device;
+  uint64_t total_words = 0;
+  int st = layout_batch(b, n_genomes, n_bases, nullptr, nullptr, &total_words);
+  if (st == SKS_OK) {
+    b->host_words = true;
+    for (int g = 0; g < n_genomes; ++g) {
+      b->h_genomes[g].word_off = dev_word[g];
+      b->h_genomes[g].n_words = (uint32_t)((n_bases[g] + 15) / 16);  // exact: nothing beyond may be read
+    }
+    st = upload_tables(ctx, b);
+  }
   if (st != SKS_OK) {
     delete b;
     return st;
@@ -1494,8 +1540,12 @@ int sks_pair_ani(sks_ctx *ctx, const uint32_t *packed_a, uint64_t n_bases_a, con
   const uint32_t *packed[2] = {packed_a, packed_b};
   const uint64_t nb[2] = {n_bases_a, n_bases_b};
   sks_batch *batch = nullptr;
-  SKS_TRY(sks_batch_upload(ctx, 2, packed, nb, nullptr, nullptr, &batch));
+  if (!ctx) return set_error(SKS_ERR_INVALID, "null context");
+  if (batch_in_place(ctx, 2, packed, nb, &batch) != SKS_OK)  // not pinned / not aligned: copy the genomes up
+    SKS_TRY(sks_batch_upload(ctx, 2, packed, nb, nullptr, nullptr, &batch));
+  if (batch->host_words) ctx->in_place_calls++;
   const int st = sks_pair_ani_resident(ctx, batch, mask, window, pred, repr, out);
+  if (batch->host_words) cudaStreamSynchronize(ctx->stream);  // nothing may read the caller's buffers after the return
   sks_batch_destroy(ctx, batch);
   return st;
 }

@@ -97,7 +97,7 @@ struct PextTable {
 };
 
 struct SketchParams {
-  const uint32_t *words;       // batch buffer
+  const uint32_t *words;       // batch buffer (nullptr when host_words: GenomeDesc::word_off is then absolute)
   const GenomeDesc *genomes;   // [n_genomes]
   const uint32_t *seg_end;     // exclusive end of every segment, relative to its genome start
   int n_genomes;
@@ -123,6 +123,7 @@ struct SketchParams {
   uint32_t n_parts;            // <= kMaxParts
   uint32_t part_cap;
   int part_shift;              // bucket = index >> part_shift
+  uint32_t host_words;         // genomes are read in place from pinned host memory (see the kernel's tile fetch)
   // OUT_BITSET
   uint32_t *bitset;            // n_genomes consecutive bitsets
   uint64_t bitset_words;       // words per genome
@@ -152,6 +153,7 @@ struct sks_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 148;
   int64_t launches = 0;
+  int64_t in_place_calls = 0;  // sks_pair_ani calls that read the genomes from pinned host memory
   // reusable scratch (grown on demand)
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -173,7 +175,8 @@ struct sks_ctx {
 struct sks_batch {
   int device = 0;
   int n_genomes = 0;
-  sks::BufferRef words;      // uint32 words of all genomes
+  sks::BufferRef words;      // uint32 words of all genomes (empty for a host-resident batch)
+  bool host_words = false;   // internal to sks_pair_ani: the genomes stay in the caller's pinned host buffers
   sks::BufferRef genomes;    // GenomeDesc[n_genomes]
   sks::BufferRef seg_end;    // uint32[total_segs]
   sks::BufferRef tile_genome;  // uint32[n_tiles] (only when n_genomes > 1)

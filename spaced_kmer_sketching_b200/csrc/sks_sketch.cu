@@ -98,6 +98,22 @@ __device__ __forceinline__ uint64_t bitset_hash(uint64_t b0, uint64_t b1) {
   return hc181(128, hc181(hc181(0, b0), b1));
 }
 
+// PEXT(masked, mask) as rotate-and-mask pieces (the table is built on the host, sks_api.cu)
+template <int NL>
+__device__ __forceinline__ uint32_t pext_index(const uint32_t (&c)[NL], const PextTable &pext) {
+  uint32_t idx = 0;
+#pragma unroll
+  for (int k = 0; k < NL; ++k) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) idx |= __funnelshift_r(c[k], c[k], pext.rot[k][p]) & pext.dmask[k][p];
+    if (pext.n_pieces[k] > 4) {  // uniform
+#pragma unroll
+      for (int p = 4; p < kPiecesPerLimb; ++p) idx |= __funnelshift_r(c[k], c[k], pext.rot[k][p]) & pext.dmask[k][p];
+    }
+  }
+  return idx;
+}
+
 struct TileMeta {
   uint32_t genome;
   uint32_t t0;       // first window start of the tile, relative to the genome
@@ -170,8 +186,10 @@ constexpr size_t sketch_smem_bytes() {
   return b;
 }
 
+// Sparse-predicate instantiations run their 16 hash chains branch-free; asking for 4 resident CTAs lets the compiler
+// spend up to 64 registers on interleaving them (measured at C3, 250 Mbp: 0.787 ms at 32 registers, 0.770 ms at 64).
 template <int NL, int PRED, int OUT>
-__global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_constant__ SketchParams P,
+__global__ void __launch_bounds__(kSketchThreads, (PRED != PRED_ALL && OUT != OUT_PART) ? (NL <= 2 ? 4 : 3) : 1) sketch_kernel(const __grid_constant__ SketchParams P,
                                                                const uint32_t *__restrict__ tile_genome) {
   using key_t = typename KeyType<NL, OUT>::type;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -234,12 +252,31 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
     m.seg_first = gd.seg_first;
     m.n_segs = gd.n_segs;
     s_meta[stage] = m;
-    uint32_t avail = gd.n_words + kPreWords - tw;  // words readable from (word_off + tw - kPreWords)
-    uint32_t copy_words = avail < (uint32_t)kStageWords ? avail : (uint32_t)kStageWords;
-    const uint32_t *src = P.words + gd.word_off + tw - kPreWords;
-    fence_proxy_async();
-    mbar_expect_tx(&s_bar[stage], copy_words * 4);
-    bulk_g2s(s_words + stage * kStageWords, src, copy_words * 4, &s_bar[stage]);
+    if (!P.host_words) {  // uniform
+      uint32_t avail = gd.n_words + kPreWords - tw;  // words readable from (word_off + tw - kPreWords)
+      uint32_t copy_words = avail < (uint32_t)kStageWords ? avail : (uint32_t)kStageWords;
+      const uint32_t *src = P.words + gd.word_off + tw - kPreWords;
+      fence_proxy_async();
+      mbar_expect_tx(&s_bar[stage], copy_words * 4);
+      bulk_g2s(s_words + stage * kStageWords, src, copy_words * 4, &s_bar[stage]);
+    } else {
+      // The genome lies in the caller's pinned host buffer (sks_pair_ani): word_off is the absolute word address of
+      // its first data word (16-byte aligned), n_words the exact number of data words, and nothing around them may
+      // be read.  The bulk copy pulls the tile over PCIe while the other resident CTAs compute -- there is no
+      // separate host-to-device copy.  The history words of the first tile are zeros; the last 1-3 words of a
+      // genome whose length is not a multiple of 16 bytes are fetched with plain loads.
+      uint32_t *dst = s_words + stage * kStageWords;
+      const uint32_t skip = (tw == 0) ? (uint32_t)kPreWords : 0u;
+      const uint32_t first = tw - kPreWords + skip;
+      const uint32_t want = (uint32_t)kStageWords - skip, avail = gd.n_words - first;
+      const uint32_t n = avail < want ? avail : want, bulk = n & ~3u;
+      const uint32_t *src = P.words + gd.word_off + first;
+      for (uint32_t i = 0; i < skip; ++i) dst[i] = 0;
+      for (uint32_t i = bulk; i < n; ++i) dst[skip + i] = __ldcv(src + i);
+      fence_proxy_async();
+      mbar_expect_tx(&s_bar[stage], bulk * 4);
+      if (bulk) bulk_g2s(dst + skip, src, bulk * 4, &s_bar[stage]);
+    }
   };
 
   // Copies the staged survivors of `genome` to its output region: one global reservation per flush.
@@ -332,16 +369,15 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
           }
         }
 
-#pragma unroll
-        for (int j = 0; j < kGroup; ++j) {
-          // ---- K2: both strands through the same mask, canonical = smaller, ties -> rc ---------
-          uint32_t f[NL], r[NL], c[NL];
+        // K2: both strands of window j of the group through the same mask, canonical = smaller, ties -> rc.
+        // `sh` = 2 * j: a compile-time constant in the unrolled loops, a run-time value when a candidate is re-derived.
+        auto canonical = [&](const int sh, uint32_t (&c)[NL], bool &lt) {
+          uint32_t f[NL], r[NL];
 #pragma unroll
           for (int k = 0; k < NL; ++k) {
-            f[k] = __funnelshift_l(fa[NL - k], fa[NL - 1 - k], 2 * j) & P.mask[k];
-            r[k] = ~__funnelshift_r(rw[k], rw[k + 1], 2 * j) & P.mask[k];
+            f[k] = __funnelshift_l(fa[NL - k], fa[NL - 1 - k], sh) & P.mask[k];
+            r[k] = ~__funnelshift_r(rw[k], rw[k + 1], sh) & P.mask[k];
           }
-          bool lt;
           if (NL == 1) {
             lt = f[0] < r[0];
           } else if (NL == 2) {
@@ -357,75 +393,115 @@ __global__ void __launch_bounds__(kSketchThreads) sketch_kernel(const __grid_con
           }
 #pragma unroll
           for (int k = 0; k < NL; ++k) c[k] = lt ? f[k] : r[k];
-
-          const uint64_t b0 = (NL >= 2) ? ((((uint64_t)c[NL >= 2 ? 1 : 0]) << 32) | c[0]) : (uint64_t)c[0];
-          const uint64_t b1 = (NL == 3)   ? (uint64_t)c[NL >= 3 ? 2 : 0]
-                              : (NL == 4) ? ((((uint64_t)c[NL >= 4 ? 3 : 0]) << 32) | c[NL >= 3 ? 2 : 0])
-                                          : 0ull;
-
-          // ---- K3: predicate -------------------------------------------------------------------
-          bool pass = (vmask >> j) & 1u;
-          if (PRED != PRED_ALL) {
-            const uint64_t h = bitset_hash<PRED>(b0, b1) ^ P.hconst;
-            // h % c == 0 with c = 2^s * d, d odd:  t = h * d^-1 (mod 2^64) has its low s bits clear and
-            // t >> s <= floor((2^64 - 1) / c), i.e. t <= mbound << s
-            const uint64_t t = mul64(h, P.minv);
-            pass = pass && ((t & P.mlow) == 0) && (t <= P.mbound);
-          }
-
-          // ---- K3/K4: emit ---------------------------------------------------------------------
-          if (OUT == OUT_PART && !pass) s_rank[j * kSketchThreads + tid] = 0xFFFFu;
-          if (pass) {
-            uint32_t idx = 0;
-            if (OUT == OUT_BITSET || OUT == OUT_INDEX || OUT == OUT_PART) {  // PEXT(masked, mask): rotate-and-mask pieces
-#pragma unroll
-              for (int k = 0; k < NL; ++k) {
-#pragma unroll
-                for (int p = 0; p < 4; ++p)
-                  idx |= __funnelshift_r(c[k], c[k], P.pext.rot[k][p]) & P.pext.dmask[k][p];
-                if (P.pext.n_pieces[k] > 4) {  // uniform
-#pragma unroll
-                  for (int p = 4; p < kPiecesPerLimb; ++p)
-                    idx |= __funnelshift_r(c[k], c[k], P.pext.rot[k][p]) & P.pext.dmask[k][p];
-                }
-              }
-            }
-            if (OUT == OUT_BITSET) {
-              const uint32_t bit = 1u << (idx & 31);
-              if (small_bitset) {
-                if (!(s_bits[idx >> 5] & bit)) atomicOr(&s_bits[idx >> 5], bit);  // mostly set already
-              } else {
-                // fire-and-forget RED into the L2-resident bitset (looking at the word first was measured: the
-                // load's latency costs 2-4x more than the redundant atomics it saves)
-                atomicOr(P.bitset + (uint64_t)tm.genome * P.bitset_words + (idx >> 5), bit);
-              }
-            } else if (OUT == OUT_PART) {
-              reinterpret_cast<uint32_t *>(s_keys)[j * kSketchThreads + tid] = idx;
-              s_rank[j * kSketchThreads + tid] = (uint16_t)atomicAdd(&s_hist[idx >> P.part_shift], 1u);
+        };
+        auto blocks = [&](const uint32_t (&c)[NL], uint64_t &b0, uint64_t &b1) {
+          b0 = (NL >= 2) ? ((((uint64_t)c[NL >= 2 ? 1 : 0]) << 32) | c[0]) : (uint64_t)c[0];
+          b1 = (NL == 3)   ? (uint64_t)c[NL >= 3 ? 2 : 0]
+               : (NL == 4) ? ((((uint64_t)c[NL >= 4 ? 3 : 0]) << 32) | c[NL >= 3 ? 2 : 0])
+                           : 0ull;
+        };
+        // K3/K4: emit the kept k-mer of window j (all modes but OUT_PART, which ranks inside the loop below)
+        auto emit = [&](const int j, const uint32_t (&c)[NL], const bool lt, const uint64_t b0, const uint64_t b1) {
+          uint32_t idx = 0;
+          if (OUT == OUT_BITSET || OUT == OUT_INDEX) idx = pext_index<NL>(c, P.pext);
+          if (OUT == OUT_BITSET) {
+            const uint32_t bit = 1u << (idx & 31);
+            if (small_bitset) {
+              if (!(s_bits[idx >> 5] & bit)) atomicOr(&s_bits[idx >> 5], bit);  // mostly set already
             } else {
-              const uint32_t slot = atomicAdd(s_count, 1u);
-              if (kSparse && slot >= (uint32_t)kStageSlots) {
-                // the stage is full (dense survivors under a sparse-mode predicate): write this one directly
-                const unsigned long long gs = atomicAdd(P.out_count + tm.genome, 1ull);
-                if (gs < P.out_cap[tm.genome]) {
-                  const unsigned long long at = P.out_off[tm.genome] + gs;
-                  if (OUT == OUT_INDEX) {
-                    reinterpret_cast<uint32_t *>(P.out_keys)[at] = idx;
-                  } else if (NL <= 2) {
-                    reinterpret_cast<unsigned long long *>(P.out_keys)[at] = b0;
-                  } else {
-                    reinterpret_cast<ulonglong2 *>(P.out_keys)[at] = make_ulonglong2(b0, b1);
-                  }
-                  if (OUT == OUT_LIST) P.out_pos[at] = (p0 + j) | (lt ? 0u : 0x80000000u);
+              // fire-and-forget RED into the L2-resident bitset (looking at the word first was measured: the
+              // load's latency costs 2-4x more than the redundant atomics it saves)
+              atomicOr(P.bitset + (uint64_t)tm.genome * P.bitset_words + (idx >> 5), bit);
+            }
+          } else {
+            const uint32_t slot = atomicAdd(s_count, 1u);
+            if (kSparse && slot >= (uint32_t)kStageSlots) {
+              // the stage is full (dense survivors under a sparse-mode predicate): write this one directly
+              const unsigned long long gs = atomicAdd(P.out_count + tm.genome, 1ull);
+              if (gs < P.out_cap[tm.genome]) {
+                const unsigned long long at = P.out_off[tm.genome] + gs;
+                if (OUT == OUT_INDEX) {
+                  reinterpret_cast<uint32_t *>(P.out_keys)[at] = idx;
+                } else if (NL <= 2) {
+                  reinterpret_cast<unsigned long long *>(P.out_keys)[at] = b0;
+                } else {
+                  reinterpret_cast<ulonglong2 *>(P.out_keys)[at] = make_ulonglong2(b0, b1);
                 }
-              } else if (OUT == OUT_INDEX) {
-                reinterpret_cast<uint32_t *>(s_keys)[slot] = idx;
-              } else if (NL <= 2) {
-                reinterpret_cast<unsigned long long *>(s_keys)[slot] = b0;
-              } else {
-                reinterpret_cast<ulonglong2 *>(s_keys)[slot] = make_ulonglong2(b0, b1);
+                if (OUT == OUT_LIST) P.out_pos[at] = (p0 + j) | (lt ? 0u : 0x80000000u);
               }
-              if (OUT == OUT_LIST && !(kSparse && slot >= (uint32_t)kStageSlots)) s_pos[slot] = (p0 + j) | (lt ? 0u : 0x80000000u);
+            } else if (OUT == OUT_INDEX) {
+              reinterpret_cast<uint32_t *>(s_keys)[slot] = idx;
+            } else if (NL <= 2) {
+              reinterpret_cast<unsigned long long *>(s_keys)[slot] = b0;
+            } else {
+              reinterpret_cast<ulonglong2 *>(s_keys)[slot] = make_ulonglong2(b0, b1);
+            }
+            if (OUT == OUT_LIST && !(kSparse && slot >= (uint32_t)kStageSlots)) s_pos[slot] = (p0 + j) | (lt ? 0u : 0x80000000u);
+          }
+        };
+
+        if (kSparse) {
+          // ---- K3, sparse predicate: the 16 hash chains run branch-free (independent chains for the scheduler, no
+          // control flow per window) and leave one candidate bit each; the few survivors (~1/c of the windows) are
+          // re-derived from the staged words and emitted afterwards.
+          // h % c == 0 with c = 2^s * d, d odd:  t = h * d^-1 (mod 2^64) has its low s bits clear and
+          // t >> s <= floor((2^64 - 1) / c), i.e. t <= mbound << s.  The low-bit test looks at the lower word only,
+          // which is the whole test for s <= 32; a modulus with more factors of two is re-tested below.
+          uint32_t cand = 0;
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j) {
+            uint32_t c[NL];
+            bool lt;
+            uint64_t b0, b1;
+            canonical(2 * j, c, lt);
+            blocks(c, b0, b1);
+            const uint64_t t = mul64(bitset_hash<PRED>(b0, b1) ^ P.hconst, P.minv);
+            if ((((uint32_t)t & (uint32_t)P.mlow) == 0) && (t <= P.mbound)) cand |= 1u << j;
+          }
+          cand &= vmask;
+          const bool wide_low = (P.mlow >> 32) != 0;  // uniform; s > 32
+#pragma unroll 1
+          while (cand) {
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1;
+            uint32_t c[NL];
+            bool lt;
+            uint64_t b0, b1;
+            canonical(2 * j, c, lt);
+            blocks(c, b0, b1);
+            if (wide_low) {
+              const uint64_t t = mul64(bitset_hash<PRED>(b0, b1) ^ P.hconst, P.minv);
+              if ((t & P.mlow) != 0) continue;
+            }
+            emit(j, c, lt, b0, b1);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j) {
+            uint32_t c[NL];
+            bool lt;
+            uint64_t b0, b1;
+            canonical(2 * j, c, lt);
+            blocks(c, b0, b1);
+
+            // ---- K3: predicate -----------------------------------------------------------------
+            bool pass = (vmask >> j) & 1u;
+            if (PRED != PRED_ALL) {
+              const uint64_t t = mul64(bitset_hash<PRED>(b0, b1) ^ P.hconst, P.minv);
+              pass = pass && ((t & P.mlow) == 0) && (t <= P.mbound);
+            }
+
+            // ---- K3/K4: emit -------------------------------------------------------------------
+            if (OUT == OUT_PART) {
+              if (pass) {
+                const uint32_t idx = pext_index<NL>(c, P.pext);
+                reinterpret_cast<uint32_t *>(s_keys)[j * kSketchThreads + tid] = idx;
+                s_rank[j * kSketchThreads + tid] = (uint16_t)atomicAdd(&s_hist[idx >> P.part_shift], 1u);
+              } else {
+                s_rank[j * kSketchThreads + tid] = 0xFFFFu;
+              }
+            } else if (pass) {
+              emit(j, c, lt, b0, b1);
             }
           }
         }

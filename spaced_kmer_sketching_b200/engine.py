@@ -193,6 +193,11 @@ class Context:
     def launches(self) -> int:
         return int(self._L.sks_ctx_launch_count(self.h))
 
+    @property
+    def in_place_calls(self) -> int:
+        """pair_ani calls that read the genomes in place from pinned host buffers (no host-to-device copy)."""
+        return int(self._L.sks_ctx_in_place_count(self.h))
+
     def profile(self, enable: bool):
         check(self._L.sks_ctx_profile(self.h, int(enable)))
 

@@ -396,6 +396,55 @@ def test_pair_pipeline_fused_build_and_onchip(ctx, ctx_bucket, ctx_exact):
     batch.close()
 
 
+def test_pair_ani_reads_pinned_host_buffers_in_place(ctx):
+    """sks_pair_ani on pinned, 16-byte aligned host buffers: the sketch kernel's bulk copies read the genomes in place
+    (no host-to-device copy).  Lengths around every boundary of the tile fetch (first tile without history words,
+    last 1-3 words by plain loads, genomes shorter than one bulk copy), every representation, dense and FracMinHash
+    predicates; pageable and misaligned buffers take the copy and give the same counts."""
+    import torch
+    rng = np.random.default_rng(17)
+    lengths = [1, 15, 16, 17, 47, 63, 64, 65, 100, 8191, 8192, 8193, 8255, 8256, 16384 + 37, 3 * 8192 - 1, 70001, 262147]
+
+    def pinned(words):
+        t = torch.empty(len(words) + 1, dtype=torch.int32).pin_memory()
+        t.numpy().view(np.uint32)[: len(words)] = words
+        assert t.data_ptr() % 16 == 0
+        return t
+
+    cases = [("1101100111011", sks.all_kmers(), port.ALL, ()),                       # weight 9: shared-memory bitset
+             ("011101110010111110011011", sks.all_kmers(), port.ALL, ()),            # weight 16: bucketed build
+             ("0011111011010111111011001011101", sks.frac_min_hash(1, 8), port.FMH, (1, 8, 181))]
+    n_in_place = ctx.in_place_calls
+    for li, L in enumerate(lengths):
+        A = rng.integers(0, 4, L, dtype=np.uint8)
+        Bm = A.copy()
+        idx = rng.integers(0, L, max(L // 40, 1))
+        Bm[idx] = (Bm[idx] + 1) & 3
+        if li % 3 == 0:
+            Bm = Bm[: max(L - 5, 1)]
+        wa, wb = sks.pack_codes(A), sks.pack_codes(Bm)
+        ta, tb = pinned(wa), pinned(wb)
+        for seed, pred, kind, args in cases:
+            mask, w = sks.seed_to_mask(seed)
+            oa = port.sketch_set(A, [len(A)], mask, w, kind, *args)
+            ob = port.sketch_set(Bm, [len(Bm)], mask, w, kind, *args)
+            want = (len(oa), len(ob), port.intersection(oa, ob))
+            reprs = (sks.REPR_SORTED,) if kind == port.FMH else (sks.REPR_BITSET, sks.REPR_BITSET_ONCHIP, sks.REPR_SORTED)
+            for r in reprs:
+                res = ctx.pair_ani_ptr(ta.data_ptr(), len(A), tb.data_ptr(), len(Bm), mask, w, pred, r)
+                n_in_place += 1
+                assert ctx.in_place_calls == n_in_place, "the pinned buffers were copied instead of read in place"
+                assert (res.size_a, res.size_b, res.intersection) == want, (L, seed, r)
+                # pageable memory, and a pinned buffer at a misaligned address: copied, same counts
+                res = ctx.pair_ani(wa, len(A), wb, len(Bm), mask, w, pred, r)
+                assert (res.size_a, res.size_b, res.intersection) == want, (L, seed, r, "pageable")
+            if len(wa) > 1:
+                off = pinned(np.concatenate([wa[:1], wa]))
+                res = ctx.pair_ani_ptr(off.data_ptr() + 4, len(A), tb.data_ptr(), len(Bm), mask, w, pred, reprs[-1])
+                assert (res.size_a, res.size_b, res.intersection) == want, (L, seed, "misaligned")
+                assert ctx.in_place_calls == n_in_place
+
+
 def test_fasta_files_to_sets(ctx, tmp_path):
     A = port.gen(50_000, 5)
     B = port.mutate(A, 6, 50)
