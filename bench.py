@@ -434,11 +434,13 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
     L3 = 250_000_000
     shard = multi_gpu.position_shard(L3, w3, rank, world)
     b3 = multi_gpu.synth_slice(ctx, L3, 7, shard, w3)
-    def c3_step():
+    def c3_step(mid=None):
         """Local sketch of the rank's slice; for N > 1 the global set on every rank: all-gather of the partial
         sketches' keys, sort + unique of the union (slices overlap by the halo only, duplicates are k-mers that
         occur in two slices)."""
         (loc,) = ctx.sketch(b3, mask3, w3, pred)
+        if mid is not None:
+            mid.record(stream)
         if world == 1:
             return loc, loc
         keys, _, kw = multi_gpu.keys_as_tensor([loc], torch)
@@ -459,8 +461,12 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 5
     e0.record(stream)
+    c3_ev = []
     for _ in range(reps):
-        s, glob = c3_step()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        s, glob = c3_step(eb)
+        c3_ev.append((ea, eb))
         n_global = glob.kmer_set_size()
         if world > 1:
             glob.close()
@@ -471,11 +477,13 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
     ks = ctx.kernel_stats()
     ctx.profile(False)
     ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+    local_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in c3_ev)) / reps   # partial sketches only, no exchange
     n_local = s.kmer_set_size()
     sk_ms = ks["sketch_kernel"][1] / ks["sketch_kernel"][0]
     bases_local = shard[1] + w3 - 1
     out["c3_sketch"] = {"workload": "250 Mbp sequence, seed " + C3_SEED + ", FMH(200, nonce 1, Boost>=1.81), position-sharded, global set on every rank",
                         "bases_per_s": L3 / (ms / 1e3), "ms": ms, "scaling": "strong",
+                        "bases_per_s_partial_sketches": L3 / (local_ms / 1e3), "ms_partial_sketches": local_ms,
                         "sketch_kernel_ms": sk_ms,
                         "sketch_kernel_gbs": bases_local * (0.25 + 8.0 / 200) / (sk_ms * 1e-3) / 1e9,
                         "sketch_kernel_frac_of_hbm": bases_local * (0.25 + 8.0 / 200) / (sk_ms * 1e-3) / 1e9 / peak,

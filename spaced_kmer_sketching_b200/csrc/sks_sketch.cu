@@ -475,6 +475,18 @@ __global__ void __launch_bounds__(kSketchThreads, (PRED != PRED_ALL && OUT != OU
             }
             emit(j, c, lt, b0, b1);
           }
+        } else if (OUT == OUT_PART && PRED == PRED_ALL && vmask == 0xFFFFu) {
+          // ---- every window of the group exists and is kept (the common case of the dense bitset build): no control
+          // flow per window, so the 16 rank atomics are in flight together
+#pragma unroll
+          for (int j = 0; j < kGroup; ++j) {
+            uint32_t c[NL];
+            bool lt;
+            canonical(2 * j, c, lt);
+            const uint32_t idx = pext_index<NL>(c, P.pext);
+            reinterpret_cast<uint32_t *>(s_keys)[j * kSketchThreads + tid] = idx;
+            s_rank[j * kSketchThreads + tid] = (uint16_t)atomicAdd(&s_hist[idx >> P.part_shift], 1u);
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < kGroup; ++j) {
