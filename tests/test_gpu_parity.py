@@ -445,6 +445,38 @@ def test_pair_ani_reads_pinned_host_buffers_in_place(ctx):
                 assert ctx.in_place_calls == n_in_place
 
 
+def test_sort_unique_of_raw_device_keys(ctx):
+    """sks_set_from_unsorted_device_keys (the union step of the position-sharded sketch): random keys under a spaced
+    mask, sizes from one key to a few hundred thousand, uniform and heavily skewed over the buckets, with duplicates --
+    against numpy's sort + unique.  Exercises the bucket sort's small and large networks and its fall-backs to the library sort."""
+    import torch
+    rng = np.random.default_rng(23)
+    mask, w = sks.seed_to_mask("0011111011010111111011001011101")
+    mbits = [b for b in range(64) if (mask >> b) & 1]
+
+    def spread(vals):   # deposit the low bits of vals at the mask's set positions (PDEP)
+        out = np.zeros(len(vals), dtype=np.uint64)
+        for k, b in enumerate(mbits):
+            out |= ((vals >> np.uint64(k)) & np.uint64(1)) << np.uint64(b)
+        return out
+
+    for n in (1, 2, 31, 32, 33, 300, 1000, 5000, 40_000, 300_000):
+        for kind in ("uniform", "skewed", "duplicates"):
+            raw = rng.integers(0, 1 << len(mbits), n, dtype=np.uint64)
+            if kind == "skewed":        # most keys share their top bits: one bucket far above the average
+                raw[: n - n // 8] &= np.uint64((1 << (len(mbits) - 9)) - 1)
+            if kind == "duplicates":
+                raw = raw[rng.integers(0, max(n // 3, 1), n)]
+            keys = spread(raw)
+            want = np.unique(keys)
+            d = torch.from_numpy(keys.view(np.int64)).cuda()
+            s = ctx.set_from_device_keys(d.data_ptr(), n, 1, mask, w, sorted_unique=False)
+            got = s.keys()
+            assert s.kmer_set_size() == len(want), (n, kind)
+            assert np.array_equal(got[:, 0], want) and not got[:, 1].any(), (n, kind)
+            s.close()
+
+
 def test_fasta_files_to_sets(ctx, tmp_path):
     A = port.gen(50_000, 5)
     B = port.mutate(A, 6, 50)
@@ -689,6 +721,6 @@ def test_alternative_routes_in_a_subprocess():
         pytest.skip("already inside the child process")
     env = dict(os.environ, SKS_ROW_INTERSECT="0", SKS_BUCKET_SORT="0")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
-                        "fuzz_all_pairs or all_pairs_row or multi_golden or fuzz_lists or sets_golden"],
+                        "fuzz_all_pairs or all_pairs_row or multi_golden or fuzz_lists or sets_golden or sort_unique"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
