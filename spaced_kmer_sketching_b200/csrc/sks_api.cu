@@ -1308,17 +1308,22 @@ int sks_set_load(sks_ctx *ctx, const char *path, sks_set **out, sks_pred *out_pr
 }
 
 // ---- comparison ----------------------------------------------------------------------------------
-int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *const *b, int64_t nb, int32_t *out) {
+// `uniform`: the caller has already checked that every set of both lists has the mask, representation, key width and
+// device of a[0] (sks_intersect_rects checks each distinct set once instead of once per pair).
+static int intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *const *b, int64_t nb, int32_t *out,
+                           bool uniform) {
   if (!ctx || (na > 0 && (!a || !b || !out))) return set_error(SKS_ERR_INVALID, "null argument");
   // src/kmer_set.cpp:147-150,174-177
   if (na != nb) return set_error(SKS_ERR_MISMATCH, "Lists of kmer sets for intersection computation have different lengths");
   if (na == 0) return SKS_OK;
   DeviceGuard guard(ctx->device);
-  for (int64_t i = 0; i < na; ++i) SKS_TRY(check_pair(a[i], b[i]));
   const int repr = a[0]->repr;
-  for (int64_t i = 0; i < na; ++i)
-    if (a[i]->repr != repr || a[i]->key_words != a[0]->key_words)
-      return set_error(SKS_ERR_MISMATCH, "pair list mixes set representations");
+  if (!uniform) {
+    for (int64_t i = 0; i < na; ++i) SKS_TRY(check_pair(a[i], b[i]));
+    for (int64_t i = 0; i < na; ++i)
+      if (a[i]->repr != repr || a[i]->key_words != a[0]->key_words)
+        return set_error(SKS_ERR_MISMATCH, "pair list mixes set representations");
+  }
 
   if (repr == SKS_REPR_BITSET) {
     unsigned long long *d_cnt = nullptr, *h_cnt = nullptr;
@@ -1345,7 +1350,7 @@ int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *co
   const int kw = a[0]->key_words;
   static const bool row_enabled = getenv("SKS_ROW_INTERSECT") ? atoi(getenv("SKS_ROW_INTERSECT")) != 0 : true;
   bool one_mask = na < (int64_t)1 << 31;
-  for (int64_t i = 1; i < na && one_mask; ++i)
+  for (int64_t i = 1; i < na && one_mask && !uniform; ++i)
     one_mask = a[i]->mask[0] == a[0]->mask[0] && a[i]->mask[1] == a[0]->mask[1];
   std::vector<RowTaskHost> tasks;
   std::vector<uint32_t> rest;
@@ -1427,6 +1432,10 @@ int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *co
   return SKS_OK;
 }
 
+int sks_intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set *const *b, int64_t nb, int32_t *out) {
+  return intersect_pairs(ctx, a, na, b, nb, out, false);
+}
+
 int sks_intersect(sks_ctx *ctx, sks_set *a, sks_set *b, int64_t *out) {
   if (!out) return set_error(SKS_ERR_INVALID, "null argument");
   int32_t r = 0;
@@ -1438,33 +1447,48 @@ int sks_intersect(sks_ctx *ctx, sks_set *a, sks_set *b, int64_t *out) {
 
 int sks_intersect_rects(sks_ctx *ctx, sks_set *const *sets, int64_t n, const int64_t *rects, int64_t n_rects, int32_t *out) {
   if (!ctx || (n > 0 && (!sets || !out)) || (n_rects > 0 && !rects)) return set_error(SKS_ERR_INVALID, "null argument");
-  std::vector<sks_set *> pa, pb;
-  std::vector<std::pair<int64_t, int64_t>> ij;
-  std::vector<char> mirrored;
+  // every set that occurs is checked once against the first one; the pair loop below then needs no checks
+  size_t cap = 0;
+  const sks_set *ref = nullptr;
   for (int64_t q = 0; q < n_rects; ++q) {
     const int64_t row_begin = rects[4 * q], row_end = rects[4 * q + 1], col_begin = rects[4 * q + 2], col_end = rects[4 * q + 3];
     if (row_begin < 0 || row_end > n || row_begin > row_end) return set_error(SKS_ERR_INVALID, "bad row range");
     if (col_begin < 0 || col_end > n || col_begin > col_end) return set_error(SKS_ERR_INVALID, "bad column range");
+    if (row_begin == row_end || col_begin == col_end) continue;
+    cap += (size_t)(row_end - row_begin) * (size_t)(col_end - col_begin);
+    for (int side = 0; side < 2; ++side)
+      for (int64_t i = side ? col_begin : row_begin; i < (side ? col_end : row_end); ++i) {
+        if (!ref) ref = sets[i];
+        SKS_TRY(check_pair(ref, sets[i]));
+      }
+  }
+  std::vector<sks_set *> pa, pb;
+  std::vector<int64_t> slot;  // pair k -> out[slot[2k]] and, unless negative, out[slot[2k+1]] (its mirror)
+  pa.reserve(cap);
+  pb.reserve(cap);
+  slot.reserve(2 * cap);
+  for (int64_t q = 0; q < n_rects; ++q) {
+    const int64_t row_begin = rects[4 * q], row_end = rects[4 * q + 1], col_begin = rects[4 * q + 2], col_end = rects[4 * q + 3];
     // |A n B| is symmetric: an unordered pair that lies in the rectangle with both orientations is evaluated once
-    // and mirrored inside it.
-    auto in_rect = [&](int64_t i, int64_t j) { return i >= row_begin && i < row_end && j >= col_begin && j < col_end; };
-    for (int64_t i = row_begin; i < row_end; ++i)
+    // and mirrored inside it.  (j, i) lies in the rectangle iff j is one of its rows and i one of its columns.
+    for (int64_t i = row_begin; i < row_end; ++i) {
+      const bool i_is_col = i >= col_begin && i < col_end;
       for (int64_t j = col_begin; j < col_end; ++j) {
         if (j == i) continue;
-        const bool both = in_rect(j, i);
+        const bool both = i_is_col && j >= row_begin && j < row_end;
         if (j < i && both) continue;  // (j, i) is in the rectangle too and comes first
         pa.push_back(sets[i]);
         pb.push_back(sets[j]);
-        ij.emplace_back(i, j);
-        mirrored.push_back(both ? 1 : 0);
+        slot.push_back(i * n + j);
+        slot.push_back(both ? j * n + i : -1);
       }
+    }
   }
   std::vector<int32_t> r(pa.size());
-  SKS_TRY(sks_intersect_pairs(ctx, pa.data(), (int64_t)pa.size(), pb.data(), (int64_t)pb.size(), r.data()));
-  for (size_t k = 0; k < ij.size(); ++k) {
-    const int64_t i = ij[k].first, j = ij[k].second;
-    out[i * n + j] = r[k];
-    if (mirrored[k]) out[j * n + i] = r[k];
+  SKS_TRY(intersect_pairs(ctx, pa.data(), (int64_t)pa.size(), pb.data(), (int64_t)pb.size(), r.data(), true));
+  for (size_t k = 0; k < r.size(); ++k) {
+    out[slot[2 * k]] = r[k];
+    if (slot[2 * k + 1] >= 0) out[slot[2 * k + 1]] = r[k];
   }
   for (int64_t q = 0; q < n_rects; ++q) {  // |A n A| = |A|
     const int64_t lo = std::max(rects[4 * q], rects[4 * q + 2]), hi = std::min(rects[4 * q + 1], rects[4 * q + 3]);
