@@ -1129,9 +1129,35 @@ __global__ void __launch_bounds__(kSortThreads)
   while (P < n) P <<= 1;
   const uint32_t tid = threadIdx.x;
   // the tail is padded with copies of the largest possible key; index < n decides what is real afterwards
-  for (uint32_t i = tid; i < P; i += kSortThreads) s[i] = i < n ? tmp[lo + i] : K::pad();
+  uint32_t k_first = 2;
+  if constexpr (KW == 1) {
+    // the first five phases (runs of 32 keys, 15 of the network's substages) never leave the registers: a warp holds
+    // a run, one key per lane, and exchanges through shuffles -- the shared-memory network below is bound by the
+    // shared-memory bandwidth (ncu profiles/r01_t_*: 81 %), and these substages would be a third of its traffic.
+    // (More keys per lane -- runs of 64 to 256 with register compare-exchanges for the short strides -- were
+    // measured too: no faster, the longer dependent chains leave the warps waiting.)
+    for (uint32_t i = tid; i < P; i += kSortThreads) {  // P is a multiple of 32: whole warps
+      unsigned long long v = i < n ? tmp[lo + i] : K::pad();
+      const uint32_t ln = tid & 31;
+#pragma unroll
+      for (uint32_t k = 2; k <= 32; k <<= 1) {
+        const bool up = (i & k) == 0;
+#pragma unroll
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, (int)j);
+          const bool want_min = ((ln & j) == 0) == up;
+          const bool take = want_min ? (o < v) : (o > v);
+          v = take ? o : v;
+        }
+      }
+      s[i] = v;
+    }
+    k_first = 64;
+  } else {
+    for (uint32_t i = tid; i < P; i += kSortThreads) s[i] = i < n ? tmp[lo + i] : K::pad();
+  }
   __syncthreads();
-  for (uint32_t k = 2; k <= P; k <<= 1) {
+  for (uint32_t k = k_first; k <= P; k <<= 1) {
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
       for (uint32_t t = tid; t < P / 2; t += kSortThreads) {
         const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
