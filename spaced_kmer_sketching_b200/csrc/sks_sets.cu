@@ -1157,8 +1157,11 @@ __global__ void __launch_bounds__(kSortThreads)
     for (uint32_t i = tid; i < P; i += kSortThreads) s[i] = i < n ? tmp[lo + i] : K::pad();
   }
   __syncthreads();
+  // 8-byte keys: only the strides from 32 up go through shared memory; the five short strides of every phase are
+  // one pass in registers (a warp loads 32 consecutive keys, exchanges through shuffles, stores them back)
+  constexpr uint32_t j_min = KW == 1 ? 32u : 1u;
   for (uint32_t k = k_first; k <= P; k <<= 1) {
-    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+    for (uint32_t j = k >> 1; j >= j_min; j >>= 1) {
       for (uint32_t t = tid; t < P / 2; t += kSortThreads) {
         const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
         const uint32_t l = i | j;
@@ -1168,6 +1171,22 @@ __global__ void __launch_bounds__(kSortThreads)
           s[i] = b;
           s[l] = a;
         }
+      }
+      __syncthreads();
+    }
+    if constexpr (KW == 1) {
+      for (uint32_t i = tid; i < P; i += kSortThreads) {
+        unsigned long long v = s[i];
+        const bool up = (i & k) == 0;
+        const uint32_t ln = tid & 31;
+#pragma unroll
+        for (uint32_t j = 16; j > 0; j >>= 1) {
+          const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, (int)j);
+          const bool want_min = ((ln & j) == 0) == up;
+          const bool take = want_min ? (o < v) : (o > v);
+          v = take ? o : v;
+        }
+        s[i] = v;
       }
       __syncthreads();
     }
