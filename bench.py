@@ -503,7 +503,8 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
     res = None
     c4_counts = None     # the n x n count matrix is reused from one iteration to the next
     ctx.profile(True)
-    for it in range(3):
+    c4_runs = []
+    for it in range(6):   # one warm-up pass, then five timed ones: the pass with the median total is reported
         barrier()
         ctx.kernel_stats()
         t = {}
@@ -530,6 +531,8 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
         barrier()
         res = [max_over_ranks(e[i].elapsed_time(e[i + 1])) for i in range(3)] + [max_over_ranks(t_host)]
         c4_kernels = {k: {"launches": v[0], "ms": v[1]} for k, v in ctx.kernel_stats().items()}
+        if it > 0:
+            c4_runs.append((sum(res), res, c4_kernels))
         n_total = len(all_sets)
         sizes = [x.kmer_set_size() for x in all_sets]
         # algorithmic bytes of this rank's intersections: (|A| + |B|) * key_bytes per unordered pair it
@@ -583,8 +586,10 @@ def extra_legs(ctx, sks, torch, dist, rank, world, stream, barrier, max_over_ran
         out["c5_multi_seed"] = {"workload": "%d synthetic 5 Mbp genomes (graded mutants of one base), random spaced seeds "
                                             "(k+10, k, seed 0) for k = 12..28, FMH(200); ANI(base, mutant) against 1 - 1/D" % n5,
                                 "per_seed": rows5}
-    total = sum(res)
-    out["c4_all_vs_all"] = {"kernels": c4_kernels,"workload": "%d synthetic 5 Mbp genomes (%d per GPU) at graded mutation rates, seed %s, "
+    c4_runs.sort(key=lambda r: r[0])
+    total, res, c4_kernels = c4_runs[len(c4_runs) // 2]
+    out["c4_all_vs_all"] = {"kernels": c4_kernels, "passes": "median of %d passes (totals %s ms)" % (
+                                len(c4_runs), ", ".join("%.2f" % r[0] for r in c4_runs)),"workload": "%d synthetic 5 Mbp genomes (%d per GPU) at graded mutation rates, seed %s, "
                                         "FMH(200), all n^2 ordered pairs; every unordered block pair on one rank" % (n_total, G, C3_SEED),
                             "ani_pairs_per_s": n_total * n_total / (total / 1e3),
                             "ani_pairs_per_s_compare_only": n_total * n_total / (res[2] / 1e3),
