@@ -12,6 +12,9 @@
 // complemented words, and the forward window is a left funnel shift of the 2-bit-group-reversed
 // words.  A thread owns 16 consecutive window starts whose first is word aligned, so after one
 // per-group alignment shift every per-window shift amount is a compile-time constant.
+#include <type_traits>
+#include <utility>
+
 #include "sks_internal.cuh"
 
 namespace sks {
@@ -448,16 +451,27 @@ __global__ void __launch_bounds__(kSketchThreads, (PRED != PRED_ALL && OUT != OU
           // t >> s <= floor((2^64 - 1) / c), i.e. t <= mbound << s.  The low-bit test looks at the lower word only,
           // which is the whole test for s <= 32; a modulus with more factors of two is re-tested below.
           uint32_t cand = 0;
-#pragma unroll
-          for (int j = 0; j < kGroup; ++j) {
+          auto window = [&](auto J) {
+            constexpr int j = decltype(J)::value;
             uint32_t c[NL];
             bool lt;
             uint64_t b0, b1;
             canonical(2 * j, c, lt);
             blocks(c, b0, b1);
             const uint64_t t = mul64(bitset_hash<PRED>(b0, b1) ^ P.hconst, P.minv);
-            if ((((uint32_t)t & (uint32_t)P.mlow) == 0) && (t <= P.mbound)) cand |= 1u << j;
-          }
+            // cand |= ((t_lo & mlow_lo) == 0 && t <= mbound) << j in four instructions: the low-bit test feeds the
+            // 64-bit compare as its combining predicate, the bit is ORed in under the result (the compiler's own
+            // version spends two selects and an OR on it)
+            asm("{\n .reg .pred q, p;\n .reg .b32 lowt;\n and.b32 lowt, %1, %2;\n setp.eq.u32 q, lowt, 0;\n"
+                " setp.le.and.u64 p, %3, %4, q;\n @p or.b32 %0, %0, %5;\n}"
+                : "+r"(cand)
+                : "r"((uint32_t)t), "r"((uint32_t)P.mlow), "l"(t), "l"(P.mbound), "n"(1u << j));
+          };
+          static_assert(kGroup == 16, "the window calls below are written out");
+#define SKS_WINDOW(j) window(std::integral_constant<int, j>{})
+          SKS_WINDOW(0); SKS_WINDOW(1); SKS_WINDOW(2); SKS_WINDOW(3); SKS_WINDOW(4); SKS_WINDOW(5); SKS_WINDOW(6); SKS_WINDOW(7);
+          SKS_WINDOW(8); SKS_WINDOW(9); SKS_WINDOW(10); SKS_WINDOW(11); SKS_WINDOW(12); SKS_WINDOW(13); SKS_WINDOW(14); SKS_WINDOW(15);
+#undef SKS_WINDOW
           cand &= vmask;
           const bool wide_low = (P.mlow >> 32) != 0;  // uniform; s > 32
 #pragma unroll 1
