@@ -100,7 +100,10 @@ int64_t sks_ctx_in_place_count(const sks_ctx *ctx);
 #define SKS_KERNEL_BITSET_BUILD 8 /* bucket sort + slice-wise bitset assembly (K4, bucketed) */
 #define SKS_KERNEL_FASTA 9        /* device-side FASTA parse + 2-bit pack                */
 #define SKS_KERNEL_PAIR_BUILD 10  /* fused slice assembly + AND/popcount of a genome pair (K4b + K5) */
-#define SKS_KERNEL_KINDS 11
+#define SKS_KERNEL_DICT 11       /* all-vs-all: dictionary of shared k-mers, sets re-coded as id bitmaps / lists */
+#define SKS_KERNEL_ALLPAIRS 12   /* all-vs-all: AND/popcount of the re-coded sets (K5, many sets)               */
+#define SKS_KERNEL_ANI 13        /* all-vs-all: mirror + diagonal + containment^(1/weight) on the device        */
+#define SKS_KERNEL_KINDS 14
 int sks_ctx_profile(sks_ctx *ctx, int enable);
 int sks_ctx_kernel_stats(sks_ctx *ctx, int kind, int64_t *out_launches, double *out_total_ms);
 const char *sks_kernel_name(int kind);
@@ -247,6 +250,17 @@ int sks_intersect_block(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t r
 /* Several such rectangles (rects[4*q .. 4*q+3] = row_begin, row_end, col_begin, col_end) in one pass over one pair
  * table: what a rank of the multi-GPU tiling evaluates. */
 int sks_intersect_rects(sks_ctx *ctx, sks_set *const *sets, int64_t n, const int64_t *rects, int64_t n_rects, int32_t *out);
+/* The comparison phase of the reference driver in one device-resident pass (src/kmer-sketching.cpp:185-200:
+ * generate_all_pairs_from_vector -> parallel_compute_pairwise_kmer_set_intersections -> containment ->
+ * binomial_estimator), for the rows [row_begin, row_end) of the n x n matrix of ordered pairs:
+ *   out_counts[(i - row_begin) * n + j] = |sets[i] n sets[j]|   (NULL: not wanted)
+ *   out_sizes[i]                        = sets[i]->kmer_set_size() for all n sets (NULL: not wanted)
+ *   out_ani[(i - row_begin) * n + j]    = binomial_estimator(containment(count, |sets[i]|), weight)  (NULL: not wanted)
+ * SORTED sets of one mask go through a dictionary of their shared k-mers (csrc/sks_allpairs.cu) and the ANI is
+ * evaluated on the device in double precision (CUDA pow, <= 2 ulp: within 1e-15 of the host's libm); any other
+ * input takes sks_intersect_all_pairs + sks_ani_from_counts. */
+int sks_all_vs_all(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, int32_t *out_counts,
+                   int32_t *out_sizes, double *out_ani);
 /* ANI matrix from counts, src/kmer-sketching.cpp:196-200: containment on the FIRST set of the
  * ordered pair, then ^(1/weight).  Host double arithmetic. */
 void sks_ani_from_counts(const int32_t *intersections, const int32_t *first_set_sizes, int64_t n_pairs,

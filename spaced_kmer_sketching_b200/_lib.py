@@ -16,7 +16,7 @@ SKS_OK, SKS_ERR_INVALID, SKS_ERR_CUDA, SKS_ERR_CAPACITY, SKS_ERR_MISMATCH, SKS_E
 PRED_ALL, PRED_FMH = 0, 1
 HASH_BOOST_171, HASH_BOOST_181 = 171, 181
 REPR_AUTO, REPR_SORTED, REPR_BITSET, REPR_BITSET_ONCHIP = 0, 1, 2, 3
-KERNEL_KINDS = 11
+KERNEL_KINDS = 14
 
 
 class SksPred(C.Structure):
@@ -101,6 +101,7 @@ PROTOTYPES = {
     "sks_intersect_all_pairs": (ci, [vp, C.POINTER(vp), i64, i64, i64, vp]),
     "sks_intersect_block": (ci, [vp, C.POINTER(vp), i64, i64, i64, i64, i64, vp]),
     "sks_intersect_rects": (ci, [vp, C.POINTER(vp), i64, vp, i64, vp]),
+    "sks_all_vs_all": (ci, [vp, C.POINTER(vp), i64, i64, i64, vp, vp, vp]),
     "sks_ani_from_counts": (None, [vp, vp, i64, ci, vp]),
     "sks_pair_ani": (ci, [vp, vp, u64, vp, u64, u64p, ci, C.POINTER(SksPred), ci, C.POINTER(SksPairResult)]),
     "sks_pair_ani_resident": (ci, [vp, vp, u64p, ci, C.POINTER(SksPred), ci, C.POINTER(SksPairResult)]),

@@ -1,0 +1,538 @@
+// All-vs-all intersection counts of many sorted k-mer sets through a dictionary of their SHARED k-mers.
+//
+// The reference evaluates every ordered pair on its own: `parallel_compute_pairwise_kmer_set_intersections` probes
+// the larger hash map with every element of the smaller one (src/kmer_set.cpp:23-41,167-184), n^2 * |sketch| probes
+// for `generate_all_pairs_from_vector` (src/generators.hpp:44-58).  Only k-mers that occur in at least two sets can
+// ever be counted, and most k-mers of a sketch are either private to their genome or shared with many.  So:
+//
+//   D1  every key of every set goes into one device-wide open-addressing table that counts in how many sets it
+//       occurs (the sets hold distinct keys, so multiplicity == number of sets);
+//   D2  keys of multiplicity >= 2 get dense 32-bit ids, the widely shared ones (>= n/16 sets) first;
+//   D3  every set is re-written as its shared ids, grouped by id range (2^16 ids): a range a set is dense in
+//       (>= 1024 ids) becomes an 8 KB bitmap, a sparse one a 16-bit id list, an empty one nothing;
+//   X   |A n B| = sum over the ranges both sets are present in of popc(bitmap_A & bitmap_B) (or of list probes
+//       into A's bitmap, which sits in shared memory for a whole chunk of columns);
+//   F   counts (+ the diagonal |A n A| = |A|), set sizes and ANI = (|A n B| / |A|)^(1/weight)
+//       (src/ani_estimation.cpp:24-42, src/kmer-sketching.cpp:196-200) are finalised on the device.
+//
+// Nothing returns to the host in between; the counts are bit-identical to the pairwise kernels' (tests compare
+// both with the oracle).  16-byte keys are first compacted through the mask (PEXT) to 64 bits, which needs
+// weight <= 32.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "sks_internal.cuh"
+
+namespace sks {
+namespace {
+
+constexpr int kRangeBits = 16;                      // ids per range
+constexpr uint32_t kRangeIds = 1u << kRangeBits;
+constexpr uint32_t kRangeWords = kRangeIds / 32;    // 2048 words = 8 KB bitmap = 512 x 16 B
+constexpr uint32_t kRange16 = kRangeWords / 4;      // the same in 16-byte units
+constexpr uint32_t kDenseMin = 1024;                // ids of a (set, range) group from which it is stored as a bitmap
+constexpr uint32_t kNoId = 0xFFFFFFFFu;
+constexpr int kDictThreads = 256;
+constexpr int kDictPer = 4;                         // entries per thread
+constexpr int kDictChunk = kDictThreads * kDictPer;
+constexpr int kPairsThreads = 256;
+constexpr int kPairsWarps = kPairsThreads / 32;
+constexpr int kPairsCols = 64;                      // columns per task
+
+// PEXT of a 16-byte key through the mask as runs of mask ones (n_runs == 0: 8-byte keys are used as they are).
+struct Compact {
+  int n_runs;
+  uint8_t src[32], len[32], dst[32];
+};
+
+struct Slot {  // 16 bytes: one sector holds the key and its counters
+  unsigned long long key;  // 0 = empty (key 0 itself lives in the extra slot `cap`)
+  uint32_t cnt;            // number of entries (== sets) that hold the key
+  uint32_t id;             // D2: dense id, or kNoId
+};
+
+enum Counter : int { C_IDS_A = 0, C_IDS_B = 1, C_ROWS = 2, C_TASK = 3, C_COUNT = 16 };
+
+struct DictView {
+  const void *const *set_ptr;  // [n] keys of set s
+  const uint32_t *set_off;     // [n + 1] first entry of set s in the flattened numbering of all keys
+  uint32_t n_sets;
+  uint32_t n_entries;
+  Slot *tab;                   // [cap + 1]
+  uint32_t cap;
+  uint32_t *entry;             // [n_entries] D1: slot of the entry's key; D3: its id (kNoId: not shared)
+  uint32_t *counters;          // [C_COUNT]
+};
+
+__device__ __forceinline__ uint32_t size16(uint32_t cnt) {  // payload of a (set, range) group in 16-byte units
+  return cnt == 0 ? 0u : (cnt >= kDenseMin ? kRange16 : (2 * cnt + 15) / 16);
+}
+struct Size16Op {
+  __device__ __forceinline__ uint32_t operator()(uint32_t cnt) const { return size16(cnt); }
+};
+
+template <int KW>
+__device__ __forceinline__ unsigned long long load_key(const void *base, uint32_t i, const Compact &c) {
+  if (KW == 1) return static_cast<const unsigned long long *>(base)[i];
+  const ulonglong2 k = static_cast<const ulonglong2 *>(base)[i];
+  unsigned long long out = 0;
+  for (int r = 0; r < c.n_runs; ++r) {
+    const int s = c.src[r];
+    const unsigned long long v = s >= 64 ? (k.y >> (s - 64)) : (s == 0 ? k.x : ((k.x >> s) | (k.y << (64 - s))));
+    const unsigned long long m = c.len[r] >= 64 ? ~0ull : ((1ull << c.len[r]) - 1);
+    out |= (v & m) << c.dst[r];
+  }
+  return out;
+}
+
+__device__ __forceinline__ uint32_t hash_slot(unsigned long long k, uint32_t cap) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return __umulhi((uint32_t)(k >> 32), cap);
+}
+
+// Largest s with set_off[s] <= e (empty sets share their offset with their successor and are never returned).
+__device__ __forceinline__ uint32_t find_set(const uint32_t *__restrict__ set_off, uint32_t n_sets, uint32_t e) {
+  uint32_t lo = 0, hi = n_sets;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(set_off + mid) <= e) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// D1: insert every key, count its occurrences, remember its slot.
+template <int KW>
+__global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_constant__ DictView D,
+                                                                   const __grid_constant__ Compact C) {
+  const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
+  uint32_t s = 0, slot[kDictPer];
+  unsigned long long key[kDictPer], cur[kDictPer];
+  bool have = false;
+#pragma unroll
+  for (int u = 0; u < kDictPer; ++u) {
+    const uint32_t e = base + u * kDictThreads + threadIdx.x;
+    slot[u] = kNoId;
+    if (e < D.n_entries) {
+      if (!have) {
+        s = find_set(D.set_off, D.n_sets, e);
+        have = true;
+      } else {
+        while (e >= __ldg(D.set_off + s + 1)) ++s;
+      }
+      key[u] = load_key<KW>(D.set_ptr[s], e - __ldg(D.set_off + s), C);
+      slot[u] = key[u] ? hash_slot(key[u], D.cap) : D.cap;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kDictPer; ++u)  // the first probes of a thread's entries are in flight together
+    if (slot[u] != kNoId && slot[u] != D.cap) cur[u] = __ldcg(&D.tab[slot[u]].key);
+#pragma unroll
+  for (int u = 0; u < kDictPer; ++u) {
+    if (slot[u] == kNoId) continue;
+    uint32_t sl = slot[u];
+    if (sl != D.cap) {
+      unsigned long long c = cur[u];
+      for (;;) {
+        if (c == key[u]) break;
+        if (c == 0) {
+          c = atomicCAS(&D.tab[sl].key, 0ull, key[u]);
+          if (c == 0 || c == key[u]) break;
+        }
+        sl = sl + 1 == D.cap ? 0 : sl + 1;
+        c = __ldcg(&D.tab[sl].key);
+      }
+    }
+    atomicAdd(&D.tab[sl].cnt, 1u);
+    D.entry[base + u * kDictThreads + threadIdx.x] = sl;
+  }
+}
+
+// D2: ids for the keys that occur in at least two sets; class A (>= thr_a sets) and class B are numbered apart,
+// class B follows class A at the next range boundary (dict_ids_kernel).
+__global__ void __launch_bounds__(256) dict_assign_kernel(Slot *__restrict__ tab, uint32_t n_slots, uint32_t thr_a,
+                                                          uint32_t *__restrict__ counters) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  const uint32_t n_round = (n_slots + 31) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    const uint32_t c = i < n_slots ? tab[i].cnt : 0u;
+    const int cls = c >= thr_a && c >= 2 ? 0 : (c >= 2 ? 1 : 2);
+    uint32_t id = kNoId;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t m = __ballot_sync(0xffffffffu, cls == k);
+      if (m == 0) continue;
+      uint32_t first = 0;
+      if (lane == (uint32_t)(__ffs(m) - 1)) first = atomicAdd(counters + k, (uint32_t)__popc(m));
+      first = __shfl_sync(0xffffffffu, first, __ffs(m) - 1);
+      if (cls == k) id = ((uint32_t)k << 31) | (first + __popc(m & ((1u << lane) - 1)));
+    }
+    if (i < n_slots) tab[i].id = id;
+  }
+}
+
+// D3a: entry -> id, and the number of ids of every (range, set) group.
+__global__ void __launch_bounds__(kDictThreads) dict_ids_kernel(const __grid_constant__ DictView D,
+                                                                uint32_t *__restrict__ group_cnt) {
+  const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
+  const uint32_t base_b = (D.counters[C_IDS_A] + kRangeIds - 1) & ~(kRangeIds - 1);
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t s = 0;
+  bool have = false;
+#pragma unroll
+  for (int u = 0; u < kDictPer; ++u) {
+    const uint32_t e = base + u * kDictThreads + threadIdx.x;
+    uint32_t bin = kNoId;
+    if (e < D.n_entries) {
+      if (!have) {
+        s = find_set(D.set_off, D.n_sets, e);
+        have = true;
+      } else {
+        while (e >= __ldg(D.set_off + s + 1)) ++s;
+      }
+      const uint32_t v = D.tab[D.entry[e]].id;
+      uint32_t id = kNoId;
+      if (v != kNoId) {
+        id = (v >> 31) ? base_b + (v & 0x7FFFFFFFu) : v;
+        bin = (id >> kRangeBits) * D.n_sets + s;
+      }
+      D.entry[e] = id;
+    }
+    // one atomic per distinct group of the warp (a warp's entries mostly belong to one set and few ranges)
+    const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+    if (bin != kNoId && lane == (uint32_t)(__ffs(peers) - 1)) atomicAdd(group_cnt + bin, (uint32_t)__popc(peers));
+  }
+}
+
+__global__ void __launch_bounds__(256) zero16_kernel(uint4 *__restrict__ p, const uint32_t *__restrict__ n16_ptr) {
+  const uint32_t n16 = *n16_ptr;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = make_uint4(0, 0, 0, 0);
+}
+
+// D3b: the groups' payloads: bitmap bits (dense) or 16-bit ids in arrival order (sparse).
+__global__ void __launch_bounds__(kDictThreads)
+    dict_payload_kernel(const __grid_constant__ DictView D, const uint32_t *__restrict__ group_cnt,
+                        const uint32_t *__restrict__ group_end, uint32_t *__restrict__ cursor, uint4 *__restrict__ payload) {
+  const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
+  uint32_t s = 0;
+  bool have = false;
+#pragma unroll
+  for (int u = 0; u < kDictPer; ++u) {
+    const uint32_t e = base + u * kDictThreads + threadIdx.x;
+    if (e >= D.n_entries) continue;
+    if (!have) {
+      s = find_set(D.set_off, D.n_sets, e);
+      have = true;
+    } else {
+      while (e >= __ldg(D.set_off + s + 1)) ++s;
+    }
+    const uint32_t id = D.entry[e];
+    if (id == kNoId) continue;
+    const uint32_t g = (id >> kRangeBits) * D.n_sets + s, c = group_cnt[g];
+    const uint32_t off = group_end[g] - size16(c), low = id & (kRangeIds - 1);
+    if (c >= kDenseMin) {
+      atomicOr(reinterpret_cast<uint32_t *>(payload + off) + (low >> 5), 1u << (low & 31));
+    } else {
+      const uint32_t pos = atomicAdd(cursor + g, 1u);
+      reinterpret_cast<uint16_t *>(payload + off)[pos] = (uint16_t)low;
+    }
+  }
+}
+
+// X0: the (range, row) groups that exist, for the rows of this call.
+__global__ void __launch_bounds__(256) rowlist_kernel(const uint32_t *__restrict__ group_cnt, uint32_t n_groups, uint32_t n_sets,
+                                                      uint32_t row_begin, uint32_t row_end, uint32_t *__restrict__ rowlist,
+                                                      uint32_t *__restrict__ counters) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups || group_cnt[g] == 0) return;
+  const uint32_t s = g % n_sets;
+  if (s < row_begin || s >= row_end) return;
+  rowlist[atomicAdd(counters + C_ROWS, 1u)] = g;
+}
+
+struct PairsView {
+  const uint32_t *group_cnt, *group_end;
+  const uint4 *payload;
+  const uint32_t *rowlist;
+  uint32_t *counters;
+  uint32_t n_sets, row_begin, n_chunks;
+  int symmetric;   // rows cover all sets: only j > i is evaluated, the finalisation mirrors
+  int32_t *out;    // [(row_end - row_begin) * n_sets], zero on entry
+};
+
+// X: persistent CTAs pull (range, row, column chunk) tasks.  The row's bitmap of that range sits in shared memory;
+// every warp takes one column at a time: AND/popcount against a dense column, bit probes for a sparse one.
+__global__ void __launch_bounds__(kPairsThreads) allpairs_kernel(const __grid_constant__ PairsView V) {
+  __shared__ __align__(16) uint32_t s_bits[kRangeWords];
+  __shared__ uint32_t s_task;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n_tasks = V.counters[C_ROWS] * V.n_chunks;
+  uint4 *s_bits4 = reinterpret_cast<uint4 *>(s_bits);
+  for (;;) {
+    __syncthreads();  // the previous task is done with s_bits and s_task
+    if (tid == 0) s_task = atomicAdd(V.counters + C_TASK, 1u);
+    __syncthreads();
+    const uint32_t task = s_task;
+    if (task >= n_tasks) break;
+    const uint32_t g = V.rowlist[task / V.n_chunks], chunk = task % V.n_chunks;
+    const uint32_t t = g / V.n_sets, i = g % V.n_sets;
+    const uint32_t j0 = chunk * kPairsCols, j1 = min(V.n_sets, j0 + kPairsCols);
+    if (V.symmetric && j1 <= i + 1) continue;
+    const uint32_t ca = V.group_cnt[g], offa = V.group_end[g] - size16(ca);
+    if (ca >= kDenseMin) {
+      for (uint32_t k = tid; k < kRange16; k += kPairsThreads) s_bits4[k] = __ldg(V.payload + offa + k);
+    } else {
+      for (uint32_t k = tid; k < kRange16; k += kPairsThreads) s_bits4[k] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      const uint16_t *la = reinterpret_cast<const uint16_t *>(V.payload + offa);
+      for (uint32_t k = tid; k < ca; k += kPairsThreads) {
+        const uint32_t id = la[k];
+        atomicOr(s_bits + (id >> 5), 1u << (id & 31));
+      }
+    }
+    __syncthreads();
+    for (uint32_t j = j0 + warp; j < j1; j += kPairsWarps) {
+      if (j == i || (V.symmetric && j < i)) continue;
+      const uint32_t gb = t * V.n_sets + j, cb = V.group_cnt[gb];
+      if (cb == 0) continue;
+      const uint32_t offb = V.group_end[gb] - size16(cb);
+      uint32_t acc = 0;
+      if (cb >= kDenseMin) {
+        const uint4 *B = V.payload + offb;
+#pragma unroll 4
+        for (uint32_t k = lane; k < kRange16; k += 32) {
+          const uint4 b = __ldg(B + k), a = s_bits4[k];
+          acc += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
+        }
+      } else {
+        const uint16_t *lb = reinterpret_cast<const uint16_t *>(V.payload + offb);
+        for (uint32_t k = lane; k < cb; k += 32) {
+          const uint32_t id = lb[k];
+          acc += (s_bits[id >> 5] >> (id & 31)) & 1u;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      if (lane == 0 && acc) atomicAdd(V.out + (size_t)(i - V.row_begin) * V.n_sets + j, (int32_t)acc);
+    }
+  }
+}
+
+// F: full rows (mirror + diagonal) and ANI.  containment(I, |first|) = I == 0 ? 0 : I / |first|
+// (src/ani_estimation.cpp:24-28); binomial_estimator(c, weight) = c <= 0 ? 0 : pow(c, 1.0 / weight) (:38-42).
+__global__ void __launch_bounds__(256)
+    finalize_kernel(const int32_t *__restrict__ raw, const int32_t *__restrict__ sizes, uint32_t n_sets, uint32_t row_begin,
+                    uint32_t n_rows, int symmetric, double inv_weight, int32_t *__restrict__ out_counts,
+                    double *__restrict__ out_ani) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n_rows * n_sets) return;
+  const uint32_t r = (uint32_t)(idx / n_sets), j = (uint32_t)(idx % n_sets), i = row_begin + r;
+  int32_t c;
+  if (i == j) c = sizes[i];
+  else if (symmetric && j < i) c = raw[(size_t)(j - row_begin) * n_sets + i];
+  else c = raw[idx];
+  if (out_counts) out_counts[idx] = c;
+  if (out_ani) {
+    double a = 0.0;
+    if (c != 0) {
+      const double cont = (double)c / (double)sizes[i];
+      a = cont <= 0.0 ? 0.0 : pow(cont, inv_weight);
+    }
+    out_ani[idx] = a;
+  }
+}
+
+bool make_compact(const uint64_t mask[2], Compact *out) {  // false: more than 64 mask bits or 32 runs
+  Compact c = {};
+  int dst = 0;
+  auto bit = [&](int b) { return (mask[b >> 6] >> (b & 63)) & 1; };
+  for (int b = 0; b < 128;) {
+    if (!bit(b)) {
+      ++b;
+      continue;
+    }
+    int e = b;
+    while (e < 128 && bit(e) && (e >> 6) == (b >> 6) ) ++e;  // a run stays inside one 64-bit word of the source
+    if (c.n_runs == 32 || dst + (e - b) > 64) return false;
+    c.src[c.n_runs] = (uint8_t)b;
+    c.len[c.n_runs] = (uint8_t)(e - b);
+    c.dst[c.n_runs] = (uint8_t)dst;
+    dst += e - b;
+    ++c.n_runs;
+    b = e;
+  }
+  *out = c;
+  return true;
+}
+
+}  // namespace
+
+bool all_pairs_dict_eligible(sks_set *const *sets, int64_t n) {
+  static const bool enabled = getenv("SKS_DICT_INTERSECT") ? atoi(getenv("SKS_DICT_INTERSECT")) != 0 : true;
+  if (!enabled || n < 2 || n > 65536) return false;
+  const sks_set *ref = sets[0];
+  if (!ref || ref->repr != SKS_REPR_SORTED) return false;
+  uint64_t total = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const sks_set *s = sets[i];
+    if (!s || s->repr != SKS_REPR_SORTED || s->key_words != ref->key_words || s->mask[0] != ref->mask[0] ||
+        s->mask[1] != ref->mask[1] || s->device != ref->device || s->count < 0)
+      return false;
+    total += (uint64_t)s->count;
+  }
+  if (total >= (1ull << 31)) return false;
+  if (ref->key_words == 2) {
+    Compact c;
+    if (!make_compact(ref->mask, &c)) return false;
+  }
+  return true;
+}
+
+// Rows [row_begin, row_end) of the n x n matrix of |sets[i] n sets[j]|, device resident: *counts receives
+// (row_end - row_begin) * n int32 (full rows incl. the diagonal), *ani (optional) as many doubles.
+int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, BufferRef *counts,
+                   BufferRef *ani, BufferRef *sizes_out) {
+  const uint32_t n_sets = (uint32_t)n, n_rows = (uint32_t)(row_end - row_begin);
+  const int kw = sets[0]->key_words;
+  Compact compact = {};
+  if (kw == 2 && !make_compact(sets[0]->mask, &compact)) return set_error(SKS_ERR_INVALID, "mask too wide for the dictionary");
+  uint64_t total = 0;
+  for (int64_t i = 0; i < n; ++i) total += (uint64_t)sets[i]->count;
+  if (total >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "too many keys for the dictionary");
+  const uint32_t K = (uint32_t)total;
+  const uint32_t cap = std::max<uint32_t>(1024u, K + K / 2);
+  // ids: class A + padding to a range boundary + class B <= K / 2 + 2^16
+  const uint32_t n_ranges = (K / 2 + kRangeIds) / kRangeIds + 1;
+  const uint64_t n_groups64 = (uint64_t)n_ranges * n_sets;
+  if (n_groups64 >= (1ull << 28)) return set_error(SKS_ERR_CAPACITY, "too many (range, set) groups for the dictionary");
+  const uint32_t n_groups = (uint32_t)n_groups64;
+  const uint32_t n_chunks = (n_sets + kPairsCols - 1) / kPairsCols;
+  if (n_groups64 * n_chunks >= (1ull << 32)) return set_error(SKS_ERR_CAPACITY, "too many tasks for the dictionary");
+  const bool symmetric = row_begin == 0 && row_end == n;
+
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  // one control block: counters | set_off | set_ptr | sizes | group_cnt | cursor | group_end | rowlist
+  const size_t sz_cnt = align(4 * C_COUNT), sz_off = align(4 * ((size_t)n_sets + 1)), sz_ptr = align(8 * (size_t)n_sets);
+  const size_t sz_sizes = align(4 * (size_t)n_sets), sz_grp = align(4 * (size_t)n_groups);
+  BufferRef ctl, tab, entry, payload, raw;
+  SKS_TRY(alloc_buffer(ctx, sz_cnt + sz_off + sz_ptr + sz_sizes + 4 * sz_grp, &ctl));
+  char *cb = static_cast<char *>(ctl->ptr);
+  uint32_t *d_counters = reinterpret_cast<uint32_t *>(cb);
+  uint32_t *d_off = reinterpret_cast<uint32_t *>(cb + sz_cnt);
+  const void **d_ptr = reinterpret_cast<const void **>(cb + sz_cnt + sz_off);
+  int32_t *d_sizes = reinterpret_cast<int32_t *>(cb + sz_cnt + sz_off + sz_ptr);
+  uint32_t *d_gcnt = reinterpret_cast<uint32_t *>(cb + sz_cnt + sz_off + sz_ptr + sz_sizes);
+  uint32_t *d_cursor = d_gcnt + sz_grp / 4, *d_gend = d_cursor + sz_grp / 4, *d_rowlist = d_gend + sz_grp / 4;
+  SKS_TRY(alloc_buffer(ctx, sizeof(Slot) * ((size_t)cap + 1), &tab));
+  SKS_TRY(alloc_buffer(ctx, 4 * (size_t)std::max<uint32_t>(K, 1), &entry));
+  // payload: a dense group holds >= kDenseMin ids in 8 KB, a sparse one 2 bytes per id rounded up to 16
+  const size_t payload16 = (size_t)K / 2 + std::min<size_t>(n_groups, K) + 16;
+  SKS_TRY(alloc_buffer(ctx, payload16 * 16, &payload));
+  SKS_TRY(alloc_buffer(ctx, 4 * (size_t)n_rows * n_sets, &raw));
+  SKS_TRY(alloc_buffer(ctx, 4 * (size_t)n_rows * n_sets, counts));
+  if (ani) SKS_TRY(alloc_buffer(ctx, 8 * (size_t)n_rows * n_sets, ani));
+
+  // host tables through the pinned ring: offsets | pointers | sizes
+  char *stage = nullptr;
+  SKS_TRY(ctx_pinned(ctx, sz_off + sz_ptr + sz_sizes, reinterpret_cast<void **>(&stage)));
+  uint32_t *h_off = reinterpret_cast<uint32_t *>(stage);
+  const void **h_ptr = reinterpret_cast<const void **>(stage + sz_off);
+  int32_t *h_sizes = reinterpret_cast<int32_t *>(stage + sz_off + sz_ptr);
+  uint32_t at = 0;
+  for (uint32_t s = 0; s < n_sets; ++s) {
+    h_off[s] = at;
+    h_ptr[s] = static_cast<const char *>(sets[s]->buf->ptr) + sets[s]->byte_off;
+    h_sizes[s] = (int32_t)sets[s]->count;
+    at += (uint32_t)sets[s]->count;
+  }
+  h_off[n_sets] = at;
+  SKS_CUDA_TRY(cudaMemcpyAsync(d_off, stage, sz_off + sz_ptr + sz_sizes, cudaMemcpyHostToDevice, ctx->stream));
+  SKS_CUDA_TRY(cudaMemsetAsync(d_counters, 0, sz_cnt, ctx->stream));
+  SKS_CUDA_TRY(cudaMemsetAsync(d_gcnt, 0, 2 * sz_grp, ctx->stream));  // group_cnt and cursor
+  SKS_CUDA_TRY(cudaMemsetAsync(tab->ptr, 0, sizeof(Slot) * ((size_t)cap + 1), ctx->stream));
+  SKS_CUDA_TRY(cudaMemsetAsync(raw->ptr, 0, 4 * (size_t)n_rows * n_sets, ctx->stream));
+
+  DictView D;
+  D.set_ptr = d_ptr;
+  D.set_off = d_off;
+  D.n_sets = n_sets;
+  D.n_entries = K;
+  D.tab = static_cast<Slot *>(tab->ptr);
+  D.cap = cap;
+  D.entry = static_cast<uint32_t *>(entry->ptr);
+  D.counters = d_counters;
+  const unsigned entry_grid = (K + kDictChunk - 1) / kDictChunk;
+  const unsigned wide_grid = (unsigned)ctx->sm_count * 8;
+  {
+    KernelTimer timer(ctx, SKS_KERNEL_DICT);
+    if (K > 0) {
+      if (kw == 1) dict_insert_kernel<1><<<entry_grid, kDictThreads, 0, ctx->stream>>>(D, compact);
+      else dict_insert_kernel<2><<<entry_grid, kDictThreads, 0, ctx->stream>>>(D, compact);
+      const uint32_t thr_a = std::max<uint32_t>(2u, n_sets / 16);
+      dict_assign_kernel<<<wide_grid, 256, 0, ctx->stream>>>(D.tab, cap + 1, thr_a, d_counters);
+      dict_ids_kernel<<<entry_grid, kDictThreads, 0, ctx->stream>>>(D, d_gcnt);
+      ctx->launches += 3;
+    }
+    // group_end = inclusive prefix sum of the groups' payload sizes
+    size_t temp_bytes = 0;
+    cub::TransformInputIterator<uint32_t, Size16Op, const uint32_t *> sizes_in(d_gcnt, Size16Op());
+    cub::DeviceScan::InclusiveSum(nullptr, temp_bytes, sizes_in, d_gend, (int)n_groups, ctx->stream);
+    void *temp = nullptr;
+    SKS_TRY(ctx_scratch(ctx, temp_bytes, &temp));
+    cub::DeviceScan::InclusiveSum(temp, temp_bytes, sizes_in, d_gend, (int)n_groups, ctx->stream);
+    zero16_kernel<<<wide_grid, 256, 0, ctx->stream>>>(static_cast<uint4 *>(payload->ptr), d_gend + n_groups - 1);
+    ctx->launches += 2;
+    if (K > 0) {
+      dict_payload_kernel<<<entry_grid, kDictThreads, 0, ctx->stream>>>(D, d_gcnt, d_gend, d_cursor,
+                                                                        static_cast<uint4 *>(payload->ptr));
+      ctx->launches++;
+    }
+    SKS_CUDA_TRY(cudaGetLastError());
+  }
+  {
+    KernelTimer timer(ctx, SKS_KERNEL_ALLPAIRS);
+    rowlist_kernel<<<(n_groups + 255) / 256, 256, 0, ctx->stream>>>(d_gcnt, n_groups, n_sets, (uint32_t)row_begin,
+                                                                    (uint32_t)row_end, d_rowlist, d_counters);
+    PairsView V;
+    V.group_cnt = d_gcnt;
+    V.group_end = d_gend;
+    V.payload = static_cast<const uint4 *>(payload->ptr);
+    V.rowlist = d_rowlist;
+    V.counters = d_counters;
+    V.n_sets = n_sets;
+    V.row_begin = (uint32_t)row_begin;
+    V.n_chunks = n_chunks;
+    V.symmetric = symmetric ? 1 : 0;
+    V.out = static_cast<int32_t *>(raw->ptr);
+    allpairs_kernel<<<wide_grid, kPairsThreads, 0, ctx->stream>>>(V);
+    ctx->launches += 2;
+    SKS_CUDA_TRY(cudaGetLastError());
+  }
+  {
+    KernelTimer timer(ctx, SKS_KERNEL_ANI);
+    const size_t cells = (size_t)n_rows * n_sets;
+    if (cells > 0) {
+      finalize_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(
+          static_cast<const int32_t *>(raw->ptr), d_sizes, n_sets, (uint32_t)row_begin, n_rows, symmetric ? 1 : 0,
+          1.0 / (double)sets[0]->weight, static_cast<int32_t *>((*counts)->ptr), ani ? static_cast<double *>((*ani)->ptr) : nullptr);
+      ctx->launches++;
+    }
+    SKS_CUDA_TRY(cudaGetLastError());
+  }
+  if (sizes_out) {  // [n] int32 set sizes, for callers that keep working on the device
+    SKS_TRY(alloc_buffer(ctx, 4 * (size_t)std::max<uint32_t>(n_sets, 4), sizes_out));
+    SKS_CUDA_TRY(cudaMemcpyAsync((*sizes_out)->ptr, d_sizes, 4 * (size_t)n_sets, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return SKS_OK;
+}
+
+}  // namespace sks

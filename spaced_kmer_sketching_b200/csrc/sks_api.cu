@@ -201,17 +201,6 @@ KernelTimer::~KernelTimer() {
 
 namespace {
 
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev); else prev = -1;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
 inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
 // Lays genomes out in one word buffer: [kPreWords zero][genome 0 data, zero padded to 4 words]
@@ -353,6 +342,7 @@ int make_plan(const sks_batch *batch, const uint64_t mask[2], int window, const 
   return SKS_OK;
 }
 
+}  // namespace
 sks_set *new_set(const sks_ctx *ctx, int repr, const uint64_t mask[2], int window, int weight) {
   sks_set *s = new (std::nothrow) sks_set();
   if (!s) return nullptr;
@@ -364,6 +354,7 @@ sks_set *new_set(const sks_ctx *ctx, int repr, const uint64_t mask[2], int windo
   s->mask[1] = mask[1];
   return s;
 }
+namespace {
 
 int sketch_raw_keys(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const sks_pred *pred, int window,
                     int out_mode, BufferRef *keys, BufferRef *pos, std::vector<uint64_t> *off,
@@ -569,6 +560,7 @@ int sketch_sorted(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
   return SKS_OK;
 }
 
+}  // namespace
 int check_pair(const sks_set *a, const sks_set *b) {
   if (!a || !b) return set_error(SKS_ERR_INVALID, "null set");
   // window_length is not part of k-mer equality (src/kmer.hpp:82-85); mask and layout are
@@ -578,7 +570,6 @@ int check_pair(const sks_set *a, const sks_set *b) {
   return SKS_OK;
 }
 
-}  // namespace
 }  // namespace sks
 
 using namespace sks;
@@ -715,7 +706,8 @@ const char *sks_kernel_name(int kind) {
   static const char *names[SKS_KERNEL_KINDS] = {"sketch_kernel", "fill_zero_kernel", "bitset_pair_counts_kernel",
                                                 "bitset_popcount_kernel", "sort_unique", "sorted_intersect_kernel",
                                                 "synth_kernel", "list_finalize", "bitset_build", "fasta_parse",
-                                                "bitset_pair_build_kernel"};
+                                                "bitset_pair_build_kernel", "dict_build", "allpairs_kernel",
+                                                "ani_finalize_kernel"};
   return (kind >= 0 && kind < SKS_KERNEL_KINDS) ? names[kind] : "?";
 }
 
@@ -1509,7 +1501,55 @@ int sks_intersect_block(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t r
 
 int sks_intersect_all_pairs(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end,
                             int32_t *out) {
+  if (ctx && sets && out && n >= 4 && row_begin >= 0 && row_begin < row_end && row_end <= n && all_pairs_dict_eligible(sets, n))
+    return sks_all_vs_all(ctx, sets, n, row_begin, row_end, out + row_begin * n, nullptr, nullptr);
   return sks_intersect_block(ctx, sets, n, row_begin, row_end, 0, n, out);
+}
+
+int sks_all_vs_all(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, int32_t *out_counts,
+                   int32_t *out_sizes, double *out_ani) {
+  if (!ctx || (n > 0 && !sets)) return set_error(SKS_ERR_INVALID, "null argument");
+  if (row_begin < 0 || row_end > n || row_begin > row_end) return set_error(SKS_ERR_INVALID, "bad row range");
+  for (int64_t i = 0; i < n; ++i) {
+    if (!sets[i]) return set_error(SKS_ERR_INVALID, "null set");
+    SKS_TRY(check_pair(sets[0], sets[i]));
+  }
+  DeviceGuard guard(ctx->device);
+  const int64_t n_rows = row_end - row_begin;
+  if (out_sizes)
+    for (int64_t i = 0; i < n; ++i) {
+      int64_t sz = 0;
+      SKS_TRY(sks_set_size(ctx, sets[i], &sz));
+      out_sizes[i] = (int32_t)sz;
+    }
+  if (n_rows == 0 || n == 0) return SKS_OK;
+  if (all_pairs_dict_eligible(sets, n)) {
+    BufferRef counts, ani;
+    int st = all_pairs_dict(ctx, sets, n, row_begin, row_end, &counts, out_ani ? &ani : nullptr, nullptr);
+    if (st == SKS_OK) {
+      if (out_counts)
+        SKS_CUDA_TRY(cudaMemcpyAsync(out_counts, counts->ptr, 4 * (size_t)n_rows * n, cudaMemcpyDeviceToHost, ctx->stream));
+      if (out_ani)
+        SKS_CUDA_TRY(cudaMemcpyAsync(out_ani, ani->ptr, 8 * (size_t)n_rows * n, cudaMemcpyDeviceToHost, ctx->stream));
+      SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+      return SKS_OK;
+    }
+    if (st != SKS_ERR_CAPACITY) return st;  // too large for the dictionary: the pairwise kernels below
+  }
+  std::vector<int32_t> full((size_t)n * n), sizes((size_t)n);
+  SKS_TRY(sks_intersect_block(ctx, sets, n, row_begin, row_end, 0, n, full.data()));
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t sz = 0;
+    SKS_TRY(sks_set_size(ctx, sets[i], &sz));
+    sizes[i] = (int32_t)sz;
+  }
+  if (out_counts) memcpy(out_counts, full.data() + row_begin * n, 4 * (size_t)n_rows * n);
+  if (out_ani) {
+    std::vector<int32_t> first((size_t)n_rows * n);
+    for (int64_t r = 0; r < n_rows; ++r) std::fill(first.begin() + r * n, first.begin() + (r + 1) * n, sizes[row_begin + r]);
+    sks_ani_from_counts(full.data() + row_begin * n, first.data(), n_rows * n, sets[0]->weight, out_ani);
+  }
+  return SKS_OK;
 }
 
 // ---- one-call pair pipeline ----------------------------------------------------------------------

@@ -205,6 +205,21 @@ struct sks_set {
 };
 
 namespace sks {
+// Makes `dev` the current device for the scope.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+sks_set *new_set(const sks_ctx *ctx, int repr, const uint64_t mask[2], int window, int weight);
+// SKS_ERR_MISMATCH unless the two sets share mask, representation, key width and device.
+int check_pair(const sks_set *a, const sks_set *b);
+
 // Brackets the kernel launches of one scope with events when the context is being profiled.
 struct KernelTimer {
   sks_ctx *ctx;
@@ -249,6 +264,11 @@ struct RowTaskHost {
 bool row_intersect_fits(int key_words, const uint64_t mask[2], int64_t n_a);
 int launch_row_intersect(sks_ctx *ctx, int key_words, const void *d_tasks, int64_t n_tasks, const void *const *d_b,
                          const int64_t *d_nb, int32_t *d_out, const uint64_t mask[2], int64_t max_n_a);
+
+// all-vs-all through the dictionary of shared k-mers (sks_allpairs.cu)
+bool all_pairs_dict_eligible(sks_set *const *sets, int64_t n);
+int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, BufferRef *counts,
+                   BufferRef *ani, BufferRef *sizes_out);
 
 int launch_list_finalize(sks_ctx *ctx, const uint32_t *words, const uint32_t *seg_end, uint32_t n_segs, int window,
                          int key_words, const void *raw_keys, const uint32_t *raw_pos, uint32_t n,

@@ -331,6 +331,21 @@ class Context:
         check(self._L.sks_intersect_all_pairs(self.h, ps, n, row_begin, row_end, out.ctypes.data))
         return out
 
+    def all_vs_all(self, sets: Sequence["KmerSet"], row_begin: int = 0, row_end: Optional[int] = None, want_ani: bool = True):
+        """Rows [row_begin, row_end) of the all-pairs matrix in one device-resident pass: (counts[rows, n] int32,
+        sizes[n] int32, ani[rows, n] float64 or None).  The comparison phase of the reference driver
+        (src/kmer-sketching.cpp:185-200)."""
+        n = len(sets)
+        row_end = n if row_end is None else row_end
+        rows = max(row_end - row_begin, 0)
+        ps = (C.c_void_p * max(n, 1))(*[s.h for s in sets])
+        counts = np.zeros((rows, n), dtype=np.int32)
+        sizes = np.zeros(n, dtype=np.int32)
+        ani = np.zeros((rows, n), dtype=np.float64) if want_ani else None
+        check(self._L.sks_all_vs_all(self.h, ps, n, row_begin, row_end, counts.ctypes.data, sizes.ctypes.data,
+                                     ani.ctypes.data if want_ani else None))
+        return counts, sizes, ani
+
     def intersect_block(self, sets: Sequence["KmerSet"], rows: Tuple[int, int], cols: Tuple[int, int],
                         out: np.ndarray) -> np.ndarray:
         """out[i, j] = |sets[i] n sets[j]| for i in rows, j in cols (half-open ranges); other entries untouched."""

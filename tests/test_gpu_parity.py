@@ -258,8 +258,10 @@ def test_all_pairs_row_resident_and_merge_paths(ctx):
         sets = ctx.sketch(batch, mask, w, pred, sks.REPR_SORTED)
         osets = [port.sketch_set(g, [len(g)], mask, w, *opred(pred)) for g in genomes]
         want = np.array([[port.intersection(a, b) for b in osets] for a in osets], dtype=np.int32)
-        got = ctx.intersect_all_pairs(sets)
+        got = ctx.intersect_all_pairs(sets)            # dictionary route where the keys allow it
         assert np.array_equal(got, want), seed
+        pairwise = ctx.intersect_block(sets, (0, n), (0, n), np.full((n, n), -1, dtype=np.int32))   # pairwise kernels
+        assert np.array_equal(pairwise, want), seed
         # rectangles, as the multi-GPU tiling issues them
         part = np.full((n, n), -1, dtype=np.int32)
         ctx.intersect_block(sets, (2, 7), (0, n), part)
@@ -297,6 +299,13 @@ def test_fuzz_all_pairs_random_masks(ctx):
         want = np.array([[len(a & b) for b in as_set] for a in as_set], dtype=np.int32)
         got = ctx.intersect_all_pairs(sets)
         assert np.array_equal(got, want), (trial, w, k, hex(mask))
+        pairwise = ctx.intersect_block(sets, (0, n), (0, n), np.full((n, n), -1, dtype=np.int32))
+        assert np.array_equal(pairwise, want), (trial, w, k, hex(mask))
+        r0, r1 = sorted(int(x) for x in rng.integers(0, n + 1, 2))
+        cnt, sizes, ani = ctx.all_vs_all(sets, r0, r1)
+        assert np.array_equal(cnt, want[r0:r1]) and sizes.tolist() == [len(a) for a in as_set]
+        wani = sks.ani_from_counts(want[r0:r1].ravel(), np.repeat(sizes[r0:r1], n), sks.mask_weight(mask))
+        assert ani.size == 0 or np.max(np.abs(ani.ravel() - wani)) <= 1e-12
         g = int(rng.integers(0, n))
         assert np.array_equal(keys[g], port.sketch_set(genomes[g], [len(genomes[g])], mask, w, *opred(pred))), (trial, g)
         # single pairs and the ring (src/generators.hpp:20-31) go through the same tables
@@ -304,6 +313,49 @@ def test_fuzz_all_pairs_random_masks(ctx):
         assert ctx.intersect(sets[a], sets[b]) == want[a, b]
         ring = ctx.intersect_pairs(sets, sets[1:] + sets[:1])
         assert ring.tolist() == [int(want[i, (i + 1) % n]) for i in range(n)]
+        for x in sets:
+            x.close()
+    batch.close()
+
+
+def test_all_vs_all_dictionary_route(ctx):
+    """sks_all_vs_all on sets that exercise every shape of the dictionary route (csrc/sks_allpairs.cu): keys shared by
+    most sets (class A ids, dense bitmaps, several id ranges), keys shared by exactly two sets (class B), private
+    keys (dropped), empty sets, the all-zero key, row ranges -- against the pairwise kernels, numpy and the host ANI
+    (src/kmer-sketching.cpp:185-200)."""
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 4, 150_000, dtype=np.uint8)
+    other = rng.integers(0, 4, 90_000, dtype=np.uint8)
+    genomes = []
+    for g in range(50):
+        src = base if g % 5 else other
+        d = [0, 2000, 300, 50, 12, 5, 3][g % 7]
+        x = src.copy()
+        if d:
+            idx = rng.integers(0, len(x), len(x) // d)
+            x[idx] = (x[idx] + rng.integers(1, 4, len(idx))) & 3
+        genomes.append(x)
+    genomes[7] = rng.integers(0, 4, 10, dtype=np.uint8)       # empty set
+    genomes[11] = np.zeros(3000, dtype=np.uint8)              # poly-A: the all-zero key only
+    genomes[13] = np.concatenate([np.zeros(500, dtype=np.uint8), base[:20000]])   # shares the all-zero key with 11
+    batch = ctx.upload_codes(genomes)
+    n = len(genomes)
+    for seed, pred in ((C3_SEED, sks.all_kmers()), (C3_SEED, sks.frac_min_hash(1, 7)),
+                       ("1110110111011011101101110110111011011101", sks.frac_min_hash(1, 3))):   # 16-byte keys, compacted
+        mask, w = sks.seed_to_mask(seed)
+        sets = ctx.sketch(batch, mask, w, pred, sks.REPR_SORTED)
+        want = ctx.intersect_block(sets, (0, n), (0, n), np.full((n, n), -1, dtype=np.int32))    # pairwise kernels
+        keys = [s.keys() for s in sets]
+        for i, j in ((0, 1), (3, 44), (11, 13), (5, 10), (7, 2)):
+            a, b = set(map(tuple, keys[i].tolist())), set(map(tuple, keys[j].tolist()))
+            assert want[i, j] == len(a & b)
+        for rows in ((0, n), (0, 1), (17, 40), (n - 1, n)):
+            cnt, sizes, ani = ctx.all_vs_all(sets, rows[0], rows[1])
+            assert np.array_equal(cnt, want[rows[0]:rows[1]]), (seed, rows)
+            assert sizes.tolist() == [len(k) for k in keys]
+            wani = sks.ani_from_counts(want[rows[0]:rows[1]].ravel(), np.repeat(sizes[rows[0]:rows[1]], n), sks.mask_weight(mask))
+            assert np.max(np.abs(ani.ravel() - wani)) <= 1e-12
+        assert np.array_equal(ctx.intersect_all_pairs(sets), want)
         for x in sets:
             x.close()
     batch.close()
