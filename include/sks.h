@@ -266,6 +266,51 @@ int sks_all_vs_all(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_be
 void sks_ani_from_counts(const int32_t *intersections, const int32_t *first_set_sizes, int64_t n_pairs,
                          int weight, double *out_ani);
 
+/* ---- several GPUs: one rank per GPU, NCCL over NVLink underneath -------------------------------------- */
+/* The reference parallelises over FASTA files and over set pairs with cilk_for (src/kmer_set.cpp:124-131,179-182).
+ * Here genome g of n belongs to rank g / ceil(n / world) (sks_shard_range); every rank sketches its block, the
+ * sketches are exchanged once, and every rank returns its own complete block rows of the pair matrix.  A rank is a
+ * process (sks_comm_init_rank: rank 0 makes the id, the caller's launcher carries its 128 bytes to the others) or a
+ * thread of one process that drives one GPU (sks_comm_init_all).  NCCL is loaded at run time (libnccl.so.2, or
+ * $SKS_NCCL_LIB); without it these calls fail with SKS_ERR_CUDA and the single-GPU API is unaffected. */
+typedef struct sks_comm sks_comm;
+#define SKS_COMM_ID_BYTES 128
+void sks_shard_range(int64_t n, int rank, int world, int64_t *begin, int64_t *end);
+int sks_comm_unique_id(void *out_id /* SKS_COMM_ID_BYTES */);
+int sks_comm_init_rank(sks_ctx *ctx, const void *id, int rank, int world, sks_comm **out);
+/* One process, n GPUs: ctxs[i] is a context on the i-th device; out[i] its communicator (rank i of n).  The sharded
+ * calls below are then made by n threads, one per context. */
+int sks_comm_init_all(sks_ctx *const *ctxs, int n, sks_comm **out);
+void sks_comm_destroy(sks_comm *c);
+int sks_comm_rank(const sks_comm *c);
+int sks_comm_world(const sks_comm *c);
+int sks_comm_nccl_version(void); /* 0 when NCCL cannot be loaded */
+/* Every rank passes the sets of its block of the n_total genomes (SORTED, one mask) and receives all n_total sets
+ * in genome order: one small all-gather of the key counts (the only host synchronisation) and one grouped
+ * send/receive of the keys, straight into the buffer the returned sets alias.  out_all[i] must be released with
+ * sks_set_destroy; the rank's own sets come back as second handles on the same keys.  comm NULL = one rank. */
+int sks_comm_allgather_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total,
+                            sks_set **out_all);
+/* parallel_compute_pairwise_kmer_set_intersections over generate_all_pairs_from_vector + containment +
+ * binomial_estimator (src/kmer-sketching.cpp:185-200), sharded: sks_comm_allgather_sets, then sks_all_vs_all for the
+ * rank's block rows [begin, end) = sks_shard_range(n_total, rank, world).  Outputs as in sks_all_vs_all:
+ * out_counts / out_ani hold (end - begin) * n_total entries, out_sizes n_total. */
+int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total,
+                           int32_t *out_counts, int32_t *out_sizes, double *out_ani);
+/* The whole path from HOST buffers: packed[g] / n_bases[g] are the rank's n_local genomes (2-bit packed, one segment
+ * each); they are uploaded (or, in pinned host memory, read in place by the sketch kernel), sketched, exchanged and
+ * compared.  = parallel_kmer_sets_from_fasta_files + the comparison loop of src/kmer-sketching.cpp:163-200. */
+int sks_all_vs_all_from_host(sks_ctx *ctx, sks_comm *comm, int n_local, const uint32_t *const *packed, const uint64_t *n_bases,
+                             int64_t n_total, const uint64_t mask[2], int window, const sks_pred *pred, int32_t *out_counts,
+                             int32_t *out_sizes, double *out_ani);
+/* One long sequence split by position (BASELINE configs[2]): `slice` holds this rank's window starts plus a
+ * (window - 1)-base halo (sks_batch_slice / sks_batch_synth_at).  The rank sketches its slice, the partial sketches
+ * are routed by key range (rank r owns the r-th share of the key space under the mask: one grouped send/receive),
+ * and every rank sort-uniques its range only.  gather == 0: *out is the rank's range of the global set (the ranges
+ * are disjoint and ordered by rank); gather != 0: every rank receives the whole set.  *out_global_size = |set|. */
+int sks_sketch_sequence_sharded(sks_ctx *ctx, sks_comm *comm, const sks_batch *slice, const uint64_t mask[2], int window,
+                                const sks_pred *pred, int gather, sks_set **out, int64_t *out_global_size);
+
 /* ---- one-call pair pipeline (bench / e2e) ---------------------------------------------------- */
 typedef struct sks_pair_result {
   int64_t size_a, size_b, intersection;

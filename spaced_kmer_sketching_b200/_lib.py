@@ -103,6 +103,18 @@ PROTOTYPES = {
     "sks_intersect_rects": (ci, [vp, C.POINTER(vp), i64, vp, i64, vp]),
     "sks_all_vs_all": (ci, [vp, C.POINTER(vp), i64, i64, i64, vp, vp, vp]),
     "sks_ani_from_counts": (None, [vp, vp, i64, ci, vp]),
+    "sks_shard_range": (None, [i64, ci, ci, i64p, i64p]),
+    "sks_comm_unique_id": (ci, [vp]),
+    "sks_comm_init_rank": (ci, [vp, vp, ci, ci, C.POINTER(vp)]),
+    "sks_comm_init_all": (ci, [C.POINTER(vp), ci, C.POINTER(vp)]),
+    "sks_comm_destroy": (None, [vp]),
+    "sks_comm_rank": (ci, [vp]),
+    "sks_comm_world": (ci, [vp]),
+    "sks_comm_nccl_version": (ci, []),
+    "sks_comm_allgather_sets": (ci, [vp, vp, C.POINTER(vp), i64, i64, C.POINTER(vp)]),
+    "sks_all_vs_all_sharded": (ci, [vp, vp, C.POINTER(vp), i64, i64, vp, vp, vp]),
+    "sks_all_vs_all_from_host": (ci, [vp, vp, ci, C.POINTER(vp), u64p, i64, u64p, ci, C.POINTER(SksPred), vp, vp, vp]),
+    "sks_sketch_sequence_sharded": (ci, [vp, vp, vp, u64p, ci, C.POINTER(SksPred), ci, C.POINTER(vp), i64p]),
     "sks_pair_ani": (ci, [vp, vp, u64, vp, u64, u64p, ci, C.POINTER(SksPred), ci, C.POINTER(SksPairResult)]),
     "sks_pair_ani_resident": (ci, [vp, vp, u64p, ci, C.POINTER(SksPred), ci, C.POINTER(SksPairResult)]),
 }

@@ -1614,6 +1614,27 @@ int sks_pair_ani(sks_ctx *ctx, const uint32_t *packed_a, uint64_t n_bases_a, con
   return st;
 }
 
+int sks_all_vs_all_from_host(sks_ctx *ctx, sks_comm *comm, int n_local, const uint32_t *const *packed, const uint64_t *n_bases,
+                             int64_t n_total, const uint64_t mask[2], int window, const sks_pred *pred, int32_t *out_counts,
+                             int32_t *out_sizes, double *out_ani) {
+  if (!ctx || n_local < 0 || (n_local > 0 && (!packed || !n_bases))) return set_error(SKS_ERR_INVALID, "null argument");
+  sks_batch *batch = nullptr;
+  std::vector<sks_set *> sets((size_t)std::max(n_local, 1), nullptr);
+  int st = SKS_OK;
+  if (n_local > 0) {
+    if (batch_in_place(ctx, n_local, packed, n_bases, &batch) != SKS_OK)  // not pinned / not aligned: copy the genomes up
+      st = sks_batch_upload(ctx, n_local, packed, n_bases, nullptr, nullptr, &batch);
+    if (st == SKS_OK && batch->host_words) ctx->in_place_calls++;
+    if (st == SKS_OK) st = sks_sketch(ctx, batch, mask, window, pred, SKS_REPR_SORTED, sets.data());
+    // sks_sketch has read the counts back: the kernel is done with the caller's buffers
+  }
+  if (st == SKS_OK) st = sks_all_vs_all_sharded(ctx, comm, sets.data(), n_local, n_total, out_counts, out_sizes, out_ani);
+  for (sks_set *s : sets)
+    if (s) sks_set_destroy(ctx, s);
+  if (batch) sks_batch_destroy(ctx, batch);
+  return st;
+}
+
 // nucleotide_string_list_to_kmers, src/kmer_sliding.cpp:224-238: ordered list with duplicates.
 int sks_kmer_list(sks_ctx *ctx, const sks_batch *batch, int genome, const uint64_t mask[2], int window,
                   const sks_pred *pred, uint64_t *out_n, uint64_t *out_masked, uint64_t *out_bits, uint64_t capacity) {

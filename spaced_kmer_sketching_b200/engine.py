@@ -346,6 +346,49 @@ class Context:
                                      ani.ctypes.data if want_ani else None))
         return counts, sizes, ani
 
+    # -- several GPUs (comm None: one rank)
+    def allgather_sets(self, comm: Optional["Comm"], local_sets: Sequence["KmerSet"], n_total: int) -> List["KmerSet"]:
+        ps = (C.c_void_p * max(len(local_sets), 1))(*[s.h for s in local_sets])
+        out = (C.c_void_p * max(n_total, 1))()
+        check(self._L.sks_comm_allgather_sets(self.h, comm.h if comm else None, ps, len(local_sets), n_total, out))
+        return [KmerSet(self, C.c_void_p(out[i])) for i in range(n_total)]
+
+    def all_vs_all_sharded(self, comm: Optional["Comm"], local_sets: Sequence["KmerSet"], n_total: int, want_ani: bool = True,
+                           out: Optional[tuple] = None):
+        """This rank's block rows of the all-pairs matrix: (counts[rows, n] int32, sizes[n] int32, ani[rows, n] float64).
+        `out`: (counts, sizes, ani) arrays to fill (e.g. views of pinned memory)."""
+        rank, world = (comm.rank, comm.world) if comm else (0, 1)
+        b, e = shard_range(n_total, rank, world)
+        if out is None:
+            out = (np.zeros((e - b, n_total), dtype=np.int32), np.zeros(n_total, dtype=np.int32),
+                   np.zeros((e - b, n_total), dtype=np.float64) if want_ani else None)
+        counts, sizes, ani = out
+        ps = (C.c_void_p * max(len(local_sets), 1))(*[s.h for s in local_sets])
+        check(self._L.sks_all_vs_all_sharded(self.h, comm.h if comm else None, ps, len(local_sets), n_total,
+                                             counts.ctypes.data, sizes.ctypes.data, ani.ctypes.data if ani is not None else None))
+        return counts, sizes, ani
+
+    def all_vs_all_from_host(self, comm: Optional["Comm"], ptrs: Sequence[int], n_bases: Sequence[int], n_total: int, mask: int,
+                             window: int, pred: Predicate, out: tuple):
+        """HOST packed genomes (raw pointers, e.g. into pinned memory) -> this rank's rows; `out` = (counts, sizes, ani)."""
+        counts, sizes, ani = out
+        n = len(ptrs)
+        pp = (C.c_void_p * max(n, 1))(*ptrs)
+        nb = (C.c_uint64 * max(n, 1))(*n_bases)
+        p = pred.c()
+        check(self._L.sks_all_vs_all_from_host(self.h, comm.h if comm else None, n, pp, nb, n_total, _w2(mask), window, C.byref(p),
+                                               counts.ctypes.data, sizes.ctypes.data, ani.ctypes.data if ani is not None else None))
+        return counts, sizes, ani
+
+    def sketch_sequence_sharded(self, comm: Optional["Comm"], slice_batch: "Batch", mask: int, window: int, pred: Predicate,
+                                gather: bool = True) -> Tuple["KmerSet", int]:
+        """One long sequence split by position: (this rank's key range of the global set, or the whole set when
+        `gather`; size of the global set)."""
+        h, n, p = C.c_void_p(), C.c_int64(), pred.c()
+        check(self._L.sks_sketch_sequence_sharded(self.h, comm.h if comm else None, slice_batch.h, _w2(mask), window, C.byref(p),
+                                                  int(gather), C.byref(h), C.byref(n)))
+        return KmerSet(self, h), n.value
+
     def intersect_block(self, sets: Sequence["KmerSet"], rows: Tuple[int, int], cols: Tuple[int, int],
                         out: np.ndarray) -> np.ndarray:
         """out[i, j] = |sets[i] n sets[j]| for i in rows, j in cols (half-open ranges); other entries untouched."""
@@ -383,6 +426,61 @@ class Context:
         r, p = SksPairResult(), pred.c()
         check(self._L.sks_pair_ani_resident(self.h, batch.h, _w2(mask), window, C.byref(p), repr_, C.byref(r)))
         return r
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """[begin, end) of the genomes (and pair-matrix rows) of `rank`: contiguous blocks of ceil(n / world)."""
+    b, e = C.c_int64(), C.c_int64()
+    _lib.load().sks_shard_range(n, rank, world, C.byref(b), C.byref(e))
+    return b.value, e.value
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """The 128-byte NCCL id rank 0 makes; the launcher carries it to the other ranks (multi_gpu.init_comm)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    check(_lib.load().sks_comm_unique_id(buf))
+    return buf.raw
+
+
+class Comm:
+    """One rank's communicator (C ABI: sks_comm_*).  `None` everywhere a Comm is expected means a single rank."""
+
+    def __init__(self, ctx: "Context", comm_id: bytes, rank: int, world: int):
+        self._L = _lib.load()
+        self.ctx, self.rank, self.world = ctx, rank, world
+        h = C.c_void_p()
+        check(self._L.sks_comm_init_rank(ctx.h, C.create_string_buffer(comm_id, COMM_ID_BYTES), rank, world, C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def init_all(cls, ctxs: Sequence["Context"]) -> List["Comm"]:
+        """One process, one context per GPU: communicators for all of them (sks_comm_init_all); the sharded calls are
+        then made from one thread per context."""
+        L = _lib.load()
+        n = len(ctxs)
+        hs = (C.c_void_p * n)(*[c.h for c in ctxs])
+        out = (C.c_void_p * n)()
+        check(L.sks_comm_init_all(hs, n, out))
+        comms = []
+        for r in range(n):
+            c = cls.__new__(cls)
+            c._L, c.ctx, c.rank, c.world, c.h = L, ctxs[r], r, n, C.c_void_p(out[r])
+            comms.append(c)
+        return comms
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.sks_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Batch:

@@ -1,0 +1,121 @@
+"""GPU tests of the sharded entry points of the C ABI (include/sks.h, sks_comm_* / *_sharded): the rank's block rows of
+the all-vs-all matrix and the key-range routed sketch of one long sequence, against the single-GPU result and the
+oracle.  With several GPUs visible the ranks are threads of this process, one per GPU (sks_comm_init_all); on a
+one-GPU box the same entry points run with a single rank."""
+import threading
+
+import numpy as np
+import pytest
+
+import spaced_kmer_sketching_b200 as sks
+from spaced_kmer_sketching_b200 import _lib, multi_gpu
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+C3_SEED = "0011111011010111111011001011101"
+DS = [0, 1000, 200, 100, 50, 20]
+
+
+def _world():
+    return max(1, min(int(_lib.load().sks_device_count()), 4))
+
+
+def _run_ranks(world, fn):
+    """fn(rank, ctx, comm) on one thread per GPU; returns the results in rank order."""
+    ctxs = [sks.Context(r) for r in range(world)]
+    comms = sks.Comm.init_all(ctxs) if world > 1 else [None]
+    out, err = [None] * world, []
+
+    def body(r):
+        try:
+            out[r] = fn(r, ctxs[r], comms[r])
+        except Exception as e:   # noqa: BLE001 -- reported by the main thread
+            err.append((r, repr(e)))
+
+    threads = [threading.Thread(target=body, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    for c in comms:
+        if c is not None:
+            c.close()
+    for c in ctxs:
+        c.close()
+    assert not err, err
+    return out
+
+
+@pytest.mark.parametrize("n_total", [11, 3])
+def test_sharded_all_vs_all_rows_match_single_gpu_and_oracle(n_total):
+    world = _world()
+    L = 300_000
+    mask, w = sks.seed_to_mask(C3_SEED)
+    pred = sks.frac_min_hash(1, 20)
+    ids = list(range(n_total))
+
+    def rank_body(rank, ctx, comm):
+        b, e = sks.shard_range(n_total, rank, world)
+        batch = ctx.synth(L, [1000] * (e - b), [2000 + g for g in ids[b:e]], [DS[g % 6] for g in ids[b:e]])
+        sets = ctx.sketch(batch, mask, w, pred, sks.REPR_SORTED) if e > b else []
+        counts, sizes, ani = ctx.all_vs_all_sharded(comm, sets, n_total)
+        everything = ctx.allgather_sets(comm, sets, n_total)
+        digest = [x.keys()[:, 0].tolist() for x in everything] if rank == 0 else None
+        for x in everything + list(sets):
+            x.close()
+        return (b, e), counts, sizes, ani, digest
+
+    res = _run_ranks(world, rank_body)
+    assert [r[0] for r in res] == [sks.shard_range(n_total, r, world) for r in range(world)]
+    counts = np.concatenate([r[1] for r in res])
+    ani = np.concatenate([r[3] for r in res])
+    # single GPU, all genomes
+    ctx = sks.Context(0)
+    batch = ctx.synth(L, [1000] * n_total, [2000 + g for g in ids], [DS[g % 6] for g in ids])
+    sets = ctx.sketch(batch, mask, w, pred, sks.REPR_SORTED)
+    want = ctx.intersect_block(sets, (0, n_total), (0, n_total), np.full((n_total, n_total), -1, dtype=np.int32))
+    sizes = np.array([s.kmer_set_size() for s in sets], dtype=np.int32)
+    assert np.array_equal(counts, want)
+    for r in res:
+        assert np.array_equal(r[2], sizes)
+    assert res[0][4] == [s.keys()[:, 0].tolist() for s in sets]     # the gathered sets are the sets, in genome order
+    wani = sks.ani_from_counts(want.ravel(), np.repeat(sizes, n_total), sks.mask_weight(mask)).reshape(n_total, n_total)
+    assert np.max(np.abs(ani - wani)) <= 1e-12
+    # oracle: two genomes from the far ends of the shard order
+    base = port.gen(L, 1000)
+    for g in (0, n_total - 1):
+        codes = base if DS[g % 6] == 0 else port.mutate(base, 2000 + g, DS[g % 6])
+        assert np.array_equal(sets[g].keys(), port.sketch_set(codes, [L], mask, w, port.FMH, 1, 20, 181))
+    ctx.close()
+
+
+@pytest.mark.parametrize("seed,L", [(C3_SEED, 3_000_017), ("1110110111011011101101110110111011011101", 400_000)])
+def test_sharded_sequence_sketch_equals_whole_sequence_sketch(seed, L):
+    """Position-split sketch routed by key range (8- and 16-byte keys): the gathered set, and the concatenation of
+    the ranks' disjoint ordered ranges, equal the single-GPU sketch of the whole sequence and the oracle's."""
+    world = _world()
+    mask, w = sks.seed_to_mask(seed)
+    pred = sks.frac_min_hash(1, 50)
+
+    def rank_body(rank, ctx, comm):
+        shard = multi_gpu.position_shard(L, w, rank, world)
+        sl = multi_gpu.synth_slice(ctx, L, 7, shard, w)
+        full, n_full = ctx.sketch_sequence_sharded(comm, sl, mask, w, pred, gather=True)
+        part, n_part = ctx.sketch_sequence_sharded(comm, sl, mask, w, pred, gather=False)
+        out = (full.keys(), n_full, part.keys(), n_part)
+        full.close()
+        part.close()
+        sl.close()
+        return out
+
+    res = _run_ranks(world, rank_body)
+    ctx = sks.Context(0)
+    (whole,) = ctx.sketch(ctx.synth(L, [7], [0], [0]), mask, w, pred, sks.REPR_SORTED)
+    want = whole.keys()
+    assert np.array_equal(want, port.sketch_set(port.gen(L, 7), [L], mask, w, port.FMH, 1, 50, 181))
+    for full, n_full, part, n_part in res:
+        assert n_full == n_part == len(want)
+        assert np.array_equal(full, want)
+    assert np.array_equal(np.concatenate([r[2] for r in res]), want)
+    ctx.close()

@@ -223,14 +223,17 @@ def test_multi_golden(ctx):
         sizes = np.repeat(np.array(case["sizes"], dtype=np.int32), n)
         ani = sks.ani_from_counts(ints.ravel(), sizes, sks.mask_weight(mask))
         assert np.max(np.abs(ani - np.array([float(x) for x in case["ani"]]))) <= 1e-12
-        # the multi-GPU tiling on one device: every rank's block pairs, row blocks stacked, mirrored
-        from spaced_kmer_sketching_b200 import multi_gpu
+        # the multi-GPU tiling on one device: every rank's block rows (sks_all_vs_all_sharded with a single rank is the
+        # same call on rows [begin, end)), stacked in rank order; and the rectangles of the pairwise kernels
         for world in (1, 2, 3, 4, 6):
+            parts = [ctx.all_vs_all(sets, *sks.shard_range(n, r, world)) for r in range(world)]
+            assert np.array_equal(np.concatenate([p[0] for p in parts]), ints), world
+            assert np.max(np.abs(np.concatenate([p[2] for p in parts]).ravel() - np.array([float(x) for x in case["ani"]]))) <= 1e-12
             full = np.full((n, n), -1, dtype=np.int32)
             for r in range(world):
-                rows = multi_gpu.row_tile(n, r, world)
-                full[rows[0]:rows[1]] = multi_gpu.tiled_counts(ctx, sets, r, world)[rows[0]:rows[1]]
-            assert np.array_equal(multi_gpu.mirror_counts(full), ints), world
+                rows = sks.shard_range(n, r, world)
+                ctx.intersect_block(sets, rows, (0, n), full)
+            assert np.array_equal(full, ints), world
 
 
 def test_all_pairs_row_resident_and_merge_paths(ctx):
@@ -614,9 +617,8 @@ def test_c3_chromosome_scale(ctx):
 
 def test_c4_all_vs_all_at_genome_size(ctx):
     """BASELINE.json configs[3] in small: 24 graded mutants of one 5 Mbp genome, weight-21 span-31 seed, FMH(200):
-    the n^2 intersection counts (row-resident and merge kernels) against numpy set intersections of the key
-    arrays, two sketches against the oracle, and the rank tiling of the multi-GPU path."""
-    from spaced_kmer_sketching_b200 import multi_gpu
+    the n^2 intersection counts (dictionary route, row-resident and merge kernels) against numpy set intersections of
+    the key arrays, two sketches against the oracle, and the rank tiling of the multi-GPU path."""
     L, n = 5_000_000, 24
     Ds = [[0, 1000, 200, 100, 50, 20][g % 6] for g in range(n)]
     batch = ctx.synth(L, [1000] * n, [2000 + g for g in range(n)], Ds)
@@ -632,10 +634,11 @@ def test_c4_all_vs_all_at_genome_size(ctx):
     want = np.array([[len(np.intersect1d(a, b, assume_unique=True)) for b in keys] for a in keys], dtype=np.int32)
     assert np.array_equal(ctx.intersect_all_pairs(sets), want)
     full = np.full((n, n), -1, dtype=np.int32)
-    for r in range(4):
-        rows = multi_gpu.row_tile(n, r, 4)
-        full[rows[0]:rows[1]] = multi_gpu.tiled_counts(ctx, sets, r, 4)[rows[0]:rows[1]]
-    assert np.array_equal(multi_gpu.mirror_counts(full), want)
+    for r in range(4):   # the pairwise kernels, rank by rank
+        ctx.intersect_block(sets, sks.shard_range(n, r, 4), (0, n), full)
+    assert np.array_equal(full, want)
+    rows = [ctx.all_vs_all(sets, *sks.shard_range(n, r, 4)) for r in range(4)]   # the dictionary route, rank by rank
+    assert np.array_equal(np.concatenate([p[0] for p in rows]), want)
     # containment on the FIRST set of the ordered pair (src/kmer-sketching.cpp:198): the matrix is not symmetric
     sizes = np.array([len(k) for k in keys], dtype=np.int32)
     ani = sks.ani_from_counts(want.ravel(), np.repeat(sizes, n), sks.mask_weight(mask)).reshape(n, n)
