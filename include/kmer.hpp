@@ -8,10 +8,15 @@
  *   - kmer_set keeps its members on the device (sorted distinct keys or a 4^weight-bit presence
  *     bitset); the `kmer_hashes` table is materialised on the host only when a caller touches it.
  *   - the sketching condition is still a std::function<bool(const kmer)>.  Recognised forms run on the
- *     device: sks::all_kmers(), sks::fmh_condition(nonce, c), and any callable that -- like the
- *     reference driver's `fmh(k) % 200 == 0` (src/kmer-sketching.cpp:29-34) -- is found by probing to
- *     be `frac_min_hash(n)(k) % c == 0`.  Any other callable is evaluated on the host over the
- *     canonical k-mer list the device produces (window sliding and canonicalisation stay on the GPU).
+ *     device: sks::all_kmers() and sks::fmh_condition(nonce, c).  Any other callable is opaque: it is
+ *     evaluated on the host, exactly once per real k-mer and in sequence order as in the reference
+ *     (src/kmer_sliding.cpp:183), over the canonical k-mer list the device produces (window sliding and
+ *     canonicalisation stay on the GPU).  Opt-in (sks::enable_predicate_probe(true) or SKS_PREDICATE_PROBE=1):
+ *     an opaque callable is first PROBED -- called a few thousand times with scripted frac_min_hash values --
+ *     and, if it behaves as `frac_min_hash(n)(k) % c == 0` like the reference driver's free function
+ *     (src/kmer-sketching.cpp:29-34), run on the device as FMH{n, c}.  Probing is off by default because a
+ *     stateful callable observes the extra calls and a condition of the form `fmh(k) % c == 0 && extra(k)`
+ *     can pass it when `extra` holds on the probe k-mers.
  */
 #ifndef SKS_KMER_HPP
 #define SKS_KMER_HPP
@@ -259,6 +264,8 @@ void set_representation_hint(set_representation r);
 
 /** How the last sketching condition seen by this thread was executed: "device:all", "device:fmh" or "host". */
 const char *last_predicate_path();
+/** Probing of opaque sketching conditions (see the top of this header); process-wide, off by default. */
+void enable_predicate_probe(bool on);
 } // namespace sks
 
 #endif // SKS_KMER_HPP

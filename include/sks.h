@@ -103,7 +103,8 @@ int64_t sks_ctx_in_place_count(const sks_ctx *ctx);
 #define SKS_KERNEL_DICT 11       /* all-vs-all: dictionary of shared k-mers, sets re-coded as id bitmaps / lists */
 #define SKS_KERNEL_ALLPAIRS 12   /* all-vs-all: AND/popcount of the re-coded sets (K5, many sets)               */
 #define SKS_KERNEL_ANI 13        /* all-vs-all: mirror + diagonal + containment^(1/weight) on the device        */
-#define SKS_KERNEL_KINDS 14
+#define SKS_KERNEL_EXCHANGE 14   /* several GPUs: NCCL exchange of the sketches (header all-gather + grouped send/recv) */
+#define SKS_KERNEL_KINDS 15
 int sks_ctx_profile(sks_ctx *ctx, int enable);
 int sks_ctx_kernel_stats(sks_ctx *ctx, int kind, int64_t *out_launches, double *out_total_ms);
 const char *sks_kernel_name(int kind);

@@ -16,7 +16,7 @@ SKS_OK, SKS_ERR_INVALID, SKS_ERR_CUDA, SKS_ERR_CAPACITY, SKS_ERR_MISMATCH, SKS_E
 PRED_ALL, PRED_FMH = 0, 1
 HASH_BOOST_171, HASH_BOOST_181 = 171, 181
 REPR_AUTO, REPR_SORTED, REPR_BITSET, REPR_BITSET_ONCHIP = 0, 1, 2, 3
-KERNEL_KINDS = 14
+KERNEL_KINDS = 15
 
 
 class SksPred(C.Structure):

@@ -7,7 +7,9 @@
 // weight k in a window of k + 10 for k = 10..40 -- every genome is sketched with the FracMinHash
 // condition frac_min_hash(1)(kmer) % 200 == 0, all n*n ordered pairs are intersected, and
 // ANI = containment(|A n B|, |A|)^(1/weight) is appended to the CSV.
-// Written against include/kmer.hpp only, so it also builds against the reference's own headers.
+// Written against include/kmer.hpp only, so it also builds against the reference's own headers (where the sketching
+// condition is the free function below; on this repository's headers it is the recognised functor
+// sks::fmh_condition, which runs on the device without probing).
 #include <chrono>
 #include <fstream>
 #include <iostream>
@@ -22,7 +24,7 @@ namespace
 {
 const frac_min_hash sketch_hash(1);
 const int sketch_modulus = 200;
-bool keep_kmer(const kmer &k) { return sketch_hash(k) % sketch_modulus == 0; }
+[[maybe_unused]] bool keep_kmer(const kmer &k) { return sketch_hash(k) % sketch_modulus == 0; }
 
 using clock_type = std::chrono::high_resolution_clock;
 double ms_between(clock_type::time_point a, clock_type::time_point b)
@@ -56,7 +58,12 @@ void run_configuration(int window, int weight_wanted, int n_files, char *files[]
     const int weight = static_cast<int>(mask.count() / NUCLEOTIDE_BIT_SIZE);
 
     const auto t0 = clock_type::now();
-    std::vector<kmer_set> sets = parallel_kmer_sets_from_fasta_files(n_files, files, mask, window, keep_kmer);
+#ifdef SKS_KMER_HPP
+    const std::function<bool(const kmer)> condition = sks::fmh_condition(1, sketch_modulus);
+#else
+    const std::function<bool(const kmer)> condition = keep_kmer;
+#endif
+    std::vector<kmer_set> sets = parallel_kmer_sets_from_fasta_files(n_files, files, mask, window, condition);
     const auto t1 = clock_type::now();
     std::cout << "Time taken for sketching = " << ms_between(t0, t1) << " ms" << std::endl;
 

@@ -79,6 +79,15 @@ struct pred_plan
     sks_pred pred{};
 };
 
+std::atomic<int> g_probe_switch{-1};  // -1: follow the environment, 0 / 1: set by sks::enable_predicate_probe
+bool probe_enabled()
+{
+    const int sw = g_probe_switch.load();
+    if (sw >= 0) return sw != 0;
+    static const bool env = [] { const char *e = getenv("SKS_PREDICATE_PROBE"); return e && atoi(e) != 0; }();
+    return env;
+}
+
 uint64_t splitmix(uint64_t &s)
 {
     s += 0x9E3779B97F4A7C15ull;
@@ -112,7 +121,11 @@ pred_plan classify(const std::function<bool(const kmer)> &f, const kmer_bitset &
         return plan;
     }
     g_ts.pred_path = "host";
-    if (getenv("SKS_NO_PREDICATE_PROBE")) return plan;
+    // Any other callable is opaque.  By default it is evaluated on the host, exactly once per real k-mer, as the
+    // reference does (src/kmer_sliding.cpp:183).  Probing is opt-in (sks::enable_predicate_probe / SKS_PREDICATE_PROBE=1):
+    // it calls the callable a few thousand times with scripted hash values, which a stateful callable observes, and a
+    // condition that merely contains `fmh(k) % c == 0` can pass it.
+    if (!probe_enabled()) return plan;
 
     // Probe: while g_probe.active, frac_min_hash::operator() returns g_probe.value.  The callable is
     // accepted as `frac_min_hash(n)(k) % c == 0` when it calls the hash exactly once per k-mer, accepts
@@ -332,6 +345,7 @@ void set_device(int device)
 }
 void set_representation_hint(set_representation r) { g_ts.repr = (int)r; }
 const char *last_predicate_path() { return g_ts.pred_path; }
+void enable_predicate_probe(bool on) { g_probe_switch.store(on ? 1 : 0); }
 } // namespace sks
 
 using sks::check;

@@ -707,7 +707,7 @@ const char *sks_kernel_name(int kind) {
                                                 "bitset_popcount_kernel", "sort_unique", "sorted_intersect_kernel",
                                                 "synth_kernel", "list_finalize", "bitset_build", "fasta_parse",
                                                 "bitset_pair_build_kernel", "dict_build", "allpairs_kernel",
-                                                "ani_finalize_kernel"};
+                                                "ani_finalize_kernel", "nccl_exchange"};
   return (kind >= 0 && kind < SKS_KERNEL_KINDS) ? names[kind] : "?";
 }
 

@@ -285,6 +285,7 @@ int sks_comm_allgather_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local,
   h_mine[4] = n_local ? (long long)local[0]->mask[1] : 0;
   for (int64_t i = 0; i < n_local; ++i) h_mine[5 + i] = local[i]->count;
   long long *d_mine = static_cast<long long *>(d_hdr->ptr), *d_all = d_mine + hdr;
+  KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
   SKS_CUDA_TRY(cudaMemcpyAsync(d_mine, h_mine, 8 * hdr, cudaMemcpyHostToDevice, ctx->stream));
   SKS_NCCL_TRY(nccl()->AllGather(d_mine, d_all, hdr, ncclInt64, comm->comm, ctx->stream));
   SKS_CUDA_TRY(cudaMemcpyAsync(h_all, d_all, 8 * hdr * world, cudaMemcpyDeviceToHost, ctx->stream));

@@ -65,16 +65,39 @@ int main(int argc, char *argv[])
         {"lambda_fmh7", [](const kmer k) { return frac_min_hash(-2)(k) % 7 == 0; }},
         {"parity", [](const kmer k) { return k.masked_bits.count() % 2 == 0; }},
     };
+    // Opaque callables are evaluated on the host by default, exactly once per real k-mer (src/kmer_sliding.cpp:183);
+    // probing is opt-in.  A counting callable shows both.
+    {
+        long calls = 0;
+        std::function<bool(const kmer)> counting = [&calls](const kmer k) { ++calls; return frac_min_hash(1)(k) % 200 == 0; };
+        kmer_set plain = kmer_set_from_fasta_file(argv[1], mask, 24, counting);
+        const std::string path_off = sks::last_predicate_path();
+        const long calls_off = calls;
+        sks::enable_predicate_probe(true);
+        calls = 0;
+        kmer_set probed = kmer_set_from_fasta_file(argv[1], mask, 24, counting);
+        const std::string path_on = sks::last_predicate_path();
+        sks::enable_predicate_probe(false);
+        std::cout << "\"counting\":{\"path_default\":\"" << path_off << "\",\"calls_default\":" << calls_off
+                  << ",\"size_default\":" << plain.kmer_set_size() << ",\"path_probe\":\"" << path_on << "\",\"calls_probe\":" << calls
+                  << ",\"size_probe\":" << probed.kmer_set_size() << ",\"same\":" << (kmer_set_intersection(plain, probed) == plain.kmer_set_size() ? "true" : "false")
+                  << "},";
+    }
     std::cout << "\"cases\":{";
     bool first_case = true;
+    for (int pass = 0; pass < 2; ++pass)
     for (const cond_case &c : cases)
     {
+        const bool opaque = std::string(c.name) == "driver" || std::string(c.name) == "lambda_fmh7";
+        if (pass == 1 && !opaque) continue;
+        sks::enable_predicate_probe(pass == 1);
         std::vector<kmer_set> sets = parallel_kmer_sets_from_fasta_files(2, files, mask, 24, c.f);
+        sks::enable_predicate_probe(false);
         const std::string path = sks::last_predicate_path();
         std::vector<kmer_set *> ptrs = {&sets[0], &sets[1]};
         const auto pairs = generate_all_pairs_from_vector(ptrs);
         const std::vector<int> inter = compute_pairwise_kmer_set_intersections(pairs.first, pairs.second);
-        std::cout << (first_case ? "" : ",") << "\"" << c.name << "\":{\"path\":\"" << path << "\",\"sizes\":["
+        std::cout << (first_case ? "" : ",") << "\"" << c.name << (pass ? "_probed" : "") << "\":{\"path\":\"" << path << "\",\"sizes\":["
                   << sets[0].kmer_set_size() << "," << sets[1].kmer_set_size() << "],\"inter\":[";
         for (size_t i = 0; i < inter.size(); ++i) std::cout << (i ? "," : "") << inter[i];
         std::cout << "],\"ani\":[";

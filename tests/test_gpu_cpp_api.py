@@ -67,9 +67,19 @@ def test_cpp_api_against_oracle(tmp_path):
     expect = {
         "all": ("device:all", oracle_sets([fa, fb], mask, w)),
         "fmh_struct": ("device:fmh", oracle_sets([fa, fb], mask, w, port.FMH, 1, 50, 181)),
-        "driver": ("device:fmh", oracle_sets([fa, fb], mask, w, port.FMH, 1, 200, 181)),       # recognised by probing
-        "lambda_fmh7": ("device:fmh", oracle_sets([fa, fb], mask, w, port.FMH, -2, 7, 181)),
+        # opaque callables: on the host by default, on the device once probing is switched on (opt-in)
+        "driver": ("host", oracle_sets([fa, fb], mask, w, port.FMH, 1, 200, 181)),
+        "lambda_fmh7": ("host", oracle_sets([fa, fb], mask, w, port.FMH, -2, 7, 181)),
+        "driver_probed": ("device:fmh", oracle_sets([fa, fb], mask, w, port.FMH, 1, 200, 181)),
+        "lambda_fmh7_probed": ("device:fmh", oracle_sets([fa, fb], mask, w, port.FMH, -2, 7, 181)),
     }
+    # a counting callable sees exactly one call per real k-mer unless probing was asked for
+    ca0, sa0 = port.fasta_parse(open(fa, "rb").read())
+    n_windows = sum(max(int(x) - w + 1, 0) for x in sa0)
+    cnt = r["counting"]
+    assert cnt["path_default"] == "host" and cnt["calls_default"] == n_windows
+    assert cnt["path_probe"] == "device:fmh" and cnt["calls_probe"] > 0 and cnt["calls_probe"] != n_windows
+    assert cnt["size_default"] == cnt["size_probe"] == len(expect["driver"][1][0]) and cnt["same"]
     par = []
     for s in oracle_sets([fa, fb], mask, w):   # opaque condition: even popcount of masked_bits, run on the host
         keep = np.array([bin(int(k[0])).count("1") % 2 == 0 for k in s], dtype=bool)
@@ -112,11 +122,15 @@ def test_reference_main_on_our_headers_writes_the_same_csv(tmp_path):
     fc = os.path.join(d, "c.fna")
     port.write_fasta(fc, port.mutate(port.gen(40_000, 77), 79, 15), "c")
     outs = {}
-    for name, exe in (("ref", ref_cli), ("dropin", dropin), ("ours", ours)):
+    # the reference's main() passes a free function as the sketching condition: once on the default route (evaluated on
+    # the host) and once with probing switched on (recognised, run on the device)
+    for name, exe, env in (("ref", ref_cli, {}), ("dropin", dropin, {"SKS_PREDICATE_PROBE": "1"}), ("dropin_host", dropin, {}),
+                           ("ours", ours, {})):
         csv = os.path.join(d, name + ".csv")
-        log = subprocess.check_output([exe, csv, fa, fb, fc], timeout=900).decode()
+        log = subprocess.check_output([exe, csv, fa, fb, fc], timeout=900, env=dict(os.environ, **env)).decode()
         assert log.count("Time taken for sketching") == 62 and log.count("Time taken for comparison") == 62
         outs[name] = open(csv).read()
     assert outs["ref"].count("\n") == 1 + 62 * 9
     assert outs["dropin"] == outs["ref"]
+    assert outs["dropin_host"] == outs["ref"]
     assert outs["ours"] == outs["ref"]
