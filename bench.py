@@ -42,8 +42,8 @@ C4_N, C4_L = 1000, 5_000_000
 C4_DS = [0, 1000, 200, 100, 50, 20]           # genome g = mutate(gen(5 Mbp, 1000), 2000 + g, C4_DS[g % 6])
 # sha256 of the 1000 x 1000 int32 count matrix and of the 1000 int32 set sizes (row-major, little endian), first
 # produced by the single-GPU pairwise kernels (row_intersect / sorted_intersect), which the tests pin to the oracle
-C4_MATRIX_SHA256 = None
-C4_SIZES_SHA256 = None
+C4_MATRIX_SHA256 = "ec7dc05ecede49acb21cfc7ecec53acf2eca73dd6cab9bc10e0c8d25f28cbf6b"
+C4_SIZES_SHA256 = "7ba010cc645a18f5b77855d0d23d40f5b4bb0d280d21e6280aff577985ca8e84"
 WORKLOAD = ("C4 = BASELINE configs[3]: %d synthetic %d-base genomes at graded mutation rates (D = %s), weight-21 span-31 seed %s, "
             "FracMinHash(200, nonce 1, Boost >= 1.81 hash), all n^2 ordered pairs: sketch + exchange + intersect + "
             "containment^(1/21) ANI; the same genomes at every N (genome g on rank g // ceil(n/N))" % (C4_N, C4_L, C4_DS, C3_SEED))
