@@ -338,12 +338,8 @@ def run_b200(args):
         pin_ani = torch.empty((max(n_loc, 1), n), dtype=torch.float64).pin_memory()
         out = (pin_counts.numpy()[:n_loc], pin_sizes.numpy(), pin_ani.numpy()[:n_loc])
 
-        def step():
-            sets = ctx.sketch(batch, mask, w, pred, sks.REPR_SORTED) if n_loc else []
-            r = ctx.all_vs_all_sharded(comm, sets, n, out=out)
-            for s in sets:
-                s.close()
-            return r
+        def step():   # sks_sketch + sks_comm_allgather_sets + sks_all_vs_all for the rank's rows, one C call
+            return ctx.all_vs_all_resident(comm, batch if n_loc else None, n, mask, w, pred, out)
 
         if rank == 0:
             sampler.start()   # nvidia-smi needs ~0.2 s to its first sample: from the warm-up to the end of the timed regions

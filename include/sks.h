@@ -293,11 +293,17 @@ int sks_comm_nccl_version(void); /* 0 when NCCL cannot be loaded */
 int sks_comm_allgather_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total,
                             sks_set **out_all);
 /* parallel_compute_pairwise_kmer_set_intersections over generate_all_pairs_from_vector + containment +
- * binomial_estimator (src/kmer-sketching.cpp:185-200), sharded: sks_comm_allgather_sets, then sks_all_vs_all for the
- * rank's block rows [begin, end) = sks_shard_range(n_total, rank, world).  Outputs as in sks_all_vs_all:
- * out_counts / out_ani hold (end - begin) * n_total entries, out_sizes n_total. */
+ * binomial_estimator (src/kmer-sketching.cpp:185-200), sharded: sks_comm_allgather_sets; then every rank enters its
+ * share of the distinct k-mers (the key space is split by a hash) into its dictionary and counts their contribution
+ * to all pairs, one NCCL reduce-scatter adds the shares up, and the rank finalises its own block rows [begin, end) =
+ * sks_shard_range(n_total, rank, world).  Outputs as in sks_all_vs_all: out_counts / out_ani hold (end - begin) *
+ * n_total entries, out_sizes n_total. */
 int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total,
                            int32_t *out_counts, int32_t *out_sizes, double *out_ani);
+/* Sketch + exchange + comparison in one call for genomes already resident in HBM: `batch` holds the rank's block of the
+ * n_total genomes (NULL: the rank has none).  = sks_sketch(SKS_REPR_SORTED) + sks_all_vs_all_sharded. */
+int sks_all_vs_all_resident(sks_ctx *ctx, sks_comm *comm, const sks_batch *batch, int64_t n_total, const uint64_t mask[2],
+                            int window, const sks_pred *pred, int32_t *out_counts, int32_t *out_sizes, double *out_ani);
 /* The whole path from HOST buffers: packed[g] / n_bases[g] are the rank's n_local genomes (2-bit packed, one segment
  * each); they are uploaded (or, in pinned host memory, read in place by the sketch kernel), sketched, exchanged and
  * compared.  = parallel_kmer_sets_from_fasta_files + the comparison loop of src/kmer-sketching.cpp:163-200. */

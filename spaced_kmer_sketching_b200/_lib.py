@@ -113,6 +113,7 @@ PROTOTYPES = {
     "sks_comm_nccl_version": (ci, []),
     "sks_comm_allgather_sets": (ci, [vp, vp, C.POINTER(vp), i64, i64, C.POINTER(vp)]),
     "sks_all_vs_all_sharded": (ci, [vp, vp, C.POINTER(vp), i64, i64, vp, vp, vp]),
+    "sks_all_vs_all_resident": (ci, [vp, vp, vp, i64, u64p, ci, C.POINTER(SksPred), vp, vp, vp]),
     "sks_all_vs_all_from_host": (ci, [vp, vp, ci, C.POINTER(vp), u64p, i64, u64p, ci, C.POINTER(SksPred), vp, vp, vp]),
     "sks_sketch_sequence_sharded": (ci, [vp, vp, vp, u64p, ci, C.POINTER(SksPred), ci, C.POINTER(vp), i64p]),
     "sks_pair_ani": (ci, [vp, vp, u64, vp, u64, u64p, ci, C.POINTER(SksPred), ci, C.POINTER(SksPairResult)]),

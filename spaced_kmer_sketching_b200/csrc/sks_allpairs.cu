@@ -3,14 +3,16 @@
 // The reference evaluates every ordered pair on its own: `parallel_compute_pairwise_kmer_set_intersections` probes
 // the larger hash map with every element of the smaller one (src/kmer_set.cpp:23-41,167-184), n^2 * |sketch| probes
 // for `generate_all_pairs_from_vector` (src/generators.hpp:44-58).  Only k-mers that occur in at least two sets can
-// ever be counted, and most k-mers of a sketch are either private to their genome or shared with many.  So:
+// ever be counted; of those, most are either shared by a handful of genomes or by a large part of them.  So:
 //
-//   D1  every key of every set goes into one device-wide open-addressing table that counts in how many sets it
-//       occurs (the sets hold distinct keys, so multiplicity == number of sets);
-//   D2  keys of multiplicity >= 2 get dense 32-bit ids, the widely shared ones (>= n/16 sets) first;
-//   D3  every set is re-written as its shared ids, grouped by id range (2^16 ids): a range a set is dense in
-//       (>= 1024 ids) becomes an 8 KB bitmap, a sparse one a 16-bit id list, an empty one nothing;
-//   X   |A n B| = sum over the ranges both sets are present in of popc(bitmap_A & bitmap_B) (or of list probes
+//   D1  every key of every set goes into one device-wide open-addressing table that counts its occurrences (the sets
+//       hold distinct keys, so occurrences == sets that hold the key); the second occurrence of a key gives it the
+//       next dense 32-bit id, and every entry remembers which occurrence it was;
+//   D2  keys held by 2 .. kPostMax sets become POSTING LISTS (the sets that hold the key); keys held by more sets
+//       are re-coded per set as id bitmaps: the set's ids grouped by id range (2^16 ids), a range the set is dense
+//       in (>= 1024 ids) as an 8 KB bitmap, a sparse one as a 16-bit id list; private keys are dropped;
+//   X1  a posting list of c sets adds 1 to each of its c (c - 1) ordered pairs;
+//   X2  |A n B| += sum over the ranges both sets are present in of popc(bitmap_A & bitmap_B) (or of list probes
 //       into A's bitmap, which sits in shared memory for a whole chunk of columns);
 //   F   counts (+ the diagonal |A n A| = |A|), set sizes and ANI = (|A n B| / |A|)^(1/weight)
 //       (src/ani_estimation.cpp:24-42, src/kmer-sketching.cpp:196-200) are finalised on the device.
@@ -51,11 +53,13 @@ struct Compact {
 
 struct Slot {  // 16 bytes: one sector holds the key and its counters
   unsigned long long key;  // 0 = empty (key 0 itself lives in the extra slot `cap`)
-  uint32_t cnt;            // number of entries (== sets) that hold the key
-  uint32_t id;             // D2: dense id, or kNoId
+  uint32_t cnt;            // occurrences == sets that hold the key
+  uint32_t id;             // dense id, given by the second occurrence
 };
+constexpr uint32_t kPostMax = 16;          // keys held by at most this many sets are posting lists
+constexpr uint32_t kPostFlag = 0x80000000u;  // entry = kPostFlag | id: the key is a posting list
 
-enum Counter : int { C_IDS_A = 0, C_IDS_B = 1, C_ROWS = 2, C_TASK = 3, C_COUNT = 16 };
+enum Counter : int { C_IDS = 0, C_ROWS = 2, C_TASK = 3, C_COUNT = 16 };
 
 struct DictView {
   const void *const *set_ptr;  // [n] keys of set s
@@ -64,8 +68,10 @@ struct DictView {
   uint32_t n_entries;
   Slot *tab;                   // [cap + 1]
   uint32_t cap;
-  uint32_t *entry;             // [n_entries] D1: slot of the entry's key; D3: its id (kNoId: not shared)
+  uint32_t *entry;             // [n_entries] D1: slot of the entry's key; D2: its id (| kPostFlag), kNoId: private key
+  uint8_t *occ;                // [n_entries] which occurrence of its key the entry was (saturating at 255)
   uint32_t *counters;          // [C_COUNT]
+  uint32_t part, n_parts;      // only keys with owner(key) == part are entered (several ranks split the key space)
 };
 
 __device__ __forceinline__ uint32_t size16(uint32_t cnt) {  // payload of a (set, range) group in 16-byte units
@@ -89,14 +95,17 @@ __device__ __forceinline__ unsigned long long load_key(const void *base, uint32_
   return out;
 }
 
-__device__ __forceinline__ uint32_t hash_slot(unsigned long long k, uint32_t cap) {
+__device__ __forceinline__ unsigned long long hash_key(unsigned long long k) {
   k ^= k >> 33;
   k *= 0xff51afd7ed558ccdull;
   k ^= k >> 33;
   k *= 0xc4ceb9fe1a85ec53ull;
   k ^= k >> 33;
-  return __umulhi((uint32_t)(k >> 32), cap);
+  return k;
 }
+// the table slot comes from the upper half of the hash, the owning rank from the lower half
+__device__ __forceinline__ uint32_t hash_slot(unsigned long long h, uint32_t cap) { return __umulhi((uint32_t)(h >> 32), cap); }
+__device__ __forceinline__ uint32_t hash_owner(unsigned long long h, uint32_t n_parts) { return (uint32_t)h % n_parts; }
 
 // Largest s with set_off[s] <= e (empty sets share their offset with their successor and are never returned).
 __device__ __forceinline__ uint32_t find_set(const uint32_t *__restrict__ set_off, uint32_t n_sets, uint32_t e) {
@@ -108,13 +117,16 @@ __device__ __forceinline__ uint32_t find_set(const uint32_t *__restrict__ set_of
   return lo;
 }
 
-// D1: insert every key, count its occurrences, remember its slot.
+// D1: insert every key (of this rank's share of the key space), count its occurrences, remember its slot and which
+// occurrence the entry was.  A key that is already known to be held by more than kPostMax sets needs neither: its
+// entries only look it up.
 template <int KW>
 __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_constant__ DictView D,
                                                                    const __grid_constant__ Compact C) {
   const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
   uint32_t s = 0, slot[kDictPer];
-  unsigned long long key[kDictPer], cur[kDictPer];
+  unsigned long long key[kDictPer];
+  uint4 cur[kDictPer];
   bool have = false;
 #pragma unroll
   for (int u = 0; u < kDictPer; ++u) {
@@ -128,62 +140,50 @@ __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_
         while (e >= __ldg(D.set_off + s + 1)) ++s;
       }
       key[u] = load_key<KW>(D.set_ptr[s], e - __ldg(D.set_off + s), C);
-      slot[u] = key[u] ? hash_slot(key[u], D.cap) : D.cap;
+      const unsigned long long h = hash_key(key[u]);
+      if (D.n_parts > 1 && hash_owner(h, D.n_parts) != D.part) D.entry[e] = kNoId;   // another rank's key
+      else slot[u] = key[u] ? hash_slot(h, D.cap) : D.cap;
     }
   }
 #pragma unroll
   for (int u = 0; u < kDictPer; ++u)  // the first probes of a thread's entries are in flight together
-    if (slot[u] != kNoId && slot[u] != D.cap) cur[u] = __ldcg(&D.tab[slot[u]].key);
+    if (slot[u] != kNoId) cur[u] = __ldcg(reinterpret_cast<const uint4 *>(D.tab + slot[u]));
 #pragma unroll
   for (int u = 0; u < kDictPer; ++u) {
     if (slot[u] == kNoId) continue;
     uint32_t sl = slot[u];
+    uint32_t seen = cur[u].z;   // the key's count when it was probed (only meaningful if the probe found the key)
     if (sl != D.cap) {
-      unsigned long long c = cur[u];
+      unsigned long long c = ((unsigned long long)cur[u].y << 32) | cur[u].x;
       for (;;) {
         if (c == key[u]) break;
+        seen = 0;
         if (c == 0) {
           c = atomicCAS(&D.tab[sl].key, 0ull, key[u]);
           if (c == 0 || c == key[u]) break;
         }
         sl = sl + 1 == D.cap ? 0 : sl + 1;
-        c = __ldcg(&D.tab[sl].key);
+        const uint4 nx = __ldcg(reinterpret_cast<const uint4 *>(D.tab + sl));
+        c = ((unsigned long long)nx.y << 32) | nx.x;
+        seen = nx.z;
       }
     }
-    atomicAdd(&D.tab[sl].cnt, 1u);
-    D.entry[base + u * kDictThreads + threadIdx.x] = sl;
-  }
-}
-
-// D2: ids for the keys that occur in at least two sets; class A (>= thr_a sets) and class B are numbered apart,
-// class B follows class A at the next range boundary (dict_ids_kernel).
-__global__ void __launch_bounds__(256) dict_assign_kernel(Slot *__restrict__ tab, uint32_t n_slots, uint32_t thr_a,
-                                                          uint32_t *__restrict__ counters) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t n_round = (n_slots + 31) & ~31u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    const uint32_t c = i < n_slots ? tab[i].cnt : 0u;
-    const int cls = c >= thr_a && c >= 2 ? 0 : (c >= 2 ? 1 : 2);
-    uint32_t id = kNoId;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const uint32_t m = __ballot_sync(0xffffffffu, cls == k);
-      if (m == 0) continue;
-      uint32_t first = 0;
-      if (lane == (uint32_t)(__ffs(m) - 1)) first = atomicAdd(counters + k, (uint32_t)__popc(m));
-      first = __shfl_sync(0xffffffffu, first, __ffs(m) - 1);
-      if (cls == k) id = ((uint32_t)k << 31) | (first + __popc(m & ((1u << lane) - 1)));
+    const uint32_t e = base + u * kDictThreads + threadIdx.x;
+    uint32_t k = 255;
+    if (seen <= kPostMax) {
+      k = atomicAdd(&D.tab[sl].cnt, 1u);
+      if (k == 1) D.tab[sl].id = atomicAdd(D.counters + C_IDS, 1u);   // read by later kernels only
     }
-    if (i < n_slots) tab[i].id = id;
+    D.entry[e] = sl;
+    D.occ[e] = (uint8_t)min(k, 255u);
   }
 }
 
-// D3a: entry -> id, and the number of ids of every (range, set) group.
+// D2a: entry -> id; sizes of the posting lists and of the (range, set) groups.
 __global__ void __launch_bounds__(kDictThreads) dict_ids_kernel(const __grid_constant__ DictView D,
-                                                                uint32_t *__restrict__ group_cnt) {
+                                                                uint32_t *__restrict__ group_cnt,
+                                                                uint32_t *__restrict__ post_cnt) {
   const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
-  const uint32_t base_b = (D.counters[C_IDS_A] + kRangeIds - 1) & ~(kRangeIds - 1);
   const uint32_t lane = threadIdx.x & 31;
   uint32_t s = 0;
   bool have = false;
@@ -198,11 +198,19 @@ __global__ void __launch_bounds__(kDictThreads) dict_ids_kernel(const __grid_con
       } else {
         while (e >= __ldg(D.set_off + s + 1)) ++s;
       }
-      const uint32_t v = D.tab[D.entry[e]].id;
+      const uint32_t at = D.entry[e];
+      Slot sl;
+      sl.cnt = 0;
+      if (at != kNoId) sl = D.tab[at];   // final: the insertion kernel has completed
       uint32_t id = kNoId;
-      if (v != kNoId) {
-        id = (v >> 31) ? base_b + (v & 0x7FFFFFFFu) : v;
-        bin = (id >> kRangeBits) * D.n_sets + s;
+      if (sl.cnt >= 2) {
+        if (sl.cnt <= kPostMax) {
+          id = kPostFlag | sl.id;
+          if (D.occ[e] == 0) post_cnt[sl.id] = sl.cnt;
+        } else {
+          id = sl.id;
+          bin = (id >> kRangeBits) * D.n_sets + s;
+        }
       }
       D.entry[e] = id;
     }
@@ -218,10 +226,11 @@ __global__ void __launch_bounds__(256) zero16_kernel(uint4 *__restrict__ p, cons
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = make_uint4(0, 0, 0, 0);
 }
 
-// D3b: the groups' payloads: bitmap bits (dense) or 16-bit ids in arrival order (sparse).
+// D2b: the members of the posting lists; the groups' payloads: bitmap bits (dense) or 16-bit ids in arrival order (sparse).
 __global__ void __launch_bounds__(kDictThreads)
     dict_payload_kernel(const __grid_constant__ DictView D, const uint32_t *__restrict__ group_cnt,
-                        const uint32_t *__restrict__ group_end, uint32_t *__restrict__ cursor, uint4 *__restrict__ payload) {
+                        const uint32_t *__restrict__ group_end, uint32_t *__restrict__ cursor, uint4 *__restrict__ payload,
+                        const uint32_t *__restrict__ post_begin, uint16_t *__restrict__ postings) {
   const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
   uint32_t s = 0;
   bool have = false;
@@ -237,6 +246,10 @@ __global__ void __launch_bounds__(kDictThreads)
     }
     const uint32_t id = D.entry[e];
     if (id == kNoId) continue;
+    if (id & kPostFlag) {  // the occurrences of a key fill its posting list
+      postings[post_begin[id & ~kPostFlag] + D.occ[e]] = (uint16_t)s;
+      continue;
+    }
     const uint32_t g = (id >> kRangeBits) * D.n_sets + s, c = group_cnt[g];
     const uint32_t off = group_end[g] - size16(c), low = id & (kRangeIds - 1);
     if (c >= kDenseMin) {
@@ -244,6 +257,37 @@ __global__ void __launch_bounds__(kDictThreads)
     } else {
       const uint32_t pos = atomicAdd(cursor + g, 1u);
       reinterpret_cast<uint16_t *>(payload + off)[pos] = (uint16_t)low;
+    }
+  }
+}
+
+// X1: every posting list adds 1 to each ordered pair of its sets (rows of this call only; j > i only when the
+// finalisation mirrors).
+__global__ void __launch_bounds__(256)
+    posting_pairs_kernel(const uint32_t *__restrict__ post_cnt, const uint32_t *__restrict__ post_begin,
+                         const uint16_t *__restrict__ postings, const uint32_t *__restrict__ counters, uint32_t n_sets,
+                         uint32_t row_begin, uint32_t row_end, int symmetric, int32_t *__restrict__ out) {
+  const uint32_t n_ids = counters[C_IDS];
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < n_ids; id += stride) {
+    const uint32_t c = post_cnt[id];
+    if (c < 2) continue;
+    const uint16_t *p = postings + post_begin[id];
+    uint32_t m[kPostMax];
+#pragma unroll
+    for (uint32_t a = 0; a < kPostMax; ++a) m[a] = a < c ? p[a] : 0u;
+#pragma unroll
+    for (uint32_t a = 0; a < kPostMax; ++a) {
+      if (a >= c) break;
+      const uint32_t i = m[a];
+      if (i < row_begin || i >= row_end) continue;
+#pragma unroll
+      for (uint32_t b = 0; b < kPostMax; ++b) {
+        if (b >= c) break;
+        const uint32_t j = m[b];
+        if (j == i || (symmetric && j < i)) continue;
+        atomicAdd(out + (size_t)(i - row_begin) * n_sets + j, 1);
+      }
     }
   }
 }
@@ -288,6 +332,9 @@ __global__ void __launch_bounds__(kPairsThreads) allpairs_kernel(const __grid_co
     const uint32_t j0 = chunk * kPairsCols, j1 = min(V.n_sets, j0 + kPairsCols);
     if (V.symmetric && j1 <= i + 1) continue;
     const uint32_t ca = V.group_cnt[g], offa = V.group_end[g] - size16(ca);
+    // ids are dense from 0: the last range is only partly used, and nothing is set beyond its last id
+    const uint32_t ids_here = min(kRangeIds, V.counters[C_IDS] - t * kRangeIds);
+    const uint32_t used16 = (ids_here + 127) / 128;
     if (ca >= kDenseMin) {
       for (uint32_t k = tid; k < kRange16; k += kPairsThreads) s_bits4[k] = __ldg(V.payload + offa + k);
     } else {
@@ -309,7 +356,7 @@ __global__ void __launch_bounds__(kPairsThreads) allpairs_kernel(const __grid_co
       if (cb >= kDenseMin) {
         const uint4 *B = V.payload + offb;
 #pragma unroll 4
-        for (uint32_t k = lane; k < kRange16; k += 32) {
+        for (uint32_t k = lane; k < used16; k += 32) {
           const uint4 b = __ldg(B + k), a = s_bits4[k];
           acc += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
         }
@@ -397,11 +444,15 @@ bool all_pairs_dict_eligible(sks_set *const *sets, int64_t n) {
   return true;
 }
 
-// Rows [row_begin, row_end) of the n x n matrix of |sets[i] n sets[j]|, device resident: *counts receives
-// (row_end - row_begin) * n int32 (full rows incl. the diagonal), *ani (optional) as many doubles.
-int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, BufferRef *counts,
-                   BufferRef *ani, BufferRef *sizes_out) {
-  const uint32_t n_sets = (uint32_t)n, n_rows = (uint32_t)(row_end - row_begin);
+// Raw counts of the rows [row_begin, row_end) of the n x n matrix of |sets[i] n sets[j]| (off-diagonal entries; with
+// `symmetric` -- which needs all rows -- only j > i), from the keys of share `part` of `n_parts` of the key space:
+// the shares of all parts add up to the counts.  *raw receives raw_rows x n int32 (rows beyond the range stay zero),
+// *sizes the n set sizes.
+int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, int part, int n_parts,
+                  bool symmetric, int64_t raw_rows, BufferRef *raw_out, BufferRef *sizes_out) {
+  const uint32_t n_sets = (uint32_t)n;
+  if (symmetric && !(row_begin == 0 && row_end == n)) return set_error(SKS_ERR_INVALID, "mirroring needs all rows");
+  if (raw_rows < row_end - row_begin) return set_error(SKS_ERR_INVALID, "raw matrix too small");
   const int kw = sets[0]->key_words;
   Compact compact = {};
   if (kw == 2 && !make_compact(sets[0]->mask, &compact)) return set_error(SKS_ERR_INVALID, "mask too wide for the dictionary");
@@ -410,20 +461,20 @@ int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_be
   if (total >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "too many keys for the dictionary");
   const uint32_t K = (uint32_t)total;
   const uint32_t cap = std::max<uint32_t>(1024u, K + K / 2);
-  // ids: class A + padding to a range boundary + class B <= K / 2 + 2^16
-  const uint32_t n_ranges = (K / 2 + kRangeIds) / kRangeIds + 1;
+  // at most K / 2 keys can occur twice
+  const uint32_t max_ids = K / 2 + 1;
+  const uint32_t n_ranges = K / 2 / kRangeIds + 1;
   const uint64_t n_groups64 = (uint64_t)n_ranges * n_sets;
   if (n_groups64 >= (1ull << 28)) return set_error(SKS_ERR_CAPACITY, "too many (range, set) groups for the dictionary");
   const uint32_t n_groups = (uint32_t)n_groups64;
   const uint32_t n_chunks = (n_sets + kPairsCols - 1) / kPairsCols;
   if (n_groups64 * n_chunks >= (1ull << 32)) return set_error(SKS_ERR_CAPACITY, "too many tasks for the dictionary");
-  const bool symmetric = row_begin == 0 && row_end == n;
 
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   // one control block: counters | set_off | set_ptr | sizes | group_cnt | cursor | group_end | rowlist
   const size_t sz_cnt = align(4 * C_COUNT), sz_off = align(4 * ((size_t)n_sets + 1)), sz_ptr = align(8 * (size_t)n_sets);
   const size_t sz_sizes = align(4 * (size_t)n_sets), sz_grp = align(4 * (size_t)n_groups);
-  BufferRef ctl, tab, entry, payload, raw;
+  BufferRef ctl, tab, entry, occ, payload, raw, post;
   SKS_TRY(alloc_buffer(ctx, sz_cnt + sz_off + sz_ptr + sz_sizes + 4 * sz_grp, &ctl));
   char *cb = static_cast<char *>(ctl->ptr);
   uint32_t *d_counters = reinterpret_cast<uint32_t *>(cb);
@@ -434,12 +485,16 @@ int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_be
   uint32_t *d_cursor = d_gcnt + sz_grp / 4, *d_gend = d_cursor + sz_grp / 4, *d_rowlist = d_gend + sz_grp / 4;
   SKS_TRY(alloc_buffer(ctx, sizeof(Slot) * ((size_t)cap + 1), &tab));
   SKS_TRY(alloc_buffer(ctx, 4 * (size_t)std::max<uint32_t>(K, 1), &entry));
+  SKS_TRY(alloc_buffer(ctx, (size_t)std::max<uint32_t>(K, 16), &occ));
+  // posting lists: sizes and starts per id, members (every entry belongs to at most one list)
+  const size_t sz_ids = align(4 * (size_t)max_ids);
+  SKS_TRY(alloc_buffer(ctx, 2 * sz_ids + 2 * (size_t)K + 16, &post));
+  uint32_t *d_pcnt = static_cast<uint32_t *>(post->ptr), *d_pbegin = d_pcnt + sz_ids / 4;
+  uint16_t *d_postings = reinterpret_cast<uint16_t *>(static_cast<char *>(post->ptr) + 2 * sz_ids);
   // payload: a dense group holds >= kDenseMin ids in 8 KB, a sparse one 2 bytes per id rounded up to 16
   const size_t payload16 = (size_t)K / 2 + std::min<size_t>(n_groups, K) + 16;
   SKS_TRY(alloc_buffer(ctx, payload16 * 16, &payload));
-  SKS_TRY(alloc_buffer(ctx, 4 * (size_t)n_rows * n_sets, &raw));
-  SKS_TRY(alloc_buffer(ctx, 4 * (size_t)n_rows * n_sets, counts));
-  if (ani) SKS_TRY(alloc_buffer(ctx, 8 * (size_t)n_rows * n_sets, ani));
+  SKS_TRY(alloc_buffer(ctx, 4 * (size_t)raw_rows * n_sets, &raw));
 
   // host tables through the pinned ring: offsets | pointers | sizes
   char *stage = nullptr;
@@ -459,7 +514,8 @@ int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_be
   SKS_CUDA_TRY(cudaMemsetAsync(d_counters, 0, sz_cnt, ctx->stream));
   SKS_CUDA_TRY(cudaMemsetAsync(d_gcnt, 0, 2 * sz_grp, ctx->stream));  // group_cnt and cursor
   SKS_CUDA_TRY(cudaMemsetAsync(tab->ptr, 0, sizeof(Slot) * ((size_t)cap + 1), ctx->stream));
-  SKS_CUDA_TRY(cudaMemsetAsync(raw->ptr, 0, 4 * (size_t)n_rows * n_sets, ctx->stream));
+  SKS_CUDA_TRY(cudaMemsetAsync(raw->ptr, 0, 4 * (size_t)raw_rows * n_sets, ctx->stream));
+  SKS_CUDA_TRY(cudaMemsetAsync(d_pcnt, 0, sz_ids, ctx->stream));
 
   DictView D;
   D.set_ptr = d_ptr;
@@ -469,7 +525,10 @@ int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_be
   D.tab = static_cast<Slot *>(tab->ptr);
   D.cap = cap;
   D.entry = static_cast<uint32_t *>(entry->ptr);
+  D.occ = static_cast<uint8_t *>(occ->ptr);
   D.counters = d_counters;
+  D.part = (uint32_t)part;
+  D.n_parts = (uint32_t)std::max(n_parts, 1);
   const unsigned entry_grid = (K + kDictChunk - 1) / kDictChunk;
   const unsigned wide_grid = (unsigned)ctx->sm_count * 8;
   {
@@ -477,29 +536,35 @@ int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_be
     if (K > 0) {
       if (kw == 1) dict_insert_kernel<1><<<entry_grid, kDictThreads, 0, ctx->stream>>>(D, compact);
       else dict_insert_kernel<2><<<entry_grid, kDictThreads, 0, ctx->stream>>>(D, compact);
-      const uint32_t thr_a = std::max<uint32_t>(2u, n_sets / 16);
-      dict_assign_kernel<<<wide_grid, 256, 0, ctx->stream>>>(D.tab, cap + 1, thr_a, d_counters);
-      dict_ids_kernel<<<entry_grid, kDictThreads, 0, ctx->stream>>>(D, d_gcnt);
-      ctx->launches += 3;
+      dict_ids_kernel<<<entry_grid, kDictThreads, 0, ctx->stream>>>(D, d_gcnt, d_pcnt);
+      ctx->launches += 2;
     }
-    // group_end = inclusive prefix sum of the groups' payload sizes
-    size_t temp_bytes = 0;
+    // group_end = inclusive prefix sum of the groups' payload sizes; post_begin = exclusive prefix sum of the list sizes
+    size_t temp_bytes = 0, temp2 = 0;
     cub::TransformInputIterator<uint32_t, Size16Op, const uint32_t *> sizes_in(d_gcnt, Size16Op());
     cub::DeviceScan::InclusiveSum(nullptr, temp_bytes, sizes_in, d_gend, (int)n_groups, ctx->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, temp2, d_pcnt, d_pbegin, (int)max_ids, ctx->stream);
+    temp_bytes = std::max(temp_bytes, temp2);
     void *temp = nullptr;
     SKS_TRY(ctx_scratch(ctx, temp_bytes, &temp));
     cub::DeviceScan::InclusiveSum(temp, temp_bytes, sizes_in, d_gend, (int)n_groups, ctx->stream);
+    cub::DeviceScan::ExclusiveSum(temp, temp_bytes, d_pcnt, d_pbegin, (int)max_ids, ctx->stream);
     zero16_kernel<<<wide_grid, 256, 0, ctx->stream>>>(static_cast<uint4 *>(payload->ptr), d_gend + n_groups - 1);
-    ctx->launches += 2;
+    ctx->launches += 3;
     if (K > 0) {
       dict_payload_kernel<<<entry_grid, kDictThreads, 0, ctx->stream>>>(D, d_gcnt, d_gend, d_cursor,
-                                                                        static_cast<uint4 *>(payload->ptr));
+                                                                        static_cast<uint4 *>(payload->ptr), d_pbegin, d_postings);
       ctx->launches++;
     }
     SKS_CUDA_TRY(cudaGetLastError());
   }
   {
     KernelTimer timer(ctx, SKS_KERNEL_ALLPAIRS);
+    if (K > 0) {
+      posting_pairs_kernel<<<wide_grid, 256, 0, ctx->stream>>>(d_pcnt, d_pbegin, d_postings, d_counters, n_sets, (uint32_t)row_begin,
+                                                               (uint32_t)row_end, symmetric ? 1 : 0, static_cast<int32_t *>(raw->ptr));
+      ctx->launches++;
+    }
     rowlist_kernel<<<(n_groups + 255) / 256, 256, 0, ctx->stream>>>(d_gcnt, n_groups, n_sets, (uint32_t)row_begin,
                                                                     (uint32_t)row_end, d_rowlist, d_counters);
     PairsView V;
@@ -517,21 +582,41 @@ int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_be
     ctx->launches += 2;
     SKS_CUDA_TRY(cudaGetLastError());
   }
-  {
-    KernelTimer timer(ctx, SKS_KERNEL_ANI);
-    const size_t cells = (size_t)n_rows * n_sets;
-    if (cells > 0) {
-      finalize_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(
-          static_cast<const int32_t *>(raw->ptr), d_sizes, n_sets, (uint32_t)row_begin, n_rows, symmetric ? 1 : 0,
-          1.0 / (double)sets[0]->weight, static_cast<int32_t *>((*counts)->ptr), ani ? static_cast<double *>((*ani)->ptr) : nullptr);
-      ctx->launches++;
-    }
-    SKS_CUDA_TRY(cudaGetLastError());
-  }
-  if (sizes_out) {  // [n] int32 set sizes, for callers that keep working on the device
+  if (sizes_out) {  // [n] int32 set sizes, for the finalisation
     SKS_TRY(alloc_buffer(ctx, 4 * (size_t)std::max<uint32_t>(n_sets, 4), sizes_out));
     SKS_CUDA_TRY(cudaMemcpyAsync((*sizes_out)->ptr, d_sizes, 4 * (size_t)n_sets, cudaMemcpyDeviceToDevice, ctx->stream));
   }
+  *raw_out = raw;
+  return SKS_OK;
+}
+
+// F: from raw off-diagonal counts of the rows [row_begin, row_begin + n_rows) to full rows (mirror, diagonal) and ANI.
+int all_pairs_finalize(sks_ctx *ctx, const int32_t *raw_rows, const int32_t *d_sizes, int64_t n, int64_t row_begin,
+                       int64_t n_rows, bool symmetric, int weight, BufferRef *counts, BufferRef *ani) {
+  SKS_TRY(alloc_buffer(ctx, 4 * (size_t)n_rows * n, counts));
+  if (ani) SKS_TRY(alloc_buffer(ctx, 8 * (size_t)n_rows * n, ani));
+  KernelTimer timer(ctx, SKS_KERNEL_ANI);
+  const size_t cells = (size_t)n_rows * n;
+  if (cells > 0) {
+    finalize_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, ctx->stream>>>(
+        raw_rows, d_sizes, (uint32_t)n, (uint32_t)row_begin, (uint32_t)n_rows, symmetric ? 1 : 0, 1.0 / (double)weight,
+        static_cast<int32_t *>((*counts)->ptr), ani ? static_cast<double *>((*ani)->ptr) : nullptr);
+    ctx->launches++;
+  }
+  SKS_CUDA_TRY(cudaGetLastError());
+  return SKS_OK;
+}
+
+// Rows [row_begin, row_end) of the n x n matrix of |sets[i] n sets[j]|, device resident: *counts receives
+// (row_end - row_begin) * n int32 (full rows incl. the diagonal), *ani (optional) as many doubles.
+int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, BufferRef *counts,
+                   BufferRef *ani, BufferRef *sizes_out) {
+  BufferRef raw, sizes;
+  const bool symmetric = row_begin == 0 && row_end == n;
+  SKS_TRY(all_pairs_raw(ctx, sets, n, row_begin, row_end, 0, 1, symmetric, row_end - row_begin, &raw, &sizes));
+  SKS_TRY(all_pairs_finalize(ctx, static_cast<const int32_t *>(raw->ptr), static_cast<const int32_t *>(sizes->ptr), n, row_begin,
+                             row_end - row_begin, symmetric, sets[0]->weight, counts, ani));
+  if (sizes_out) *sizes_out = sizes;
   return SKS_OK;
 }
 

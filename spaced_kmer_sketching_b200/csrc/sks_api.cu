@@ -1614,6 +1614,19 @@ int sks_pair_ani(sks_ctx *ctx, const uint32_t *packed_a, uint64_t n_bases_a, con
   return st;
 }
 
+int sks_all_vs_all_resident(sks_ctx *ctx, sks_comm *comm, const sks_batch *batch, int64_t n_total, const uint64_t mask[2],
+                            int window, const sks_pred *pred, int32_t *out_counts, int32_t *out_sizes, double *out_ani) {
+  if (!ctx) return set_error(SKS_ERR_INVALID, "null context");
+  const int n_local = batch ? batch->n_genomes : 0;
+  std::vector<sks_set *> sets((size_t)std::max(n_local, 1), nullptr);
+  int st = SKS_OK;
+  if (n_local > 0) st = sks_sketch(ctx, batch, mask, window, pred, SKS_REPR_SORTED, sets.data());
+  if (st == SKS_OK) st = sks_all_vs_all_sharded(ctx, comm, sets.data(), n_local, n_total, out_counts, out_sizes, out_ani);
+  for (sks_set *s : sets)
+    if (s) sks_set_destroy(ctx, s);
+  return st;
+}
+
 int sks_all_vs_all_from_host(sks_ctx *ctx, sks_comm *comm, int n_local, const uint32_t *const *packed, const uint64_t *n_bases,
                              int64_t n_total, const uint64_t mask[2], int window, const sks_pred *pred, int32_t *out_counts,
                              int32_t *out_sizes, double *out_ani) {

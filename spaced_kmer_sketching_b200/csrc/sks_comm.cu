@@ -2,9 +2,10 @@
 //
 // The reference's only parallelism is `cilk_for` over FASTA files (src/kmer_set.cpp:124-131) and over set pairs
 // (src/kmer_set.cpp:179-182).  Sharded over GPUs that becomes: genomes are split into contiguous blocks by rank,
-// every rank sketches its block, the sketches are exchanged ONCE (sks_comm_allgather_sets), and every rank then
-// fills its own block rows of the n x n pair matrix (generate_all_pairs_from_vector order, src/generators.hpp:44-58)
-// with sks_all_vs_all -- no second exchange, the rows a rank returns are complete.  One long sequence (BASELINE
+// every rank sketches its block, the sketches are exchanged once (sks_comm_allgather_sets), the ranks then split the KEY
+// SPACE of the all-vs-all dictionary (csrc/sks_allpairs.cu): each enters its share of the distinct k-mers and counts
+// what they contribute to every pair, and one reduce-scatter of the n x n partial counts leaves every rank with its
+// own complete block rows of the pair matrix (generate_all_pairs_from_vector order, src/generators.hpp:44-58).  One long sequence (BASELINE
 // configs[2]) is split by position instead; its partial sketches are routed by key range, so that every rank
 // sort-uniques 1/world of the keys (sks_sketch_sequence_sharded).
 //
@@ -36,6 +37,7 @@ struct NcclApi {
   decltype(&ncclCommInitAll) CommInitAll = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclReduceScatter) ReduceScatter = nullptr;
   decltype(&ncclSend) Send = nullptr;
   decltype(&ncclRecv) Recv = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -64,6 +66,7 @@ NcclApi *load_nccl() {
   SKS_NCCL_SYM(CommInitAll)
   SKS_NCCL_SYM(CommDestroy)
   SKS_NCCL_SYM(AllGather)
+  SKS_NCCL_SYM(ReduceScatter)
   SKS_NCCL_SYM(Send)
   SKS_NCCL_SYM(Recv)
   SKS_NCCL_SYM(GroupStart)
@@ -353,16 +356,45 @@ int sks_comm_allgather_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local,
 int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total,
                            int32_t *out_counts, int32_t *out_sizes, double *out_ani) {
   if (!ctx) return set_error(SKS_ERR_INVALID, "null context");
+  const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
   std::vector<sks_set *> all((size_t)std::max<int64_t>(n_total, 1), nullptr);
-  int st = sks_comm_allgather_sets(ctx, comm, local, n_local, n_total, all.data());
-  if (st == SKS_OK) {
-    int64_t begin = 0, end = 0;
-    sks_shard_range(n_total, comm ? comm->rank : 0, comm ? comm->world : 1, &begin, &end);
-    st = sks_all_vs_all(ctx, all.data(), n_total, begin, end, out_counts, out_sizes, out_ani);
+  struct Release {
+    sks_ctx *c;
+    std::vector<sks_set *> &v;
+    ~Release() {
+      for (sks_set *s : v)
+        if (s) sks_set_destroy(c, s);
+    }
+  } release{ctx, all};
+  SKS_TRY(sks_comm_allgather_sets(ctx, comm, local, n_local, n_total, all.data()));
+  int64_t begin = 0, end = 0;
+  sks_shard_range(n_total, rank, world, &begin, &end);
+  if (world == 1 || n_total < 2 || !all_pairs_dict_eligible(all.data(), n_total))
+    return sks_all_vs_all(ctx, all.data(), n_total, begin, end, out_counts, out_sizes, out_ani);
+  // Several ranks split the KEY SPACE of the dictionary, not the rows: every rank enters 1 / world of the distinct
+  // keys (all sets are here after the exchange), counts what its keys contribute to every pair, and one reduce-scatter
+  // adds the shares up and leaves every rank with its own block rows.
+  DeviceGuard guard(ctx->device);
+  const int64_t per = (n_total + world - 1) / world, n_rows = end - begin;
+  BufferRef raw, sizes, mine, counts, ani;
+  int st = all_pairs_raw(ctx, all.data(), n_total, 0, n_total, rank, world, false, (int64_t)world * per, &raw, &sizes);
+  if (st == SKS_ERR_CAPACITY) return sks_all_vs_all(ctx, all.data(), n_total, begin, end, out_counts, out_sizes, out_ani);
+  SKS_TRY(st);
+  SKS_TRY(alloc_buffer(ctx, 4 * (size_t)per * n_total, &mine));
+  {
+    KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
+    SKS_NCCL_TRY(nccl()->ReduceScatter(raw->ptr, mine->ptr, (size_t)per * n_total, ncclInt32, ncclSum, comm->comm, ctx->stream));
   }
-  for (sks_set *s : all)
-    if (s) sks_set_destroy(ctx, s);
-  return st;
+  SKS_TRY(all_pairs_finalize(ctx, static_cast<const int32_t *>(mine->ptr), static_cast<const int32_t *>(sizes->ptr), n_total, begin,
+                             n_rows, false, all[0]->weight, &counts, out_ani ? &ani : nullptr));
+  if (out_counts && n_rows)
+    SKS_CUDA_TRY(cudaMemcpyAsync(out_counts, counts->ptr, 4 * (size_t)n_rows * n_total, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_ani && n_rows)
+    SKS_CUDA_TRY(cudaMemcpyAsync(out_ani, ani->ptr, 8 * (size_t)n_rows * n_total, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_sizes)
+    for (int64_t i = 0; i < n_total; ++i) out_sizes[i] = (int32_t)all[i]->count;
+  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return SKS_OK;
 }
 
 int sks_sketch_sequence_sharded(sks_ctx *ctx, sks_comm *comm, const sks_batch *slice, const uint64_t mask[2], int window,

@@ -269,6 +269,10 @@ int launch_row_intersect(sks_ctx *ctx, int key_words, const void *d_tasks, int64
 bool all_pairs_dict_eligible(sks_set *const *sets, int64_t n);
 int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, BufferRef *counts,
                    BufferRef *ani, BufferRef *sizes_out);
+int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, int part, int n_parts,
+                  bool symmetric, int64_t raw_rows, BufferRef *raw_out, BufferRef *sizes_out);
+int all_pairs_finalize(sks_ctx *ctx, const int32_t *raw_rows, const int32_t *d_sizes, int64_t n, int64_t row_begin,
+                       int64_t n_rows, bool symmetric, int weight, BufferRef *counts, BufferRef *ani);
 
 int launch_list_finalize(sks_ctx *ctx, const uint32_t *words, const uint32_t *seg_end, uint32_t n_segs, int window,
                          int key_words, const void *raw_keys, const uint32_t *raw_pos, uint32_t n,

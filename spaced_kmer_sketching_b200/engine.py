@@ -368,6 +368,16 @@ class Context:
                                              counts.ctypes.data, sizes.ctypes.data, ani.ctypes.data if ani is not None else None))
         return counts, sizes, ani
 
+    def all_vs_all_resident(self, comm: Optional["Comm"], batch: Optional["Batch"], n_total: int, mask: int, window: int,
+                            pred: Predicate, out: tuple):
+        """Sketch + exchange + comparison for the rank's resident genomes; `out` = (counts, sizes, ani) arrays to fill."""
+        counts, sizes, ani = out
+        p = pred.c()
+        check(self._L.sks_all_vs_all_resident(self.h, comm.h if comm else None, batch.h if batch is not None else None, n_total,
+                                              _w2(mask), window, C.byref(p), counts.ctypes.data, sizes.ctypes.data,
+                                              ani.ctypes.data if ani is not None else None))
+        return counts, sizes, ani
+
     def all_vs_all_from_host(self, comm: Optional["Comm"], ptrs: Sequence[int], n_bases: Sequence[int], n_total: int, mask: int,
                              window: int, pred: Predicate, out: tuple):
         """HOST packed genomes (raw pointers, e.g. into pinned memory) -> this rank's rows; `out` = (counts, sizes, ani)."""
