@@ -47,7 +47,8 @@ extern "C" {
 #define SKS_HASH_BOOST_181 181 /* Boost >= 1.81 (default) */
 
 /* Device representation of a kmer_set (src/kmer.hpp:160-190). */
-#define SKS_REPR_AUTO 0   /* SORTED for FMH, BITSET for ALL when weight <= 16, else SORTED      */
+#define SKS_REPR_AUTO 0   /* BITSET for predicate ALL with weight <= 16 when the bitset is at most ~128 B per window of
+                             the largest genome and the batch's bitsets fit half the free memory; SORTED otherwise */
 #define SKS_REPR_SORTED 1 /* ascending distinct masked_bits, 8 B (window <= 32) or 16 B per key  */
 #define SKS_REPR_BITSET 2 /* 4^weight-bit presence bitset indexed by PEXT(masked_bits, mask)     */
 /* sks_pair_ani* only: the two presence bitsets are assembled and compared slice by slice in shared memory
@@ -207,6 +208,10 @@ int sks_set_size(sks_ctx *ctx, sks_set *s, int64_t *out);
 int sks_set_keys(sks_ctx *ctx, sks_set *s, uint64_t *out_lohi, uint64_t capacity);
 /* Raw device view of a SORTED set (for collectives): pointer, key count, words (uint64) per key. */
 int sks_set_device_keys(sks_ctx *ctx, sks_set *s, const void **dptr, int64_t *n_keys, int *words_per_key);
+/* Imports.  Stream contract: the keys are copied on the context's stream and validated (subsets of the mask; where
+ * sortedness is claimed, strictly ascending inside every set) before the call returns, which synchronises the stream:
+ * the caller's buffer is free on return.  A caller that produced the keys on another stream must order that stream
+ * before the call (event or sync).  words_per_key must be 1 for window <= 32 and 2 above. */
 /* Builds a SORTED set from ascending distinct keys already on the device (copied). */
 int sks_set_from_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int words_per_key,
                              const uint64_t mask[2], int window, sks_set **out);

@@ -343,6 +343,25 @@ int make_plan(const sks_batch *batch, const uint64_t mask[2], int window, const 
 }
 
 }  // namespace
+// SKS_REPR_AUTO: the presence bitset pays off for an unfiltered sketch when it is not much larger than the genome's
+// own k-mer list (a 4^16-bit set is 512 MiB: right for a 5 Mbp genome, absurd for a 100 kbp one) and the bitsets of
+// the whole batch fit a memory budget; everything else becomes sorted distinct keys.
+int auto_repr(const sks_batch *batch, const SketchPlan &plan, const sks_pred *pred, int window) {
+  if (pred->kind != SKS_PRED_ALL || plan.weight > 16) return SKS_REPR_SORTED;
+  const uint64_t bitset_bytes = std::max<uint64_t>(((uint64_t)1 << (2 * plan.weight)) / 8, 4);
+  uint64_t max_windows = 0;
+  for (int g = 0; g < batch->n_genomes; ++g) max_windows = std::max(max_windows, genome_windows(batch, g, window));
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+    cudaGetLastError();
+    free_b = (size_t)8 << 30;
+  }
+  const uint64_t budget = std::min<uint64_t>(free_b / 2, (uint64_t)32 << 30);
+  if (bitset_bytes > 65536 && bitset_bytes > 128 * max_windows) return SKS_REPR_SORTED;
+  if (bitset_bytes * (uint64_t)std::max(batch->n_genomes, 1) > budget) return SKS_REPR_SORTED;
+  return SKS_REPR_BITSET;
+}
+
 sks_set *new_set(const sks_ctx *ctx, int repr, const uint64_t mask[2], int window, int weight) {
   sks_set *s = new (std::nothrow) sks_set();
   if (!s) return nullptr;
@@ -992,8 +1011,7 @@ int sks_sketch(sks_ctx *ctx, const sks_batch *batch, const uint64_t mask[2], int
   SketchPlan plan;
   SKS_TRY(make_plan(batch, mask, window, pred, &plan));
   if (batch->device != ctx->device) return set_error(SKS_ERR_INVALID, "batch lives on another device");
-  if (repr == SKS_REPR_AUTO)
-    repr = (pred->kind == SKS_PRED_ALL && plan.weight <= 16) ? SKS_REPR_BITSET : SKS_REPR_SORTED;
+  if (repr == SKS_REPR_AUTO) repr = auto_repr(batch, plan, pred, window);
   for (int g = 0; g < batch->n_genomes; ++g) out_sets[g] = nullptr;
   int st;
   if (repr == SKS_REPR_BITSET) {
@@ -1100,10 +1118,23 @@ int sks_set_device_keys(sks_ctx *ctx, sks_set *s, const void **dptr, int64_t *n_
   return SKS_OK;
 }
 
+// window in 1..64, no mask bits at or above 2 * window, and the key width the sketch kernel uses for that window
+static int check_import(const uint64_t mask[2], int window, int words_per_key) {
+  if (window < 1 || window > 64) return set_error(SKS_ERR_INVALID, "window length %d outside 1..64", window);
+  if (window < 64) {
+    const unsigned __int128 m = ((unsigned __int128)mask[1] << 64) | mask[0];
+    if (m >> (2 * window)) return set_error(SKS_ERR_INVALID, "mask has bits at or above 2*window");
+  }
+  if (words_per_key != (window <= 32 ? 1 : 2))
+    return set_error(SKS_ERR_INVALID, "window %d takes %d-word keys, not %d", window, window <= 32 ? 1 : 2, words_per_key);
+  return SKS_OK;
+}
+
 int sks_set_from_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int words_per_key, const uint64_t mask[2],
                              int window, sks_set **out) {
   if (!ctx || !out || !mask || n_keys < 0 || (n_keys > 0 && !dptr) || (words_per_key != 1 && words_per_key != 2))
     return set_error(SKS_ERR_INVALID, "bad argument");
+  SKS_TRY(check_import(mask, window, words_per_key));
   DeviceGuard guard(ctx->device);
   sks_set *s = new_set(ctx, SKS_REPR_SORTED, mask, window, sks_mask_weight(mask));
   if (!s) return set_error(SKS_ERR_INVALID, "out of host memory");
@@ -1113,6 +1144,10 @@ int sks_set_from_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_keys, int
   if (st == SKS_OK && n_keys > 0 &&
       cudaMemcpyAsync(s->buf->ptr, dptr, (size_t)n_keys * 8 * words_per_key, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess)
     st = set_error(SKS_ERR_CUDA, "device copy failed");
+  // foreign keys: subsets of the mask, ascending and distinct (synchronises: the caller's buffer is free on return)
+  const int64_t start0 = 0;
+  if (st == SKS_OK) st = validate_keys(ctx, s->buf->ptr, n_keys, words_per_key, mask, true, &start0, 1);
+  if (st == SKS_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = set_error(SKS_ERR_CUDA, "device copy failed");
   if (st != SKS_OK) {
     delete s;
     return st;
@@ -1125,6 +1160,7 @@ int sks_sets_from_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_sets, co
                               const uint64_t mask[2], int window, sks_set **out) {
   if (!ctx || !out || !mask || n_sets < 0 || (n_sets > 0 && !counts) || (words_per_key != 1 && words_per_key != 2))
     return set_error(SKS_ERR_INVALID, "bad argument");
+  SKS_TRY(check_import(mask, window, words_per_key));
   DeviceGuard guard(ctx->device);
   int64_t total = 0;
   for (int64_t i = 0; i < n_sets; ++i) {
@@ -1137,6 +1173,17 @@ int sks_sets_from_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_sets, co
   SKS_TRY(alloc_buffer(ctx, (size_t)total * kb, &buf));
   if (total > 0)
     SKS_CUDA_TRY(cudaMemcpyAsync(buf->ptr, dptr, (size_t)total * kb, cudaMemcpyDeviceToDevice, ctx->stream));
+  {
+    std::vector<int64_t> starts((size_t)n_sets);
+    int64_t at = 0;
+    for (int64_t i = 0; i < n_sets; ++i) {
+      starts[(size_t)i] = at;
+      at += counts[i];
+    }
+    starts.erase(std::unique(starts.begin(), starts.end()), starts.end());  // empty sets share their start
+    SKS_TRY(validate_keys(ctx, buf->ptr, total, words_per_key, mask, true, starts.data(), (int)starts.size()));
+    SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the caller's buffer is free on return
+  }
   const int weight = sks_mask_weight(mask);
   int64_t off = 0;
   for (int64_t i = 0; i < n_sets; ++i) {
@@ -1159,11 +1206,13 @@ int sks_set_from_unsorted_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_
                                       const uint64_t mask[2], int window, sks_set **out) {
   if (!ctx || !out || !mask || n_keys < 0 || (n_keys > 0 && !dptr) || (words_per_key != 1 && words_per_key != 2))
     return set_error(SKS_ERR_INVALID, "bad argument");
+  SKS_TRY(check_import(mask, window, words_per_key));
   DeviceGuard guard(ctx->device);
   BufferRef raw, uniq;
   SKS_TRY(alloc_buffer(ctx, (size_t)n_keys * 8 * words_per_key, &raw));
   if (n_keys > 0)
     SKS_CUDA_TRY(cudaMemcpyAsync(raw->ptr, dptr, (size_t)n_keys * 8 * words_per_key, cudaMemcpyDeviceToDevice, ctx->stream));
+  SKS_TRY(validate_keys(ctx, raw->ptr, n_keys, words_per_key, mask, false, nullptr, 0));  // also: the caller's buffer is free
   const uint64_t off = 0, cnt = (uint64_t)n_keys;
   std::vector<uint64_t> uoff, ucount;
   SKS_TRY(sort_unique_regions(ctx, words_per_key, raw->ptr, &off, &cnt, 1, cnt, &uniq, &uoff, &ucount, mask));
@@ -1238,7 +1287,7 @@ int sks_set_save(sks_ctx *ctx, sks_set *s, const sks_pred *pred, const char *pat
   h.nonce = pred ? pred->nonce : 0;
   h.modulus = pred ? pred->modulus : 0;
   h.hash_variant = pred ? (uint32_t)(pred->hash_variant ? pred->hash_variant : SKS_HASH_BOOST_181) : 0;
-  h.key_words = s->window <= 32 ? 1 : 2;
+  h.key_words = s->repr == SKS_REPR_SORTED ? (uint32_t)s->key_words : (s->window <= 32 ? 1u : 2u);
   h.n_keys = (uint64_t)n;
   FILE *f = fopen(path, "wb");
   if (!f) return set_error(SKS_ERR_IO, "Unable to open %s for writing", path);
@@ -1261,16 +1310,32 @@ int sks_set_load(sks_ctx *ctx, const char *path, sks_set **out, sks_pred *out_pr
   SketchFileHeader h;
   int st = SKS_OK;
   std::vector<uint64_t> keys;
+  long file_bytes = 0;
+  if (fseek(f, 0, SEEK_END) == 0) file_bytes = ftell(f);
+  rewind(f);
   if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "SKSKETCH", 8) != 0 || h.version != 1 ||
-      (h.key_words != 1 && h.key_words != 2) || h.window < 1 || h.window > 64 || h.n_keys > (1ull << 40)) {
+      (h.key_words != 1 && h.key_words != 2) || h.window < 1 || h.window > 64) {
     st = set_error(SKS_ERR_IO, "%s is not a version-1 sketch file", path);
+  } else if (check_import(h.mask, (int)h.window, (int)h.key_words) != SKS_OK) {
+    st = set_error(SKS_ERR_IO, "%s: mask, window and key width do not fit together", path);
+  } else if (file_bytes < (long)sizeof(h) || h.n_keys > (uint64_t)(file_bytes - (long)sizeof(h)) / (8 * h.key_words)) {
+    st = set_error(SKS_ERR_IO, "%s is truncated", path);   // the header promises more keys than the file holds
   } else {
-    keys.resize((size_t)h.n_keys * h.key_words);
-    if (h.n_keys && fread(keys.data(), 8 * h.key_words, (size_t)h.n_keys, f) != (size_t)h.n_keys)
+    try {
+      keys.resize((size_t)h.n_keys * h.key_words);
+    } catch (const std::exception &) {
+      st = set_error(SKS_ERR_IO, "%s: out of host memory for %llu keys", path, (unsigned long long)h.n_keys);
+    }
+    if (st == SKS_OK && h.n_keys && fread(keys.data(), 8 * h.key_words, (size_t)h.n_keys, f) != (size_t)h.n_keys)
       st = set_error(SKS_ERR_IO, "%s is truncated", path);
   }
   fclose(f);
   SKS_TRY(st);
+  for (uint64_t i = 0; i < h.n_keys; ++i) {  // members are subsets of the mask (the intersection kernels rely on it)
+    const uint64_t *k = &keys[(size_t)i * h.key_words];
+    if ((k[0] & ~h.mask[0]) || (h.key_words == 2 ? (k[1] & ~h.mask[1]) : 0))
+      return set_error(SKS_ERR_IO, "%s: a key has bits outside the mask", path);
+  }
   for (uint64_t i = 1; i < h.n_keys; ++i) {  // the file must hold ascending distinct keys
     const uint64_t *a = &keys[(size_t)(i - 1) * h.key_words], *b = &keys[(size_t)i * h.key_words];
     const bool less = h.key_words == 1 ? a[0] < b[0] : (a[1] != b[1] ? a[1] < b[1] : a[0] < b[0]);
@@ -1561,8 +1626,7 @@ int sks_pair_ani_resident(sks_ctx *ctx, const sks_batch *batch, const uint64_t m
   DeviceGuard guard(ctx->device);
   SketchPlan plan;
   SKS_TRY(make_plan(batch, mask, window, pred, &plan));
-  if (repr == SKS_REPR_AUTO)
-    repr = (pred->kind == SKS_PRED_ALL && plan.weight <= 16) ? SKS_REPR_BITSET : SKS_REPR_SORTED;
+  if (repr == SKS_REPR_AUTO) repr = auto_repr(batch, plan, pred, window);
   sks_set *sets[2] = {nullptr, nullptr};
   int64_t inter = 0, sa = 0, sb = 0;
   int st = SKS_OK;
@@ -1664,6 +1728,12 @@ int sks_kmer_list(sks_ctx *ctx, const sks_batch *batch, int genome, const uint64
   BufferRef raw, pos, outbuf;
   std::vector<uint64_t> off, count;
   uint64_t span = 0;
+  // list entries carry (strand << 31 | start position) in 32 bits and the list is finalised with 32-bit counts
+  if (one->h_genomes[0].n_bases >= (1u << 31)) {
+    if (tmp) sks_batch_destroy(ctx, tmp);
+    return set_error(SKS_ERR_CAPACITY, "the ordered k-mer list is limited to genomes below 2^31 bases (this one has %u)",
+                     one->h_genomes[0].n_bases);
+  }
   int st = make_plan(one, mask, window, pred, &plan);
   if (st == SKS_OK) st = sketch_raw_keys(ctx, one, plan, pred, window, OUT_LIST, &raw, &pos, &off, &count, &span);
   if (st == SKS_OK) {

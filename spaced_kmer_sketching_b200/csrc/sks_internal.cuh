@@ -256,6 +256,8 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
 int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const *d_a, const int64_t *d_na,
                                   const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out,
                                   const uint32_t *d_pair_idx = nullptr, int slices = 1);
+int validate_keys(sks_ctx *ctx, const void *d_keys, int64_t n, int key_words, const uint64_t mask[2], bool need_sorted,
+                  const int64_t *h_starts, int n_starts);
 // Row-resident variant: tasks (RowTask, 24 bytes: a, n_a, first, n_cols, pad) over the same pair tables.
 struct RowTaskHost {
   const void *a;

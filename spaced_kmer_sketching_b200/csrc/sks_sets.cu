@@ -1505,6 +1505,69 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
   return SKS_OK;
 }
 
+// Imported keys (files, host lists, device buffers of other producers) are only trusted after this check: every key
+// must be a subset of the mask (the row-resident intersection and the bucket sort index keys by their mask-selected
+// bits) and, where the caller claims sorted distinct sets, strictly ascending inside every set.
+template <int KW>
+__global__ void __launch_bounds__(256)
+    validate_keys_kernel(const unsigned long long *__restrict__ keys, unsigned long long n, unsigned long long nm_lo,
+                         unsigned long long nm_hi, int need_sorted, const long long *__restrict__ starts, int n_starts,
+                         uint32_t *__restrict__ flag) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const unsigned long long lo = keys[KW * i], hi = KW == 2 ? keys[KW * i + 1] : 0ull;
+    if ((lo & nm_lo) || (hi & nm_hi)) atomicOr(flag, 1u);
+    if (need_sorted && i > 0) {
+      const unsigned long long plo = keys[KW * (i - 1)], phi = KW == 2 ? keys[KW * (i - 1) + 1] : 0ull;
+      const bool less = phi != hi ? phi < hi : plo < lo;
+      if (!less) {  // allowed only where a new set starts
+        int a = 0, b = n_starts;
+        bool is_start = false;
+        while (a < b) {
+          const int m = (a + b) >> 1;
+          const long long v = starts[m];
+          if (v == (long long)i) { is_start = true; break; }
+          if (v < (long long)i) a = m + 1; else b = m;
+        }
+        if (!is_start) atomicOr(flag, 2u);
+      }
+    }
+  }
+}
+
+// h_starts: first key of every set (ascending), only used with need_sorted.  Synchronises the stream.
+int validate_keys(sks_ctx *ctx, const void *d_keys, int64_t n, int key_words, const uint64_t mask[2], bool need_sorted,
+                  const int64_t *h_starts, int n_starts) {
+  if (n <= 0) return SKS_OK;
+  char *scratch = nullptr;
+  const size_t sz_starts = ((size_t)std::max(n_starts, 1) * 8 + 255) & ~(size_t)255;
+  SKS_TRY(ctx_scratch(ctx, sz_starts + 256, reinterpret_cast<void **>(&scratch)));
+  long long *d_starts = reinterpret_cast<long long *>(scratch);
+  uint32_t *d_flag = reinterpret_cast<uint32_t *>(scratch + sz_starts);
+  uint32_t *h_flag = nullptr;
+  SKS_TRY(ctx_pinned(ctx, sz_starts + 64, reinterpret_cast<void **>(&h_flag)));
+  if (need_sorted && n_starts > 0) {
+    memcpy(h_flag + 16, h_starts, (size_t)n_starts * 8);
+    SKS_CUDA_TRY(cudaMemcpyAsync(d_starts, h_flag + 16, (size_t)n_starts * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  SKS_CUDA_TRY(cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
+  const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+  const unsigned long long *k = static_cast<const unsigned long long *>(d_keys);
+  if (key_words == 1)
+    validate_keys_kernel<1><<<grid, 256, 0, ctx->stream>>>(k, (unsigned long long)n, ~mask[0], ~0ull, need_sorted ? 1 : 0, d_starts,
+                                                           need_sorted ? n_starts : 0, d_flag);
+  else
+    validate_keys_kernel<2><<<grid, 256, 0, ctx->stream>>>(k, (unsigned long long)n, ~mask[0], ~mask[1], need_sorted ? 1 : 0, d_starts,
+                                                           need_sorted ? n_starts : 0, d_flag);
+  SKS_CUDA_TRY(cudaGetLastError());
+  ctx->launches++;
+  SKS_CUDA_TRY(cudaMemcpyAsync(h_flag, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (*h_flag & 1u) return set_error(SKS_ERR_INVALID, "a key has bits outside the mask");
+  if (*h_flag & 2u) return set_error(SKS_ERR_INVALID, "keys are not ascending and distinct");
+  return SKS_OK;
+}
+
 // `slices` > 1: that many CTAs share every pair and add their partial counts (d_out must be zero on entry).
 int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const *d_a, const int64_t *d_na,
                                   const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out,

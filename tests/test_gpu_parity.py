@@ -364,6 +364,88 @@ def test_all_vs_all_dictionary_route(ctx):
     batch.close()
 
 
+def test_imported_keys_are_validated(ctx, tmp_path):
+    """Foreign keys (device buffers, host lists, sketch files) are checked before a set is built from them: subsets of
+    the mask, ascending and distinct where that is claimed, a key width that fits the window; a sketch file whose
+    header lies about its length is refused without a huge allocation."""
+    import torch
+    mask, w = sks.seed_to_mask(C3_SEED)
+    good = np.sort(np.array([0, mask & 0x3, mask & 0xFFFF0000, mask], dtype=np.uint64))
+    good = np.unique(good)
+    def dev(a):
+        return torch.from_numpy(a.view(np.int64)).cuda()
+    t = dev(good)
+    s = ctx.set_from_device_keys(t.data_ptr(), len(good), 1, mask, w)
+    assert s.keys()[:, 0].tolist() == good.tolist()
+    s.close()
+    for bad, what in ((np.array([1, 2, 4 | (1 << 63)], dtype=np.uint64), "outside the mask"),     # bit 63 is not in a 62-bit mask
+                      (good[::-1].copy(), "ascending"),
+                      (np.concatenate([good[:2], good[1:]]), "ascending")):
+        t = dev(bad)
+        with pytest.raises(sks.SksError) as e:
+            ctx.set_from_device_keys(t.data_ptr(), len(bad), 1, mask, w)
+        assert what in str(e.value), (what, str(e.value))
+    t = dev(np.array([5, 1, 1 << 63], dtype=np.uint64))
+    with pytest.raises(sks.SksError) as e:   # unsorted import: only the mask is checked
+        ctx.set_from_device_keys(t.data_ptr(), 3, 1, mask, w, sorted_unique=False)
+    assert "outside the mask" in str(e.value)
+    t = dev(good)
+    with pytest.raises(sks.SksError):        # window 31 takes one-word keys
+        ctx.set_from_device_keys(t.data_ptr(), len(good) // 2, 2, mask, w)
+    # several sets back to back: ascending inside every set only
+    two = np.concatenate([good, good[:2]])
+    t = dev(two)
+    a, b = ctx.sets_from_device_keys(t.data_ptr(), [len(good), 2], 1, mask, w)
+    assert a.kmer_set_size() == len(good) and ctx.intersect(a, b) == 2
+    with pytest.raises(sks.SksError):
+        ctx.sets_from_device_keys(t.data_ptr(), [len(good) + 1, 1], 1, mask, w)
+    # sketch files
+    path = str(tmp_path / "s.sks")
+    a.save(path, sks.frac_min_hash(1, 200))
+    raw = bytearray(open(path, "rb").read())
+    lying = bytearray(raw)
+    lying[56:64] = (1 << 39).to_bytes(8, "little")          # n_keys: 2^39 keys in a 100-byte file
+    open(path, "wb").write(lying)
+    with pytest.raises(sks.SksError) as e:
+        ctx.load_set(path)
+    assert "truncated" in str(e.value)
+    off_mask = bytearray(raw)
+    off_mask[64 + 7] |= 0x80                                 # first key gets bit 63
+    open(path, "wb").write(off_mask)
+    with pytest.raises(sks.SksError) as e:
+        ctx.load_set(path)
+    assert "outside the mask" in str(e.value) or "ascending" in str(e.value)
+    open(path, "wb").write(raw)
+    back, _ = ctx.load_set(path)
+    assert back.keys()[:, 0].tolist() == good.tolist()
+    for x in (a, b, back):
+        x.close()
+
+
+def test_auto_representation_follows_cost_and_list_capacity(ctx):
+    """SKS_REPR_AUTO: a 4^16-bit presence bitset for a 5 Mbp genome, sorted keys for a 100 kbp one (512 MiB per tiny
+    genome would be absurd); the ordered k-mer list refuses genomes of 2^31 bases and more instead of aliasing the
+    strand bit."""
+    mask, w = sks.seed_to_mask(C2_SEED)
+    small = ctx.synth(100_000, [1, 2, 3], [0, 0, 0], [0, 0, 0])
+    sets = ctx.sketch(small, mask, w, sks.all_kmers())
+    assert [s.repr for s in sets] == [sks.REPR_SORTED] * 3
+    big = ctx.synth(5_000_000, [42], [0], [0])
+    (b,) = ctx.sketch(big, mask, w, sks.all_kmers())
+    assert b.repr == sks.REPR_BITSET and b.kmer_set_size() == 4994572      # KAT-4 |A|
+    (t,) = ctx.sketch(small, sks.seed_to_mask("11001011")[0], 8, sks.all_kmers())[:1]
+    assert t.repr == sks.REPR_BITSET                                       # 4^5 bits: always
+    for x in sets + [b, t]:
+        x.close()
+    huge = ctx.synth(1 << 31, [9], [0], [0])
+    with pytest.raises(sks.SksError) as e:
+        ctx.kmer_list(huge, 0, mask, w, sks.frac_min_hash(1, 200))
+    assert e.value.code == 3 and "2^31" in str(e.value)
+    huge.close()
+    small.close()
+    big.close()
+
+
 def test_synth_matches_oracle_generator(ctx):
     batch = ctx.synth(100_003, [42, 42, 9], [0, 43, 5], [0, 100, 3])
     A = port.gen(100_003, 42)
