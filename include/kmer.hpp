@@ -266,6 +266,16 @@ void set_representation_hint(set_representation r);
 const char *last_predicate_path();
 /** Probing of opaque sketching conditions (see the top of this header); process-wide, off by default. */
 void enable_predicate_probe(bool on);
+/**
+ * Several GPUs in one process (default 1; also SKS_DEVICES=n|all).  With n > 1, kmer_sets_from_fasta_files and
+ * parallel_kmer_sets_from_fasta_files sketch contiguous blocks of files on devices 0 .. n-1 (one worker thread each --
+ * the reference's cilk_for over files, src/kmer_set.cpp:124-131), and (parallel_)compute_pairwise_kmer_set_intersections
+ * runs an all-pairs list (generate_all_pairs_from_vector) over such sets as the sharded all-vs-all: one NCCL exchange
+ * of the sketches, every device fills its block rows (the reference's cilk_for over pairs, src/kmer_set.cpp:179-182).
+ * Any other pair list that mixes devices is evaluated on the calling thread's device after peer copies.
+ */
+void set_devices(int n);
+int devices();
 } // namespace sks
 
 #endif // SKS_KMER_HPP

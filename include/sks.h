@@ -227,6 +227,10 @@ int sks_set_from_unsorted_device_keys(sks_ctx *ctx, const void *dptr, int64_t n_
  * host-built list, or the survivors of a host-evaluated sketching condition. */
 int sks_set_from_host_keys(sks_ctx *ctx, const uint64_t *keys_lohi, int64_t n_keys, const uint64_t mask[2], int window,
                            sks_set **out);
+/* Device the set lives on, and a copy of it on the device of `dst` (peer-to-peer over NVLink where available): what a
+ * single-process, several-GPU caller needs to compare sets that were sketched on different devices. */
+int sks_set_device_index(const sks_set *s);
+int sks_set_clone_to(sks_ctx *dst, sks_set *src, sks_set **out);
 void sks_set_destroy(sks_ctx *ctx, sks_set *s);
 
 /* ---- sketch files (not in the reference: it never persists a sketch) ---------- */

@@ -93,6 +93,8 @@ PROTOTYPES = {
     "sks_sets_from_device_keys": (ci, [vp, vp, i64, i64p, ci, u64p, ci, C.POINTER(vp)]),
     "sks_set_from_unsorted_device_keys": (ci, [vp, vp, i64, ci, u64p, ci, C.POINTER(vp)]),
     "sks_set_from_host_keys": (ci, [vp, vp, i64, u64p, ci, C.POINTER(vp)]),
+    "sks_set_device_index": (ci, [vp]),
+    "sks_set_clone_to": (ci, [vp, vp, C.POINTER(vp)]),
     "sks_set_destroy": (None, [vp, vp]),
     "sks_set_save": (ci, [vp, vp, C.POINTER(SksPred), C.c_char_p]),
     "sks_set_load": (ci, [vp, C.c_char_p, C.POINTER(vp), C.POINTER(SksPred)]),

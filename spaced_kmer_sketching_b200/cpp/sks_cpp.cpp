@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <sstream>
@@ -36,11 +37,12 @@ struct thread_state
 {
     int device = -1;
     sks_ctx *ctx = nullptr;
+    bool owns_ctx = true; // false: a worker thread of run_on_devices borrows a context of the device pool
     int repr = SKS_REPR_AUTO;
     const char *pred_path = "none";
     ~thread_state()
     {
-        if (ctx) sks_ctx_destroy(ctx);
+        if (ctx && owns_ctx) sks_ctx_destroy(ctx);
     }
 };
 thread_local thread_state g_ts;
@@ -62,6 +64,81 @@ sks_ctx *ctx()
 }
 
 int g_hash_variant = SKS_HASH_BOOST_181;
+
+// ---- several GPUs in one process ----------------------------------------------------------------------
+// The reference spreads files and pairs over Cilk workers (src/kmer_set.cpp:124-131,179-182); with sks::set_devices(n)
+// (or SKS_DEVICES=n|all) the same two loops are spread over n GPUs: file i of m goes to device
+// i / ceil(m / n) (sks_shard_range), one worker thread per device, and an all-pairs comparison of sets that were
+// sketched that way runs as the sharded all-vs-all of the C ABI (sks_all_vs_all_sharded over sks_comm_init_all).
+std::atomic<int> g_devices{0}; // 0: follow SKS_DEVICES
+int devices_wanted()
+{
+    int n = g_devices.load();
+    if (n <= 0)
+    {
+        const char *e = getenv("SKS_DEVICES");
+        if (!e || !*e) return 1;
+        n = (strcmp(e, "all") == 0) ? sks_device_count() : atoi(e);
+    }
+    return std::max(1, std::min(n, sks_device_count()));
+}
+
+struct device_pool
+{
+    std::mutex mu;
+    std::vector<sks_ctx *> ctxs;
+    std::vector<sks_comm *> comms;
+    // contexts (and, on demand, communicators) for devices 0 .. n-1; grown under the lock, never shrunk
+    void ensure(int n, bool with_comms)
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        while ((int)ctxs.size() < n)
+        {
+            sks_ctx *c = nullptr;
+            check(sks_ctx_create((int)ctxs.size(), &c), "sks_ctx_create");
+            ctxs.push_back(c);
+        }
+        if (with_comms && (int)comms.size() != n)
+        {
+            for (sks_comm *c : comms) sks_comm_destroy(c);
+            comms.assign((size_t)n, nullptr);
+            check(sks_comm_init_all(ctxs.data(), n, comms.data()), "sks_comm_init_all");
+        }
+    }
+};
+device_pool &pool()
+{
+    static device_pool *p = new device_pool(); // never destroyed: the CUDA runtime may be gone at exit
+    return *p;
+}
+
+// fn(rank) on one thread per device; the worker's implicit context is the pool's context of that device.
+template <typename F>
+void run_on_devices(int n, F fn)
+{
+    std::vector<std::thread> workers;
+    std::vector<std::string> errors((size_t)n);
+    const int repr = g_ts.repr;
+    for (int r = 0; r < n; ++r)
+        workers.emplace_back([&, r]() {
+            g_ts.device = r;
+            g_ts.ctx = pool().ctxs[(size_t)r];
+            g_ts.owns_ctx = false;
+            g_ts.repr = repr;
+            try
+            {
+                fn(r);
+            }
+            catch (const std::exception &e)
+            {
+                errors[(size_t)r] = e.what()[0] ? e.what() : "error";
+            }
+            g_ts.ctx = nullptr;
+        });
+    for (std::thread &t : workers) t.join();
+    for (const std::string &e : errors)
+        if (!e.empty()) throw std::runtime_error(e);
+}
 
 // ---- probing of opaque sketching conditions ------------------------------------------------------
 struct probe_state
@@ -344,6 +421,8 @@ void set_device(int device)
     g_ts.device = device;
 }
 void set_representation_hint(set_representation r) { g_ts.repr = (int)r; }
+void set_devices(int n) { g_devices.store(n); }
+int devices() { return devices_wanted(); }
 const char *last_predicate_path() { return g_ts.pred_path; }
 void enable_predicate_probe(bool on) { g_probe_switch.store(on ? 1 : 0); }
 } // namespace sks
@@ -545,13 +624,45 @@ std::vector<kmer> nucleotide_string_list_to_kmers(const std::vector<std::vector<
 }
 
 // ---- FASTA -> sets ------------------------------------------------------------------------------------------------------
+namespace
+{
+std::vector<kmer_set> kmer_sets_on_this_device(const int num_files, char *fasta_filenames[], const kmer_bitset &mask,
+                                               const int window_length, const sks::pred_plan &plan,
+                                               const std::function<bool(const kmer)> &sketching_cond);
+}
+
 std::vector<kmer_set> kmer_sets_from_fasta_files(const int num_files, char *fasta_filenames[], const kmer_bitset &mask,
                                                  const int window_length,
                                                  const std::function<bool(const kmer)> &sketching_cond)
 {
+    if (num_files <= 0) return std::vector<kmer_set>();
+    const sks::pred_plan plan = sks::classify(sketching_cond, mask, window_length);
+    const int nd = std::min(sks::devices_wanted(), num_files);
+    // an opaque condition is evaluated by the caller's callable: keep that on the calling thread
+    if (nd <= 1 || plan.kind != sks::pred_plan::DEVICE)
+        return kmer_sets_on_this_device(num_files, fasta_filenames, mask, window_length, plan, sketching_cond);
+    // contiguous blocks of files per device, one worker thread each (the reference: cilk_for over files)
+    sks::pool().ensure(nd, false);
+    std::vector<kmer_set> out((size_t)num_files);
+    sks::run_on_devices(nd, [&](int r) {
+        int64_t b = 0, e = 0;
+        sks_shard_range(num_files, r, nd, &b, &e);
+        if (e <= b) return;
+        std::vector<kmer_set> part =
+            kmer_sets_on_this_device((int)(e - b), fasta_filenames + b, mask, window_length, plan, sketching_cond);
+        for (int64_t i = b; i < e; ++i) out[(size_t)i] = std::move(part[(size_t)(i - b)]);
+    });
+    return out;
+}
+
+namespace
+{
+std::vector<kmer_set> kmer_sets_on_this_device(const int num_files, char *fasta_filenames[], const kmer_bitset &mask,
+                                               const int window_length, const sks::pred_plan &plan,
+                                               const std::function<bool(const kmer)> &sketching_cond)
+{
     std::vector<kmer_set> out((size_t)std::max(num_files, 0));
     if (num_files <= 0) return out;
-    const sks::pred_plan plan = sks::classify(sketching_cond, mask, window_length);
     uint64_t m[2];
     sks::mask_words(mask, m);
 
@@ -661,6 +772,7 @@ std::vector<kmer_set> kmer_sets_from_fasta_files(const int num_files, char *fast
     }
     return out;
 }
+} // namespace
 
 std::vector<kmer_set> parallel_kmer_sets_from_fasta_files(const int num_files, char *fasta_filenames[],
                                                           const kmer_bitset &mask, const int window_length,
@@ -677,6 +789,54 @@ kmer_set kmer_set_from_fasta_file(const char fasta_filename[], const kmer_bitset
     return std::move(v[0]);
 }
 
+namespace sks
+{
+// generate_all_pairs_from_vector (src/generators.hpp:44-58) over sets that were sketched in contiguous blocks on
+// several devices (kmer_sets_from_fasta_files with sks::set_devices(n)): the sharded all-vs-all of the C ABI, one
+// worker thread per device.  Returns false when the lists are anything else (the caller then takes the general route).
+bool sharded_all_pairs(const std::vector<kmer_set *> &v1, const std::vector<kmer_set *> &v2, std::vector<int> &out)
+{
+    const size_t len = v1.size();
+    size_t n = 0;
+    while (n * n < len) ++n;
+    if (n < 2 || n * n != len) return false;
+    std::vector<sks_set *> sets(n, nullptr);
+    int nd = 0;
+    for (size_t i = 0; i < n; ++i)
+    {
+        kmer_set *s = v1[i * n];
+        if (!s || s != v2[i]) return false;
+        device_set *d = set_access::device(*s);
+        if (!d || sks_set_repr(d->h) != SKS_REPR_SORTED) return false;
+        sets[i] = d->h;
+        nd = std::max(nd, sks_set_device_index(d->h) + 1);
+    }
+    if (nd < 2) return false;
+    for (size_t i = 0; i < n; ++i)
+        for (size_t j = 0; j < n; ++j)
+            if (v1[i * n + j] != v1[i * n] || v2[i * n + j] != v2[j]) return false;
+    for (int r = 0; r < nd; ++r)
+    { // the blocks must be the ones sks_shard_range assigns
+        int64_t b = 0, e = 0;
+        sks_shard_range((int64_t)n, r, nd, &b, &e);
+        for (int64_t i = b; i < e; ++i)
+            if (sks_set_device_index(sets[(size_t)i]) != r) return false;
+    }
+    pool().ensure(nd, true);
+    run_on_devices(nd, [&](int r) {
+        int64_t b = 0, e = 0;
+        sks_shard_range((int64_t)n, r, nd, &b, &e);
+        std::vector<int32_t> rows((size_t)std::max<int64_t>(e - b, 1) * n);
+        check(sks_all_vs_all_sharded(pool().ctxs[(size_t)r], pool().comms[(size_t)r], sets.data() + b, e - b, (int64_t)n,
+                                     rows.data(), nullptr, nullptr),
+              "sks_all_vs_all_sharded");
+        for (int64_t i = b; i < e; ++i)
+            for (size_t j = 0; j < n; ++j) out[(size_t)i * n + j] = rows[(size_t)(i - b) * n + j];
+    });
+    return true;
+}
+} // namespace sks
+
 // ---- intersections --------------------------------------------------------------------------------------------------------
 std::vector<int> compute_pairwise_kmer_set_intersections(const std::vector<kmer_set *> &kmer_sets_1,
                                                          const std::vector<kmer_set *> &kmer_sets_2)
@@ -685,17 +845,31 @@ std::vector<int> compute_pairwise_kmer_set_intersections(const std::vector<kmer_
         throw std::runtime_error("Lists of kmer sets for intersection computation have different lengths");
     const size_t n = kmer_sets_1.size();
     std::vector<int> out(n, 0);
+    if (sks::sharded_all_pairs(kmer_sets_1, kmer_sets_2, out)) return out;
     // pairs the device can take in one launch: both sides resident, same mask and representation
     std::vector<sks_set *> a, b;
     std::vector<size_t> where;
     std::vector<std::shared_ptr<sks::device_set>> keep_alive;
+    std::map<sks_set *, sks_set *> here; // sets of other devices -> their copies on this thread's device
+    auto local_handle = [&](sks::device_set *d) {
+        const int dev = sks_set_device_index(d->h);
+        (void)ctx();
+        if (dev == sks::g_ts.device) return d->h;
+        auto it = here.find(d->h);
+        if (it != here.end()) return it->second;
+        sks_set *copy = nullptr;
+        check(sks_set_clone_to(ctx(), d->h, &copy), "sks_set_clone_to");
+        keep_alive.push_back(std::make_shared<sks::device_set>(copy, d->window, d->mask));
+        here[d->h] = copy;
+        return copy;
+    };
     for (size_t i = 0; i < n; ++i)
     {
         sks::device_set *da = sks::set_access::device(*kmer_sets_1[i]);
         sks::device_set *db = sks::set_access::device(*kmer_sets_2[i]);
         if (!da || !db) continue;                 // an empty set intersects nothing
         if (!(da->mask == db->mask)) continue;    // k-mers under different masks are never equal (src/kmer.hpp:82-85)
-        sks_set *ha = da->h, *hb = db->h;
+        sks_set *ha = local_handle(da), *hb = local_handle(db);
         if (sks_set_repr(ha) != sks_set_repr(hb))
         {
             // mixed representations (bitset vs sorted keys): re-key the bitset side as sorted keys

@@ -1250,6 +1250,49 @@ int sks_set_from_host_keys(sks_ctx *ctx, const uint64_t *keys_lohi, int64_t n_ke
   return sks_set_from_unsorted_device_keys(ctx, raw->ptr, n_keys, kw, mask, window, out);
 }
 
+int sks_set_device_index(const sks_set *s) { return s ? s->device : -1; }
+
+int sks_set_clone_to(sks_ctx *dst, sks_set *src, sks_set **out) {
+  if (!dst || !src || !out) return set_error(SKS_ERR_INVALID, "null argument");
+  DeviceGuard guard(dst->device);
+  size_t bytes = 0;
+  if (src->repr == SKS_REPR_SORTED) {
+    if (src->count < 0) return set_error(SKS_ERR_INVALID, "set without a size");
+    bytes = (size_t)src->count * 8 * src->key_words;
+  } else {
+    bytes = (size_t)src->bitset_words * 4;
+  }
+  sks_set *c = new (std::nothrow) sks_set(*src);
+  if (!c) return set_error(SKS_ERR_INVALID, "out of host memory");
+  c->device = dst->device;
+  c->byte_off = 0;
+  c->buf.reset();
+  c->count_buf.reset();   // a bitset's device-side popcount stays behind: the copy counts again if asked
+  c->count_off = 0;
+  if (src->repr != SKS_REPR_SORTED && src->count < 0 && src->count_buf) {
+    // bring the size along instead (the source's control block holds it once its build has run)
+    c->count = -1;
+  }
+  int st = alloc_buffer(dst, std::max<size_t>(bytes, 16), &c->buf);
+  if (st == SKS_OK && bytes) {
+    const char *sp = static_cast<const char *>(src->buf->ptr) + src->byte_off;
+    // the source's stream may still be writing the set: wait for that device first
+    if (src->device != dst->device) {
+      DeviceGuard g2(src->device);
+      cudaDeviceSynchronize();
+    }
+    cudaError_t e = cudaMemcpyPeerAsync(c->buf->ptr, dst->device, sp, src->device, bytes, dst->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(dst->stream);
+    if (e != cudaSuccess) st = set_error(SKS_ERR_CUDA, "peer copy of a set failed: %s", cudaGetErrorString(e));
+  }
+  if (st != SKS_OK) {
+    delete c;
+    return st;
+  }
+  *out = c;
+  return SKS_OK;
+}
+
 void sks_set_destroy(sks_ctx *ctx, sks_set *s) {
   (void)ctx;
   delete s;
@@ -1374,6 +1417,40 @@ static int intersect_pairs(sks_ctx *ctx, sks_set *const *a, int64_t na, sks_set 
   if (na != nb) return set_error(SKS_ERR_MISMATCH, "Lists of kmer sets for intersection computation have different lengths");
   if (na == 0) return SKS_OK;
   DeviceGuard guard(ctx->device);
+  // A pair list that covers a good part of all pairs of its distinct sets (generate_all_pairs_from_vector,
+  // src/generators.hpp:44-58, is all of them) goes through the all-vs-all dictionary: one pass over the sets instead
+  // of one lookup pass per pair.
+  if (!uniform && na >= 16) {
+    std::map<const sks_set *, int32_t> index;
+    std::vector<sks_set *> distinct;
+    std::vector<int32_t> ia((size_t)na), ib((size_t)na);
+    bool ok = true;
+    for (int64_t i = 0; i < na && ok; ++i)
+      for (int side = 0; side < 2; ++side) {
+        sks_set *s = side ? b[i] : a[i];
+        if (!s) {
+          ok = false;
+          break;
+        }
+        auto it = index.find(s);
+        if (it == index.end()) {
+          it = index.emplace(s, (int32_t)distinct.size()).first;
+          distinct.push_back(s);
+        }
+        (side ? ib : ia)[(size_t)i] = it->second;
+      }
+    const int64_t d = (int64_t)distinct.size();
+    if (ok && d >= 4 && na * 4 >= d * d && all_pairs_dict_eligible(distinct.data(), d)) {
+      for (int64_t i = 0; i < na; ++i) SKS_TRY(check_pair(a[i], b[i]));
+      std::vector<int32_t> full((size_t)d * d);
+      const int st = sks_all_vs_all(ctx, distinct.data(), d, 0, d, full.data(), nullptr, nullptr);
+      if (st == SKS_OK) {
+        for (int64_t i = 0; i < na; ++i) out[i] = full[(size_t)ia[(size_t)i] * d + ib[(size_t)i]];
+        return SKS_OK;
+      }
+      if (st != SKS_ERR_CAPACITY) return st;
+    }
+  }
   const int repr = a[0]->repr;
   if (!uniform) {
     for (int64_t i = 0; i < na; ++i) SKS_TRY(check_pair(a[i], b[i]));

@@ -150,6 +150,42 @@ int main(int argc, char *argv[])
         for (int t = 0; t < 8; ++t) std::cout << (t ? "," : "") << inter[(size_t)t];
         std::cout << "]},";
     }
+    // Several GPUs in one process (sks::set_devices): files in contiguous blocks per device, the all-pairs list as
+    // the sharded all-vs-all, any other list after peer copies -- all equal to the single-device results.
+    {
+        char *files4[5] = {argv[1], argv[2], argv[2], argv[1], argv[2]};
+        auto run = [&](int nd, std::vector<int> &all, std::vector<int> &ring, std::vector<int> &sizes) {
+            sks::set_devices(nd);
+            std::vector<kmer_set> sets = parallel_kmer_sets_from_fasta_files(5, files4, mask, 24, sks::fmh_condition(1, 50));
+            std::vector<kmer_set *> ptrs;
+            for (kmer_set &s : sets) ptrs.push_back(&s);
+            const auto pairs = generate_all_pairs_from_vector(ptrs);
+            all = parallel_compute_pairwise_kmer_set_intersections(pairs.first, pairs.second);
+            const auto rp = generate_pairwise_from_vector(ptrs);
+            ring = compute_pairwise_kmer_set_intersections(rp.first, rp.second);
+            for (kmer_set &s : sets) sizes.push_back(s.kmer_set_size());
+            sks::set_devices(1);
+        };
+        sks::set_devices(2);
+        const int nd = sks::devices();
+        sks::set_devices(1);
+        std::cout << "\"multi\":{\"devices\":" << nd;
+        std::vector<int> all1, ring1, sizes1, alln, ringn, sizesn;
+        run(1, all1, ring1, sizes1);
+        if (nd >= 2) run(nd, alln, ringn, sizesn);
+        auto dump = [&](const char *name, const std::vector<int> &v) {
+            std::cout << ",\"" << name << "\":[";
+            for (size_t i = 0; i < v.size(); ++i) std::cout << (i ? "," : "") << v[i];
+            std::cout << "]";
+        };
+        dump("all_1", all1);
+        dump("ring_1", ring1);
+        dump("sizes_1", sizes1);
+        dump("all_n", alln);
+        dump("ring_n", ringn);
+        dump("sizes_n", sizesn);
+        std::cout << "},";
+    }
     bool mismatch_threw = false;
     try
     {

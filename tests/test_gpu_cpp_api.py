@@ -101,6 +101,16 @@ def test_cpp_api_against_oracle(tmp_path):
         assert th["sizes"][base:base + 4] == [len(sets[0]), len(sets[1])] * 2, name
         assert th["inter"][base:base + 4] == [port.intersection(sets[0], sets[1])] * 4, name
 
+    # several GPUs in one process: equal to the single-device results, which equal the oracle's
+    mu = r["multi"]
+    fsets = expect["fmh_struct"][1]
+    five = [fsets[0], fsets[1], fsets[1], fsets[0], fsets[1]]
+    assert mu["sizes_1"] == [len(x) for x in five]
+    assert mu["all_1"] == [port.intersection(a, b) for a in five for b in five]
+    assert mu["ring_1"] == [port.intersection(five[i], five[(i + 1) % 5]) for i in range(5)]
+    if mu["devices"] >= 2:
+        assert (mu["all_n"], mu["ring_n"], mu["sizes_n"]) == (mu["all_1"], mu["ring_1"], mu["sizes_1"])
+
     m9, _ = port.seed_to_mask("110101101")
     ca, sa = port.fasta_parse(open(fa, "rb").read())
     lst = port.kmers(ca, list(sa), m9, 9)
