@@ -50,7 +50,9 @@ def test_cpp_api_against_oracle(tmp_path):
     exe = os.path.join(PKG, "test_cpp_api")
     assert os.path.exists(exe), "run __graft_entry__.build() first"
     fa, fb = write_inputs(str(tmp_path))
-    r = json.loads(subprocess.check_output([exe, fa, fb], timeout=300))
+    # (NCCL writes its version banner to stdout when NCCL_DEBUG is set: keep it out of the JSON)
+    env = {k: v for k, v in os.environ.items() if k != "NCCL_DEBUG"}
+    r = json.loads(subprocess.check_output([exe, fa, fb], timeout=300, env=env))
     assert ival(r["mask_24_16"]) == port.random_mask(24, 16, 0)
     assert ival(r["mask_31_21_s3"]) == port.random_mask(31, 21, 3)
     assert ival(r["contig_33"]) == port.contiguous_mask(33) and r["contig_65_throws"]
