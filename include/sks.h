@@ -296,8 +296,8 @@ int sks_comm_rank(const sks_comm *c);
 int sks_comm_world(const sks_comm *c);
 int sks_comm_nccl_version(void); /* 0 when NCCL cannot be loaded */
 /* Every rank passes the sets of its block of the n_total genomes (SORTED, one mask) and receives all n_total sets
- * in genome order: one small all-gather of the key counts (the only host synchronisation) and one grouped
- * send/receive of the keys, straight into the buffer the returned sets alias.  out_all[i] must be released with
+ * in genome order: one small all-gather of the key counts (the only host synchronisation) and one in-place
+ * ncclAllGather of the keys, straight into the buffer the returned sets alias.  out_all[i] must be released with
  * sks_set_destroy; the rank's own sets come back as second handles on the same keys.  comm NULL = one rank. */
 int sks_comm_allgather_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total,
                             sks_set **out_all);

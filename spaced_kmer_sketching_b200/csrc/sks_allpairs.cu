@@ -59,7 +59,7 @@ struct Slot {  // 16 bytes: one sector holds the key and its counters
 constexpr uint32_t kPostMax = 16;          // keys held by at most this many sets are posting lists
 constexpr uint32_t kPostFlag = 0x80000000u;  // entry = kPostFlag | id: the key is a posting list
 
-enum Counter : int { C_IDS = 0, C_ROWS = 2, C_TASK = 3, C_COUNT = 16 };
+enum Counter : int { C_IDS = 0, C_OVERFLOW = 1, C_ROWS = 2, C_TASK = 3, C_COUNT = 16 };
 
 struct DictView {
   const void *const *set_ptr;  // [n] keys of set s
@@ -155,12 +155,17 @@ __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_
     uint32_t seen = cur[u].z;   // the key's count when it was probed (only meaningful if the probe found the key)
     if (sl != D.cap) {
       unsigned long long c = ((unsigned long long)cur[u].y << 32) | cur[u].x;
-      for (;;) {
+      for (uint32_t probes = 0;; ++probes) {
         if (c == key[u]) break;
         seen = 0;
         if (c == 0) {
           c = atomicCAS(&D.tab[sl].key, 0ull, key[u]);
           if (c == 0 || c == key[u]) break;
+        }
+        if (probes >= D.cap) {  // the table is full (a very uneven split of the key space): the caller starts over
+          D.counters[C_OVERFLOW] = 1u;
+          sl = kNoId;
+          break;
         }
         sl = sl + 1 == D.cap ? 0 : sl + 1;
         const uint4 nx = __ldcg(reinterpret_cast<const uint4 *>(D.tab + sl));
@@ -169,6 +174,10 @@ __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_
       }
     }
     const uint32_t e = base + u * kDictThreads + threadIdx.x;
+    if (sl == kNoId) {
+      D.entry[e] = kNoId;
+      continue;
+    }
     uint32_t k = 255;
     if (seen <= kPostMax) {
       k = atomicAdd(&D.tab[sl].cnt, 1u);
@@ -448,8 +457,11 @@ bool all_pairs_dict_eligible(sks_set *const *sets, int64_t n) {
 // `symmetric` -- which needs all rows -- only j > i), from the keys of share `part` of `n_parts` of the key space:
 // the shares of all parts add up to the counts.  *raw receives raw_rows x n int32 (rows beyond the range stay zero),
 // *sizes the n set sizes.
+// *raw_out may come in holding the matrix of earlier calls (other shares of the key space): the counts are added to
+// it.  *h_overflow points at a pinned word that is non-zero, once the stream has been synchronised, if the table was
+// too small (then the counts are incomplete and the caller takes another route).
 int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, int part, int n_parts,
-                  bool symmetric, int64_t raw_rows, BufferRef *raw_out, BufferRef *sizes_out) {
+                  bool symmetric, int64_t raw_rows, BufferRef *raw_out, BufferRef *sizes_out, const uint32_t **h_overflow) {
   const uint32_t n_sets = (uint32_t)n;
   if (symmetric && !(row_begin == 0 && row_end == n)) return set_error(SKS_ERR_INVALID, "mirroring needs all rows");
   if (raw_rows < row_end - row_begin) return set_error(SKS_ERR_INVALID, "raw matrix too small");
@@ -460,7 +472,11 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
   for (int64_t i = 0; i < n; ++i) total += (uint64_t)sets[i]->count;
   if (total >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "too many keys for the dictionary");
   const uint32_t K = (uint32_t)total;
-  const uint32_t cap = std::max<uint32_t>(1024u, K + K / 2);
+  // this rank enters about K / n_parts keys (the hash spreads the DISTINCT keys evenly; a widely shared key brings all
+  // its occurrences to one rank, but they take one slot); 1.5 slots per entered key, and room for an uneven split
+  const uint32_t n_parts_u = (uint32_t)std::max(n_parts, 1);
+  const uint32_t k_here = n_parts_u == 1 ? K : (uint32_t)std::min<uint64_t>(K, (uint64_t)K / n_parts_u + K / (4 * n_parts_u) + 65536);
+  const uint32_t cap = std::max<uint32_t>(1024u, k_here + k_here / 2);
   // at most K / 2 keys can occur twice
   const uint32_t max_ids = K / 2 + 1;
   const uint32_t n_ranges = K / 2 / kRangeIds + 1;
@@ -494,7 +510,9 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
   // payload: a dense group holds >= kDenseMin ids in 8 KB, a sparse one 2 bytes per id rounded up to 16
   const size_t payload16 = (size_t)K / 2 + std::min<size_t>(n_groups, K) + 16;
   SKS_TRY(alloc_buffer(ctx, payload16 * 16, &payload));
-  SKS_TRY(alloc_buffer(ctx, 4 * (size_t)raw_rows * n_sets, &raw));
+  const bool accumulate = raw_out && *raw_out && (*raw_out)->bytes >= 4 * (size_t)raw_rows * n_sets;
+  if (accumulate) raw = *raw_out;
+  else SKS_TRY(alloc_buffer(ctx, 4 * (size_t)raw_rows * n_sets, &raw));
 
   // host tables through the pinned ring: offsets | pointers | sizes
   char *stage = nullptr;
@@ -514,7 +532,7 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
   SKS_CUDA_TRY(cudaMemsetAsync(d_counters, 0, sz_cnt, ctx->stream));
   SKS_CUDA_TRY(cudaMemsetAsync(d_gcnt, 0, 2 * sz_grp, ctx->stream));  // group_cnt and cursor
   SKS_CUDA_TRY(cudaMemsetAsync(tab->ptr, 0, sizeof(Slot) * ((size_t)cap + 1), ctx->stream));
-  SKS_CUDA_TRY(cudaMemsetAsync(raw->ptr, 0, 4 * (size_t)raw_rows * n_sets, ctx->stream));
+  if (!accumulate) SKS_CUDA_TRY(cudaMemsetAsync(raw->ptr, 0, 4 * (size_t)raw_rows * n_sets, ctx->stream));
   SKS_CUDA_TRY(cudaMemsetAsync(d_pcnt, 0, sz_ids, ctx->stream));
 
   DictView D;
@@ -586,6 +604,13 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
     SKS_TRY(alloc_buffer(ctx, 4 * (size_t)std::max<uint32_t>(n_sets, 4), sizes_out));
     SKS_CUDA_TRY(cudaMemcpyAsync((*sizes_out)->ptr, d_sizes, 4 * (size_t)n_sets, cudaMemcpyDeviceToDevice, ctx->stream));
   }
+  if (h_overflow) {
+    uint32_t *h = nullptr;
+    SKS_TRY(ctx_pinned(ctx, 64, reinterpret_cast<void **>(&h)));
+    *h = 0;
+    SKS_CUDA_TRY(cudaMemcpyAsync(h, d_counters + C_OVERFLOW, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    *h_overflow = h;
+  }
   *raw_out = raw;
   return SKS_OK;
 }
@@ -610,10 +635,14 @@ int all_pairs_finalize(sks_ctx *ctx, const int32_t *raw_rows, const int32_t *d_s
 // Rows [row_begin, row_end) of the n x n matrix of |sets[i] n sets[j]|, device resident: *counts receives
 // (row_end - row_begin) * n int32 (full rows incl. the diagonal), *ani (optional) as many doubles.
 int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, BufferRef *counts,
-                   BufferRef *ani, BufferRef *sizes_out) {
+                   BufferRef *ani, BufferRef *sizes_out, const uint32_t **h_overflow) {
   BufferRef raw, sizes;
-  const bool symmetric = row_begin == 0 && row_end == n;
-  SKS_TRY(all_pairs_raw(ctx, sets, n, row_begin, row_end, 0, 1, symmetric, row_end - row_begin, &raw, &sizes));
+  // SKS_DICT_PARTS=p (tests, profiling): the key space is entered in p shares one after the other, as p ranks would
+  static const int parts = [] { const char *e = getenv("SKS_DICT_PARTS"); return e ? std::max(1, atoi(e)) : 1; }();
+  const bool symmetric = row_begin == 0 && row_end == n && parts == 1;
+  for (int p = 0; p < parts; ++p)
+    SKS_TRY(all_pairs_raw(ctx, sets, n, row_begin, row_end, p, parts, symmetric, row_end - row_begin, &raw, p == 0 ? &sizes : nullptr,
+                          p == parts - 1 ? h_overflow : nullptr));
   SKS_TRY(all_pairs_finalize(ctx, static_cast<const int32_t *>(raw->ptr), static_cast<const int32_t *>(sizes->ptr), n, row_begin,
                              row_end - row_begin, symmetric, sets[0]->weight, counts, ani));
   if (sizes_out) *sizes_out = sizes;

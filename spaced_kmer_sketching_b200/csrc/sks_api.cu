@@ -557,6 +557,24 @@ int sketch_raw_keys(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, cons
   return set_error(SKS_ERR_CAPACITY, "sketch output overflowed twice");
 }
 
+}  // namespace
+// The kept k-mers of a single-genome batch as they leave the sketch kernel: unsorted, duplicates included.
+int sketch_raw_one(sks_ctx *ctx, const sks_batch *batch, const uint64_t mask[2], int window, const sks_pred *pred,
+                   BufferRef *keys, uint64_t *count, int *key_words) {
+  if (!batch || batch->n_genomes != 1) return set_error(SKS_ERR_INVALID, "a single-genome batch is needed");
+  if (batch->device != ctx->device) return set_error(SKS_ERR_INVALID, "batch lives on another device");
+  SketchPlan plan;
+  SKS_TRY(make_plan(batch, mask, window, pred, &plan));
+  BufferRef pos;
+  std::vector<uint64_t> off, cnt;
+  uint64_t span = 0;
+  SKS_TRY(sketch_raw_keys(ctx, batch, plan, pred, window, OUT_KEYS, keys, &pos, &off, &cnt, &span));
+  *count = cnt[0];
+  *key_words = plan.n_limbs <= 2 ? 1 : 2;
+  return SKS_OK;
+}
+namespace {
+
 int sketch_sorted(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const sks_pred *pred,
                   const uint64_t mask[2], int window, sks_set **out_sets) {
   const int G = batch->n_genomes;
@@ -1667,14 +1685,16 @@ int sks_all_vs_all(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_be
   if (n_rows == 0 || n == 0) return SKS_OK;
   if (all_pairs_dict_eligible(sets, n)) {
     BufferRef counts, ani;
-    int st = all_pairs_dict(ctx, sets, n, row_begin, row_end, &counts, out_ani ? &ani : nullptr, nullptr);
+    const uint32_t *overflow = nullptr;
+    int st = all_pairs_dict(ctx, sets, n, row_begin, row_end, &counts, out_ani ? &ani : nullptr, nullptr, &overflow);
     if (st == SKS_OK) {
       if (out_counts)
         SKS_CUDA_TRY(cudaMemcpyAsync(out_counts, counts->ptr, 4 * (size_t)n_rows * n, cudaMemcpyDeviceToHost, ctx->stream));
       if (out_ani)
         SKS_CUDA_TRY(cudaMemcpyAsync(out_ani, ani->ptr, 8 * (size_t)n_rows * n, cudaMemcpyDeviceToHost, ctx->stream));
       SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-      return SKS_OK;
+      if (!overflow || *overflow == 0) return SKS_OK;
+      st = SKS_ERR_CAPACITY;
     }
     if (st != SKS_ERR_CAPACITY) return st;  // too large for the dictionary: the pairwise kernels below
   }

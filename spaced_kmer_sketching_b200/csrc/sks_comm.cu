@@ -95,23 +95,68 @@ int need_nccl() {
   return SKS_OK;
 }
 
-// lower_bound of every splitter in an ascending key array: out[r] = number of keys < split[r]
+// Key range of a key: the number of splitters (ascending, the first is 0) that are <= key, minus one.
 template <int KW>
-__global__ void split_offsets_kernel(const unsigned long long *__restrict__ keys, uint32_t n,
-                                     const unsigned long long *__restrict__ split, int n_split,
-                                     unsigned long long *__restrict__ out) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_split) return;
-  const unsigned long long slo = split[2 * r], shi = split[2 * r + 1];
-  uint32_t lo = 0, hi = n;
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    bool less;
-    if (KW == 1) less = keys[mid] < slo;
-    else less = keys[2 * mid + 1] != shi ? keys[2 * mid + 1] < shi : keys[2 * mid] < slo;
-    if (less) lo = mid + 1; else hi = mid;
+__device__ __forceinline__ int key_range(const unsigned long long *s_split, int world, unsigned long long lo, unsigned long long hi) {
+  int a = 0, b = world;  // split[a] <= key < split[b]
+  while (b - a > 1) {
+    const int m = (a + b) >> 1;
+    const unsigned long long slo = s_split[2 * m], shi = s_split[2 * m + 1];
+    const bool le = KW == 1 ? slo <= lo : (shi != hi ? shi < hi : slo <= lo);
+    if (le) a = m; else b = m;
   }
-  out[r] = lo;
+  return a;
+}
+
+// Routing of unsorted keys by range.  kScatter == false: counts[r] += keys of range r.  kScatter == true: the keys go
+// to out[offset[r] + position], positions handed out by cursor[r] (order inside a range does not matter: the
+// receiver sorts).
+template <int KW, bool kScatter>
+__global__ void __launch_bounds__(256)
+    route_kernel(const unsigned long long *__restrict__ keys, unsigned long long n, const unsigned long long *__restrict__ split,
+                 int world, unsigned long long *__restrict__ counts, const unsigned long long *__restrict__ offset,
+                 unsigned long long *__restrict__ cursor, unsigned long long *__restrict__ out) {
+  __shared__ unsigned long long s_split[128];
+  for (int i = threadIdx.x; i < 2 * world; i += blockDim.x) s_split[i] = split[i];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long n_round = (n + 31) & ~31ull;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    unsigned long long lo = 0, hi = 0;
+    int r = -1;
+    if (i < n) {
+      lo = keys[KW * i];
+      hi = KW == 2 ? keys[KW * i + 1] : 0ull;
+      r = key_range<KW>(s_split, world, lo, hi);
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, r);
+    if (r < 0) continue;
+    const uint32_t leader = (uint32_t)(__ffs(peers) - 1), rank_in = (uint32_t)__popc(peers & ((1u << lane) - 1));
+    if (!kScatter) {
+      if (lane == leader) atomicAdd(counts + r, (unsigned long long)__popc(peers));
+    } else {
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(cursor + r, (unsigned long long)__popc(peers));
+      base = __shfl_sync(peers, base, (int)leader);
+      const unsigned long long at = offset[r] + base + rank_in;
+      out[KW * at] = lo;
+      if (KW == 2) out[KW * at + 1] = hi;
+    }
+  }
+}
+
+// offset[r] = counts[0] + ... + counts[r - 1]; cursor[r] = 0
+__global__ void route_offsets_kernel(const unsigned long long *__restrict__ counts, int world, unsigned long long *__restrict__ offset,
+                                     unsigned long long *__restrict__ cursor) {
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int r = 0; r < world; ++r) {
+      offset[r] = run;
+      cursor[r] = 0;
+      run += counts[r];
+    }
+  }
 }
 
 // PDEP of a (2 * weight)-bit value into the mask's set bits: the r-th quantile of the key space under the mask
@@ -311,25 +356,21 @@ int sks_comm_allgather_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local,
     if (r != rank) total_remote += h[0];
   }
   const size_t kb = (size_t)std::max(kw, 1) * 8;
+  // One in-place ncclAllGather of equal slots (the ranks' key counts differ by a few per cent at most: the slot is the
+  // largest): slot r of the inbox receives rank r's keys, mine go there by a device copy first.
+  int64_t slot_keys = 0;
+  for (int r = 0; r < world; ++r) slot_keys = std::max<int64_t>(slot_keys, h_all[hdr * r]);
+  const size_t slot = ((size_t)slot_keys * kb + 255) & ~(size_t)255;
+  (void)total_remote;
   BufferRef inbox;
-  SKS_TRY(alloc_buffer(ctx, (size_t)total_remote * kb, &inbox));
-  // one grouped exchange: my keys to every peer, every peer's keys into its place of the inbox
+  SKS_TRY(alloc_buffer(ctx, std::max<size_t>(slot * world, 16), &inbox));
   std::vector<size_t> at(world, 0);
-  {
-    size_t off = 0;
-    for (int r = 0; r < world; ++r) {
-      at[r] = off;
-      if (r != rank) off += (size_t)h_all[hdr * r] * kb;
-    }
+  for (int r = 0; r < world; ++r) at[r] = slot * r;
+  if (slot > 0) {
+    char *mine = static_cast<char *>(inbox->ptr) + at[rank];
+    if (my_n > 0) SKS_CUDA_TRY(cudaMemcpyAsync(mine, my_keys, (size_t)my_n * kb, cudaMemcpyDeviceToDevice, ctx->stream));
+    SKS_NCCL_TRY(nccl()->AllGather(mine, inbox->ptr, slot, ncclUint8, comm->comm, ctx->stream));
   }
-  SKS_NCCL_TRY(nccl()->GroupStart());
-  for (int r = 0; r < world; ++r) {
-    if (r == rank) continue;
-    if (my_n > 0) SKS_NCCL_TRY(nccl()->Send(my_keys, (size_t)my_n * kb, ncclUint8, r, comm->comm, ctx->stream));
-    const size_t bytes = (size_t)h_all[hdr * r] * kb;
-    if (bytes) SKS_NCCL_TRY(nccl()->Recv(static_cast<char *>(inbox->ptr) + at[r], bytes, ncclUint8, r, comm->comm, ctx->stream));
-  }
-  SKS_NCCL_TRY(nccl()->GroupEnd());
   const int weight = sks_mask_weight(mask);
   for (int r = 0; r < world; ++r) {
     int64_t b = 0, e = 0;
@@ -377,7 +418,8 @@ int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, 
   DeviceGuard guard(ctx->device);
   const int64_t per = (n_total + world - 1) / world, n_rows = end - begin;
   BufferRef raw, sizes, mine, counts, ani;
-  int st = all_pairs_raw(ctx, all.data(), n_total, 0, n_total, rank, world, false, (int64_t)world * per, &raw, &sizes);
+  const uint32_t *overflow = nullptr;
+  int st = all_pairs_raw(ctx, all.data(), n_total, 0, n_total, rank, world, false, (int64_t)world * per, &raw, &sizes, &overflow);
   if (st == SKS_ERR_CAPACITY) return sks_all_vs_all(ctx, all.data(), n_total, begin, end, out_counts, out_sizes, out_ani);
   SKS_TRY(st);
   SKS_TRY(alloc_buffer(ctx, 4 * (size_t)per * n_total, &mine));
@@ -394,6 +436,8 @@ int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, 
   if (out_sizes)
     for (int64_t i = 0; i < n_total; ++i) out_sizes[i] = (int32_t)all[i]->count;
   SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if (overflow && *overflow)  // (every rank completes the collective first; a full table is reported, not papered over)
+    return set_error(SKS_ERR_CAPACITY, "the dictionary of rank %d overflowed: its share of the key space is too uneven", rank);
   return SKS_OK;
 }
 
@@ -403,31 +447,31 @@ int sks_sketch_sequence_sharded(sks_ctx *ctx, sks_comm *comm, const sks_batch *s
   if (sks_batch_n_genomes(slice) != 1) return set_error(SKS_ERR_INVALID, "a sequence slice is a single-genome batch");
   const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
   if (world > 64) return set_error(SKS_ERR_INVALID, "at most 64 ranks");
-  sks_set *loc = nullptr;
-  SKS_TRY(sks_sketch(ctx, slice, mask, window, pred, SKS_REPR_SORTED, &loc));
   if (world == 1) {
+    sks_set *loc = nullptr;
+    SKS_TRY(sks_sketch(ctx, slice, mask, window, pred, SKS_REPR_SORTED, &loc));
     *out = loc;
     if (out_global_size) *out_global_size = loc->count;
     return SKS_OK;
   }
-  struct Drop {  // the local sketch is an intermediate from here on
-    sks_ctx *c;
-    sks_set *s;
-    ~Drop() { sks_set_destroy(c, s); }
-  } drop{ctx, loc};
   SKS_TRY(need_nccl());
   DeviceGuard guard(ctx->device);
-  const int kw = loc->key_words;
+  // the slice's kept k-mers as the sketch kernel leaves them (unsorted, duplicates included): they are sorted once,
+  // by the rank that owns their key range
+  BufferRef raw;
+  uint64_t n_raw = 0;
+  int kw = 1;
+  SKS_TRY(sketch_raw_one(ctx, slice, mask, window, pred, &raw, &n_raw, &kw));
   const size_t kb = (size_t)kw * 8;
   const int weight = sks_mask_weight(mask);
   // key range r = [split[r], split[r + 1]): equal shares of the 4^weight possible keys under the mask
+  const size_t W = (size_t)world;
   unsigned long long *h_tab = nullptr;
-  const size_t n_tab = 2 * (size_t)world + (size_t)world * world + 2 * (size_t)world;
-  SKS_TRY(ctx_pinned(ctx, 8 * n_tab, reinterpret_cast<void **>(&h_tab)));
-  BufferRef d_tab;
-  SKS_TRY(alloc_buffer(ctx, 8 * n_tab, &d_tab));
-  unsigned long long *d_split = static_cast<unsigned long long *>(d_tab->ptr), *d_lb = d_split + 2 * world,
-                     *d_all = d_lb + world;
+  SKS_TRY(ctx_pinned(ctx, 8 * (2 * W + W * W + W + 8), reinterpret_cast<void **>(&h_tab)));
+  BufferRef d_tab, routed;
+  SKS_TRY(alloc_buffer(ctx, 8 * (2 * W + 3 * W + W * W + 8), &d_tab));
+  unsigned long long *d_split = static_cast<unsigned long long *>(d_tab->ptr), *d_cnt = d_split + 2 * W, *d_off = d_cnt + W,
+                     *d_cur = d_off + W, *d_all = d_cur + W;
   for (int r = 0; r < world; ++r) {
     uint64_t s[2] = {0, 0};
     if (r > 0) {
@@ -440,62 +484,89 @@ int sks_sketch_sequence_sharded(sks_ctx *ctx, sks_comm *comm, const sks_batch *s
     h_tab[2 * r] = s[0];
     h_tab[2 * r + 1] = s[1];
   }
-  SKS_CUDA_TRY(cudaMemcpyAsync(d_split, h_tab, 16 * (size_t)world, cudaMemcpyHostToDevice, ctx->stream));
-  const unsigned long long *keys = reinterpret_cast<const unsigned long long *>(static_cast<const char *>(loc->buf->ptr) + loc->byte_off);
-  if (kw == 1) split_offsets_kernel<1><<<1, 64, 0, ctx->stream>>>(keys, (uint32_t)loc->count, d_split, world, d_lb);
-  else split_offsets_kernel<2><<<1, 64, 0, ctx->stream>>>(keys, (uint32_t)loc->count, d_split, world, d_lb);
-  SKS_CUDA_TRY(cudaGetLastError());
-  ctx->launches++;
-  // every rank's lower bounds to every rank: row r of the table = where rank r's key ranges start
-  SKS_NCCL_TRY(nccl()->AllGather(d_lb, d_all, (size_t)world, ncclUint64, comm->comm, ctx->stream));
-  unsigned long long *h_all = h_tab + 2 * world;
-  unsigned long long *h_cnt = h_all + (size_t)world * world;  // [world] local key counts, all-gathered below
-  // the counts travel in the same table: rank r's total = its last range's end; all-gather them as well
-  BufferRef d_cnt;
-  SKS_TRY(alloc_buffer(ctx, 8 * ((size_t)world + 1), &d_cnt));
-  unsigned long long *d_mycnt = static_cast<unsigned long long *>(d_cnt->ptr), *d_cnts = d_mycnt + 1;
-  h_cnt[world] = (unsigned long long)loc->count;
-  SKS_CUDA_TRY(cudaMemcpyAsync(d_mycnt, h_cnt + world, 8, cudaMemcpyHostToDevice, ctx->stream));
-  SKS_NCCL_TRY(nccl()->AllGather(d_mycnt, d_cnts, 1, ncclUint64, comm->comm, ctx->stream));
-  SKS_CUDA_TRY(cudaMemcpyAsync(h_all, d_all, 8 * (size_t)world * world, cudaMemcpyDeviceToHost, ctx->stream));
-  SKS_CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnts, 8 * (size_t)world, cudaMemcpyDeviceToHost, ctx->stream));
-  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  SKS_CUDA_TRY(cudaMemcpyAsync(d_split, h_tab, 16 * W, cudaMemcpyHostToDevice, ctx->stream));
+  SKS_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 8 * W, ctx->stream));
+  SKS_TRY(alloc_buffer(ctx, std::max<size_t>((size_t)n_raw * kb, 16), &routed));
+  const unsigned long long *keys = static_cast<const unsigned long long *>(raw->ptr);
+  unsigned long long *d_routed = static_cast<unsigned long long *>(routed->ptr);
+  const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_raw + 255) / 256, (uint64_t)ctx->sm_count * 8));
+  {
+    KernelTimer timer(ctx, SKS_KERNEL_SORT_UNIQUE);
+    if (kw == 1) {
+      route_kernel<1, false><<<grid, 256, 0, ctx->stream>>>(keys, n_raw, d_split, world, d_cnt, nullptr, nullptr, nullptr);
+      route_offsets_kernel<<<1, 32, 0, ctx->stream>>>(d_cnt, world, d_off, d_cur);
+      route_kernel<1, true><<<grid, 256, 0, ctx->stream>>>(keys, n_raw, d_split, world, nullptr, d_off, d_cur, d_routed);
+    } else {
+      route_kernel<2, false><<<grid, 256, 0, ctx->stream>>>(keys, n_raw, d_split, world, d_cnt, nullptr, nullptr, nullptr);
+      route_offsets_kernel<<<1, 32, 0, ctx->stream>>>(d_cnt, world, d_off, d_cur);
+      route_kernel<2, true><<<grid, 256, 0, ctx->stream>>>(keys, n_raw, d_split, world, nullptr, d_off, d_cur, d_routed);
+    }
+    SKS_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 3;
+  }
+  // every rank's counts per range to every rank (row r of the table = what rank r sends where)
+  unsigned long long *h_all = h_tab + 2 * W;
+  {
+    KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
+    SKS_NCCL_TRY(nccl()->AllGather(d_cnt, d_all, W, ncclUint64, comm->comm, ctx->stream));
+    SKS_CUDA_TRY(cudaMemcpyAsync(h_all, d_all, 8 * W * W, cudaMemcpyDeviceToHost, ctx->stream));
+    SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  }
   // (the pinned ring may hand the staging area out again inside the calls below: keep what is needed)
-  const std::vector<unsigned long long> all_lb(h_all, h_all + (size_t)world * world), all_cnt(h_cnt, h_cnt + world);
-  auto range_begin = [&](int src, int r) { return (int64_t)all_lb[(size_t)src * world + r]; };
-  auto range_end = [&](int src, int r) { return r + 1 < world ? (int64_t)all_lb[(size_t)src * world + r + 1] : (int64_t)all_cnt[src]; };
+  const std::vector<unsigned long long> cnt(h_all, h_all + W * W);
+  auto sends = [&](int src, int dst) { return (int64_t)cnt[(size_t)src * W + dst]; };
   // inbox: the keys of my range from every rank (mine by a device copy)
   int64_t n_in = 0;
-  std::vector<int64_t> in_at(world);
+  std::vector<int64_t> in_at(world), out_at(world);
   for (int src = 0; src < world; ++src) {
     in_at[src] = n_in;
-    n_in += range_end(src, rank) - range_begin(src, rank);
+    n_in += sends(src, rank);
+  }
+  {
+    int64_t at = 0;
+    for (int dst = 0; dst < world; ++dst) {
+      out_at[dst] = at;
+      at += sends(rank, dst);
+    }
   }
   BufferRef inbox;
   SKS_TRY(alloc_buffer(ctx, (size_t)std::max<int64_t>(n_in, 1) * kb, &inbox));
-  SKS_NCCL_TRY(nccl()->GroupStart());
-  for (int r = 0; r < world; ++r) {
-    if (r == rank) continue;
-    const int64_t sb = range_begin(rank, r), se = range_end(rank, r);
-    if (se > sb)
-      SKS_NCCL_TRY(nccl()->Send(reinterpret_cast<const char *>(keys) + (size_t)sb * kb, (size_t)(se - sb) * kb, ncclUint8, r,
-                                comm->comm, ctx->stream));
-    const int64_t rn = range_end(r, rank) - range_begin(r, rank);
-    if (rn > 0)
-      SKS_NCCL_TRY(nccl()->Recv(static_cast<char *>(inbox->ptr) + (size_t)in_at[r] * kb, (size_t)rn * kb, ncclUint8, r,
-                                comm->comm, ctx->stream));
-  }
-  SKS_NCCL_TRY(nccl()->GroupEnd());
   {
-    const int64_t sb = range_begin(rank, rank), se = range_end(rank, rank);
-    if (se > sb)
+    KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
+    SKS_NCCL_TRY(nccl()->GroupStart());
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) continue;
+      if (sends(rank, r) > 0)
+        SKS_NCCL_TRY(nccl()->Send(reinterpret_cast<const char *>(d_routed) + (size_t)out_at[r] * kb, (size_t)sends(rank, r) * kb,
+                                  ncclUint8, r, comm->comm, ctx->stream));
+      if (sends(r, rank) > 0)
+        SKS_NCCL_TRY(nccl()->Recv(static_cast<char *>(inbox->ptr) + (size_t)in_at[r] * kb, (size_t)sends(r, rank) * kb, ncclUint8, r,
+                                  comm->comm, ctx->stream));
+    }
+    SKS_NCCL_TRY(nccl()->GroupEnd());
+    if (sends(rank, rank) > 0)
       SKS_CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(inbox->ptr) + (size_t)in_at[rank] * kb,
-                                   reinterpret_cast<const char *>(keys) + (size_t)sb * kb, (size_t)(se - sb) * kb,
+                                   reinterpret_cast<const char *>(d_routed) + (size_t)out_at[rank] * kb, (size_t)sends(rank, rank) * kb,
                                    cudaMemcpyDeviceToDevice, ctx->stream));
   }
+  unsigned long long *h_cnt = nullptr;
+  BufferRef d_cntbuf;
+  SKS_TRY(alloc_buffer(ctx, 8 * (W + 1), &d_cntbuf));
+  unsigned long long *d_mycnt = static_cast<unsigned long long *>(d_cntbuf->ptr), *d_cnts = d_mycnt + 1;
   // my range of the global set: sort + unique of what arrived (the same k-mer can occur in several slices)
   sks_set *mine = nullptr;
-  SKS_TRY(sks_set_from_unsorted_device_keys(ctx, inbox->ptr, n_in, kw, mask, window, &mine));
+  {
+    const uint64_t off = 0, cnt_in = (uint64_t)n_in;
+    std::vector<uint64_t> uoff, ucount;
+    BufferRef uniq;
+    SKS_TRY(sort_unique_regions(ctx, kw, inbox->ptr, &off, &cnt_in, 1, cnt_in, &uniq, &uoff, &ucount, mask));
+    mine = new_set(ctx, SKS_REPR_SORTED, mask, window, weight);
+    if (!mine) return set_error(SKS_ERR_INVALID, "out of host memory");
+    mine->buf = uniq;
+    mine->key_words = kw;
+    mine->byte_off = (size_t)uoff[0] * kb;
+    mine->count = (int64_t)ucount[0];
+  }
   // sizes of all ranges (for the global size, and for the optional gather)
   SKS_TRY(ctx_pinned(ctx, 8 * ((size_t)world + 1), reinterpret_cast<void **>(&h_cnt)));
   h_cnt[world] = (unsigned long long)mine->count;

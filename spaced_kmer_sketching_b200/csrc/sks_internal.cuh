@@ -267,12 +267,14 @@ bool row_intersect_fits(int key_words, const uint64_t mask[2], int64_t n_a);
 int launch_row_intersect(sks_ctx *ctx, int key_words, const void *d_tasks, int64_t n_tasks, const void *const *d_b,
                          const int64_t *d_nb, int32_t *d_out, const uint64_t mask[2], int64_t max_n_a);
 
+int sketch_raw_one(sks_ctx *ctx, const sks_batch *batch, const uint64_t mask[2], int window, const sks_pred *pred,
+                   BufferRef *keys, uint64_t *count, int *key_words);
 // all-vs-all through the dictionary of shared k-mers (sks_allpairs.cu)
 bool all_pairs_dict_eligible(sks_set *const *sets, int64_t n);
 int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, BufferRef *counts,
-                   BufferRef *ani, BufferRef *sizes_out);
+                   BufferRef *ani, BufferRef *sizes_out, const uint32_t **h_overflow);
 int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, int part, int n_parts,
-                  bool symmetric, int64_t raw_rows, BufferRef *raw_out, BufferRef *sizes_out);
+                  bool symmetric, int64_t raw_rows, BufferRef *raw_out, BufferRef *sizes_out, const uint32_t **h_overflow);
 int all_pairs_finalize(sks_ctx *ctx, const int32_t *raw_rows, const int32_t *d_sizes, int64_t n, int64_t row_begin,
                        int64_t n_rows, bool symmetric, int weight, BufferRef *counts, BufferRef *ani);
 

@@ -854,10 +854,19 @@ def test_alternative_routes_in_a_subprocess():
     import os
     import subprocess
     import sys
-    if os.environ.get("SKS_ROW_INTERSECT") == "0":
+    if os.environ.get("SKS_ROW_INTERSECT") in ("0", "2"):
         pytest.skip("already inside the child process")
     env = dict(os.environ, SKS_ROW_INTERSECT="0", SKS_BUCKET_SORT="0")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
                         "fuzz_all_pairs or all_pairs_row or multi_golden or fuzz_lists or sets_golden or sort_unique"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    # the all-vs-all dictionary with the key space entered in three shares one after the other -- what three ranks do
+    # before their reduce-scatter (csrc/sks_comm.cu) -- and, in another child, without the dictionary at all
+    for extra in ({"SKS_DICT_PARTS": "3"}, {"SKS_DICT_INTERSECT": "0"}):
+        env = dict(os.environ, SKS_ROW_INTERSECT="1", **extra)
+        env["SKS_ROW_INTERSECT"] = "0" if "SKS_DICT_INTERSECT" in extra else "2"   # "2": enabled, and marks the child
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                            "dictionary or fuzz_all_pairs or all_pairs_row or multi_golden"],
+                           env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, (extra, r.stdout[-2000:] + r.stderr[-2000:])
