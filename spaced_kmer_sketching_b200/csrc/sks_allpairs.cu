@@ -59,7 +59,11 @@ struct Slot {  // 16 bytes: one sector holds the key and its counters
 constexpr uint32_t kPostMax = 16;          // keys held by at most this many sets are posting lists
 constexpr uint32_t kPostFlag = 0x80000000u;  // entry = kPostFlag | id: the key is a posting list
 
-enum Counter : int { C_IDS = 0, C_OVERFLOW = 1, C_ROWS = 2, C_TASK = 3, C_COUNT = 16 };
+// C_IDS numbers the keys held by at least two sets (their posting lists), C_HIGH those held by more than kPostMax
+// sets (their bits in the sets' bitmaps): a key gets the first kind of id at its second occurrence and the second
+// kind at occurrence kPostMax + 1.
+enum Counter : int { C_IDS = 0, C_OVERFLOW = 1, C_ROWS = 2, C_TASK = 3, C_MINE = 4, C_HIGH = 5, C_COUNT = 16 };
+constexpr uint32_t kHighFlag = 0x80000000u;  // Slot::id = kHighFlag | bitmap id once the key has one (atomicMax keeps it)
 
 struct DictView {
   const void *const *set_ptr;  // [n] keys of set s
@@ -68,17 +72,33 @@ struct DictView {
   uint32_t n_entries;
   Slot *tab;                   // [cap + 1]
   uint32_t cap;
-  uint32_t *entry;             // [n_entries] D1: slot of the entry's key; D2: its id (| kPostFlag), kNoId: private key
+  // Per entered key occurrence q.  One rank: q = the entry's number e, its set is found from set_off.  Several ranks
+  // (n_parts > 1): the occurrences of this rank's keys are compacted, q counts them (counters[C_MINE]) and set_of[q]
+  // is the set.
+  uint32_t *entry;             // [n_entries] D1: slot of the key; D2: its id (| kPostFlag), kNoId: private key
   uint8_t *occ;                // [n_entries] which occurrence of its key the entry was (saturating at 255)
+  uint16_t *set_of;            // [n_entries] (n_parts > 1 only)
   uint32_t *counters;          // [C_COUNT]
   uint32_t part, n_parts;      // only keys with owner(key) == part are entered (several ranks split the key space)
 };
 
-__device__ __forceinline__ uint32_t size16(uint32_t cnt) {  // payload of a (set, range) group in 16-byte units
-  return cnt == 0 ? 0u : (cnt >= kDenseMin ? kRange16 : (2 * cnt + 15) / 16);
+// A (set, range) group becomes a bitmap from this many ids on: 1024 in a range that is in full use (a list of 16-bit
+// ids is then a quarter of the 8 KB bitmap), less in a range of which only the first few thousand ids exist (the
+// last range; the only one when several ranks split the key space), where the bitmap is short as well.
+__device__ __forceinline__ uint32_t dense_min(uint32_t n_high, uint32_t t) {
+  const uint32_t first = t * kRangeIds;
+  const uint32_t ids_here = n_high > first ? min(kRangeIds, n_high - first) : 0u;
+  return max(64u, min(kDenseMin, ids_here / 16));
 }
-struct Size16Op {
-  __device__ __forceinline__ uint32_t operator()(uint32_t cnt) const { return size16(cnt); }
+__device__ __forceinline__ uint32_t size16(uint32_t cnt, uint32_t dmin) {  // payload of a group in 16-byte units
+  return cnt == 0 ? 0u : (cnt >= dmin ? kRange16 : (2 * cnt + 15) / 16);
+}
+struct GroupSize16 {  // group g -> its payload size (for the prefix sum over all groups)
+  const uint32_t *group_cnt, *counters;
+  uint32_t n_sets;
+  __device__ __forceinline__ uint32_t operator()(uint32_t g) const {
+    return size16(group_cnt[g], dense_min(counters[5 /* C_HIGH */], g / n_sets));
+  }
 };
 
 template <int KW>
@@ -124,7 +144,9 @@ template <int KW>
 __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_constant__ DictView D,
                                                                    const __grid_constant__ Compact C) {
   const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
-  uint32_t s = 0, slot[kDictPer];
+  const uint32_t lane = threadIdx.x & 31;
+  const bool compact = D.n_parts > 1;
+  uint32_t s = 0, slot[kDictPer], set_id[kDictPer];
   unsigned long long key[kDictPer];
   uint4 cur[kDictPer];
   bool have = false;
@@ -132,6 +154,7 @@ __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_
   for (int u = 0; u < kDictPer; ++u) {
     const uint32_t e = base + u * kDictThreads + threadIdx.x;
     slot[u] = kNoId;
+    set_id[u] = 0;
     if (e < D.n_entries) {
       if (!have) {
         s = find_set(D.set_off, D.n_sets, e);
@@ -139,52 +162,94 @@ __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_
       } else {
         while (e >= __ldg(D.set_off + s + 1)) ++s;
       }
+      set_id[u] = s;
       key[u] = load_key<KW>(D.set_ptr[s], e - __ldg(D.set_off + s), C);
       const unsigned long long h = hash_key(key[u]);
-      if (D.n_parts > 1 && hash_owner(h, D.n_parts) != D.part) D.entry[e] = kNoId;   // another rank's key
-      else slot[u] = key[u] ? hash_slot(h, D.cap) : D.cap;
+      if (!compact || hash_owner(h, D.n_parts) == D.part) slot[u] = key[u] ? hash_slot(h, D.cap) : D.cap;
     }
   }
 #pragma unroll
   for (int u = 0; u < kDictPer; ++u)  // the first probes of a thread's entries are in flight together
     if (slot[u] != kNoId) cur[u] = __ldcg(reinterpret_cast<const uint4 *>(D.tab + slot[u]));
+  // compact list: the CTA's entered occurrences take consecutive places, one reservation per CTA
+  uint32_t q_next = 0;
+  if (compact) {
+    __shared__ uint32_t s_warp[kDictThreads / 32], s_base;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int u = 0; u < kDictPer; ++u) mine += slot[u] != kNoId ? 1u : 0u;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= (uint32_t)o) incl += x;
+    }
+    if (lane == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t total = 0;
+      for (int w = 0; w < kDictThreads / 32; ++w) {
+        const uint32_t c = s_warp[w];
+        s_warp[w] = total;
+        total += c;
+      }
+      s_base = total ? atomicAdd(D.counters + C_MINE, total) : 0u;
+    }
+    __syncthreads();
+    q_next = s_base + s_warp[threadIdx.x >> 5] + incl - mine;
+  }
 #pragma unroll
   for (int u = 0; u < kDictPer; ++u) {
-    if (slot[u] == kNoId) continue;
-    uint32_t sl = slot[u];
-    uint32_t seen = cur[u].z;   // the key's count when it was probed (only meaningful if the probe found the key)
-    if (sl != D.cap) {
-      unsigned long long c = ((unsigned long long)cur[u].y << 32) | cur[u].x;
-      for (uint32_t probes = 0;; ++probes) {
-        if (c == key[u]) break;
-        seen = 0;
-        if (c == 0) {
-          c = atomicCAS(&D.tab[sl].key, 0ull, key[u]);
-          if (c == 0 || c == key[u]) break;
+    uint32_t sl = slot[u], k = 255;
+    if (sl != kNoId) {
+      uint32_t seen = cur[u].z;   // the key's count when it was probed (only meaningful if the probe found the key)
+      if (sl != D.cap) {
+        unsigned long long c = ((unsigned long long)cur[u].y << 32) | cur[u].x;
+        for (uint32_t probes = 0;; ++probes) {
+          if (c == key[u]) break;
+          seen = 0;
+          if (c == 0) {
+            c = atomicCAS(&D.tab[sl].key, 0ull, key[u]);
+            if (c == 0 || c == key[u]) break;
+          }
+          if (probes >= D.cap) {  // the table is full (a very uneven split of the key space): the caller starts over
+            D.counters[C_OVERFLOW] = 1u;
+            sl = kNoId;
+            break;
+          }
+          sl = sl + 1 == D.cap ? 0 : sl + 1;
+          const uint4 nx = __ldcg(reinterpret_cast<const uint4 *>(D.tab + sl));
+          c = ((unsigned long long)nx.y << 32) | nx.x;
+          seen = nx.z;
         }
-        if (probes >= D.cap) {  // the table is full (a very uneven split of the key space): the caller starts over
-          D.counters[C_OVERFLOW] = 1u;
-          sl = kNoId;
-          break;
-        }
-        sl = sl + 1 == D.cap ? 0 : sl + 1;
-        const uint4 nx = __ldcg(reinterpret_cast<const uint4 *>(D.tab + sl));
-        c = ((unsigned long long)nx.y << 32) | nx.x;
-        seen = nx.z;
       }
+      if (sl != kNoId && seen <= kPostMax) k = atomicAdd(&D.tab[sl].cnt, 1u);
+    }
+    // new ids: one reservation per warp and kind (the counters are single words: a million lone atomics on one
+    // address would take longer than the rest of the kernel)
+#pragma unroll
+    for (int kind = 0; kind < 2; ++kind) {
+      const bool want = sl != kNoId && k == (kind ? kPostMax : 1u);
+      const uint32_t m = __ballot_sync(0xffffffffu, want);
+      if (m == 0) continue;
+      uint32_t first = 0;
+      const uint32_t leader = (uint32_t)(__ffs(m) - 1);
+      if (lane == leader) first = atomicAdd(D.counters + (kind ? C_HIGH : C_IDS), (uint32_t)__popc(m));
+      first = __shfl_sync(0xffffffffu, first, (int)leader);
+      if (want) atomicMax(&D.tab[sl].id, (kind ? kHighFlag : 0u) | (first + (uint32_t)__popc(m & ((1u << lane) - 1))));
     }
     const uint32_t e = base + u * kDictThreads + threadIdx.x;
-    if (sl == kNoId) {
-      D.entry[e] = kNoId;
-      continue;
+    if (!compact) {
+      if (e < D.n_entries) {
+        D.entry[e] = sl;
+        D.occ[e] = (uint8_t)min(k, 255u);
+      }
+    } else if (slot[u] != kNoId) {
+      D.entry[q_next] = sl;   // kNoId if the table overflowed
+      D.occ[q_next] = (uint8_t)min(k, 255u);
+      D.set_of[q_next] = (uint16_t)set_id[u];
+      ++q_next;
     }
-    uint32_t k = 255;
-    if (seen <= kPostMax) {
-      k = atomicAdd(&D.tab[sl].cnt, 1u);
-      if (k == 1) D.tab[sl].id = atomicAdd(D.counters + C_IDS, 1u);   // read by later kernels only
-    }
-    D.entry[e] = sl;
-    D.occ[e] = (uint8_t)min(k, 255u);
   }
 }
 
@@ -194,14 +259,19 @@ __global__ void __launch_bounds__(kDictThreads) dict_ids_kernel(const __grid_con
                                                                 uint32_t *__restrict__ post_cnt) {
   const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
   const uint32_t lane = threadIdx.x & 31;
+  const bool compact = D.n_parts > 1;
+  const uint32_t n_occ = compact ? D.counters[C_MINE] : D.n_entries;
+  if (base >= n_occ) return;
   uint32_t s = 0;
   bool have = false;
 #pragma unroll
   for (int u = 0; u < kDictPer; ++u) {
     const uint32_t e = base + u * kDictThreads + threadIdx.x;
     uint32_t bin = kNoId;
-    if (e < D.n_entries) {
-      if (!have) {
+    if (e < n_occ) {
+      if (compact) {
+        s = D.set_of[e];
+      } else if (!have) {
         s = find_set(D.set_off, D.n_sets, e);
         have = true;
       } else {
@@ -217,7 +287,7 @@ __global__ void __launch_bounds__(kDictThreads) dict_ids_kernel(const __grid_con
           id = kPostFlag | sl.id;
           if (D.occ[e] == 0) post_cnt[sl.id] = sl.cnt;
         } else {
-          id = sl.id;
+          id = sl.id & ~kHighFlag;
           bin = (id >> kRangeBits) * D.n_sets + s;
         }
       }
@@ -241,13 +311,17 @@ __global__ void __launch_bounds__(kDictThreads)
                         const uint32_t *__restrict__ group_end, uint32_t *__restrict__ cursor, uint4 *__restrict__ payload,
                         const uint32_t *__restrict__ post_begin, uint16_t *__restrict__ postings) {
   const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
+  const bool compact = D.n_parts > 1;
+  const uint32_t n_occ = compact ? D.counters[C_MINE] : D.n_entries;
   uint32_t s = 0;
   bool have = false;
 #pragma unroll
   for (int u = 0; u < kDictPer; ++u) {
     const uint32_t e = base + u * kDictThreads + threadIdx.x;
-    if (e >= D.n_entries) continue;
-    if (!have) {
+    if (e >= n_occ) continue;
+    if (compact) {
+      s = D.set_of[e];
+    } else if (!have) {
       s = find_set(D.set_off, D.n_sets, e);
       have = true;
     } else {
@@ -260,8 +334,9 @@ __global__ void __launch_bounds__(kDictThreads)
       continue;
     }
     const uint32_t g = (id >> kRangeBits) * D.n_sets + s, c = group_cnt[g];
-    const uint32_t off = group_end[g] - size16(c), low = id & (kRangeIds - 1);
-    if (c >= kDenseMin) {
+    const uint32_t dmin = dense_min(D.counters[C_HIGH], id >> kRangeBits);
+    const uint32_t off = group_end[g] - size16(c, dmin), low = id & (kRangeIds - 1);
+    if (c >= dmin) {
       atomicOr(reinterpret_cast<uint32_t *>(payload + off) + (low >> 5), 1u << (low & 31));
     } else {
       const uint32_t pos = atomicAdd(cursor + g, 1u);
@@ -322,13 +397,17 @@ struct PairsView {
   int32_t *out;    // [(row_end - row_begin) * n_sets], zero on entry
 };
 
-// X: persistent CTAs pull (range, row, column chunk) tasks.  The row's bitmap of that range sits in shared memory;
-// every warp takes one column at a time: AND/popcount against a dense column, bit probes for a sparse one.
+// X: persistent CTAs pull (range, row, column chunk) tasks.  The row's bitmap of that range sits in shared memory.
+// A range that is in full use: every warp takes one column at a time, AND/popcount against a dense column, bit probes
+// for a sparse one.  A range with few ids (the last one; the only one when several ranks split the key space): every
+// THREAD takes a column -- the bitmaps are a few hundred bytes and a warp per column would be all overhead.
+constexpr uint32_t kSmall16 = 32;  // ranges of up to 4096 ids take the thread-per-column route
 __global__ void __launch_bounds__(kPairsThreads) allpairs_kernel(const __grid_constant__ PairsView V) {
   __shared__ __align__(16) uint32_t s_bits[kRangeWords];
   __shared__ uint32_t s_task;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t n_tasks = V.counters[C_ROWS] * V.n_chunks;
+  const uint32_t n_high = V.counters[C_HIGH];
   uint4 *s_bits4 = reinterpret_cast<uint4 *>(s_bits);
   for (;;) {
     __syncthreads();  // the previous task is done with s_bits and s_task
@@ -338,16 +417,19 @@ __global__ void __launch_bounds__(kPairsThreads) allpairs_kernel(const __grid_co
     if (task >= n_tasks) break;
     const uint32_t g = V.rowlist[task / V.n_chunks], chunk = task % V.n_chunks;
     const uint32_t t = g / V.n_sets, i = g % V.n_sets;
-    const uint32_t j0 = chunk * kPairsCols, j1 = min(V.n_sets, j0 + kPairsCols);
-    if (V.symmetric && j1 <= i + 1) continue;
-    const uint32_t ca = V.group_cnt[g], offa = V.group_end[g] - size16(ca);
-    // ids are dense from 0: the last range is only partly used, and nothing is set beyond its last id
-    const uint32_t ids_here = min(kRangeIds, V.counters[C_IDS] - t * kRangeIds);
+    // bitmap ids are dense from 0: the last range is only partly used, and nothing is set beyond its last id
+    const uint32_t ids_here = min(kRangeIds, n_high - t * kRangeIds);
     const uint32_t used16 = (ids_here + 127) / 128;
-    if (ca >= kDenseMin) {
-      for (uint32_t k = tid; k < kRange16; k += kPairsThreads) s_bits4[k] = __ldg(V.payload + offa + k);
+    const bool small = used16 <= kSmall16;
+    const uint32_t dmin = dense_min(n_high, t);
+    if (small && (chunk & 3)) continue;  // thread-per-column tasks cover four chunks
+    const uint32_t j0 = chunk * kPairsCols, j1 = min(V.n_sets, j0 + (small ? 4 * kPairsCols : kPairsCols));
+    if (V.symmetric && j1 <= i + 1) continue;
+    const uint32_t ca = V.group_cnt[g], offa = V.group_end[g] - size16(ca, dmin);
+    if (ca >= dmin) {
+      for (uint32_t k = tid; k < used16; k += kPairsThreads) s_bits4[k] = __ldg(V.payload + offa + k);
     } else {
-      for (uint32_t k = tid; k < kRange16; k += kPairsThreads) s_bits4[k] = make_uint4(0, 0, 0, 0);
+      for (uint32_t k = tid; k < used16; k += kPairsThreads) s_bits4[k] = make_uint4(0, 0, 0, 0);
       __syncthreads();
       const uint16_t *la = reinterpret_cast<const uint16_t *>(V.payload + offa);
       for (uint32_t k = tid; k < ca; k += kPairsThreads) {
@@ -356,13 +438,37 @@ __global__ void __launch_bounds__(kPairsThreads) allpairs_kernel(const __grid_co
       }
     }
     __syncthreads();
+    if (small) {
+      const uint32_t j = j0 + tid;
+      if (j >= j1 || j == i || (V.symmetric && j < i)) continue;
+      const uint32_t gb = t * V.n_sets + j, cb = V.group_cnt[gb];
+      if (cb == 0) continue;
+      const uint32_t offb = V.group_end[gb] - size16(cb, dmin);
+      uint32_t acc = 0;
+      if (cb >= dmin) {
+        const uint4 *B = V.payload + offb;
+#pragma unroll 4
+        for (uint32_t k = 0; k < used16; ++k) {
+          const uint4 b = __ldg(B + k), a = s_bits4[k];
+          acc += __popc(a.x & b.x) + __popc(a.y & b.y) + __popc(a.z & b.z) + __popc(a.w & b.w);
+        }
+      } else {
+        const uint16_t *lb = reinterpret_cast<const uint16_t *>(V.payload + offb);
+        for (uint32_t k = 0; k < cb; ++k) {
+          const uint32_t id = lb[k];
+          acc += (s_bits[id >> 5] >> (id & 31)) & 1u;
+        }
+      }
+      if (acc) atomicAdd(V.out + (size_t)(i - V.row_begin) * V.n_sets + j, (int32_t)acc);
+      continue;
+    }
     for (uint32_t j = j0 + warp; j < j1; j += kPairsWarps) {
       if (j == i || (V.symmetric && j < i)) continue;
       const uint32_t gb = t * V.n_sets + j, cb = V.group_cnt[gb];
       if (cb == 0) continue;
-      const uint32_t offb = V.group_end[gb] - size16(cb);
+      const uint32_t offb = V.group_end[gb] - size16(cb, dmin);
       uint32_t acc = 0;
-      if (cb >= kDenseMin) {
+      if (cb >= dmin) {
         const uint4 *B = V.payload + offb;
 #pragma unroll 4
         for (uint32_t k = lane; k < used16; k += 32) {
@@ -479,7 +585,7 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
   const uint32_t cap = std::max<uint32_t>(1024u, k_here + k_here / 2);
   // at most K / 2 keys can occur twice
   const uint32_t max_ids = K / 2 + 1;
-  const uint32_t n_ranges = K / 2 / kRangeIds + 1;
+  const uint32_t n_ranges = K / (kPostMax + 1) / kRangeIds + 1;   // bitmap ids: keys held by more than kPostMax sets
   const uint64_t n_groups64 = (uint64_t)n_ranges * n_sets;
   if (n_groups64 >= (1ull << 28)) return set_error(SKS_ERR_CAPACITY, "too many (range, set) groups for the dictionary");
   const uint32_t n_groups = (uint32_t)n_groups64;
@@ -501,14 +607,16 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
   uint32_t *d_cursor = d_gcnt + sz_grp / 4, *d_gend = d_cursor + sz_grp / 4, *d_rowlist = d_gend + sz_grp / 4;
   SKS_TRY(alloc_buffer(ctx, sizeof(Slot) * ((size_t)cap + 1), &tab));
   SKS_TRY(alloc_buffer(ctx, 4 * (size_t)std::max<uint32_t>(K, 1), &entry));
-  SKS_TRY(alloc_buffer(ctx, (size_t)std::max<uint32_t>(K, 16), &occ));
+  SKS_TRY(alloc_buffer(ctx, (size_t)std::max<uint32_t>(K, 16) * (n_parts > 1 ? 3 : 1), &occ));   // occ | set_of
   // posting lists: sizes and starts per id, members (every entry belongs to at most one list)
   const size_t sz_ids = align(4 * (size_t)max_ids);
   SKS_TRY(alloc_buffer(ctx, 2 * sz_ids + 2 * (size_t)K + 16, &post));
   uint32_t *d_pcnt = static_cast<uint32_t *>(post->ptr), *d_pbegin = d_pcnt + sz_ids / 4;
   uint16_t *d_postings = reinterpret_cast<uint16_t *>(static_cast<char *>(post->ptr) + 2 * sz_ids);
   // payload: a dense group holds >= kDenseMin ids in 8 KB, a sparse one 2 bytes per id rounded up to 16
-  const size_t payload16 = (size_t)K / 2 + std::min<size_t>(n_groups, K) + 16;
+  // (a bitmap group holds at least 64 ids, and there are at most n_groups groups)
+  const size_t payload16 = std::min<size_t>((size_t)n_groups * kRange16, (size_t)K / 64 * kRange16 + n_groups) + (size_t)K / 8 +
+                           std::min<size_t>(n_groups, K) + 16;
   SKS_TRY(alloc_buffer(ctx, payload16 * 16, &payload));
   const bool accumulate = raw_out && *raw_out && (*raw_out)->bytes >= 4 * (size_t)raw_rows * n_sets;
   if (accumulate) raw = *raw_out;
@@ -544,6 +652,7 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
   D.cap = cap;
   D.entry = static_cast<uint32_t *>(entry->ptr);
   D.occ = static_cast<uint8_t *>(occ->ptr);
+  D.set_of = reinterpret_cast<uint16_t *>(static_cast<uint8_t *>(occ->ptr) + (((size_t)std::max<uint32_t>(K, 16) + 1) & ~(size_t)1));
   D.counters = d_counters;
   D.part = (uint32_t)part;
   D.n_parts = (uint32_t)std::max(n_parts, 1);
@@ -559,7 +668,9 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
     }
     // group_end = inclusive prefix sum of the groups' payload sizes; post_begin = exclusive prefix sum of the list sizes
     size_t temp_bytes = 0, temp2 = 0;
-    cub::TransformInputIterator<uint32_t, Size16Op, const uint32_t *> sizes_in(d_gcnt, Size16Op());
+    cub::CountingInputIterator<uint32_t> group_ids(0);
+    cub::TransformInputIterator<uint32_t, GroupSize16, cub::CountingInputIterator<uint32_t>> sizes_in(
+        group_ids, GroupSize16{d_gcnt, d_counters, n_sets});
     cub::DeviceScan::InclusiveSum(nullptr, temp_bytes, sizes_in, d_gend, (int)n_groups, ctx->stream);
     cub::DeviceScan::ExclusiveSum(nullptr, temp2, d_pcnt, d_pbegin, (int)max_ids, ctx->stream);
     temp_bytes = std::max(temp_bytes, temp2);
