@@ -559,7 +559,12 @@ int sks_sketch_sequence_sharded(sks_ctx *ctx, sks_comm *comm, const sks_batch *s
     const uint64_t off = 0, cnt_in = (uint64_t)n_in;
     std::vector<uint64_t> uoff, ucount;
     BufferRef uniq;
-    SKS_TRY(sort_unique_regions(ctx, kw, inbox->ptr, &off, &cnt_in, 1, cnt_in, &uniq, &uoff, &ucount, mask));
+    // a power-of-two world cuts the key space at bit boundaries: the top log2(world) mask bits are the same in all of
+    // my keys, and the bucket sort indexes by the bits below them
+    int skip = 0;
+    if ((world & (world - 1)) == 0)
+      while ((1 << skip) < world) ++skip;
+    SKS_TRY(sort_unique_regions(ctx, kw, inbox->ptr, &off, &cnt_in, 1, cnt_in, &uniq, &uoff, &ucount, mask, skip));
     mine = new_set(ctx, SKS_REPR_SORTED, mask, window, weight);
     if (!mine) return set_error(SKS_ERR_INVALID, "out of host memory");
     mine->buf = uniq;

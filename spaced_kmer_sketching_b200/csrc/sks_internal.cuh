@@ -252,7 +252,8 @@ int launch_bitset_pair_build(sks_ctx *ctx, const uint32_t *regions, const uint32
 int launch_bitset_popcount(sks_ctx *ctx, const uint32_t *a, uint64_t n_words, unsigned long long *out1);
 int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t *h_off, const uint64_t *h_count,
                         int n_regions, uint64_t span, BufferRef *out_buf, std::vector<uint64_t> *out_off,
-                        std::vector<uint64_t> *out_count, const uint64_t *mask = nullptr);  // mask: enables the bucket sort
+                        std::vector<uint64_t> *out_count, const uint64_t *mask = nullptr,  // mask: enables the bucket sort
+                        int skip_bits = 0);  // the mask's top skip_bits set bits are the same in every key of a region
 int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const *d_a, const int64_t *d_na,
                                   const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out,
                                   const uint32_t *d_pair_idx = nullptr, int slices = 1);

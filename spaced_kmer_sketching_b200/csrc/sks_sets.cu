@@ -971,10 +971,17 @@ struct SortKey<2> {
 
 // Plan for `bb` bucket bits under `mask`; false when the mask has fewer set bits than that or needs more than six
 // pieces.
-inline bool sort_plan(const uint64_t mask[2], int bb, SortPlan *out) {
+// `skip`: that many of the mask's top set bits are passed over first (they are the same in every key of the region:
+// keys routed to the owner of a key range).
+inline bool sort_plan(const uint64_t mask[2], int bb, SortPlan *out, int skip = 0) {
   SortPlan p = {};
   int got = 0, bit = 127;
   auto set = [&](int b) { return b >= 0 && ((mask[b >> 6] >> (b & 63)) & 1); };
+  for (int s = 0; s < skip; ++s) {
+    while (bit >= 0 && !set(bit)) --bit;
+    if (bit < 0) return false;
+    --bit;
+  }
   while (got < bb) {
     while (bit >= 0 && !set(bit)) --bit;
     if (bit < 0 || p.n_pieces == 6) return false;
@@ -1263,7 +1270,7 @@ __global__ void __launch_bounds__(256)
 template <int KW>
 int sort_unique_buckets(sks_ctx *ctx, typename SortKey<KW>::T *keys, const uint64_t *h_off, const uint64_t *h_count, int n_regions,
                         uint64_t span, uint64_t total, const uint64_t mask[2], BufferRef *out_buf,
-                        std::vector<uint64_t> *out_off, std::vector<uint64_t> *out_count, bool *handled) {
+                        std::vector<uint64_t> *out_off, std::vector<uint64_t> *out_count, bool *handled, int skip_bits) {
   *handled = false;
   uint64_t max_count = 0;
   for (int g = 0; g < n_regions; ++g) max_count = std::max(max_count, h_count[g]);
@@ -1279,9 +1286,9 @@ int sort_unique_buckets(sks_ctx *ctx, typename SortKey<KW>::T *keys, const uint6
   if ((max_count >> bb) > big_cap / 2 || ((uint64_t)n_regions << bb) > (1u << 22)) return SKS_OK;  // too large for this scheme
   const int mask_bits = __builtin_popcountll(mask[0]) + __builtin_popcountll(mask[1]);
   // fewer possible keys than 4 per raw key: the input is mostly duplicates and the partition would be all contention
-  if (mask_bits < 62 && ((uint64_t)1 << mask_bits) < 4 * max_count) return SKS_OK;
+  if (mask_bits - skip_bits < 62 && ((uint64_t)1 << std::max(mask_bits - skip_bits, 0)) < 4 * max_count) return SKS_OK;
   SortPlan plan;
-  if (!sort_plan(mask, bb, &plan)) return SKS_OK;
+  if (!sort_plan(mask, bb, &plan, skip_bits)) return SKS_OK;
   using KT = typename SortKey<KW>::T;
   constexpr size_t kb = sizeof(KT);
   const size_t n_b = (size_t)n_regions << bb;
@@ -1356,7 +1363,7 @@ int sort_unique_buckets(sks_ctx *ctx, typename SortKey<KW>::T *keys, const uint6
 
 int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t *h_off, const uint64_t *h_count,
                         int n_regions, uint64_t span, BufferRef *out_buf, std::vector<uint64_t> *out_off,
-                        std::vector<uint64_t> *out_count, const uint64_t *mask) {
+                        std::vector<uint64_t> *out_count, const uint64_t *mask, int skip_bits) {
   out_off->assign(n_regions, 0);
   out_count->assign(n_regions, 0);
   uint64_t total = 0;
@@ -1371,10 +1378,10 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
     bool handled = false;
     if (key_words == 1)
       SKS_TRY(sort_unique_buckets<1>(ctx, static_cast<unsigned long long *>(keys), h_off, h_count, n_regions, span, total,
-                                     mask, out_buf, out_off, out_count, &handled));
+                                     mask, out_buf, out_off, out_count, &handled, skip_bits));
     else
       SKS_TRY(sort_unique_buckets<2>(ctx, static_cast<ulonglong2 *>(keys), h_off, h_count, n_regions, span, total, mask,
-                                     out_buf, out_off, out_count, &handled));
+                                     out_buf, out_off, out_count, &handled, skip_bits));
     if (handled) return SKS_OK;
   }
 
