@@ -302,11 +302,14 @@ int sks_comm_nccl_version(void); /* 0 when NCCL cannot be loaded */
 int sks_comm_allgather_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total,
                             sks_set **out_all);
 /* parallel_compute_pairwise_kmer_set_intersections over generate_all_pairs_from_vector + containment +
- * binomial_estimator (src/kmer-sketching.cpp:185-200), sharded: sks_comm_allgather_sets; then every rank enters its
- * share of the distinct k-mers (the key space is split by a hash) into its dictionary and counts their contribution
- * to all pairs, one NCCL reduce-scatter adds the shares up, and the rank finalises its own block rows [begin, end) =
- * sks_shard_range(n_total, rank, world).  Outputs as in sks_all_vs_all: out_counts / out_ani hold (end - begin) *
- * n_total entries, out_sizes n_total. */
+ * binomial_estimator (src/kmer-sketching.cpp:185-200), sharded.  The ranks split the KEY SPACE of the all-vs-all
+ * dictionary, not the rows: a k-mer belongs to the rank its hash names; every rank sends each of its keys (with the
+ * number of its set) to the owner -- one small all-gather of counts and one grouped send/receive, 1/world of what an
+ * all-gather of the sketches would move --, the owner enters what arrives into its dictionary and counts what its
+ * keys contribute to every pair, one NCCL reduce-scatter of the n x n partial counts adds the shares up, and the rank
+ * finalises its own block rows [begin, end) = sks_shard_range(n_total, rank, world).  (Sets the dictionary cannot
+ * take -- 16-byte keys of weight > 32 -- are all-gathered and compared row block by row block instead.)  Outputs as in
+ * sks_all_vs_all: out_counts / out_ani hold (end - begin) * n_total entries, out_sizes n_total. */
 int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total,
                            int32_t *out_counts, int32_t *out_sizes, double *out_ani);
 /* Sketch + exchange + comparison in one call for genomes already resident in HBM: `batch` holds the rank's block of the

@@ -80,6 +80,9 @@ struct DictView {
   uint16_t *set_of;            // [n_entries] (n_parts > 1 only)
   uint32_t *counters;          // [C_COUNT]
   uint32_t part, n_parts;      // only keys with owner(key) == part are entered (several ranks split the key space)
+  // FLAT source: the occurrences arrive as arrays (the keys this rank owns, routed here by the other ranks):
+  // flat_keys[q] is the 64-bit key, set_of[q] its set; set_ptr / set_off are not used.
+  const unsigned long long *flat_keys;
 };
 
 // A (set, range) group becomes a bitmap from this many ids on: 1024 in a range that is in full use (a list of 16-bit
@@ -145,7 +148,8 @@ __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_
                                                                    const __grid_constant__ Compact C) {
   const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
   const uint32_t lane = threadIdx.x & 31;
-  const bool compact = D.n_parts > 1;
+  const bool flat = D.flat_keys != nullptr;
+  const bool compact = D.n_parts > 1 && !flat;
   uint32_t s = 0, slot[kDictPer], set_id[kDictPer];
   unsigned long long key[kDictPer];
   uint4 cur[kDictPer];
@@ -155,7 +159,10 @@ __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_
     const uint32_t e = base + u * kDictThreads + threadIdx.x;
     slot[u] = kNoId;
     set_id[u] = 0;
-    if (e < D.n_entries) {
+    if (e < D.n_entries && flat) {
+      key[u] = D.flat_keys[e];
+      slot[u] = key[u] ? hash_slot(hash_key(key[u]), D.cap) : D.cap;
+    } else if (e < D.n_entries) {
       if (!have) {
         s = find_set(D.set_off, D.n_sets, e);
         have = true;
@@ -253,13 +260,70 @@ __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_
   }
 }
 
+// R: several ranks, before the exchange: every key of the rank's own sets, compacted to 64 bits, with the global number
+// of its set, grouped by the rank that owns the key (hash_owner).  kScatter == false counts, true scatters to
+// out[offset[owner] + position] (positions handed out by cursor[owner]; the order inside a group does not matter).
+template <int KW, bool kScatter>
+__global__ void __launch_bounds__(kDictThreads)
+    route_owner_kernel(const __grid_constant__ DictView D, const __grid_constant__ Compact C, uint32_t world, uint32_t set_base,
+                       unsigned long long *__restrict__ counts, const unsigned long long *__restrict__ offset,
+                       unsigned long long *__restrict__ cursor, unsigned long long *__restrict__ out_keys,
+                       uint16_t *__restrict__ out_sets) {
+  const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t s = 0;
+  bool have = false;
+#pragma unroll
+  for (int u = 0; u < kDictPer; ++u) {
+    const uint32_t e = base + u * kDictThreads + threadIdx.x;
+    int owner = -1;
+    unsigned long long key = 0;
+    if (e < D.n_entries) {
+      if (!have) {
+        s = find_set(D.set_off, D.n_sets, e);
+        have = true;
+      } else {
+        while (e >= __ldg(D.set_off + s + 1)) ++s;
+      }
+      key = load_key<KW>(D.set_ptr[s], e - __ldg(D.set_off + s), C);
+      owner = (int)hash_owner(hash_key(key), world);
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, owner);
+    if (owner < 0) continue;
+    const uint32_t leader = (uint32_t)(__ffs(peers) - 1);
+    if (!kScatter) {
+      if (lane == leader) atomicAdd(counts + owner, (unsigned long long)__popc(peers));
+    } else {
+      unsigned long long first = 0;
+      if (lane == leader) first = atomicAdd(cursor + owner, (unsigned long long)__popc(peers));
+      first = __shfl_sync(peers, first, (int)leader);
+      const unsigned long long at = offset[owner] + first + (unsigned long long)__popc(peers & ((1u << lane) - 1));
+      out_keys[at] = key;
+      out_sets[at] = (uint16_t)(set_base + s);
+    }
+  }
+}
+
+__global__ void route_owner_offsets_kernel(const unsigned long long *__restrict__ counts, int world,
+                                           unsigned long long *__restrict__ offset, unsigned long long *__restrict__ cursor) {
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int r = 0; r < world; ++r) {
+      offset[r] = run;
+      cursor[r] = 0;
+      run += counts[r];
+    }
+  }
+}
+
 // D2a: entry -> id; sizes of the posting lists and of the (range, set) groups.
 __global__ void __launch_bounds__(kDictThreads) dict_ids_kernel(const __grid_constant__ DictView D,
                                                                 uint32_t *__restrict__ group_cnt,
                                                                 uint32_t *__restrict__ post_cnt) {
   const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
   const uint32_t lane = threadIdx.x & 31;
-  const bool compact = D.n_parts > 1;
+  const bool flat = D.flat_keys != nullptr;
+  const bool compact = D.n_parts > 1 && !flat;
   const uint32_t n_occ = compact ? D.counters[C_MINE] : D.n_entries;
   if (base >= n_occ) return;
   uint32_t s = 0;
@@ -269,7 +333,7 @@ __global__ void __launch_bounds__(kDictThreads) dict_ids_kernel(const __grid_con
     const uint32_t e = base + u * kDictThreads + threadIdx.x;
     uint32_t bin = kNoId;
     if (e < n_occ) {
-      if (compact) {
+      if (compact || flat) {
         s = D.set_of[e];
       } else if (!have) {
         s = find_set(D.set_off, D.n_sets, e);
@@ -311,7 +375,8 @@ __global__ void __launch_bounds__(kDictThreads)
                         const uint32_t *__restrict__ group_end, uint32_t *__restrict__ cursor, uint4 *__restrict__ payload,
                         const uint32_t *__restrict__ post_begin, uint16_t *__restrict__ postings) {
   const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
-  const bool compact = D.n_parts > 1;
+  const bool flat = D.flat_keys != nullptr;
+  const bool compact = D.n_parts > 1 && !flat;
   const uint32_t n_occ = compact ? D.counters[C_MINE] : D.n_entries;
   uint32_t s = 0;
   bool have = false;
@@ -319,7 +384,7 @@ __global__ void __launch_bounds__(kDictThreads)
   for (int u = 0; u < kDictPer; ++u) {
     const uint32_t e = base + u * kDictThreads + threadIdx.x;
     if (e >= n_occ) continue;
-    if (compact) {
+    if (compact || flat) {
       s = D.set_of[e];
     } else if (!have) {
       s = find_set(D.set_off, D.n_sets, e);
@@ -566,16 +631,25 @@ bool all_pairs_dict_eligible(sks_set *const *sets, int64_t n) {
 // *raw_out may come in holding the matrix of earlier calls (other shares of the key space): the counts are added to
 // it.  *h_overflow points at a pinned word that is non-zero, once the stream has been synchronised, if the table was
 // too small (then the counts are incomplete and the caller takes another route).
+// With `flat` the occurrences do not come from `sets` (unused then) but as arrays: the keys this rank owns, routed here
+// by all ranks (all_pairs_route + an all-to-all), each with the global number of its set.
 int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, int part, int n_parts,
-                  bool symmetric, int64_t raw_rows, BufferRef *raw_out, BufferRef *sizes_out, const uint32_t **h_overflow) {
+                  bool symmetric, int64_t raw_rows, BufferRef *raw_out, BufferRef *sizes_out, const uint32_t **h_overflow,
+                  const FlatKeys *flat) {
   const uint32_t n_sets = (uint32_t)n;
   if (symmetric && !(row_begin == 0 && row_end == n)) return set_error(SKS_ERR_INVALID, "mirroring needs all rows");
   if (raw_rows < row_end - row_begin) return set_error(SKS_ERR_INVALID, "raw matrix too small");
-  const int kw = sets[0]->key_words;
+  const int kw = flat ? 1 : sets[0]->key_words;
   Compact compact = {};
   if (kw == 2 && !make_compact(sets[0]->mask, &compact)) return set_error(SKS_ERR_INVALID, "mask too wide for the dictionary");
   uint64_t total = 0;
-  for (int64_t i = 0; i < n; ++i) total += (uint64_t)sets[i]->count;
+  if (flat) {
+    total = flat->n;
+    part = 0;
+    n_parts = 1;
+  } else {
+    for (int64_t i = 0; i < n; ++i) total += (uint64_t)sets[i]->count;
+  }
   if (total >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "too many keys for the dictionary");
   const uint32_t K = (uint32_t)total;
   // this rank enters about K / n_parts keys (the hash spreads the DISTINCT keys evenly; a widely shared key brings all
@@ -631,9 +705,9 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
   uint32_t at = 0;
   for (uint32_t s = 0; s < n_sets; ++s) {
     h_off[s] = at;
-    h_ptr[s] = static_cast<const char *>(sets[s]->buf->ptr) + sets[s]->byte_off;
-    h_sizes[s] = (int32_t)sets[s]->count;
-    at += (uint32_t)sets[s]->count;
+    h_ptr[s] = flat ? nullptr : static_cast<const char *>(sets[s]->buf->ptr) + sets[s]->byte_off;
+    h_sizes[s] = flat ? flat->h_sizes[s] : (int32_t)sets[s]->count;
+    at += flat ? 0u : (uint32_t)sets[s]->count;
   }
   h_off[n_sets] = at;
   SKS_CUDA_TRY(cudaMemcpyAsync(d_off, stage, sz_off + sz_ptr + sz_sizes, cudaMemcpyHostToDevice, ctx->stream));
@@ -656,6 +730,8 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
   D.counters = d_counters;
   D.part = (uint32_t)part;
   D.n_parts = (uint32_t)std::max(n_parts, 1);
+  D.flat_keys = flat ? flat->keys : nullptr;
+  if (flat) D.set_of = const_cast<uint16_t *>(flat->sets);
   const unsigned entry_grid = (K + kDictChunk - 1) / kDictChunk;
   const unsigned wide_grid = (unsigned)ctx->sm_count * 8;
   {
@@ -726,6 +802,76 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
   return SKS_OK;
 }
 
+// R (several ranks): the keys of this rank's sets (compacted to 64 bits) and the global numbers of their sets, grouped
+// by owning rank: *out_keys / *out_sets hold all of them, group r at offset sum(counts[0..r)); d_counts = `world`
+// 64-bit counts on the device (for the ranks' exchange of counts).
+int all_pairs_route(sks_ctx *ctx, sks_set *const *sets, int64_t n_local, int64_t set_base, int world, BufferRef *out_keys,
+                    BufferRef *out_sets, BufferRef *ctl_out, unsigned long long **d_counts) {
+  uint64_t total = 0;
+  for (int64_t i = 0; i < n_local; ++i) total += (uint64_t)sets[i]->count;
+  if (total >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "too many keys for the dictionary");
+  const uint32_t K = (uint32_t)total, n_sets = (uint32_t)n_local;
+  const int kw = n_local ? sets[0]->key_words : 1;
+  Compact compact = {};
+  if (kw == 2 && !make_compact(sets[0]->mask, &compact)) return set_error(SKS_ERR_INVALID, "mask too wide for the dictionary");
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t sz_w = align(8 * (size_t)world), sz_off = align(4 * ((size_t)n_sets + 1)), sz_ptr = align(8 * (size_t)std::max<uint32_t>(n_sets, 1));
+  SKS_TRY(alloc_buffer(ctx, 3 * sz_w + sz_off + sz_ptr, ctl_out));
+  char *cb = static_cast<char *>((*ctl_out)->ptr);
+  unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(cb), *d_offs = d_cnt + sz_w / 8, *d_cur = d_offs + sz_w / 8;
+  uint32_t *d_off = reinterpret_cast<uint32_t *>(cb + 3 * sz_w);
+  const void **d_ptr = reinterpret_cast<const void **>(cb + 3 * sz_w + sz_off);
+  SKS_TRY(alloc_buffer(ctx, 8 * (size_t)std::max<uint32_t>(K, 2), out_keys));
+  SKS_TRY(alloc_buffer(ctx, 2 * (size_t)std::max<uint32_t>(K, 8), out_sets));
+  char *stage = nullptr;
+  SKS_TRY(ctx_pinned(ctx, sz_off + sz_ptr, reinterpret_cast<void **>(&stage)));
+  uint32_t *h_off = reinterpret_cast<uint32_t *>(stage);
+  const void **h_ptr = reinterpret_cast<const void **>(stage + sz_off);
+  uint32_t at = 0;
+  for (uint32_t s = 0; s < n_sets; ++s) {
+    h_off[s] = at;
+    h_ptr[s] = static_cast<const char *>(sets[s]->buf->ptr) + sets[s]->byte_off;
+    at += (uint32_t)sets[s]->count;
+  }
+  h_off[n_sets] = at;
+  SKS_CUDA_TRY(cudaMemcpyAsync(d_off, stage, sz_off + sz_ptr, cudaMemcpyHostToDevice, ctx->stream));
+  SKS_CUDA_TRY(cudaMemsetAsync(d_cnt, 0, sz_w, ctx->stream));
+  *d_counts = d_cnt;
+  if (K == 0) return SKS_OK;
+  DictView D = {};
+  D.set_ptr = d_ptr;
+  D.set_off = d_off;
+  D.n_sets = n_sets;
+  D.n_entries = K;
+  const unsigned grid = (K + kDictChunk - 1) / kDictChunk;
+  unsigned long long *ok = static_cast<unsigned long long *>((*out_keys)->ptr);
+  uint16_t *os = static_cast<uint16_t *>((*out_sets)->ptr);
+  KernelTimer timer(ctx, SKS_KERNEL_DICT);
+  if (kw == 1) {
+    route_owner_kernel<1, false><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, (uint32_t)world, (uint32_t)set_base, d_cnt, nullptr, nullptr, nullptr, nullptr);
+    route_owner_offsets_kernel<<<1, 32, 0, ctx->stream>>>(d_cnt, world, d_offs, d_cur);
+    route_owner_kernel<1, true><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, (uint32_t)world, (uint32_t)set_base, nullptr, d_offs, d_cur, ok, os);
+  } else {
+    route_owner_kernel<2, false><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, (uint32_t)world, (uint32_t)set_base, d_cnt, nullptr, nullptr, nullptr, nullptr);
+    route_owner_offsets_kernel<<<1, 32, 0, ctx->stream>>>(d_cnt, world, d_offs, d_cur);
+    route_owner_kernel<2, true><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, (uint32_t)world, (uint32_t)set_base, nullptr, d_offs, d_cur, ok, os);
+  }
+  SKS_CUDA_TRY(cudaGetLastError());
+  ctx->launches += 3;
+  return SKS_OK;
+}
+
+// Can the sets of a sharded run take the dictionary (decided from what every rank knows after the header exchange)?
+bool all_pairs_dict_usable(int key_words, const uint64_t mask[2], int64_t n_total, uint64_t total_keys) {
+  static const bool enabled = getenv("SKS_DICT_INTERSECT") ? atoi(getenv("SKS_DICT_INTERSECT")) != 0 : true;
+  if (!enabled || n_total < 2 || n_total > 65536 || total_keys >= (1ull << 31)) return false;
+  if (key_words == 2) {
+    Compact c;
+    if (!make_compact(mask, &c)) return false;
+  }
+  return key_words == 1 || key_words == 2;
+}
+
 // F: from raw off-diagonal counts of the rows [row_begin, row_begin + n_rows) to full rows (mirror, diagonal) and ANI.
 int all_pairs_finalize(sks_ctx *ctx, const int32_t *raw_rows, const int32_t *d_sizes, int64_t n, int64_t row_begin,
                        int64_t n_rows, bool symmetric, int weight, BufferRef *counts, BufferRef *ani) {
@@ -753,7 +899,7 @@ int all_pairs_dict(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_be
   const bool symmetric = row_begin == 0 && row_end == n && parts == 1;
   for (int p = 0; p < parts; ++p)
     SKS_TRY(all_pairs_raw(ctx, sets, n, row_begin, row_end, p, parts, symmetric, row_end - row_begin, &raw, p == 0 ? &sizes : nullptr,
-                          p == parts - 1 ? h_overflow : nullptr));
+                          p == parts - 1 ? h_overflow : nullptr, nullptr));
   SKS_TRY(all_pairs_finalize(ctx, static_cast<const int32_t *>(raw->ptr), static_cast<const int32_t *>(sizes->ptr), n, row_begin,
                              row_end - row_begin, symmetric, sets[0]->weight, counts, ani));
   if (sizes_out) *sizes_out = sizes;

@@ -2,10 +2,11 @@
 //
 // The reference's only parallelism is `cilk_for` over FASTA files (src/kmer_set.cpp:124-131) and over set pairs
 // (src/kmer_set.cpp:179-182).  Sharded over GPUs that becomes: genomes are split into contiguous blocks by rank,
-// every rank sketches its block, the sketches are exchanged once (sks_comm_allgather_sets), the ranks then split the KEY
-// SPACE of the all-vs-all dictionary (csrc/sks_allpairs.cu): each enters its share of the distinct k-mers and counts
-// what they contribute to every pair, and one reduce-scatter of the n x n partial counts leaves every rank with its
-// own complete block rows of the pair matrix (generate_all_pairs_from_vector order, src/generators.hpp:44-58).  One long sequence (BASELINE
+// every rank sketches its block, the ranks split the KEY SPACE of the all-vs-all dictionary (csrc/sks_allpairs.cu) by a
+// hash, every key travels once to the rank that owns it, each owner counts what its k-mers contribute to every pair, and
+// one reduce-scatter of the n x n partial counts leaves every rank with its own complete block rows of the pair matrix
+// (generate_all_pairs_from_vector order, src/generators.hpp:44-58).  sks_comm_allgather_sets puts every sketch on every
+// rank for callers that want that.  One long sequence (BASELINE
 // configs[2]) is split by position instead; its partial sketches are routed by key range, so that every rank
 // sort-uniques 1/world of the keys (sks_sketch_sequence_sharded).
 //
@@ -208,6 +209,80 @@ int contiguous_keys(sks_ctx *ctx, sks_set *const *local, int64_t n_local, const 
 
 }  // namespace sks
 
+namespace sks {
+namespace {
+// What every rank knows about every rank's sets after one small all-gather (the only host synchronisation of the
+// exchange): per rank [n_keys, key_words, window, mask lo, mask hi, count of each of its `per` sets].
+struct Headers {
+  std::vector<long long> all;
+  size_t hdr = 0;
+  int kw = 0, window = 0;
+  uint64_t mask[2] = {0, 0};
+  uint64_t total_keys = 0;
+  const long long *of(int r) const { return all.data() + hdr * (size_t)r; }
+};
+
+int check_local_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total) {
+  const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
+  int64_t begin = 0, end = 0;
+  sks_shard_range(n_total, rank, world, &begin, &end);
+  if (end - begin != n_local)
+    return set_error(SKS_ERR_MISMATCH, "rank %d holds %lld sets, its block of %lld sets over %d ranks has %lld", rank,
+                     (long long)n_local, (long long)n_total, world, (long long)(end - begin));
+  for (int64_t i = 0; i < n_local; ++i) {
+    if (!local[i] || local[i]->repr != SKS_REPR_SORTED) return set_error(SKS_ERR_INVALID, "the exchange needs SORTED sets");
+    SKS_TRY(check_pair(local[0], local[i]));
+    if (local[i]->device != ctx->device) return set_error(SKS_ERR_INVALID, "set lives on another device");
+  }
+  if (comm && comm->device != ctx->device) return set_error(SKS_ERR_INVALID, "communicator and context are on different devices");
+  return SKS_OK;
+}
+
+int exchange_headers(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total, Headers *H) {
+  const int world = comm->world;
+  const int64_t per = (n_total + world - 1) / world;
+  const size_t hdr = 5 + (size_t)per;
+  BufferRef d_hdr;
+  SKS_TRY(alloc_buffer(ctx, 8 * hdr * ((size_t)world + 1), &d_hdr));
+  long long *h_mine = nullptr, *h_all = nullptr;
+  SKS_TRY(ctx_pinned(ctx, 8 * hdr * ((size_t)world + 1), reinterpret_cast<void **>(&h_mine)));
+  h_all = h_mine + hdr;
+  memset(h_mine, 0, 8 * hdr);
+  int64_t my_n = 0;
+  for (int64_t i = 0; i < n_local; ++i) my_n += local[i]->count;
+  h_mine[0] = my_n;
+  h_mine[1] = n_local ? local[0]->key_words : 0;
+  h_mine[2] = n_local ? local[0]->window : 0;
+  h_mine[3] = n_local ? (long long)local[0]->mask[0] : 0;
+  h_mine[4] = n_local ? (long long)local[0]->mask[1] : 0;
+  for (int64_t i = 0; i < n_local; ++i) h_mine[5 + i] = local[i]->count;
+  long long *d_mine = static_cast<long long *>(d_hdr->ptr), *d_all = d_mine + hdr;
+  SKS_CUDA_TRY(cudaMemcpyAsync(d_mine, h_mine, 8 * hdr, cudaMemcpyHostToDevice, ctx->stream));
+  SKS_NCCL_TRY(nccl()->AllGather(d_mine, d_all, hdr, ncclInt64, comm->comm, ctx->stream));
+  SKS_CUDA_TRY(cudaMemcpyAsync(h_all, d_all, 8 * hdr * world, cudaMemcpyDeviceToHost, ctx->stream));
+  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  H->all.assign(h_all, h_all + hdr * world);  // (the pinned ring may hand the staging area out again)
+  H->hdr = hdr;
+  H->kw = H->window = 0;
+  H->total_keys = 0;
+  for (int r = 0; r < world; ++r) {  // every non-empty rank must agree on the key layout
+    const long long *h = H->of(r);
+    H->total_keys += (uint64_t)h[0];
+    if (h[1] == 0) continue;  // a rank without sets
+    if (H->kw == 0) {
+      H->kw = (int)h[1];
+      H->window = (int)h[2];
+      H->mask[0] = (uint64_t)h[3];
+      H->mask[1] = (uint64_t)h[4];
+    } else if (H->kw != (int)h[1] || H->mask[0] != (uint64_t)h[3] || H->mask[1] != (uint64_t)h[4]) {
+      return set_error(SKS_ERR_MISMATCH, "ranks sketched with different masks or key widths");
+    }
+  }
+  return SKS_OK;
+}
+}  // namespace
+}  // namespace sks
+
 using namespace sks;
 
 extern "C" {
@@ -292,16 +367,7 @@ int sks_comm_allgather_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local,
                             sks_set **out_all) {
   if (!ctx || !out_all || n_local < 0 || n_total < 0 || (n_local > 0 && !local)) return set_error(SKS_ERR_INVALID, "bad argument");
   const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
-  int64_t begin = 0, end = 0;
-  sks_shard_range(n_total, rank, world, &begin, &end);
-  if (end - begin != n_local)
-    return set_error(SKS_ERR_MISMATCH, "rank %d holds %lld sets, its block of %lld sets over %d ranks has %lld", rank,
-                     (long long)n_local, (long long)n_total, world, (long long)(end - begin));
-  for (int64_t i = 0; i < n_local; ++i) {
-    if (!local[i] || local[i]->repr != SKS_REPR_SORTED) return set_error(SKS_ERR_INVALID, "the exchange needs SORTED sets");
-    SKS_TRY(check_pair(local[0], local[i]));
-    if (local[i]->device != ctx->device) return set_error(SKS_ERR_INVALID, "set lives on another device");
-  }
+  SKS_TRY(check_local_sets(ctx, comm, local, n_local, n_total));
   DeviceGuard guard(ctx->device);
   auto share = [&](const sks_set *s) {  // a second handle on the same keys
     sks_set *c = new sks_set(*s);
@@ -311,50 +377,18 @@ int sks_comm_allgather_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local,
     for (int64_t i = 0; i < n_local; ++i) out_all[i] = share(local[i]);
     return SKS_OK;
   }
-  if (comm->device != ctx->device) return set_error(SKS_ERR_INVALID, "communicator and context are on different devices");
   SKS_TRY(need_nccl());
-  // header of every rank: [n_keys, key_words, window, mask lo, mask hi, count of each of its `per` sets]
-  const int64_t per = (n_total + world - 1) / world;
-  const size_t hdr = 5 + (size_t)per;
-  BufferRef d_hdr;
-  SKS_TRY(alloc_buffer(ctx, 8 * hdr * ((size_t)world + 1), &d_hdr));
-  long long *h_mine = nullptr, *h_all = nullptr;
-  SKS_TRY(ctx_pinned(ctx, 8 * hdr * ((size_t)world + 1), reinterpret_cast<void **>(&h_mine)));
-  h_all = h_mine + hdr;
+  KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
+  Headers H;
+  SKS_TRY(exchange_headers(ctx, comm, local, n_local, n_total, &H));
+  const size_t hdr = H.hdr;
+  const long long *h_all = H.all.data();
+  const int kw = H.kw, window = H.window;
+  uint64_t mask[2] = {H.mask[0], H.mask[1]};
   const void *my_keys = nullptr;
-  int64_t my_n = 0;
+  int64_t my_n = 0, total_remote = 0;
   BufferRef packed;
   SKS_TRY(contiguous_keys(ctx, local, n_local, &my_keys, &my_n, &packed));
-  memset(h_mine, 0, 8 * hdr);
-  h_mine[0] = my_n;
-  h_mine[1] = n_local ? local[0]->key_words : 0;
-  h_mine[2] = n_local ? local[0]->window : 0;
-  h_mine[3] = n_local ? (long long)local[0]->mask[0] : 0;
-  h_mine[4] = n_local ? (long long)local[0]->mask[1] : 0;
-  for (int64_t i = 0; i < n_local; ++i) h_mine[5 + i] = local[i]->count;
-  long long *d_mine = static_cast<long long *>(d_hdr->ptr), *d_all = d_mine + hdr;
-  KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
-  SKS_CUDA_TRY(cudaMemcpyAsync(d_mine, h_mine, 8 * hdr, cudaMemcpyHostToDevice, ctx->stream));
-  SKS_NCCL_TRY(nccl()->AllGather(d_mine, d_all, hdr, ncclInt64, comm->comm, ctx->stream));
-  SKS_CUDA_TRY(cudaMemcpyAsync(h_all, d_all, 8 * hdr * world, cudaMemcpyDeviceToHost, ctx->stream));
-  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the one host synchronisation of the exchange
-  // every non-empty rank must agree on the key layout
-  int kw = 0, window = 0;
-  uint64_t mask[2] = {0, 0};
-  int64_t total_remote = 0;
-  for (int r = 0; r < world; ++r) {
-    const long long *h = h_all + hdr * r;
-    if (h[1] == 0) continue;  // a rank without sets
-    if (kw == 0) {
-      kw = (int)h[1];
-      window = (int)h[2];
-      mask[0] = (uint64_t)h[3];
-      mask[1] = (uint64_t)h[4];
-    } else if (kw != (int)h[1] || mask[0] != (uint64_t)h[3] || mask[1] != (uint64_t)h[4]) {
-      return set_error(SKS_ERR_MISMATCH, "ranks sketched with different masks or key widths");
-    }
-    if (r != rank) total_remote += h[0];
-  }
   const size_t kb = (size_t)std::max(kw, 1) * 8;
   // One in-place ncclAllGather of equal slots (the ranks' key counts differ by a few per cent at most: the slot is the
   // largest): slot r of the inbox receives rank r's keys, mine go there by a device copy first.
@@ -396,48 +430,115 @@ int sks_comm_allgather_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local,
 
 int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total,
                            int32_t *out_counts, int32_t *out_sizes, double *out_ani) {
-  if (!ctx) return set_error(SKS_ERR_INVALID, "null context");
+  if (!ctx || n_local < 0 || n_total < 0 || (n_local > 0 && !local)) return set_error(SKS_ERR_INVALID, "bad argument");
   const int world = comm ? comm->world : 1, rank = comm ? comm->rank : 0;
-  std::vector<sks_set *> all((size_t)std::max<int64_t>(n_total, 1), nullptr);
-  struct Release {
-    sks_ctx *c;
-    std::vector<sks_set *> &v;
-    ~Release() {
-      for (sks_set *s : v)
-        if (s) sks_set_destroy(c, s);
-    }
-  } release{ctx, all};
-  SKS_TRY(sks_comm_allgather_sets(ctx, comm, local, n_local, n_total, all.data()));
   int64_t begin = 0, end = 0;
   sks_shard_range(n_total, rank, world, &begin, &end);
-  if (world == 1 || n_total < 2 || !all_pairs_dict_eligible(all.data(), n_total))
-    return sks_all_vs_all(ctx, all.data(), n_total, begin, end, out_counts, out_sizes, out_ani);
-  // Several ranks split the KEY SPACE of the dictionary, not the rows: every rank enters 1 / world of the distinct
-  // keys (all sets are here after the exchange), counts what its keys contribute to every pair, and one reduce-scatter
-  // adds the shares up and leaves every rank with its own block rows.
+  auto by_rows = [&]() {  // every set on every rank, then the rank's rows through the single-device call
+    std::vector<sks_set *> all((size_t)std::max<int64_t>(n_total, 1), nullptr);
+    int st = sks_comm_allgather_sets(ctx, comm, local, n_local, n_total, all.data());
+    if (st == SKS_OK) st = sks_all_vs_all(ctx, all.data(), n_total, begin, end, out_counts, out_sizes, out_ani);
+    for (sks_set *s : all)
+      if (s) sks_set_destroy(ctx, s);
+    return st;
+  };
+  if (world == 1) return by_rows();
+  SKS_TRY(check_local_sets(ctx, comm, local, n_local, n_total));
+  SKS_TRY(need_nccl());
   DeviceGuard guard(ctx->device);
+  Headers H;
+  {
+    KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
+    SKS_TRY(exchange_headers(ctx, comm, local, n_local, n_total, &H));
+  }
+  if (!all_pairs_dict_usable(H.kw, H.mask, n_total, H.total_keys)) return by_rows();  // the same decision on every rank
+  // The ranks split the KEY SPACE of the all-vs-all dictionary (csrc/sks_allpairs.cu), not the rows.  A key belongs to
+  // the rank its hash names: every rank sends each of its keys (with the number of its set) to the owner -- 1/world
+  // of what an all-gather of the sketches would move --, the owner enters what arrives into its dictionary and counts
+  // what its keys contribute to EVERY pair, and one reduce-scatter of the n x n partial counts leaves every rank with
+  // its own complete block rows.
+  const size_t W = (size_t)world;
+  BufferRef r_keys, r_sets, r_ctl, d_all_buf, in_keys, in_sets;
+  unsigned long long *d_counts = nullptr;
+  SKS_TRY(all_pairs_route(ctx, local, n_local, begin, world, &r_keys, &r_sets, &r_ctl, &d_counts));
+  SKS_TRY(alloc_buffer(ctx, 8 * W * W, &d_all_buf));
+  unsigned long long *h_all = nullptr;
+  SKS_TRY(ctx_pinned(ctx, 8 * W * W, reinterpret_cast<void **>(&h_all)));
+  std::vector<unsigned long long> cnt;
+  {
+    KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
+    SKS_NCCL_TRY(nccl()->AllGather(d_counts, d_all_buf->ptr, W, ncclUint64, comm->comm, ctx->stream));
+    SKS_CUDA_TRY(cudaMemcpyAsync(h_all, d_all_buf->ptr, 8 * W * W, cudaMemcpyDeviceToHost, ctx->stream));
+    SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    cnt.assign(h_all, h_all + W * W);
+  }
+  auto sends = [&](int src, int dst) { return (size_t)cnt[(size_t)src * W + dst]; };
+  size_t n_in = 0;
+  std::vector<size_t> in_at(W), out_at(W);
+  for (int src = 0; src < world; ++src) {
+    in_at[src] = n_in;
+    n_in += sends(src, rank);
+  }
+  {
+    size_t at = 0;
+    for (int dst = 0; dst < world; ++dst) {
+      out_at[dst] = at;
+      at += sends(rank, dst);
+    }
+  }
+  if (n_in >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "too many keys arrive at rank %d", rank);
+  SKS_TRY(alloc_buffer(ctx, 8 * std::max<size_t>(n_in, 2), &in_keys));
+  SKS_TRY(alloc_buffer(ctx, 2 * std::max<size_t>(n_in, 8), &in_sets));
+  {
+    KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
+    const char *sk = static_cast<const char *>(r_keys->ptr), *ss = static_cast<const char *>(r_sets->ptr);
+    char *ik = static_cast<char *>(in_keys->ptr), *is = static_cast<char *>(in_sets->ptr);
+    SKS_NCCL_TRY(nccl()->GroupStart());
+    for (int r = 0; r < world; ++r) {
+      if (r == rank) continue;
+      if (sends(rank, r)) {
+        SKS_NCCL_TRY(nccl()->Send(sk + 8 * out_at[r], 8 * sends(rank, r), ncclUint8, r, comm->comm, ctx->stream));
+        SKS_NCCL_TRY(nccl()->Send(ss + 2 * out_at[r], 2 * sends(rank, r), ncclUint8, r, comm->comm, ctx->stream));
+      }
+      if (sends(r, rank)) {
+        SKS_NCCL_TRY(nccl()->Recv(ik + 8 * in_at[r], 8 * sends(r, rank), ncclUint8, r, comm->comm, ctx->stream));
+        SKS_NCCL_TRY(nccl()->Recv(is + 2 * in_at[r], 2 * sends(r, rank), ncclUint8, r, comm->comm, ctx->stream));
+      }
+    }
+    SKS_NCCL_TRY(nccl()->GroupEnd());
+    if (sends(rank, rank)) {
+      SKS_CUDA_TRY(cudaMemcpyAsync(ik + 8 * in_at[rank], sk + 8 * out_at[rank], 8 * sends(rank, rank), cudaMemcpyDeviceToDevice, ctx->stream));
+      SKS_CUDA_TRY(cudaMemcpyAsync(is + 2 * in_at[rank], ss + 2 * out_at[rank], 2 * sends(rank, rank), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  // the sizes of all sets (ANI denominators, the diagonal) came with the headers
+  std::vector<int32_t> h_sizes((size_t)n_total);
+  for (int r = 0; r < world; ++r) {
+    int64_t b = 0, e = 0;
+    sks_shard_range(n_total, r, world, &b, &e);
+    for (int64_t i = b; i < e; ++i) h_sizes[(size_t)i] = (int32_t)H.of(r)[5 + (i - b)];
+  }
+  const FlatKeys flat = {static_cast<const unsigned long long *>(in_keys->ptr), static_cast<const uint16_t *>(in_sets->ptr),
+                         (uint32_t)n_in, h_sizes.data()};
   const int64_t per = (n_total + world - 1) / world, n_rows = end - begin;
   BufferRef raw, sizes, mine, counts, ani;
   const uint32_t *overflow = nullptr;
-  int st = all_pairs_raw(ctx, all.data(), n_total, 0, n_total, rank, world, false, (int64_t)world * per, &raw, &sizes, &overflow);
-  if (st == SKS_ERR_CAPACITY) return sks_all_vs_all(ctx, all.data(), n_total, begin, end, out_counts, out_sizes, out_ani);
-  SKS_TRY(st);
+  SKS_TRY(all_pairs_raw(ctx, nullptr, n_total, 0, n_total, 0, 1, false, (int64_t)world * per, &raw, &sizes, &overflow, &flat));
   SKS_TRY(alloc_buffer(ctx, 4 * (size_t)per * n_total, &mine));
   {
     KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
     SKS_NCCL_TRY(nccl()->ReduceScatter(raw->ptr, mine->ptr, (size_t)per * n_total, ncclInt32, ncclSum, comm->comm, ctx->stream));
   }
   SKS_TRY(all_pairs_finalize(ctx, static_cast<const int32_t *>(mine->ptr), static_cast<const int32_t *>(sizes->ptr), n_total, begin,
-                             n_rows, false, all[0]->weight, &counts, out_ani ? &ani : nullptr));
+                             n_rows, false, sks_mask_weight(H.mask), &counts, out_ani ? &ani : nullptr));
   if (out_counts && n_rows)
     SKS_CUDA_TRY(cudaMemcpyAsync(out_counts, counts->ptr, 4 * (size_t)n_rows * n_total, cudaMemcpyDeviceToHost, ctx->stream));
   if (out_ani && n_rows)
     SKS_CUDA_TRY(cudaMemcpyAsync(out_ani, ani->ptr, 8 * (size_t)n_rows * n_total, cudaMemcpyDeviceToHost, ctx->stream));
-  if (out_sizes)
-    for (int64_t i = 0; i < n_total; ++i) out_sizes[i] = (int32_t)all[i]->count;
+  if (out_sizes) memcpy(out_sizes, h_sizes.data(), 4 * (size_t)n_total);
   SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  if (overflow && *overflow)  // (every rank completes the collective first; a full table is reported, not papered over)
-    return set_error(SKS_ERR_CAPACITY, "the dictionary of rank %d overflowed: its share of the key space is too uneven", rank);
+  if (overflow && *overflow)  // cannot happen: the table is sized by what arrived; reported, not papered over
+    return set_error(SKS_ERR_CAPACITY, "the dictionary of rank %d overflowed", rank);
   return SKS_OK;
 }
 
