@@ -263,12 +263,14 @@ __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_
 // R: several ranks, before the exchange: every key of the rank's own sets, compacted to 64 bits, with the global number
 // of its set, grouped by the rank that owns the key (hash_owner).  kScatter == false counts, true scatters to
 // out[offset[owner] + position] (positions handed out by cursor[owner]; the order inside a group does not matter).
+// `region_cap` > 0 (one pass): group r has room for region_cap entries at r * region_cap; the counts keep running past
+// it, which is how the caller notices an overflow and comes back with the exact two passes.
 template <int KW, bool kScatter>
 __global__ void __launch_bounds__(kDictThreads)
     route_owner_kernel(const __grid_constant__ DictView D, const __grid_constant__ Compact C, uint32_t world, uint32_t set_base,
                        unsigned long long *__restrict__ counts, const unsigned long long *__restrict__ offset,
                        unsigned long long *__restrict__ cursor, unsigned long long *__restrict__ out_keys,
-                       uint16_t *__restrict__ out_sets) {
+                       uint16_t *__restrict__ out_sets, unsigned long long region_cap) {
   const uint32_t base = blockIdx.x * (uint32_t)kDictChunk;
   const uint32_t lane = threadIdx.x & 31;
   uint32_t s = 0;
@@ -297,7 +299,9 @@ __global__ void __launch_bounds__(kDictThreads)
       unsigned long long first = 0;
       if (lane == leader) first = atomicAdd(cursor + owner, (unsigned long long)__popc(peers));
       first = __shfl_sync(peers, first, (int)leader);
-      const unsigned long long at = offset[owner] + first + (unsigned long long)__popc(peers & ((1u << lane) - 1));
+      const unsigned long long pos = first + (unsigned long long)__popc(peers & ((1u << lane) - 1));
+      if (region_cap && pos >= region_cap) continue;
+      const unsigned long long at = (region_cap ? (unsigned long long)owner * region_cap : offset[owner]) + pos;
       out_keys[at] = key;
       out_sets[at] = (uint16_t)(set_base + s);
     }
@@ -805,8 +809,11 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
 // R (several ranks): the keys of this rank's sets (compacted to 64 bits) and the global numbers of their sets, grouped
 // by owning rank: *out_keys / *out_sets hold all of them, group r at offset sum(counts[0..r)); d_counts = `world`
 // 64-bit counts on the device (for the ranks' exchange of counts).
-int all_pairs_route(sks_ctx *ctx, sks_set *const *sets, int64_t n_local, int64_t set_base, int world, BufferRef *out_keys,
-                    BufferRef *out_sets, BufferRef *ctl_out, unsigned long long **d_counts) {
+// region_cap > 0: one pass into fixed regions of that many entries per owner (group r at r * region_cap; counts beyond
+// the capacity mean the pass has to be repeated exactly); region_cap == 0: count, then scatter (two passes).
+size_t all_pairs_route_cap(uint64_t n_keys, int world) { return (size_t)(n_keys / world + n_keys / (4 * (uint64_t)world) + 4096); }
+int all_pairs_route(sks_ctx *ctx, sks_set *const *sets, int64_t n_local, int64_t set_base, int world, size_t region_cap,
+                    BufferRef *out_keys, BufferRef *out_sets, BufferRef *ctl_out, unsigned long long **d_counts) {
   uint64_t total = 0;
   for (int64_t i = 0; i < n_local; ++i) total += (uint64_t)sets[i]->count;
   if (total >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "too many keys for the dictionary");
@@ -821,8 +828,9 @@ int all_pairs_route(sks_ctx *ctx, sks_set *const *sets, int64_t n_local, int64_t
   unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(cb), *d_offs = d_cnt + sz_w / 8, *d_cur = d_offs + sz_w / 8;
   uint32_t *d_off = reinterpret_cast<uint32_t *>(cb + 3 * sz_w);
   const void **d_ptr = reinterpret_cast<const void **>(cb + 3 * sz_w + sz_off);
-  SKS_TRY(alloc_buffer(ctx, 8 * (size_t)std::max<uint32_t>(K, 2), out_keys));
-  SKS_TRY(alloc_buffer(ctx, 2 * (size_t)std::max<uint32_t>(K, 8), out_sets));
+  const size_t slots = region_cap ? region_cap * (size_t)world : (size_t)K;
+  SKS_TRY(alloc_buffer(ctx, 8 * std::max<size_t>(slots, 2), out_keys));
+  SKS_TRY(alloc_buffer(ctx, 2 * std::max<size_t>(slots, 8), out_sets));
   char *stage = nullptr;
   SKS_TRY(ctx_pinned(ctx, sz_off + sz_ptr, reinterpret_cast<void **>(&stage)));
   uint32_t *h_off = reinterpret_cast<uint32_t *>(stage);
@@ -847,17 +855,23 @@ int all_pairs_route(sks_ctx *ctx, sks_set *const *sets, int64_t n_local, int64_t
   unsigned long long *ok = static_cast<unsigned long long *>((*out_keys)->ptr);
   uint16_t *os = static_cast<uint16_t *>((*out_sets)->ptr);
   KernelTimer timer(ctx, SKS_KERNEL_DICT);
-  if (kw == 1) {
-    route_owner_kernel<1, false><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, (uint32_t)world, (uint32_t)set_base, d_cnt, nullptr, nullptr, nullptr, nullptr);
+  const uint32_t w = (uint32_t)world, sb = (uint32_t)set_base;
+  if (region_cap) {  // one pass: the cursors are the counts
+    if (kw == 1) route_owner_kernel<1, true><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, w, sb, nullptr, nullptr, d_cnt, ok, os, region_cap);
+    else route_owner_kernel<2, true><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, w, sb, nullptr, nullptr, d_cnt, ok, os, region_cap);
+    ctx->launches += 1;
+  } else if (kw == 1) {
+    route_owner_kernel<1, false><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, w, sb, d_cnt, nullptr, nullptr, nullptr, nullptr, 0);
     route_owner_offsets_kernel<<<1, 32, 0, ctx->stream>>>(d_cnt, world, d_offs, d_cur);
-    route_owner_kernel<1, true><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, (uint32_t)world, (uint32_t)set_base, nullptr, d_offs, d_cur, ok, os);
+    route_owner_kernel<1, true><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, w, sb, nullptr, d_offs, d_cur, ok, os, 0);
+    ctx->launches += 3;
   } else {
-    route_owner_kernel<2, false><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, (uint32_t)world, (uint32_t)set_base, d_cnt, nullptr, nullptr, nullptr, nullptr);
+    route_owner_kernel<2, false><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, w, sb, d_cnt, nullptr, nullptr, nullptr, nullptr, 0);
     route_owner_offsets_kernel<<<1, 32, 0, ctx->stream>>>(d_cnt, world, d_offs, d_cur);
-    route_owner_kernel<2, true><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, (uint32_t)world, (uint32_t)set_base, nullptr, d_offs, d_cur, ok, os);
+    route_owner_kernel<2, true><<<grid, kDictThreads, 0, ctx->stream>>>(D, compact, w, sb, nullptr, d_offs, d_cur, ok, os, 0);
+    ctx->launches += 3;
   }
   SKS_CUDA_TRY(cudaGetLastError());
-  ctx->launches += 3;
   return SKS_OK;
 }
 

@@ -219,7 +219,9 @@ struct Headers {
   int kw = 0, window = 0;
   uint64_t mask[2] = {0, 0};
   uint64_t total_keys = 0;
+  size_t n_extra = 0;
   const long long *of(int r) const { return all.data() + hdr * (size_t)r; }
+  const long long *extra(int r) const { return of(r) + (hdr - n_extra); }
 };
 
 int check_local_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total) {
@@ -238,10 +240,13 @@ int check_local_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_
   return SKS_OK;
 }
 
-int exchange_headers(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total, Headers *H) {
+// d_extra / n_extra: device words every rank appends to its record (H->extra(r) afterwards).
+int exchange_headers(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total, Headers *H,
+                     const unsigned long long *d_extra = nullptr, size_t n_extra = 0) {
   const int world = comm->world;
   const int64_t per = (n_total + world - 1) / world;
-  const size_t hdr = 5 + (size_t)per;
+  const size_t hdr = 5 + (size_t)per + n_extra;
+  H->n_extra = n_extra;
   BufferRef d_hdr;
   SKS_TRY(alloc_buffer(ctx, 8 * hdr * ((size_t)world + 1), &d_hdr));
   long long *h_mine = nullptr, *h_all = nullptr;
@@ -257,7 +262,9 @@ int exchange_headers(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_
   h_mine[4] = n_local ? (long long)local[0]->mask[1] : 0;
   for (int64_t i = 0; i < n_local; ++i) h_mine[5 + i] = local[i]->count;
   long long *d_mine = static_cast<long long *>(d_hdr->ptr), *d_all = d_mine + hdr;
-  SKS_CUDA_TRY(cudaMemcpyAsync(d_mine, h_mine, 8 * hdr, cudaMemcpyHostToDevice, ctx->stream));
+  SKS_CUDA_TRY(cudaMemcpyAsync(d_mine, h_mine, 8 * (hdr - n_extra), cudaMemcpyHostToDevice, ctx->stream));
+  if (n_extra)
+    SKS_CUDA_TRY(cudaMemcpyAsync(d_mine + (hdr - n_extra), d_extra, 8 * n_extra, cudaMemcpyDeviceToDevice, ctx->stream));
   SKS_NCCL_TRY(nccl()->AllGather(d_mine, d_all, hdr, ncclInt64, comm->comm, ctx->stream));
   SKS_CUDA_TRY(cudaMemcpyAsync(h_all, d_all, 8 * hdr * world, cudaMemcpyDeviceToHost, ctx->stream));
   SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
@@ -446,26 +453,107 @@ int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, 
   SKS_TRY(check_local_sets(ctx, comm, local, n_local, n_total));
   SKS_TRY(need_nccl());
   DeviceGuard guard(ctx->device);
+  const size_t W = (size_t)world;
+  const int64_t per = (n_total + world - 1) / world, n_rows = end - begin;
+  BufferRef raw, sizes, mine, counts, ani;
+  const uint32_t *overflow = nullptr;
   Headers H;
+  std::vector<int32_t> h_sizes;
+  auto sizes_from_headers = [&]() {  // the sizes of all sets (ANI denominators, the diagonal) come with the headers
+    h_sizes.assign((size_t)n_total, 0);
+    for (int r = 0; r < world; ++r) {
+      int64_t b = 0, e = 0;
+      sks_shard_range(n_total, r, world, &b, &e);
+      for (int64_t i = b; i < e; ++i) h_sizes[(size_t)i] = (int32_t)H.of(r)[5 + (i - b)];
+    }
+  };
+  auto finish = [&]() -> int {  // partial counts of all rows -> my complete rows -> counts / ANI on the host
+    SKS_TRY(alloc_buffer(ctx, 4 * (size_t)per * n_total, &mine));
+    {
+      KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
+      SKS_NCCL_TRY(nccl()->ReduceScatter(raw->ptr, mine->ptr, (size_t)per * n_total, ncclInt32, ncclSum, comm->comm, ctx->stream));
+    }
+    SKS_TRY(all_pairs_finalize(ctx, static_cast<const int32_t *>(mine->ptr), static_cast<const int32_t *>(sizes->ptr), n_total, begin,
+                               n_rows, false, sks_mask_weight(H.mask), &counts, out_ani ? &ani : nullptr));
+    if (out_counts && n_rows)
+      SKS_CUDA_TRY(cudaMemcpyAsync(out_counts, counts->ptr, 4 * (size_t)n_rows * n_total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_ani && n_rows)
+      SKS_CUDA_TRY(cudaMemcpyAsync(out_ani, ani->ptr, 8 * (size_t)n_rows * n_total, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_sizes) memcpy(out_sizes, h_sizes.data(), 4 * (size_t)n_total);
+    SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (overflow && *overflow)  // (every rank completes the collective first; a full table is reported, not papered over)
+      return set_error(SKS_ERR_CAPACITY, "the dictionary of rank %d overflowed", rank);
+    return SKS_OK;
+  };
+  // The ranks split the KEY SPACE of the all-vs-all dictionary (csrc/sks_allpairs.cu), not the rows: a key belongs to the
+  // rank its hash names, the owner counts what its keys contribute to EVERY pair, and one reduce-scatter of the n x n
+  // partial counts leaves every rank with its own complete block rows.  Two ways for the keys to reach their owners:
+  //   gather (two ranks): every sketch to every rank (sks_comm_allgather_sets), each rank enters only the keys it owns;
+  //   owner (more ranks): every rank sends each of its keys, with the number of its set, to the owner -- 1 / world of
+  //                       the bytes, and nobody scans keys that are not theirs.
+  static const int forced = [] {
+    const char *e = getenv("SKS_SHARD_ROUTE");
+    return !e ? 0 : (strcmp(e, "gather") == 0 ? 1 : (strcmp(e, "owner") == 0 ? 2 : 0));
+  }();
+  const bool by_owner = forced ? forced == 2 : world > 2;
+  if (!by_owner) {
+    std::vector<sks_set *> all((size_t)std::max<int64_t>(n_total, 1), nullptr);
+    struct Release {
+      sks_ctx *c;
+      std::vector<sks_set *> &v;
+      ~Release() {
+        for (sks_set *s : v)
+          if (s) sks_set_destroy(c, s);
+      }
+    } release{ctx, all};
+    SKS_TRY(sks_comm_allgather_sets(ctx, comm, local, n_local, n_total, all.data()));
+    if (!all_pairs_dict_eligible(all.data(), n_total))  // the same decision on every rank: all hold the same sets
+      return sks_all_vs_all(ctx, all.data(), n_total, begin, end, out_counts, out_sizes, out_ani);
+    H.mask[0] = all[0]->mask[0];
+    H.mask[1] = all[0]->mask[1];
+    h_sizes.resize((size_t)n_total);
+    for (int64_t i = 0; i < n_total; ++i) h_sizes[(size_t)i] = (int32_t)all[i]->count;
+    int st = all_pairs_raw(ctx, all.data(), n_total, 0, n_total, rank, world, false, (int64_t)world * per, &raw, &sizes, &overflow, nullptr);
+    if (st != SKS_OK) return st;
+    return finish();
+  }
+  // owner route: group my keys by owner first (one pass into regions with 25 % slack; the exact two passes if that
+  // overflows anywhere), then ONE all-gather carries the set sizes and the group counts of every rank
+  uint64_t my_keys_n = 0;
+  for (int64_t i = 0; i < n_local; ++i) my_keys_n += (uint64_t)local[i]->count;
+  const bool local_ok = n_local == 0 || all_pairs_dict_usable(local[0]->key_words, local[0]->mask, 2, my_keys_n);
+  BufferRef r_keys, r_sets, r_ctl, zero_counts, in_keys, in_sets;
+  unsigned long long *d_counts = nullptr;
+  size_t my_cap = all_pairs_route_cap(my_keys_n, world);
+  if (local_ok) {
+    SKS_TRY(all_pairs_route(ctx, local, n_local, begin, world, my_cap, &r_keys, &r_sets, &r_ctl, &d_counts));
+  } else {  // these sets cannot take the dictionary: say so with counts of ~0 (all ranks then fall back together)
+    SKS_TRY(alloc_buffer(ctx, 8 * W, &zero_counts));
+    SKS_CUDA_TRY(cudaMemsetAsync(zero_counts->ptr, 0xFF, 8 * W, ctx->stream));
+    d_counts = static_cast<unsigned long long *>(zero_counts->ptr);
+  }
   {
     KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
-    SKS_TRY(exchange_headers(ctx, comm, local, n_local, n_total, &H));
+    SKS_TRY(exchange_headers(ctx, comm, local, n_local, n_total, &H, d_counts, W));
   }
-  if (!all_pairs_dict_usable(H.kw, H.mask, n_total, H.total_keys)) return by_rows();  // the same decision on every rank
-  // The ranks split the KEY SPACE of the all-vs-all dictionary (csrc/sks_allpairs.cu), not the rows.  A key belongs to
-  // the rank its hash names: every rank sends each of its keys (with the number of its set) to the owner -- 1/world
-  // of what an all-gather of the sketches would move --, the owner enters what arrives into its dictionary and counts
-  // what its keys contribute to EVERY pair, and one reduce-scatter of the n x n partial counts leaves every rank with
-  // its own complete block rows.
-  const size_t W = (size_t)world;
-  BufferRef r_keys, r_sets, r_ctl, d_all_buf, in_keys, in_sets;
-  unsigned long long *d_counts = nullptr;
-  SKS_TRY(all_pairs_route(ctx, local, n_local, begin, world, &r_keys, &r_sets, &r_ctl, &d_counts));
-  SKS_TRY(alloc_buffer(ctx, 8 * W * W, &d_all_buf));
-  unsigned long long *h_all = nullptr;
-  SKS_TRY(ctx_pinned(ctx, 8 * W * W, reinterpret_cast<void **>(&h_all)));
-  std::vector<unsigned long long> cnt;
-  {
+  bool usable = all_pairs_dict_usable(H.kw, H.mask, n_total, H.total_keys), refused = false, spilled = false;
+  for (int src = 0; src < world; ++src)
+    for (int dst = 0; dst < world; ++dst) {
+      const unsigned long long c = (unsigned long long)H.extra(src)[dst];
+      if (c == ~0ull) refused = true;
+      else if (c > all_pairs_route_cap((uint64_t)H.of(src)[0], world)) spilled = true;
+    }
+  if (!usable || refused) return by_rows();  // the same decision on every rank
+  std::vector<unsigned long long> cnt(W * W);
+  for (int src = 0; src < world; ++src)
+    for (int dst = 0; dst < world; ++dst) cnt[(size_t)src * W + dst] = (unsigned long long)H.extra(src)[dst];
+  if (spilled) {  // somebody's region was too small: everybody groups exactly (count, then scatter) and says so again
+    my_cap = 0;
+    SKS_TRY(all_pairs_route(ctx, local, n_local, begin, world, 0, &r_keys, &r_sets, &r_ctl, &d_counts));
+    BufferRef d_all_buf;
+    SKS_TRY(alloc_buffer(ctx, 8 * W * W, &d_all_buf));
+    unsigned long long *h_all = nullptr;
+    SKS_TRY(ctx_pinned(ctx, 8 * W * W, reinterpret_cast<void **>(&h_all)));
     KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
     SKS_NCCL_TRY(nccl()->AllGather(d_counts, d_all_buf->ptr, W, ncclUint64, comm->comm, ctx->stream));
     SKS_CUDA_TRY(cudaMemcpyAsync(h_all, d_all_buf->ptr, 8 * W * W, cudaMemcpyDeviceToHost, ctx->stream));
@@ -482,7 +570,7 @@ int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, 
   {
     size_t at = 0;
     for (int dst = 0; dst < world; ++dst) {
-      out_at[dst] = at;
+      out_at[dst] = my_cap ? my_cap * (size_t)dst : at;   // fixed regions, or packed groups after the exact passes
       at += sends(rank, dst);
     }
   }
@@ -511,35 +599,11 @@ int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, 
       SKS_CUDA_TRY(cudaMemcpyAsync(is + 2 * in_at[rank], ss + 2 * out_at[rank], 2 * sends(rank, rank), cudaMemcpyDeviceToDevice, ctx->stream));
     }
   }
-  // the sizes of all sets (ANI denominators, the diagonal) came with the headers
-  std::vector<int32_t> h_sizes((size_t)n_total);
-  for (int r = 0; r < world; ++r) {
-    int64_t b = 0, e = 0;
-    sks_shard_range(n_total, r, world, &b, &e);
-    for (int64_t i = b; i < e; ++i) h_sizes[(size_t)i] = (int32_t)H.of(r)[5 + (i - b)];
-  }
+  sizes_from_headers();
   const FlatKeys flat = {static_cast<const unsigned long long *>(in_keys->ptr), static_cast<const uint16_t *>(in_sets->ptr),
                          (uint32_t)n_in, h_sizes.data()};
-  const int64_t per = (n_total + world - 1) / world, n_rows = end - begin;
-  BufferRef raw, sizes, mine, counts, ani;
-  const uint32_t *overflow = nullptr;
   SKS_TRY(all_pairs_raw(ctx, nullptr, n_total, 0, n_total, 0, 1, false, (int64_t)world * per, &raw, &sizes, &overflow, &flat));
-  SKS_TRY(alloc_buffer(ctx, 4 * (size_t)per * n_total, &mine));
-  {
-    KernelTimer timer(ctx, SKS_KERNEL_EXCHANGE);
-    SKS_NCCL_TRY(nccl()->ReduceScatter(raw->ptr, mine->ptr, (size_t)per * n_total, ncclInt32, ncclSum, comm->comm, ctx->stream));
-  }
-  SKS_TRY(all_pairs_finalize(ctx, static_cast<const int32_t *>(mine->ptr), static_cast<const int32_t *>(sizes->ptr), n_total, begin,
-                             n_rows, false, sks_mask_weight(H.mask), &counts, out_ani ? &ani : nullptr));
-  if (out_counts && n_rows)
-    SKS_CUDA_TRY(cudaMemcpyAsync(out_counts, counts->ptr, 4 * (size_t)n_rows * n_total, cudaMemcpyDeviceToHost, ctx->stream));
-  if (out_ani && n_rows)
-    SKS_CUDA_TRY(cudaMemcpyAsync(out_ani, ani->ptr, 8 * (size_t)n_rows * n_total, cudaMemcpyDeviceToHost, ctx->stream));
-  if (out_sizes) memcpy(out_sizes, h_sizes.data(), 4 * (size_t)n_total);
-  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  if (overflow && *overflow)  // cannot happen: the table is sized by what arrived; reported, not papered over
-    return set_error(SKS_ERR_CAPACITY, "the dictionary of rank %d overflowed", rank);
-  return SKS_OK;
+  return finish();
 }
 
 int sks_sketch_sequence_sharded(sks_ctx *ctx, sks_comm *comm, const sks_batch *slice, const uint64_t mask[2], int window,

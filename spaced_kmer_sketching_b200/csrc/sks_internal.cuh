@@ -283,8 +283,9 @@ struct FlatKeys {  // occurrences as arrays instead of sets: 64-bit keys, the gl
 int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_begin, int64_t row_end, int part, int n_parts,
                   bool symmetric, int64_t raw_rows, BufferRef *raw_out, BufferRef *sizes_out, const uint32_t **h_overflow,
                   const FlatKeys *flat);
-int all_pairs_route(sks_ctx *ctx, sks_set *const *sets, int64_t n_local, int64_t set_base, int world, BufferRef *out_keys,
-                    BufferRef *out_sets, BufferRef *ctl_out, unsigned long long **d_counts);
+size_t all_pairs_route_cap(uint64_t n_keys, int world);
+int all_pairs_route(sks_ctx *ctx, sks_set *const *sets, int64_t n_local, int64_t set_base, int world, size_t region_cap,
+                    BufferRef *out_keys, BufferRef *out_sets, BufferRef *ctl_out, unsigned long long **d_counts);
 bool all_pairs_dict_usable(int key_words, const uint64_t mask[2], int64_t n_total, uint64_t total_keys);
 int all_pairs_finalize(sks_ctx *ctx, const int32_t *raw_rows, const int32_t *d_sizes, int64_t n, int64_t row_begin,
                        int64_t n_rows, bool symmetric, int weight, BufferRef *counts, BufferRef *ani);

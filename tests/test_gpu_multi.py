@@ -119,3 +119,21 @@ def test_sharded_sequence_sketch_equals_whole_sequence_sketch(seed, L):
         assert np.array_equal(full, want)
     assert np.array_equal(np.concatenate([r[2] for r in res]), want)
     ctx.close()
+
+
+def test_both_exchange_routes_in_child_processes():
+    """The sharded all-vs-all has two ways to bring the keys to the ranks that own them (csrc/sks_comm.cu): all sketches
+    to every rank (default for two ranks) and every key to its owner only (default beyond two).  The switch is read
+    once per process: the all-vs-all test again, in child processes, with each route forced."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("SKS_SHARD_ROUTE"):
+        pytest.skip("already inside the child process")
+    if _world() < 2:
+        pytest.skip("one GPU: a single rank exchanges nothing")
+    for route in ("gather", "owner"):
+        r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
+                            "sharded_all_vs_all"], env=dict(os.environ, SKS_SHARD_ROUTE=route), capture_output=True, text=True,
+                           timeout=900)
+        assert r.returncode == 0, (route, r.stdout[-2000:] + r.stderr[-2000:])
