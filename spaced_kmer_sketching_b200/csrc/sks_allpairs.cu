@@ -64,6 +64,9 @@ constexpr uint32_t kPostFlag = 0x80000000u;  // entry = kPostFlag | id: the key 
 // kind at occurrence kPostMax + 1.
 enum Counter : int { C_IDS = 0, C_OVERFLOW = 1, C_ROWS = 2, C_TASK = 3, C_MINE = 4, C_HIGH = 5, C_COUNT = 16 };
 constexpr uint32_t kHighFlag = 0x80000000u;  // Slot::id = kHighFlag | bitmap id once the key has one (atomicMax keeps it)
+// entry[q] after D1: the slot of the key (< 2^31), or kHighFlag | bitmap id when the probe already saw the key with more
+// than kPostMax occurrences and its bitmap id (most occurrences of widely shared keys): D2a then has nothing to look up
+// for them.
 
 struct DictView {
   const void *const *set_ptr;  // [n] keys of set s
@@ -207,9 +210,10 @@ __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_
   }
 #pragma unroll
   for (int u = 0; u < kDictPer; ++u) {
-    uint32_t sl = slot[u], k = 255;
+    uint32_t sl = slot[u], k = 255, known = 0;
     if (sl != kNoId) {
       uint32_t seen = cur[u].z;   // the key's count when it was probed (only meaningful if the probe found the key)
+      uint32_t idw = cur[u].w;    // and its id word
       if (sl != D.cap) {
         unsigned long long c = ((unsigned long long)cur[u].y << 32) | cur[u].x;
         for (uint32_t probes = 0;; ++probes) {
@@ -228,9 +232,11 @@ __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_
           const uint4 nx = __ldcg(reinterpret_cast<const uint4 *>(D.tab + sl));
           c = ((unsigned long long)nx.y << 32) | nx.x;
           seen = nx.z;
+          idw = nx.w;
         }
       }
       if (sl != kNoId && seen <= kPostMax) k = atomicAdd(&D.tab[sl].cnt, 1u);
+      else if (sl != kNoId && (idw & kHighFlag)) known = idw;   // widely shared, and already numbered
     }
     // new ids: one reservation per warp and kind (the counters are single words: a million lone atomics on one
     // address would take longer than the rest of the kernel)
@@ -246,6 +252,7 @@ __global__ void __launch_bounds__(kDictThreads) dict_insert_kernel(const __grid_
       if (want) atomicMax(&D.tab[sl].id, (kind ? kHighFlag : 0u) | (first + (uint32_t)__popc(m & ((1u << lane) - 1))));
     }
     const uint32_t e = base + u * kDictThreads + threadIdx.x;
+    if (known) sl = known;
     if (!compact) {
       if (e < D.n_entries) {
         D.entry[e] = sl;
@@ -348,7 +355,12 @@ __global__ void __launch_bounds__(kDictThreads) dict_ids_kernel(const __grid_con
       const uint32_t at = D.entry[e];
       Slot sl;
       sl.cnt = 0;
-      if (at != kNoId) sl = D.tab[at];   // final: the insertion kernel has completed
+      if (at != kNoId && (at & kHighFlag)) {  // numbered at insertion
+        sl.cnt = kPostMax + 1;
+        sl.id = at;
+      } else if (at != kNoId) {
+        sl = D.tab[at];   // final: the insertion kernel has completed
+      }
       uint32_t id = kNoId;
       if (sl.cnt >= 2) {
         if (sl.cnt <= kPostMax) {
@@ -620,7 +632,7 @@ bool all_pairs_dict_eligible(sks_set *const *sets, int64_t n) {
       return false;
     total += (uint64_t)s->count;
   }
-  if (total >= (1ull << 31)) return false;
+  if (total >= (1ull << 30)) return false;
   if (ref->key_words == 2) {
     Compact c;
     if (!make_compact(ref->mask, &c)) return false;
@@ -654,7 +666,7 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
   } else {
     for (int64_t i = 0; i < n; ++i) total += (uint64_t)sets[i]->count;
   }
-  if (total >= (1ull << 31)) return set_error(SKS_ERR_CAPACITY, "too many keys for the dictionary");
+  if (total >= (1ull << 30)) return set_error(SKS_ERR_CAPACITY, "too many keys for the dictionary");   // slots stay below 2^31
   const uint32_t K = (uint32_t)total;
   // this rank enters about K / n_parts keys (the hash spreads the DISTINCT keys evenly; a widely shared key brings all
   // its occurrences to one rank, but they take one slot); 1.5 slots per entered key, and room for an uneven split
@@ -878,7 +890,7 @@ int all_pairs_route(sks_ctx *ctx, sks_set *const *sets, int64_t n_local, int64_t
 // Can the sets of a sharded run take the dictionary (decided from what every rank knows after the header exchange)?
 bool all_pairs_dict_usable(int key_words, const uint64_t mask[2], int64_t n_total, uint64_t total_keys) {
   static const bool enabled = getenv("SKS_DICT_INTERSECT") ? atoi(getenv("SKS_DICT_INTERSECT")) != 0 : true;
-  if (!enabled || n_total < 2 || n_total > 65536 || total_keys >= (1ull << 31)) return false;
+  if (!enabled || n_total < 2 || n_total > 65536 || total_keys >= (1ull << 30)) return false;
   if (key_words == 2) {
     Compact c;
     if (!make_compact(mask, &c)) return false;
