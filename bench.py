@@ -51,6 +51,15 @@ METRIC = "all_vs_all_ani_pairs_per_s"
 UNIT = "pairs/s"
 
 
+def bench_config(n=C4_N):
+    """The `config` of both arms (ours and --impl reference): what is computed, and how the GPU arm keeps the L2 cold."""
+    return {"workload": WORKLOAD if n == C4_N else WORKLOAD.replace("%d synthetic" % C4_N, "%d (of the %d) synthetic" % (n, C4_N)),
+            "genomes": n, "bases_per_step": n * C4_L, "ordered_pairs_per_step": n * n,
+            "l2": "%.2f GB of packed genomes per step (> 126 MB L2) and a 256 MiB flush write between timed steps" % (n * C4_L / 4e9),
+            "parallelism": "genomes sharded over ranks in contiguous blocks; every key travels once to the rank that owns it "
+                           "(NCCL), one reduce-scatter of the partial counts; every rank returns its own block rows"}
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -208,9 +217,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_full, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": text,
-                   "note": "reference CPU path: parallel_kmer_sets_from_fasta_files (FASTA parse, sliding window, FracMinHash, "
-                           "unordered_map sets) + parallel_compute_pairwise_kmer_set_intersections + containment/binomial_estimator"},
+        "config": bench_config(),
+        "reference_note": "reference CPU path: parallel_kmer_sets_from_fasta_files (FASTA parse, sliding window, FracMinHash, "
+                          "unordered_map sets) + parallel_compute_pairwise_kmer_set_intersections + containment/binomial_estimator; "
+                          "bounded sample: " + text,
         "cpu_baseline": dict({"value": value, "unit": UNIT, "cores": sample.threads, "kind": kind, "sample": text}, **host_threads()),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "sample_ms_per_step": 1e3 * (ts + tc),
@@ -509,11 +519,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD if n == C4_N else WORKLOAD.replace("%d synthetic" % C4_N, "%d (of the %d) synthetic" % (n, C4_N)),
-                       "genomes": n, "bases_per_step": n * C4_L, "ordered_pairs_per_step": n * n,
-                       "l2": "%.2f GB of packed genomes per step (> 126 MB L2) and a 256 MiB flush write between timed steps" % (n * C4_L / 4e9),
-                       "parallelism": "genomes sharded over ranks in contiguous blocks; one NCCL exchange of the sketches "
-                                      "(sks_comm_allgather_sets); every rank fills its own block rows"},
+            "config": bench_config(n),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": e2e_ms / args.steps,
                     "call": "sks_all_vs_all_from_host (host packed genomes in; counts, sizes and ANI rows out)",

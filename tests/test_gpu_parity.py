@@ -695,6 +695,33 @@ def test_c3_chromosome_scale(ctx):
     assert np.array_equal(sub[:64], port.gen(lo + 64, 7)[lo:])
     osub = port.sketch_set(sub, [len(sub)], mask, w, port.FMH, 1, 200, 181)
     assert len(osub) > 4000 and np.isin(osub[:, 0], keys[:, 0]).all()
+    # full size, exactly: the 8-way position split of the whole chromosome -- the slices a run on 8 GPUs
+    # sketches, a (w-1)-base halo each -- unites to the whole-sequence sketch ...
+    from spaced_kmer_sketching_b200 import multi_gpu
+    parts, cuts = [], []
+    for r in range(8):
+        first, count = multi_gpu.position_shard(L, w, r, 8)
+        cuts.append(first)
+        (p,) = ctx.sketch(batch.slice(0, first, count, w), mask, w, pred)
+        parts.append(p.keys()[:, 0])
+        p.close()
+    assert np.array_equal(np.unique(np.concatenate(parts)), keys[:, 0])
+    # ... 25 Mbp contiguous across the first cut are sketched identically by the oracle (every k-mer, not a sample) ...
+    lo25 = cuts[1] - 12_500_000
+    sl = batch.slice(0, lo25, 25_000_000, w)
+    codes = sks.unpack_codes(sl.download(0), 25_000_000 + w - 1)
+    (g25,) = ctx.sketch(sl, mask, w, pred)
+    o25 = port.sketch_set(codes, [len(codes)], mask, w, port.FMH, 1, 200, 181)
+    assert np.array_equal(g25.keys(), o25) and np.isin(o25[:, 0], keys[:, 0]).all()
+    g25.close()
+    # ... and so are the 400 kbp around every other cut point (windows that straddle two ranks' slices)
+    for c in cuts[2:]:
+        sl = batch.slice(0, c - 200_000, 400_000, w)
+        codes = sks.unpack_codes(sl.download(0), 400_000 + w - 1)
+        (gc,) = ctx.sketch(sl, mask, w, pred)
+        oc = port.sketch_set(codes, [len(codes)], mask, w, port.FMH, 1, 200, 181)
+        assert np.array_equal(gc.keys(), oc) and np.isin(oc[:, 0], keys[:, 0]).all(), c
+        gc.close()
 
 
 def test_c4_all_vs_all_at_genome_size(ctx):
