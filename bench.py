@@ -507,6 +507,7 @@ def run_b200(args):
                 extra.update(c2_pair_leg(args, ctx, sks, torch, stream, barrier, peak, peak_src, flush, consts))
                 if not args.no_cpu_baseline:
                     extra["reference_cli"] = cli_wall_times()
+                    extra.update(fasta_leg(ctx, sks, np))
             extra.update(c3_leg(ctx, comm, sks, multi_gpu, torch, rank, world, stream, barrier, max_over_ranks, peak))
             # the same path where the sequence is long enough for the sketching itself to dominate the fixed costs
             extra.update(c3_leg(ctx, comm, sks, multi_gpu, torch, rank, world, stream, barrier, max_over_ranks, peak,
@@ -791,6 +792,60 @@ def c3_leg(ctx, comm, sks, multi_gpu, torch, rank, world, stream, barrier, max_o
     b3.close()
     del flush
     return {name: out}
+
+
+def fasta_leg(ctx, sks, np):
+    """FASTA ingest.  8 x 5 Mbp files: parse + split at non-ACGT + 2-bit pack on the device
+    (sks_batch_from_fasta_text: raw bytes up, kernels do the rest), libsks' own host parser, and the reference's
+    nucleotide_strings_from_fasta_file (/root/reference/src/fasta_processing.cpp:79-211), one thread each; then files ->
+    kmer_sets (device parse + sketch) against the reference's parallel_kmer_sets_from_fasta_files on all threads."""
+    from oracle import port, ref
+    n, L = 8, 5_000_000
+    mask, w = sks.seed_to_mask(C3_SEED)
+    out = {"files": "%d x %d bases, 80 columns, LF" % (n, L)}
+    with tempfile.TemporaryDirectory() as d:
+        base = port.gen(L, 1000)
+        paths = []
+        for g in range(n):
+            paths.append(os.path.join(d, "g%d.fna" % g))
+            port.write_fasta(paths[-1], c4_genome(port, base, g), "g%d" % g)
+        texts = [open(p, "rb").read() for p in paths]
+        best = {}
+        for rep in range(3):
+            ctx.profile(True)
+            ctx.kernel_stats()
+            t0 = time.perf_counter()
+            b = ctx.batch_from_fasta_text(texts)
+            ctx.sync()
+            t1 = time.perf_counter()
+            ks = ctx.kernel_stats()
+            ctx.profile(False)
+            t2 = time.perf_counter()
+            sets = sks.kmer_sets_from_fasta_files(ctx, paths, mask, w, sks.frac_min_hash(1, 200))
+            t3 = time.perf_counter()
+            sizes = [s.kmer_set_size() for s in sets]
+            for s in sets:
+                s.close()
+            b.close()
+            best["device_ingest_ms"] = min(best.get("device_ingest_ms", 1e9), (t1 - t0) * 1e3)
+            best["device_ingest_kernels_ms"] = min(best.get("device_ingest_kernels_ms", 1e9), sum(v[1] for v in ks.values()))
+            best["files_to_sets_ms"] = min(best.get("files_to_sets_ms", 1e9), (t3 - t2) * 1e3)
+        t0 = time.perf_counter()
+        for p in paths[:2]:
+            sks.fasta_parse_file(p)
+        best["libsks_host_parser_bases_per_s_1_thread"] = 2 * L / (time.perf_counter() - t0)
+        if ref.available():
+            t0 = time.perf_counter()
+            ref.Strings.from_fasta(paths[0])
+            best["reference_parser_bases_per_s_1_thread"] = L / (time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            rsets = ref.sets_from_fasta_files(paths, mask, w, ref.FMH, 1, 200, parallel=True)
+            best["reference_files_to_sets_ms"] = (time.perf_counter() - t0) * 1e3
+            best["sizes_equal_reference"] = [s.size() for s in rsets] == sizes
+    best["device_ingest_bases_per_s"] = n * L / (best["device_ingest_ms"] / 1e3)
+    best["device_ingest_kernels_bases_per_s"] = n * L / (best["device_ingest_kernels_ms"] / 1e3)
+    out.update(best)
+    return {"fasta_ingest": out}
 
 
 def c5_leg(ctx, sks, np, torch, stream):

@@ -823,7 +823,11 @@ int all_pairs_raw(sks_ctx *ctx, sks_set *const *sets, int64_t n, int64_t row_beg
 // 64-bit counts on the device (for the ranks' exchange of counts).
 // region_cap > 0: one pass into fixed regions of that many entries per owner (group r at r * region_cap; counts beyond
 // the capacity mean the pass has to be repeated exactly); region_cap == 0: count, then scatter (two passes).
-size_t all_pairs_route_cap(uint64_t n_keys, int world) { return (size_t)(n_keys / world + n_keys / (4 * (uint64_t)world) + 4096); }
+size_t all_pairs_route_cap(uint64_t n_keys, int world) {
+  static const bool tight = getenv("SKS_ROUTE_TIGHT") != nullptr;  // tests: regions that are sure to overflow
+  if (tight) return (size_t)(n_keys / (2 * (uint64_t)world) + 1);
+  return (size_t)(n_keys / world + n_keys / (4 * (uint64_t)world) + 4096);
+}
 int all_pairs_route(sks_ctx *ctx, sks_set *const *sets, int64_t n_local, int64_t set_base, int world, size_t region_cap,
                     BufferRef *out_keys, BufferRef *out_sets, BufferRef *ctl_out, unsigned long long **d_counts) {
   uint64_t total = 0;

@@ -514,6 +514,8 @@ int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, 
     h_sizes.resize((size_t)n_total);
     for (int64_t i = 0; i < n_total; ++i) h_sizes[(size_t)i] = (int32_t)all[i]->count;
     int st = all_pairs_raw(ctx, all.data(), n_total, 0, n_total, rank, world, false, (int64_t)world * per, &raw, &sizes, &overflow, nullptr);
+    if (st == SKS_ERR_CAPACITY)  // too large for the dictionary (decided from global sizes: on every rank alike)
+      return sks_all_vs_all(ctx, all.data(), n_total, begin, end, out_counts, out_sizes, out_ani);
     if (st != SKS_OK) return st;
     return finish();
   }

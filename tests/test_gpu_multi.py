@@ -132,8 +132,9 @@ def test_both_exchange_routes_in_child_processes():
         pytest.skip("already inside the child process")
     if _world() < 2:
         pytest.skip("one GPU: a single rank exchanges nothing")
-    for route in ("gather", "owner"):
+    # (SKS_ROUTE_TIGHT: the one-pass grouping by owner gets regions that are sure to overflow, so that every rank has
+    # to come back with the exact two passes)
+    for env in ({"SKS_SHARD_ROUTE": "gather"}, {"SKS_SHARD_ROUTE": "owner"}, {"SKS_SHARD_ROUTE": "owner", "SKS_ROUTE_TIGHT": "1"}):
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
-                            "sharded_all_vs_all"], env=dict(os.environ, SKS_SHARD_ROUTE=route), capture_output=True, text=True,
-                           timeout=900)
-        assert r.returncode == 0, (route, r.stdout[-2000:] + r.stderr[-2000:])
+                            "sharded_all_vs_all"], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, (env, r.stdout[-2000:] + r.stderr[-2000:])
