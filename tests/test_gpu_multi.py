@@ -138,3 +138,65 @@ def test_both_exchange_routes_in_child_processes():
         r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k",
                             "sharded_all_vs_all"], env=dict(os.environ, **env), capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, (env, r.stdout[-2000:] + r.stderr[-2000:])
+
+
+def test_one_call_entry_points_from_resident_and_host_buffers():
+    """sks_all_vs_all_resident / sks_all_vs_all_from_host (what bench.py times) against sketch + sks_all_vs_all: genomes in
+    a resident batch, in pageable host memory (copied up) and in pinned host memory (read in place by the sketch
+    kernel's bulk copies), single rank."""
+    import torch
+    ctx = sks.Context(0)
+    n, L = 9, 400_003      # not a multiple of 16 bases: the in-place path fetches the last words with plain loads
+    mask, w = sks.seed_to_mask(C3_SEED)
+    pred = sks.frac_min_hash(1, 20)
+    batch = ctx.synth(L, [1000] * n, [2000 + g for g in range(n)], [DS[g % 6] for g in range(n)])
+    sets = ctx.sketch(batch, mask, w, pred, sks.REPR_SORTED)
+    want = ctx.all_vs_all(sets)
+    for s in sets:
+        s.close()
+
+    def fresh():
+        return np.zeros((n, n), np.int32), np.zeros(n, np.int32), np.zeros((n, n), np.float64)
+
+    got = ctx.all_vs_all_resident(None, batch, n, mask, w, pred, fresh())
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    words = (L + 15) // 16
+    stride = (words + 3) // 4 * 4
+    pageable = np.zeros(n * stride, dtype=np.uint32)
+    for g in range(n):
+        pageable[g * stride:g * stride + words] = batch.download(g)
+    pinned = torch.from_numpy(pageable.view(np.int32).copy()).pin_memory()
+    before = ctx.in_place_calls
+    for base_ptr, in_place in ((pageable.ctypes.data, 0), (pinned.data_ptr(), 1)):
+        ptrs = [base_ptr + 4 * g * stride for g in range(n)]
+        got = ctx.all_vs_all_from_host(None, ptrs, [L] * n, n, mask, w, pred, fresh())
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]), in_place
+        assert ctx.in_place_calls - before == in_place
+    ctx.close()
+
+
+def test_configs3_full_size_matrix_digest():
+    """BASELINE configs[3] at full size (1000 x 5 Mbp, all 10^6 ordered pairs) on one GPU: the sha256 of the count matrix and
+    of the sizes equal the recorded values (bench.py; first produced by the pairwise kernels, which the parity tests pin
+    to the oracle), the matrix is symmetric with the sizes on its diagonal, and the ANI follows the substitution rate."""
+    import hashlib
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ctx = sks.Context(0)
+    n = bench.C4_N
+    mask, w = sks.seed_to_mask(bench.C3_SEED)
+    batch = ctx.synth(bench.C4_L, [1000] * n, [2000 + g for g in range(n)], [bench.C4_DS[g % 6] for g in range(n)])
+    out = (np.zeros((n, n), np.int32), np.zeros(n, np.int32), np.zeros((n, n), np.float64))
+    ctx.all_vs_all_resident(None, batch, n, mask, w, sks.frac_min_hash(1, 200), out)
+    counts, sizes, ani = out
+    assert hashlib.sha256(counts.astype("<i4").tobytes()).hexdigest() == bench.C4_MATRIX_SHA256
+    assert hashlib.sha256(sizes.astype("<i4").tobytes()).hexdigest() == bench.C4_SIZES_SHA256
+    assert (counts == counts.T).all() and (np.diag(counts) == sizes).all()
+    for g in range(1, 60):
+        d = bench.C4_DS[g % 6]
+        want = 1.0 if d == 0 else 1.0 - 1.0 / d
+        assert abs(ani[0, g] - want) < 0.002, (g, ani[0, g])
+    ctx.close()
