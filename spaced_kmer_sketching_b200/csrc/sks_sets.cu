@@ -1074,7 +1074,13 @@ __global__ void __launch_bounds__(256)
                          const __grid_constant__ SortPlan plan, const uint32_t *__restrict__ flag) {
   __shared__ uint32_t s_hist[1 << kSortMaxBucketBits];
   __shared__ uint32_t s_base[1 << kSortMaxBucketBits];
-  if (*flag) return;  // the scan found an oversized bucket: the call is going to the library sort anyway
+  __shared__ uint32_t s_abort;
+  // the scan found an oversized bucket: the call is going to the library sort anyway.  The decision is made once per CTA:
+  // the flag can be raised while this CTA runs, and threads that left on their own would leave the others with
+  // half-filled shared tables
+  if (threadIdx.x == 0) s_abort = *flag;
+  __syncthreads();
+  if (s_abort) return;
   const Region r = regions[blockIdx.y];
   const uint32_t nb = 1u << bb;
   uint32_t *cur = cursor + ((size_t)blockIdx.y << bb);
@@ -1121,7 +1127,12 @@ __global__ void __launch_bounds__(kSortThreads)
   using K = SortKey<KW>;
   __shared__ typename K::T s[kCap];
   __shared__ uint32_t s_warp[kSortThreads / 32];
-  if (*flag) return;
+  __shared__ uint32_t s_abort;
+  // one decision per CTA (another CTA may raise the flag while this one runs: threads leaving on their own would leave
+  // holes in the shared arrays and garbage in the compaction's prefix sums)
+  if (threadIdx.x == 0) s_abort = *flag;
+  __syncthreads();
+  if (s_abort) return;
   const uint32_t n = hist[blockIdx.x];
   if (n == 0 || n > (uint32_t)kCap) {  // uniform; an oversized bucket sends the whole call to the library sort
     if (threadIdx.x == 0) {
@@ -1327,8 +1338,11 @@ int sort_unique_buckets(sks_ctx *ctx, typename SortKey<KW>::T *keys, const uint6
   dim3 grid(per_region, (unsigned)n_regions);
   const uint32_t nb = 1u << bb;
   sortp_hist_kernel<KW><<<grid, 256, 0, ctx->stream>>>(keys, d_regions, d_hist, bb, plan);
+  SKS_CUDA_TRY(cudaGetLastError());
   sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_hist, d_boff, d_cursor, nb, nullptr, (uint32_t)big_cap, d_flag);
+  SKS_CUDA_TRY(cudaGetLastError());
   sortp_scatter_kernel<KW><<<grid, 256, 0, ctx->stream>>>(keys, d_regions, d_cursor, d_tmp, bb, plan, d_flag);
+  SKS_CUDA_TRY(cudaGetLastError());
   if ((max_count >> bb) > 600)  // 2048-key networks: more threads per bucket
     sortp_bucket_kernel<KW, 512, kSortCap / KW><<<(unsigned)n_b, 512, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2,
                                                                              d_ucount, bb, d_flag);
@@ -1336,8 +1350,11 @@ int sort_unique_buckets(sks_ctx *ctx, typename SortKey<KW>::T *keys, const uint6
         // 8 KB of shared memory per CTA keeps many buckets in flight per SM
     sortp_bucket_kernel<KW, 128, 1024><<<(unsigned)n_b, 128, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2, d_ucount,
                                                                          bb, d_flag);
+  SKS_CUDA_TRY(cudaGetLastError());
   sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_ucount, d_uboff, nullptr, nb, d_utot, 0xFFFFFFFFu, d_flag);
+  SKS_CUDA_TRY(cudaGetLastError());
   sortp_region_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(d_utot, d_uoff, n_regions);
+  SKS_CUDA_TRY(cudaGetLastError());
   sortp_copy_kernel<KW><<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp2, d_regions, d_boff, d_uboff, d_ucount, d_uoff, d_out, bb,
                                                             d_flag);
   SKS_CUDA_TRY(cudaGetLastError());

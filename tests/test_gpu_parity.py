@@ -446,6 +446,32 @@ def test_auto_representation_follows_cost_and_list_capacity(ctx):
     big.close()
 
 
+def test_bucket_sort_overflow_among_many_regions(ctx):
+    """One region whose keys are all equal (poly-A) overflows its bucket while the buckets of 60 other regions are being
+    sorted: the bucket sort has to give up as a whole and hand over to the library sort.  (Found by
+    tools/stress_allpairs.py: threads used to leave a CTA one by one when the overflow flag went up, and the rest wrote
+    through garbage prefix sums.)"""
+    rng = np.random.default_rng(48)
+    base = rng.integers(0, 4, 32838, dtype=np.uint8)
+    genomes = [base.copy() for _ in range(60)]
+    for g in genomes[1:]:
+        idx = rng.integers(0, len(g), 300)
+        g[idx] = (g[idx] + rng.integers(1, 4, len(idx))) & 3
+    genomes.insert(35, np.zeros(1671, dtype=np.uint8))
+    genomes[0] = genomes[0][:14]
+    mask, w = 0xfcfffffffcf3fff3fff3cfffff3fc, 58          # 16-byte keys
+    batch = ctx.upload_codes(genomes)
+    want = {i: port.sketch_set(genomes[i], [len(genomes[i])], mask, w) for i in (0, 1, 35, 60)}
+    for rep in range(6):
+        sets = ctx.sketch(batch, mask, w, sks.all_kmers(), sks.REPR_SORTED)
+        assert sets[35].kmer_set_size() == 1 and sets[0].kmer_set_size() == 0
+        for i, o in want.items():
+            assert np.array_equal(sets[i].keys(), o), (rep, i)
+        for x in sets:
+            x.close()
+    batch.close()
+
+
 def test_synth_matches_oracle_generator(ctx):
     batch = ctx.synth(100_003, [42, 42, 9], [0, 43, 5], [0, 100, 3])
     A = port.gen(100_003, 42)
