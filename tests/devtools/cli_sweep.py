@@ -1,7 +1,7 @@
 """Dev tool: the reference's own main() on this repository's headers (oracle/_ref/dropin_cli) over 4 x 2 Mbp FASTA
 files: its 62 configurations with the reference's timing lines, slowest first."""
 import os, re, subprocess, sys, tempfile, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import port   # FASTA writer only
 exe = os.path.join(ROOT, "oracle", "_ref", "dropin_cli")
