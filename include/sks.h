@@ -278,8 +278,8 @@ void sks_ani_from_counts(const int32_t *intersections, const int32_t *first_set_
 
 /* ---- several GPUs: one rank per GPU, NCCL over NVLink underneath -------------------------------------- */
 /* The reference parallelises over FASTA files and over set pairs with cilk_for (src/kmer_set.cpp:124-131,179-182).
- * Here genome g of n belongs to rank g / ceil(n / world) (sks_shard_range); every rank sketches its block, the
- * sketches are exchanged once, and every rank returns its own complete block rows of the pair matrix.  A rank is a
+ * Here genome g of n belongs to rank g / ceil(n / world) (sks_shard_range); every rank sketches its block, every k-mer
+ * travels once to the rank that owns it, and every rank returns its own complete block rows of the pair matrix.  A rank is a
  * process (sks_comm_init_rank: rank 0 makes the id, the caller's launcher carries its 128 bytes to the others) or a
  * thread of one process that drives one GPU (sks_comm_init_all).  NCCL is loaded at run time (libnccl.so.2, or
  * $SKS_NCCL_LIB); without it these calls fail with SKS_ERR_CUDA and the single-GPU API is unaffected. */
@@ -305,10 +305,12 @@ int sks_comm_allgather_sets(sks_ctx *ctx, sks_comm *comm, sks_set *const *local,
  * binomial_estimator (src/kmer-sketching.cpp:185-200), sharded.  The ranks split the KEY SPACE of the all-vs-all
  * dictionary, not the rows: a k-mer belongs to the rank its hash names; every rank sends each of its keys (with the
  * number of its set) to the owner -- one small all-gather of counts and one grouped send/receive, 1/world of what an
- * all-gather of the sketches would move --, the owner enters what arrives into its dictionary and counts what its
- * keys contribute to every pair, one NCCL reduce-scatter of the n x n partial counts adds the shares up, and the rank
- * finalises its own block rows [begin, end) = sks_shard_range(n_total, rank, world).  (Sets the dictionary cannot
- * take -- 16-byte keys of weight > 32 -- are all-gathered and compared row block by row block instead.)  Outputs as in
+ * all-gather of the sketches would move (with two ranks the sketches are all-gathered instead and each rank enters
+ * the keys it owns) --, the owner enters what arrives into its dictionary and counts what its keys contribute to
+ * every pair, one NCCL reduce-scatter of the n x n partial counts adds the shares up, and the rank finalises its own
+ * block rows [begin, end) = sks_shard_range(n_total, rank, world).  Every rank must make the call (it is collective)
+ * with the same n_total.  (Sets the dictionary cannot take -- 16-byte keys of weight > 32 -- are all-gathered and
+ * compared row block by row block instead.)  Outputs as in
  * sks_all_vs_all: out_counts / out_ani hold (end - begin) * n_total entries, out_sizes n_total. */
 int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, int64_t n_local, int64_t n_total,
                            int32_t *out_counts, int32_t *out_sizes, double *out_ani);
