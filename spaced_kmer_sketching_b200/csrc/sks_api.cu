@@ -582,9 +582,51 @@ int sketch_sorted(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
   BufferRef raw, pos, uniq;
   std::vector<uint64_t> off, count, uoff, ucount;
   uint64_t span = 0;
-  SKS_TRY(sketch_raw_keys(ctx, batch, plan, pred, window, OUT_KEYS, &raw, &pos, &off, &count, &span));
-  SKS_TRY(sort_unique_regions(ctx, key_words, raw->ptr, off.data(), count.data(), G, span, &uniq, &uoff, &ucount,
-                              mask));
+  bool done = false;
+  if (key_words == 1 && plan.pred_mode != PRED_ALL && pred->modulus > 1) {
+    // A sparse condition on 8-byte keys: the first level of the bucket sort (histogram + scatter by the keys' top mask
+    // bits) is folded into the sketch kernel's emit -- the kept k-mers go straight into per-(genome, bucket) regions,
+    // and the sort starts at its bucket kernel.  Nothing is read back in between.  A region that overflows (a genome
+    // whose k-mers crowd a few buckets) sends the call to the route below.
+    uint64_t max_expect = 0, total_bound = 0;
+    for (int g = 0; g < G; ++g) {
+      const uint64_t wins = genome_windows(batch, g, window);
+      const uint64_t e = std::min<uint64_t>(wins, (uint64_t)((double)wins / (double)pred->modulus * 1.25) + 1024);
+      max_expect = std::max(max_expect, e);
+      total_bound += e;   // room of the output; more distinct keys than that raise the flag (sortp_region_offsets_kernel)
+    }
+    int bb = 0;
+    uint32_t cap = 0;
+    SortPlan kplan;
+    if (bucket_regions_plan(mask, G, max_expect, &bb, &cap, &kplan)) {
+      BufferRef regions, ctl;
+      const size_t n_regions = (size_t)G << bb;
+      SKS_TRY(alloc_buffer(ctx, n_regions * cap * 8, &regions));
+      SKS_TRY(alloc_buffer(ctx, 4 * n_regions + 256, &ctl));
+      SKS_CUDA_TRY(cudaMemsetAsync(ctl->ptr, 0, 4 * n_regions + 256, ctx->stream));
+      uint32_t *d_cursor = static_cast<uint32_t *>(ctl->ptr), *d_flag = d_cursor + n_regions;
+      plan.p.out_keys = regions->ptr;
+      plan.p.out_pos = nullptr;
+      plan.p.out_off = nullptr;
+      plan.p.out_cap = nullptr;
+      plan.p.out_count = nullptr;
+      plan.p.kpart_bits = (uint32_t)bb;
+      plan.p.kpart_cap = cap;
+      plan.p.kpart_cursor = d_cursor;
+      plan.p.kpart_overflow = d_flag;
+      plan.p.kpart_plan = kplan;
+      SKS_TRY(launch_sketch(ctx, plan.p, batch->tile_genome ? static_cast<const uint32_t *>(batch->tile_genome->ptr) : nullptr,
+                            plan.n_limbs, plan.pred_mode, OUT_KEYS));
+      plan.p.kpart_bits = 0;
+      SKS_TRY(sort_unique_from_buckets(ctx, static_cast<unsigned long long *>(regions->ptr), G, bb, cap, d_cursor, d_flag, total_bound,
+                                       &uniq, &uoff, &ucount, &done));
+    }
+  }
+  if (!done) {
+    SKS_TRY(sketch_raw_keys(ctx, batch, plan, pred, window, OUT_KEYS, &raw, &pos, &off, &count, &span));
+    SKS_TRY(sort_unique_regions(ctx, key_words, raw->ptr, off.data(), count.data(), G, span, &uniq, &uoff, &ucount,
+                                mask));
+  }
   for (int g = 0; g < G; ++g) {
     sks_set *s = new_set(ctx, SKS_REPR_SORTED, mask, window, plan.weight);
     if (!s) return set_error(SKS_ERR_INVALID, "out of host memory");

@@ -96,6 +96,49 @@ struct PextTable {
   uint32_t n_pieces[4];
 };
 
+// Bucket index of the bucket sort: the top `bb` MASK-SELECTED bits of the key (up to six runs of the mask,
+// concatenated from the top, so the index is monotone in the key).  A plain bit field below the mask's highest bit
+// would include the positions a spaced seed skips, which are zero in every key: a quarter of the buckets would
+// get all the keys.
+struct SortPlan {
+  int n_pieces;
+  int word[6];       // 0: low 64 bits of the key, 1: high 64 bits
+  int s[6];          // piece i = ((word >> s[i]) & m[i]) << o[i]
+  uint32_t m[6];
+  int o[6];
+};
+// Plan for `bb` bucket bits under `mask`; false when the mask has fewer set bits than that or needs more than six
+// pieces.
+// `skip`: that many of the mask's top set bits are passed over first (they are the same in every key of the region:
+// keys routed to the owner of a key range).
+inline bool sort_plan(const uint64_t mask[2], int bb, SortPlan *out, int skip = 0) {
+  SortPlan p = {};
+  int got = 0, bit = 127;
+  auto set = [&](int b) { return b >= 0 && ((mask[b >> 6] >> (b & 63)) & 1); };
+  for (int s = 0; s < skip; ++s) {
+    while (bit >= 0 && !set(bit)) --bit;
+    if (bit < 0) return false;
+    --bit;
+  }
+  while (got < bb) {
+    while (bit >= 0 && !set(bit)) --bit;
+    if (bit < 0 || p.n_pieces == 6) return false;
+    const int hi = bit;
+    // a piece stays inside one 64-bit word and takes at most what is still missing
+    while (bit >= 0 && set(bit) && (bit >> 6) == (hi >> 6) && hi - bit + 1 <= bb - got) --bit;
+    const int len = hi - bit;
+    p.word[p.n_pieces] = hi >> 6;
+    p.s[p.n_pieces] = (bit + 1) & 63;
+    p.m[p.n_pieces] = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1);
+    got += len;
+    p.o[p.n_pieces] = bb - got;
+    ++p.n_pieces;
+  }
+  *out = p;
+  return true;
+}
+
+
 struct SketchParams {
   const uint32_t *words;       // batch buffer (nullptr when host_words: GenomeDesc::word_off is then absolute)
   const GenomeDesc *genomes;   // [n_genomes]
@@ -124,6 +167,13 @@ struct SketchParams {
   uint32_t part_cap;
   int part_shift;              // bucket = index >> part_shift
   uint32_t host_words;         // genomes are read in place from pinned host memory (see the kernel's tile fetch)
+  // OUT_KEYS under a sparse predicate, 8-byte keys: the first level of the bucket sort folded into the emit.  The kept
+  // k-mers of genome g go straight to the region of (g, bucket of the key) -- kpart_cap slots at
+  // ((g << kpart_bits) + bucket) * kpart_cap of out_keys, positions handed out by kpart_cursor (zero on entry); a full
+  // region raises kpart_overflow and the caller falls back to emit + histogram + scatter.  kpart_bits == 0: off.
+  uint32_t kpart_bits, kpart_cap;
+  uint32_t *kpart_cursor, *kpart_overflow;
+  SortPlan kpart_plan;
   // OUT_BITSET
   uint32_t *bitset;            // n_genomes consecutive bitsets
   uint64_t bitset_words;       // words per genome
@@ -254,6 +304,10 @@ int sort_unique_regions(sks_ctx *ctx, int key_words, void *keys, const uint64_t 
                         int n_regions, uint64_t span, BufferRef *out_buf, std::vector<uint64_t> *out_off,
                         std::vector<uint64_t> *out_count, const uint64_t *mask = nullptr,  // mask: enables the bucket sort
                         int skip_bits = 0);  // the mask's top skip_bits set bits are the same in every key of a region
+bool bucket_regions_plan(const uint64_t mask[2], int n_genomes, uint64_t max_count, int *bb_out, uint32_t *cap_out, SortPlan *plan);
+int sort_unique_from_buckets(sks_ctx *ctx, unsigned long long *regions, int n_genomes, int bb, uint32_t cap, const uint32_t *d_cursor,
+                             uint32_t *d_flag, uint64_t total_bound, BufferRef *out_buf, std::vector<uint64_t> *out_off,
+                             std::vector<uint64_t> *out_count, bool *handled);
 int launch_sorted_intersect_pairs(sks_ctx *ctx, int key_words, const void *const *d_a, const int64_t *d_na,
                                   const void *const *d_b, const int64_t *d_nb, int64_t n_pairs, int32_t *d_out,
                                   const uint32_t *d_pair_idx = nullptr, int slices = 1);

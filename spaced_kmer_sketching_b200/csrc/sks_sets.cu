@@ -926,17 +926,6 @@ int launch_bitset_popcount(sks_ctx *ctx, const uint32_t *a, uint64_t n_words, un
 constexpr int kSortCap = 4096;          // keys per bucket (32 KB of shared memory)
 constexpr int kSortMaxBucketBits = 12;
 
-// Bucket index of the bucket sort: the top `bb` MASK-SELECTED bits of the key (up to six runs of the mask,
-// concatenated from the top, so the index is monotone in the key).  A plain bit field below the mask's highest bit
-// would include the positions a spaced seed skips, which are zero in every key: a quarter of the buckets would
-// get all the keys.
-struct SortPlan {
-  int n_pieces;
-  int word[6];       // 0: low 64 bits of the key, 1: high 64 bits
-  int s[6];          // piece i = ((word >> s[i]) & m[i]) << o[i]
-  uint32_t m[6];
-  int o[6];
-};
 // Key of the bucket sort: 8 bytes (windows <= 32) or 16 bytes as {lo, hi}.
 template <int KW>
 struct SortKey;
@@ -968,37 +957,6 @@ struct SortKey<2> {
     return b;
   }
 };
-
-// Plan for `bb` bucket bits under `mask`; false when the mask has fewer set bits than that or needs more than six
-// pieces.
-// `skip`: that many of the mask's top set bits are passed over first (they are the same in every key of the region:
-// keys routed to the owner of a key range).
-inline bool sort_plan(const uint64_t mask[2], int bb, SortPlan *out, int skip = 0) {
-  SortPlan p = {};
-  int got = 0, bit = 127;
-  auto set = [&](int b) { return b >= 0 && ((mask[b >> 6] >> (b & 63)) & 1); };
-  for (int s = 0; s < skip; ++s) {
-    while (bit >= 0 && !set(bit)) --bit;
-    if (bit < 0) return false;
-    --bit;
-  }
-  while (got < bb) {
-    while (bit >= 0 && !set(bit)) --bit;
-    if (bit < 0 || p.n_pieces == 6) return false;
-    const int hi = bit;
-    // a piece stays inside one 64-bit word and takes at most what is still missing
-    while (bit >= 0 && set(bit) && (bit >> 6) == (hi >> 6) && hi - bit + 1 <= bb - got) --bit;
-    const int len = hi - bit;
-    p.word[p.n_pieces] = hi >> 6;
-    p.s[p.n_pieces] = (bit + 1) & 63;
-    p.m[p.n_pieces] = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1);
-    got += len;
-    p.o[p.n_pieces] = bb - got;
-    ++p.n_pieces;
-  }
-  *out = p;
-  return true;
-}
 
 template <int KW>
 __global__ void __launch_bounds__(256)
@@ -1123,7 +1081,9 @@ __global__ void __launch_bounds__(kSortThreads)
     sortp_bucket_kernel(const typename SortKey<KW>::T *__restrict__ tmp, const Region *__restrict__ regions,
                         const uint32_t *__restrict__ boff, const uint32_t *__restrict__ hist,
                         typename SortKey<KW>::T *__restrict__ tmp2, uint32_t *__restrict__ ucount, int bb,
-                        uint32_t *__restrict__ flag) {
+                        uint32_t *__restrict__ flag, uint32_t uniform_cap) {
+  // uniform_cap != 0: bucket q occupies the slots [q * uniform_cap, q * uniform_cap + hist[q]) (the sketch kernel wrote
+  // the kept k-mers straight into per-bucket regions); regions / boff are not used then
   using K = SortKey<KW>;
   __shared__ typename K::T s[kCap];
   __shared__ uint32_t s_warp[kSortThreads / 32];
@@ -1141,8 +1101,8 @@ __global__ void __launch_bounds__(kSortThreads)
     }
     return;
   }
-  const Region r = regions[blockIdx.x >> bb];
-  const unsigned long long lo = r.begin + boff[blockIdx.x];
+  const unsigned long long lo = uniform_cap ? (unsigned long long)blockIdx.x * uniform_cap
+                                            : regions[blockIdx.x >> bb].begin + boff[blockIdx.x];
   uint32_t P = 32;
   while (P < n) P <<= 1;
   const uint32_t tid = threadIdx.x;
@@ -1237,7 +1197,8 @@ __global__ void __launch_bounds__(kSortThreads)
 
 // Exclusive prefix over the regions' distinct totals (one CTA; n_regions is at most a few thousand).
 __global__ void __launch_bounds__(1024)
-    sortp_region_offsets_kernel(const unsigned long long *__restrict__ utot, unsigned long long *__restrict__ uoff, int n_regions) {
+    sortp_region_offsets_kernel(const unsigned long long *__restrict__ utot, unsigned long long *__restrict__ uoff, int n_regions,
+                                unsigned long long bound = ~0ull, uint32_t *__restrict__ flag = nullptr) {
   __shared__ unsigned long long s_carry;
   __shared__ unsigned long long s_warp[32];
   if (threadIdx.x == 0) s_carry = 0;
@@ -1261,6 +1222,7 @@ __global__ void __launch_bounds__(1024)
     if (threadIdx.x == 1023) s_carry = before + v;
     __syncthreads();
   }
+  if (flag && threadIdx.x == 0 && s_carry > bound) *flag = 1u;  // more distinct keys than the output holds: the caller starts over
 }
 
 template <int KW>
@@ -1268,11 +1230,11 @@ __global__ void __launch_bounds__(256)
     sortp_copy_kernel(const typename SortKey<KW>::T *__restrict__ tmp2, const Region *__restrict__ regions,
                       const uint32_t *__restrict__ boff, const uint32_t *__restrict__ uboff, const uint32_t *__restrict__ ucount,
                       const unsigned long long *__restrict__ uoff, typename SortKey<KW>::T *__restrict__ out, int bb,
-                      const uint32_t *__restrict__ flag) {
+                      const uint32_t *__restrict__ flag, uint32_t uniform_cap) {
   if (*flag) return;
   const uint32_t n = ucount[blockIdx.x];
   const uint32_t region = blockIdx.x >> bb;
-  const unsigned long long src = regions[region].begin + boff[blockIdx.x];
+  const unsigned long long src = uniform_cap ? (unsigned long long)blockIdx.x * uniform_cap : regions[region].begin + boff[blockIdx.x];
   const unsigned long long dst = uoff[region] + uboff[blockIdx.x];
   for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[dst + i] = tmp2[src + i];
 }
@@ -1345,18 +1307,18 @@ int sort_unique_buckets(sks_ctx *ctx, typename SortKey<KW>::T *keys, const uint6
   SKS_CUDA_TRY(cudaGetLastError());
   if ((max_count >> bb) > 600)  // 2048-key networks: more threads per bucket
     sortp_bucket_kernel<KW, 512, kSortCap / KW><<<(unsigned)n_b, 512, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2,
-                                                                             d_ucount, bb, d_flag);
+                                                                             d_ucount, bb, d_flag, 0);
   else  // ~300 keys per bucket on average: a 256/512-key network keeps 128 threads busy (half of 256 would idle);
         // 8 KB of shared memory per CTA keeps many buckets in flight per SM
     sortp_bucket_kernel<KW, 128, 1024><<<(unsigned)n_b, 128, 0, ctx->stream>>>(d_tmp, d_regions, d_boff, d_hist, d_tmp2, d_ucount,
-                                                                         bb, d_flag);
+                                                                         bb, d_flag, 0);
   SKS_CUDA_TRY(cudaGetLastError());
   sortp_scan_kernel<<<n_regions, 1024, 0, ctx->stream>>>(d_ucount, d_uboff, nullptr, nb, d_utot, 0xFFFFFFFFu, d_flag);
   SKS_CUDA_TRY(cudaGetLastError());
   sortp_region_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(d_utot, d_uoff, n_regions);
   SKS_CUDA_TRY(cudaGetLastError());
   sortp_copy_kernel<KW><<<(unsigned)n_b, 256, 0, ctx->stream>>>(d_tmp2, d_regions, d_boff, d_uboff, d_ucount, d_uoff, d_out, bb,
-                                                            d_flag);
+                                                            d_flag, 0);
   SKS_CUDA_TRY(cudaGetLastError());
   ctx->launches += 7;
 
@@ -1373,6 +1335,84 @@ int sort_unique_buckets(sks_ctx *ctx, typename SortKey<KW>::T *keys, const uint6
   for (int g = 0; g < n_regions; ++g) {
     (*out_count)[g] = h_back[g];
     (*out_off)[g] = h_back[n_regions + g];
+  }
+  *handled = true;
+  return SKS_OK;
+}
+
+// Geometry of the bucket sort when its first level is folded into the sketch kernel's emit (SketchParams::kpart_*):
+// bucket bits and slots per (genome, bucket) region for genomes of up to `max_count` kept k-mers each.  False when the
+// input is not for this scheme (the caller then emits per genome and partitions afterwards).
+bool bucket_regions_plan(const uint64_t mask[2], int n_genomes, uint64_t max_count, int *bb_out, uint32_t *cap_out, SortPlan *plan) {
+  static const bool enabled = getenv("SKS_SKETCH_PART") ? atoi(getenv("SKS_SKETCH_PART")) != 0 : true;
+  static const bool bucket_sort = getenv("SKS_BUCKET_SORT") ? atoi(getenv("SKS_BUCKET_SORT")) != 0 : true;
+  if (!enabled || !bucket_sort || n_genomes < 1 || max_count < 64) return false;
+  int bb = 0;
+  while (bb < 10 && (max_count >> bb) > 320) ++bb;
+  while (bb < kSortMaxBucketBits && (max_count >> bb) > 1536) ++bb;
+  const uint64_t avg = max_count >> bb;
+  if (avg > (uint64_t)kSortCap / 4 || ((uint64_t)n_genomes << bb) > (1u << 22)) return false;
+  const int mask_bits = __builtin_popcountll(mask[0]) + __builtin_popcountll(mask[1]);
+  if (mask_bits < 62 && ((uint64_t)1 << mask_bits) < 4 * max_count) return false;  // mostly duplicates: see sort_unique_buckets
+  if (!sort_plan(mask, bb, plan)) return false;
+  // three times the mean load of a bucket: uniform keys (random sequence) stay far below, a skewed genome overflows and
+  // takes the exact route
+  const uint64_t cap = std::min<uint64_t>(3 * avg + 64, avg > 300 ? kSortCap : 1024);
+  if (((uint64_t)n_genomes << bb) * cap * 8 > ((uint64_t)4 << 30)) return false;
+  *bb_out = bb;
+  *cap_out = (uint32_t)cap;
+  return true;
+}
+
+// Second half of the bucket sort on regions the sketch kernel filled: region q = (genome << bb) + bucket holds
+// d_cursor[q] keys at q * cap.  *handled == false: a region overflowed or a bucket was too large -- nothing was produced.
+int sort_unique_from_buckets(sks_ctx *ctx, unsigned long long *regions, int n_genomes, int bb, uint32_t cap, const uint32_t *d_cursor,
+                             uint32_t *d_flag, uint64_t total_bound, BufferRef *out_buf, std::vector<uint64_t> *out_off,
+                             std::vector<uint64_t> *out_count, bool *handled) {
+  *handled = false;
+  out_off->assign(n_genomes, 0);
+  out_count->assign(n_genomes, 0);
+  const size_t n_b = (size_t)n_genomes << bb;
+  const uint32_t nb = 1u << bb;
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t sz_tab = align(4 * n_b), sz_u64 = align(8 * (size_t)n_genomes);
+  char *base = nullptr;
+  SKS_TRY(ctx_scratch(ctx, 2 * sz_tab + 2 * sz_u64, reinterpret_cast<void **>(&base)));
+  uint32_t *d_ucount = reinterpret_cast<uint32_t *>(base), *d_uboff = reinterpret_cast<uint32_t *>(base + sz_tab);
+  unsigned long long *d_utot = reinterpret_cast<unsigned long long *>(base + 2 * sz_tab);
+  unsigned long long *d_uoff = reinterpret_cast<unsigned long long *>(base + 2 * sz_tab + sz_u64);
+  SKS_TRY(alloc_buffer(ctx, 8 * std::max<uint64_t>(total_bound, 2), out_buf));
+  unsigned long long *d_out = static_cast<unsigned long long *>((*out_buf)->ptr);
+  {
+    KernelTimer timer(ctx, SKS_KERNEL_SORT_UNIQUE);
+    if (cap > 1024)
+      sortp_bucket_kernel<1, 512, kSortCap><<<(unsigned)n_b, 512, 0, ctx->stream>>>(regions, nullptr, nullptr, d_cursor, regions, d_ucount,
+                                                                              bb, d_flag, cap);
+    else
+      sortp_bucket_kernel<1, 128, 1024><<<(unsigned)n_b, 128, 0, ctx->stream>>>(regions, nullptr, nullptr, d_cursor, regions, d_ucount, bb,
+                                                                            d_flag, cap);
+    SKS_CUDA_TRY(cudaGetLastError());
+    sortp_scan_kernel<<<n_genomes, 1024, 0, ctx->stream>>>(d_ucount, d_uboff, nullptr, nb, d_utot, 0xFFFFFFFFu, d_flag);
+    SKS_CUDA_TRY(cudaGetLastError());
+    sortp_region_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(d_utot, d_uoff, n_genomes, total_bound, d_flag);
+    SKS_CUDA_TRY(cudaGetLastError());
+    sortp_copy_kernel<1><<<(unsigned)n_b, 256, 0, ctx->stream>>>(regions, nullptr, nullptr, d_uboff, d_ucount, d_uoff, d_out, bb, d_flag, cap);
+    SKS_CUDA_TRY(cudaGetLastError());
+    ctx->launches += 4;
+  }
+  unsigned long long *h_back = nullptr;
+  SKS_TRY(ctx_pinned(ctx, 16 * (size_t)n_genomes + 64, reinterpret_cast<void **>(&h_back)));
+  SKS_CUDA_TRY(cudaMemcpyAsync(h_back, d_utot, 8 * (size_t)n_genomes, cudaMemcpyDeviceToHost, ctx->stream));
+  SKS_CUDA_TRY(cudaMemcpyAsync(h_back + n_genomes, d_uoff, 8 * (size_t)n_genomes, cudaMemcpyDeviceToHost, ctx->stream));
+  SKS_CUDA_TRY(cudaMemcpyAsync(h_back + 2 * n_genomes, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  SKS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  if ((uint32_t)h_back[2 * n_genomes] != 0) {
+    out_buf->reset();
+    return SKS_OK;
+  }
+  for (int g = 0; g < n_genomes; ++g) {
+    (*out_count)[g] = h_back[g];
+    (*out_off)[g] = h_back[n_genomes + g];
   }
   *handled = true;
   return SKS_OK;

@@ -117,6 +117,15 @@ __device__ __forceinline__ uint32_t pext_index(const uint32_t (&c)[NL], const Pe
   return idx;
 }
 
+// Bucket of an 8-byte key in the bucket sort (sks_sets.cu, SortKey<1>::bucket): its top mask-selected bits.
+__device__ __forceinline__ uint32_t kpart_bucket(unsigned long long k, const SortPlan &p) {
+  uint32_t b = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+    if (i < p.n_pieces) b |= ((uint32_t)(k >> p.s[i]) & p.m[i]) << p.o[i];
+  return b;
+}
+
 struct TileMeta {
   uint32_t genome;
   uint32_t t0;       // first window start of the tile, relative to the genome
@@ -285,8 +294,25 @@ __global__ void __launch_bounds__(kSketchThreads, (PRED != PRED_ALL && OUT != OU
   // Copies the staged survivors of `genome` to its output region: one global reservation per flush.
   // `staged` is the value of *s_count every thread read between two barriers (so it is uniform and nobody
   // is staging any more).
+  // the first level of the bucket sort folded into the emit (8-byte keys only): see SketchParams::kpart_*
+  auto kpart_put = [&](uint32_t genome, unsigned long long key) {
+    const uint32_t region = (genome << P.kpart_bits) + kpart_bucket(key, P.kpart_plan);
+    const uint32_t pos = atomicAdd(P.kpart_cursor + region, 1u);
+    if (pos < P.kpart_cap) reinterpret_cast<unsigned long long *>(P.out_keys)[(size_t)region * P.kpart_cap + pos] = key;
+    else *P.kpart_overflow = 1u;
+  };
   auto flush = [&](uint32_t genome, uint32_t staged) {
     const uint32_t n = staged < (uint32_t)kStageSlots ? staged : (uint32_t)kStageSlots;  // the rest was spilled
+    if (OUT == OUT_KEYS && NL <= 2 && P.kpart_bits != 0) {  // uniform
+      if (n > 0) {
+        if (tid == 0) *s_count = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += kSketchThreads)
+          if (NL <= 2) kpart_put(genome, reinterpret_cast<const unsigned long long *>(s_keys)[i]);
+        __syncthreads();
+      }
+      return;
+    }
     if (n > 0) {      // uniform
       if (tid == 0) {
         *s_base = atomicAdd(P.out_count + genome, (unsigned long long)n);
@@ -418,7 +444,9 @@ __global__ void __launch_bounds__(kSketchThreads, (PRED != PRED_ALL && OUT != OU
             }
           } else {
             const uint32_t slot = atomicAdd(s_count, 1u);
-            if (kSparse && slot >= (uint32_t)kStageSlots) {
+            if (kSparse && slot >= (uint32_t)kStageSlots && OUT == OUT_KEYS && NL <= 2 && P.kpart_bits != 0) {
+              kpart_put(tm.genome, b0);
+            } else if (kSparse && slot >= (uint32_t)kStageSlots) {
               // the stage is full (dense survivors under a sparse-mode predicate): write this one directly
               const unsigned long long gs = atomicAdd(P.out_count + tm.genome, 1ull);
               if (gs < P.out_cap[tm.genome]) {
