@@ -1347,7 +1347,7 @@ bool bucket_regions_plan(const uint64_t mask[2], int n_genomes, uint64_t max_cou
   static const bool enabled = getenv("SKS_SKETCH_PART") ? atoi(getenv("SKS_SKETCH_PART")) != 0 : true;
   static const bool bucket_sort = getenv("SKS_BUCKET_SORT") ? atoi(getenv("SKS_BUCKET_SORT")) != 0 : true;
   if (!enabled || !bucket_sort || n_genomes < 1 || max_count < 64) return false;
-  int bb = 0;
+  int bb = 1;  // SketchParams::kpart_bits == 0 means "route off" to the kernel: at least two buckets per genome
   while (bb < 10 && (max_count >> bb) > 320) ++bb;
   while (bb < kSortMaxBucketBits && (max_count >> bb) > 1536) ++bb;
   const uint64_t avg = max_count >> bb;

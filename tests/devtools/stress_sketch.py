@@ -46,6 +46,8 @@ while time.time() < t_end:
         var = int(rng.choice([171, 181]))
         pred, opred = sks.frac_min_hash(nonce, mod, var), (port.FMH, nonce, mod, var)
     reprs = [sks.REPR_SORTED] + ([sks.REPR_BITSET] if pred.kind == sks.PRED_ALL and weight <= 12 else [])
+    if os.environ.get("STRESS_VERBOSE"):
+        print("trial %d lens %r w %d k %d mask %x pred %r" % (trial, [len(g) for g in genomes], w, k, mask, opred), flush=True)
     batch = ctx.upload_codes(genomes, segs)
     want = [port.sketch_set(g, s, mask, w, *opred) for g, s in zip(genomes, segs)]
     for r in reprs:
