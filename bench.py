@@ -400,7 +400,7 @@ def run_b200(args):
             e2e_step()
             flush.zero_()
         barrier()
-        in_place0 = ctx.in_place_calls
+        in_place0, streamed0 = ctx.in_place_calls, ctx.streamed_calls
         e2e_ev, e2e_wall = [], 0.0
         for _ in range(args.steps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -417,6 +417,7 @@ def run_b200(args):
         assert np.array_equal(out[0], counts0) and np.array_equal(out[1], sizes0)
         e2e_value = n * n * args.steps / (e2e_ms / 1e3)
         in_place = ctx.in_place_calls - in_place0 == args.steps
+        streamed = ctx.streamed_calls - streamed0 == args.steps
         h2d = int(n_loc * words * 4 + n_loc * (32 + 4 + 4))       # packed bases + genome descriptors + segment ends + tile map (per rank)
         d2h = int(n_loc * n * 12 + n * 4)                         # the rank's rows: int32 counts + float64 ANI, and the n sizes
         # pageable host buffers take the copy path (cudaMemcpyAsync through the driver's staging)
@@ -524,7 +525,9 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                     "ms_per_step": e2e_ms / args.steps,
                     "call": "sks_all_vs_all_from_host (host packed genomes in; counts, sizes and ANI rows out)",
-                    "host_to_device": ("the sketch kernel's bulk copies read the pinned host buffers in place, tile by tile "
+                    "host_to_device": ("the copy engine brings the pinned host buffers 16 MB at a time while the sketch kernel "
+                                       "works on the chunks that have arrived") if streamed else
+                                      ("the sketch kernel's bulk copies read the pinned host buffers in place, tile by tile "
                                        "(no separate copy)") if in_place else "cudaMemcpyAsync before the sketch kernel",
                     "pageable_host_buffers_ms_per_step": e2e_pageable_ms,
                     "l2": "256 MiB flush write between steps"},

@@ -85,6 +85,9 @@ int64_t sks_ctx_launch_count(const sks_ctx *ctx);
 /* Number of sks_pair_ani calls of this context that read the genomes in place from the caller's pinned host
  * buffers (no host-to-device copy; see sks_pair_ani). */
 int64_t sks_ctx_in_place_count(const sks_ctx *ctx);
+/* Number of sks_all_vs_all_from_host calls of this context whose genomes were copied from the caller's pinned host
+ * buffers chunk by chunk while the sketch kernel already worked on the chunks that had arrived. */
+int64_t sks_ctx_streamed_count(const sks_ctx *ctx);
 
 /* Per-kernel CUDA-event timing (bench.py's roofline numbers).  While enabled, every kernel launch of
  * the context is bracketed by a pair of events on the context's stream; sks_ctx_kernel_stats
@@ -319,8 +322,11 @@ int sks_all_vs_all_sharded(sks_ctx *ctx, sks_comm *comm, sks_set *const *local, 
 int sks_all_vs_all_resident(sks_ctx *ctx, sks_comm *comm, const sks_batch *batch, int64_t n_total, const uint64_t mask[2],
                             int window, const sks_pred *pred, int32_t *out_counts, int32_t *out_sizes, double *out_ani);
 /* The whole path from HOST buffers: packed[g] / n_bases[g] are the rank's n_local genomes (2-bit packed, one segment
- * each); they are uploaded (or, in pinned host memory, read in place by the sketch kernel), sketched, exchanged and
- * compared.  = parallel_kmer_sets_from_fasta_files + the comparison loop of src/kmer-sketching.cpp:163-200. */
+ * each); they are brought to the device, sketched, exchanged and compared.  = parallel_kmer_sets_from_fasta_files + the
+ * comparison loop of src/kmer-sketching.cpp:163-200.  Pinned host memory of 64 MB and more is copied chunk by chunk
+ * (16 MB) by the copy engine while the sketch kernel works on the chunks that are there (sks_ctx_streamed_count);
+ * smaller pinned inputs are read in place by the kernel (sks_ctx_in_place_count); pageable memory is copied up first.
+ * The call returns after the device has finished with the buffers. */
 int sks_all_vs_all_from_host(sks_ctx *ctx, sks_comm *comm, int n_local, const uint32_t *const *packed, const uint64_t *n_bases,
                              int64_t n_total, const uint64_t mask[2], int window, const sks_pred *pred, int32_t *out_counts,
                              int32_t *out_sizes, double *out_ani);

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "sks_timer_end": (ci, [vp, C.POINTER(C.c_float)]),
     "sks_ctx_launch_count": (i64, [vp]),
     "sks_ctx_in_place_count": (i64, [vp]),
+    "sks_ctx_streamed_count": (i64, [vp]),
     "sks_ctx_profile": (ci, [vp, ci]),
     "sks_ctx_kernel_stats": (ci, [vp, ci, i64p, C.POINTER(C.c_double)]),
     "sks_kernel_name": (C.c_char_p, [ci]),

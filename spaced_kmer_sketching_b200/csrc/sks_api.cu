@@ -575,6 +575,12 @@ int sketch_raw_one(sks_ctx *ctx, const sks_batch *batch, const uint64_t mask[2],
 }
 namespace {
 
+// The context's stream waits for the last copy of a batch that is still arriving (no-op for every other batch).
+int batch_arrived(sks_ctx *ctx, const sks_batch *batch) {
+  if (!batch->arriving.empty()) SKS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, batch->arriving.back().ready, 0));
+  return SKS_OK;
+}
+
 int sketch_sorted(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const sks_pred *pred,
                   const uint64_t mask[2], int window, sks_set **out_sets) {
   const int G = batch->n_genomes;
@@ -615,14 +621,28 @@ int sketch_sorted(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
       plan.p.kpart_cursor = d_cursor;
       plan.p.kpart_overflow = d_flag;
       plan.p.kpart_plan = kplan;
-      SKS_TRY(launch_sketch(ctx, plan.p, batch->tile_genome ? static_cast<const uint32_t *>(batch->tile_genome->ptr) : nullptr,
-                            plan.n_limbs, plan.pred_mode, OUT_KEYS));
+      const uint32_t *tile_genome = batch->tile_genome ? static_cast<const uint32_t *>(batch->tile_genome->ptr) : nullptr;
+      if (batch->arriving.empty()) {
+        SKS_TRY(launch_sketch(ctx, plan.p, tile_genome, plan.n_limbs, plan.pred_mode, OUT_KEYS));
+      } else {
+        // the genomes are still on their way from the host: every chunk is sketched as soon as it is there, into the same
+        // regions, while the copy engine brings the next one
+        for (const sks_batch::Arriving &chunk : batch->arriving) {
+          SKS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, chunk.ready, 0));
+          plan.p.tile_begin = chunk.tile_begin;
+          plan.p.n_tiles = chunk.tile_end;
+          SKS_TRY(launch_sketch(ctx, plan.p, tile_genome, plan.n_limbs, plan.pred_mode, OUT_KEYS));
+        }
+        plan.p.tile_begin = 0;
+        plan.p.n_tiles = batch->n_tiles;
+      }
       plan.p.kpart_bits = 0;
       SKS_TRY(sort_unique_from_buckets(ctx, static_cast<unsigned long long *>(regions->ptr), G, bb, cap, d_cursor, d_flag, total_bound,
                                        &uniq, &uoff, &ucount, &done));
     }
   }
   if (!done) {
+    SKS_TRY(batch_arrived(ctx, batch));
     SKS_TRY(sketch_raw_keys(ctx, batch, plan, pred, window, OUT_KEYS, &raw, &pos, &off, &count, &span));
     SKS_TRY(sort_unique_regions(ctx, key_words, raw->ptr, off.data(), count.data(), G, span, &uniq, &uoff, &ucount,
                                 mask));
@@ -708,6 +728,8 @@ void sks_ctx_destroy(sks_ctx *ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (cudaEvent_t e : ctx->sync_events) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto &v : ctx->prof)
     for (auto &pr : v) {
       cudaEventDestroy(pr.first);
@@ -758,6 +780,7 @@ int sks_timer_end(sks_ctx *ctx, float *out_ms) {
 }
 int64_t sks_ctx_launch_count(const sks_ctx *ctx) { return ctx ? ctx->launches : 0; }
 int64_t sks_ctx_in_place_count(const sks_ctx *ctx) { return ctx ? ctx->in_place_calls : 0; }
+int64_t sks_ctx_streamed_count(const sks_ctx *ctx) { return ctx ? ctx->streamed_calls : 0; }
 
 int sks_ctx_profile(sks_ctx *ctx, int enable) {
   if (!ctx) return set_error(SKS_ERR_INVALID, "null context");
@@ -863,6 +886,118 @@ static int batch_in_place(sks_ctx *ctx, int n_genomes, const uint32_t *const *pa
     st = upload_tables(ctx, b);
   }
   if (st != SKS_OK) {
+    delete b;
+    return st;
+  }
+  *out = b;
+  return SKS_OK;
+}
+
+// Zeroes what lies between the genomes of a batch buffer (history words, 16-byte rounding, the halo behind the last
+// genome): a warp per gap.
+__global__ void zero_pads_kernel(uint32_t *words, const GenomeDesc *genomes, int n_genomes, unsigned long long total_words) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g > n_genomes) return;
+  const unsigned long long lo = g == 0 ? 0ull : genomes[g - 1].word_off + (genomes[g - 1].n_bases + 15ull) / 16;
+  const unsigned long long hi = g == n_genomes ? total_words : genomes[g].word_off;
+  for (unsigned long long i = lo + (threadIdx.x & 31); i < hi; i += 32) words[i] = 0;
+}
+
+// A device batch for genomes in pinned host buffers that is filled WHILE it is sketched: the copy engine brings the
+// genomes chunk by chunk (SKS_HOST_CHUNK_MB, default 16 MB: large copies reach 55 GB/s on PCIe 5 where the sketch
+// kernel's own 2 KB reads of host memory stay at 44 GB/s; 8 to 64 MB measure the same, 27.3 ms against 31.1 ms for
+// 1000 x 5 Mbp), every chunk records an event, and sketch_sorted launches the
+// kernel chunk by chunk behind them.  Only for sks_all_vs_all_from_host, which keeps the batch to itself, and only from
+// SKS_HOST_STREAM_MIN_MB (default 64) on: below that the in-place route has less to set up.  SKS_HOST_STREAM=0: off.
+static int batch_streamed(sks_ctx *ctx, int n_genomes, const uint32_t *const *packed, const uint64_t *n_bases,
+                          sks_batch **out) {
+  // (read at every call: the tests change them)
+  const char *e_on = getenv("SKS_HOST_STREAM"), *e_min = getenv("SKS_HOST_STREAM_MIN_MB"), *e_chunk = getenv("SKS_HOST_CHUNK_MB");
+  const bool enabled = !e_on || atoi(e_on) != 0;
+  const uint64_t min_bytes = (uint64_t)std::max<long long>(e_min ? atoll(e_min) : 64, 0) << 20;
+  const uint64_t chunk_bytes = (uint64_t)std::max<long long>(e_chunk ? atoll(e_chunk) : 16, 1) << 20;
+  if (!enabled || n_genomes <= 0) return SKS_ERR_INVALID;
+  DeviceGuard guard(ctx->device);
+  uint64_t total_bytes = 0;
+  for (int g = 0; g < n_genomes; ++g) {
+    if (!packed[g] || n_bases[g] == 0) return SKS_ERR_INVALID;
+    total_bytes += (n_bases[g] + 15) / 16 * 4;
+  }
+  if (total_bytes < min_bytes) return SKS_ERR_INVALID;
+  for (int g = 0; g < n_genomes; ++g) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, packed[g]) != cudaSuccess) {
+      cudaGetLastError();
+      return SKS_ERR_INVALID;
+    }
+    if (attr.type != cudaMemoryTypeHost) return SKS_ERR_INVALID;  // pageable: the copies would not be asynchronous
+  }
+  sks_batch *b = new (std::nothrow) sks_batch();
+  if (!b) return SKS_ERR_INVALID;
+  b->device = ctx->device;
+  uint64_t total_words = 0;
+  int st = layout_batch(b, n_genomes, n_bases, nullptr, nullptr, &total_words);
+  if (st == SKS_OK) st = alloc_buffer(ctx, (size_t)total_words * 4, &b->words);
+  if (st == SKS_OK) st = upload_tables(ctx, b);
+  auto fail = [&](cudaError_t e) { return e == cudaSuccess ? SKS_OK : set_error(SKS_ERR_CUDA, "streamed batch: %s", cudaGetErrorString(e)); };
+  if (st == SKS_OK && !ctx->copy_stream) st = fail(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  size_t n_events = 0;
+  auto next_event = [&](cudaEvent_t *ev) {
+    if (n_events == ctx->sync_events.size()) {
+      cudaEvent_t e;
+      if (int r = fail(cudaEventCreateWithFlags(&e, cudaEventDisableTiming))) return r;
+      ctx->sync_events.push_back(e);
+    }
+    *ev = ctx->sync_events[n_events++];
+    return (int)SKS_OK;
+  };
+  if (st == SKS_OK) {
+    uint32_t *d = static_cast<uint32_t *>(b->words->ptr);
+    // the buffer may have been in use by earlier work of the context's stream: the copies start behind it
+    cudaEvent_t free_ev = nullptr;
+    st = next_event(&free_ev);
+    if (st == SKS_OK) st = fail(cudaEventRecord(free_ev, ctx->stream));
+    if (st == SKS_OK) st = fail(cudaStreamWaitEvent(ctx->copy_stream, free_ev, 0));
+    if (st == SKS_OK) {
+      zero_pads_kernel<<<(unsigned)((n_genomes + 1 + 7) / 8), 256, 0, ctx->stream>>>(d, static_cast<const GenomeDesc *>(b->genomes->ptr),
+                                                                                 n_genomes, (unsigned long long)total_words);
+      st = fail(cudaGetLastError());
+      ctx->launches++;
+    }
+    int g = 0;
+    while (g < n_genomes && st == SKS_OK) {
+      const int chunk_first = g;
+      uint64_t bytes = 0;
+      while (g < n_genomes && bytes < chunk_bytes && st == SKS_OK) {
+        // a run of equally long, equally spaced genomes is one strided copy
+        const uint64_t row = (n_bases[g] + 15) / 16 * 4;
+        int run = 1;
+        if (g + 1 < n_genomes && n_bases[g + 1] == n_bases[g] && packed[g + 1] > packed[g]) {
+          const uint64_t pitch = (uint64_t)(reinterpret_cast<const char *>(packed[g + 1]) - reinterpret_cast<const char *>(packed[g]));
+          if (pitch >= row && pitch < ((uint64_t)1 << 31)) {
+            while (g + run < n_genomes && n_bases[g + run] == n_bases[g] && bytes + (uint64_t)run * row < chunk_bytes &&
+                   reinterpret_cast<const char *>(packed[g + run]) == reinterpret_cast<const char *>(packed[g]) + (uint64_t)run * pitch)
+              ++run;
+            if (run > 1)
+              st = fail(cudaMemcpy2DAsync(d + b->h_genomes[g].word_off, (size_t)(b->h_genomes[g + 1].word_off - b->h_genomes[g].word_off) * 4,
+                                          packed[g], (size_t)pitch, (size_t)row, (size_t)run, cudaMemcpyHostToDevice, ctx->copy_stream));
+          }
+        }
+        if (run == 1) st = fail(cudaMemcpyAsync(d + b->h_genomes[g].word_off, packed[g], (size_t)row, cudaMemcpyHostToDevice, ctx->copy_stream));
+        bytes += (uint64_t)run * row;
+        g += run;
+      }
+      cudaEvent_t ready = nullptr;
+      if (st == SKS_OK) st = next_event(&ready);
+      if (st == SKS_OK) st = fail(cudaEventRecord(ready, ctx->copy_stream));
+      if (st == SKS_OK) {
+        const GenomeDesc &last = b->h_genomes[g - 1];
+        b->arriving.push_back({b->h_genomes[chunk_first].tile_first, last.tile_first + last.n_tiles, ready});
+      }
+    }
+  }
+  if (st != SKS_OK) {
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);  // nothing of a failed call may touch the caller's buffers later
     delete b;
     return st;
   }
@@ -1838,11 +1973,17 @@ int sks_all_vs_all_from_host(sks_ctx *ctx, sks_comm *comm, int n_local, const ui
   std::vector<sks_set *> sets((size_t)std::max(n_local, 1), nullptr);
   int st = SKS_OK;
   if (n_local > 0) {
-    if (batch_in_place(ctx, n_local, packed, n_bases, &batch) != SKS_OK)  // not pinned / not aligned: copy the genomes up
+    // pinned and large: copied chunk by chunk under the sketch kernel; pinned and small: read in place by the kernel;
+    // pageable (or misaligned): copied up first
+    if (batch_streamed(ctx, n_local, packed, n_bases, &batch) == SKS_OK)
+      ctx->streamed_calls++;
+    else if (batch_in_place(ctx, n_local, packed, n_bases, &batch) != SKS_OK)
       st = sks_batch_upload(ctx, n_local, packed, n_bases, nullptr, nullptr, &batch);
     if (st == SKS_OK && batch->host_words) ctx->in_place_calls++;
     if (st == SKS_OK) st = sks_sketch(ctx, batch, mask, window, pred, SKS_REPR_SORTED, sets.data());
-    // sks_sketch has read the counts back: the kernel is done with the caller's buffers
+    // sks_sketch has read the counts back: the copies and the kernel are done with the caller's buffers -- unless it
+    // failed on the way
+    if (st != SKS_OK && batch && !batch->arriving.empty()) cudaStreamSynchronize(ctx->copy_stream);
   }
   if (st == SKS_OK) st = sks_all_vs_all_sharded(ctx, comm, sets.data(), n_local, n_total, out_counts, out_sizes, out_ani);
   for (sks_set *s : sets)

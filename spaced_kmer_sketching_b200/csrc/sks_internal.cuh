@@ -145,6 +145,7 @@ struct SketchParams {
   const uint32_t *seg_end;     // exclusive end of every segment, relative to its genome start
   int n_genomes;
   uint32_t n_tiles;            // over the whole batch
+  uint32_t tile_begin;         // the launch works on tiles [tile_begin, n_tiles): 0 but for a batch that is still arriving
   int window;                  // w, 1..64
   uint32_t mask[4];            // 128-bit mask as four 32-bit limbs
   // predicate (FMH), modulus = 2^s * d with d odd: pass <=> t = (H(masked) ^ hconst) * minv has (t & mlow) == 0
@@ -204,6 +205,9 @@ struct sks_ctx {
   int sm_count = 148;
   int64_t launches = 0;
   int64_t in_place_calls = 0;  // sks_pair_ani calls that read the genomes from pinned host memory
+  int64_t streamed_calls = 0;  // sks_all_vs_all_from_host calls whose genomes arrived chunk by chunk under the sketch kernel
+  cudaStream_t copy_stream = nullptr;    // host-to-device copies of a batch that is sketched while it arrives
+  std::vector<cudaEvent_t> sync_events;  // one per chunk of such a batch (no timing), reused by the next call
   // reusable scratch (grown on demand)
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -234,6 +238,13 @@ struct sks_batch {
   std::vector<uint32_t> h_seg_end;
   uint32_t n_tiles = 0;
   uint64_t total_bases = 0;
+  // sks_all_vs_all_from_host: the words of tiles [tile_begin, tile_end) are there once `ready` has happened (the copies run
+  // on the context's copy stream, in this order); empty for every other batch
+  struct Arriving {
+    uint32_t tile_begin, tile_end;
+    cudaEvent_t ready;
+  };
+  std::vector<Arriving> arriving;
 };
 
 struct sks_set {

@@ -332,10 +332,10 @@ __global__ void __launch_bounds__(kSketchThreads, (PRED != PRED_ALL && OUT != OU
     }
   };
 
-  if (tid == 0 && blockIdx.x < P.n_tiles) issue(blockIdx.x, 0);
+  if (tid == 0 && P.tile_begin + blockIdx.x < P.n_tiles) issue(P.tile_begin + blockIdx.x, 0);
 
   for (uint32_t it = 0;; ++it) {
-    const uint32_t tile = blockIdx.x + it * gridDim.x;
+    const uint32_t tile = P.tile_begin + blockIdx.x + it * gridDim.x;
     if (tile >= P.n_tiles) break;
     const int stage = it & 1;
     if (tid == 0 && tile + gridDim.x < P.n_tiles) issue(tile + gridDim.x, stage ^ 1);
@@ -623,11 +623,12 @@ int launch_one(sks_ctx *ctx, const SketchParams &p, const uint32_t *tile_genome)
     SKS_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kSketchThreads, smem));
     if (occ < 1) occ = 1;
   }
-  if (p.n_tiles == 0) return SKS_OK;
+  const uint32_t n_tiles = p.n_tiles - p.tile_begin;
+  if (p.n_tiles <= p.tile_begin) return SKS_OK;
   // Persistent CTAs: a whole number of waves of resident CTAs, capped by the tile count.
   uint32_t grid = (uint32_t)(ctx->sm_count * occ);
   // fewer than two tiles per resident CTA: one CTA per tile balances better than a 1-or-2 split (C2: 88 -> 83 us)
-  if (p.n_tiles <= 2 * grid) grid = p.n_tiles;
+  if (n_tiles <= 2 * grid) grid = n_tiles;
   KernelTimer timer(ctx, SKS_KERNEL_SKETCH);
   kern<<<grid, kSketchThreads, smem, ctx->stream>>>(p, tile_genome);
   SKS_CUDA_TRY(cudaGetLastError());

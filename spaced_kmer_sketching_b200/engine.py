@@ -198,6 +198,11 @@ class Context:
         """pair_ani calls that read the genomes in place from pinned host buffers (no host-to-device copy)."""
         return int(self._L.sks_ctx_in_place_count(self.h))
 
+    @property
+    def streamed_calls(self) -> int:
+        """all_vs_all_from_host calls whose pinned host genomes were copied chunk by chunk under the sketch kernel."""
+        return int(self._L.sks_ctx_streamed_count(self.h))
+
     def profile(self, enable: bool):
         check(self._L.sks_ctx_profile(self.h, int(enable)))
 

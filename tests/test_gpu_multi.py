@@ -175,6 +175,64 @@ def test_one_call_entry_points_from_resident_and_host_buffers():
     ctx.close()
 
 
+def test_pinned_host_genomes_are_streamed_under_the_sketch_kernel():
+    """sks_all_vs_all_from_host on pinned host buffers above the streaming threshold (csrc/sks_api.cu, batch_streamed): the
+    copy engine brings the genomes chunk by chunk, every chunk is sketched behind its own event.  Equally long, equally
+    spaced genomes travel as one strided copy, the others one by one; thresholds lowered so that 30 small genomes make
+    several chunks.  Same matrix as from a resident batch; SKS_HOST_STREAM=0 takes the in-place route again."""
+    import os
+    import torch
+    ctx = sks.Context(0)
+    mask, w = sks.seed_to_mask(C3_SEED)
+    pred = sks.frac_min_hash(1, 20)
+    lens = [400_003] * 12 + [150_000 + 7919 * g for g in range(10)] + [262_144] * 8      # a run, ragged ones, a run
+    n = len(lens)
+    batches = [ctx.synth(L, [1000 + g % 3], [2000 + g], [DS[g % 6]]) for g, L in enumerate(lens)]
+    words = [(L + 15) // 16 for L in lens]
+    offs, at = [], 0
+    for g in range(n):
+        offs.append(at)
+        at += (words[g] + 3) // 4 * 4 + (8 if g == 15 else 0)       # 16-byte aligned starts; one irregular gap
+    host = torch.zeros(at, dtype=torch.int32).pin_memory()
+    hnp = host.numpy().view(np.uint32)
+    for g in range(n):
+        hnp[offs[g]:offs[g] + words[g]] = batches[g].download(0)
+    ptrs = [host.data_ptr() + 4 * o for o in offs]
+    # expected: every genome sketched on its own, all-vs-all of the sets
+    sets = [ctx.sketch(b, mask, w, pred, sks.REPR_SORTED)[0] for b in batches]
+    want = ctx.all_vs_all(sets)
+    for g in (0, 13, 29):
+        assert np.array_equal(sets[g].keys(), port.sketch_set(port.mutate(port.gen(lens[g], 1000 + g % 3), 2000 + g, DS[g % 6]) if DS[g % 6] else port.gen(lens[g], 1000 + g % 3),
+                                                              [lens[g]], mask, w, port.FMH, 1, 20, 181))
+    for s_ in sets:
+        s_.close()
+
+    def fresh():
+        return np.zeros((n, n), np.int32), np.zeros(n, np.int32), np.zeros((n, n), np.float64)
+
+    saved = {k: os.environ.get(k) for k in ("SKS_HOST_STREAM", "SKS_HOST_STREAM_MIN_MB", "SKS_HOST_CHUNK_MB")}
+    try:
+        os.environ["SKS_HOST_STREAM_MIN_MB"] = "0"
+        os.environ["SKS_HOST_CHUNK_MB"] = "1"
+        os.environ.pop("SKS_HOST_STREAM", None)
+        s0, p0 = ctx.streamed_calls, ctx.in_place_calls
+        for _ in range(3):
+            got = ctx.all_vs_all_from_host(None, ptrs, lens, n, mask, w, pred, fresh())
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+        assert ctx.streamed_calls - s0 == 3 and ctx.in_place_calls == p0
+        os.environ["SKS_HOST_STREAM"] = "0"
+        got = ctx.all_vs_all_from_host(None, ptrs, lens, n, mask, w, pred, fresh())
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+        assert ctx.streamed_calls - s0 == 3 and ctx.in_place_calls == p0 + 1
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    ctx.close()
+
+
 def test_configs3_full_size_matrix_digest():
     """BASELINE configs[3] at full size (1000 x 5 Mbp, all 10^6 ordered pairs) on one GPU: the sha256 of the count matrix and
     of the sizes equal the recorded values (bench.py; first produced by the pairwise kernels, which the parity tests pin
