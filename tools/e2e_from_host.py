@@ -1,6 +1,7 @@
+"""Dev tool: sks_all_vs_all_from_host on 1000 x 5 Mbp pinned host genomes, in place against streamed, by chunk size."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import spaced_kmer_sketching_b200 as sks
 G = 1000; L = 5_000_000

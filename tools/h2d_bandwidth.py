@@ -1,3 +1,4 @@
+"""Dev tool: host-to-device copy bandwidth of the box by chunk size (pinned memory)."""
 import torch, time
 n = 1_250_000_000
 h = torch.empty(n, dtype=torch.uint8).pin_memory()
