@@ -325,8 +325,10 @@ int sks_all_vs_all_resident(sks_ctx *ctx, sks_comm *comm, const sks_batch *batch
  * each); they are brought to the device, sketched, exchanged and compared.  = parallel_kmer_sets_from_fasta_files + the
  * comparison loop of src/kmer-sketching.cpp:163-200.  Pinned host memory of 64 MB and more is copied chunk by chunk
  * (16 MB) by the copy engine while the sketch kernel works on the chunks that are there (sks_ctx_streamed_count);
- * smaller pinned inputs are read in place by the kernel (sks_ctx_in_place_count); pageable memory is copied up first.
- * The call returns after the device has finished with the buffers. */
+ * pageable memory of that size goes the same way through pinned staging buffers that a few host threads fill
+ * (SKS_HOST_THREADS, default: the cores divided by the ranks, at most 8).  Smaller pinned inputs are read in place by
+ * the kernel (sks_ctx_in_place_count), smaller pageable ones are copied up first.  The call returns after the device
+ * has finished with the buffers. */
 int sks_all_vs_all_from_host(sks_ctx *ctx, sks_comm *comm, int n_local, const uint32_t *const *packed, const uint64_t *n_bases,
                              int64_t n_total, const uint64_t mask[2], int window, const sks_pred *pred, int32_t *out_counts,
                              int32_t *out_sizes, double *out_ani);

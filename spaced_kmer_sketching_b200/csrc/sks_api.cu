@@ -5,8 +5,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 
@@ -576,9 +578,20 @@ int sketch_raw_one(sks_ctx *ctx, const sks_batch *batch, const uint64_t mask[2],
 namespace {
 
 // The context's stream waits for the last copy of a batch that is still arriving (no-op for every other batch).
-int batch_arrived(sks_ctx *ctx, const sks_batch *batch) {
-  if (!batch->arriving.empty()) SKS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, batch->arriving.back().ready, 0));
+// Chunk c of a batch that is still arriving: its copy and its event are queued (pageable sources: the feeder thread
+// gets there in its own time), the context's stream waits for the event.
+int batch_chunk_ready(sks_ctx *ctx, const sks_batch *batch, size_t c) {
+  if (batch->feed) {
+    sks_batch::Feed *feed = batch->feed.get();
+    std::unique_lock<std::mutex> lk(feed->m);
+    feed->cv.wait(lk, [&] { return feed->n_queued > c || feed->status != SKS_OK; });
+    if (feed->status != SKS_OK) return set_error(feed->status, "copying the host genomes to the device failed");
+  }
+  SKS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, batch->arriving[c].ready, 0));
   return SKS_OK;
+}
+int batch_arrived(sks_ctx *ctx, const sks_batch *batch) {
+  return batch->arriving.empty() ? (int)SKS_OK : batch_chunk_ready(ctx, batch, batch->arriving.size() - 1);
 }
 
 int sketch_sorted(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const sks_pred *pred,
@@ -627,8 +640,9 @@ int sketch_sorted(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
       } else {
         // the genomes are still on their way from the host: every chunk is sketched as soon as it is there, into the same
         // regions, while the copy engine brings the next one
-        for (const sks_batch::Arriving &chunk : batch->arriving) {
-          SKS_CUDA_TRY(cudaStreamWaitEvent(ctx->stream, chunk.ready, 0));
+        for (size_t c = 0; c < batch->arriving.size(); ++c) {
+          const sks_batch::Arriving &chunk = batch->arriving[c];
+          SKS_TRY(batch_chunk_ready(ctx, batch, c));
           plan.p.tile_begin = chunk.tile_begin;
           plan.p.n_tiles = chunk.tile_end;
           SKS_TRY(launch_sketch(ctx, plan.p, tile_genome, plan.n_limbs, plan.pred_mode, OUT_KEYS));
@@ -730,6 +744,7 @@ void sks_ctx_destroy(sks_ctx *ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (cudaEvent_t e : ctx->sync_events) cudaEventDestroy(e);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->stage_ring) cudaFreeHost(ctx->stage_ring);
   for (auto &v : ctx->prof)
     for (auto &pr : v) {
       cudaEventDestroy(pr.first);
@@ -903,16 +918,86 @@ __global__ void zero_pads_kernel(uint32_t *words, const GenomeDesc *genomes, int
   for (unsigned long long i = lo + (threadIdx.x & 31); i < hi; i += 32) words[i] = 0;
 }
 
-// A device batch for genomes in pinned host buffers that is filled WHILE it is sketched: the copy engine brings the
-// genomes chunk by chunk (SKS_HOST_CHUNK_MB, default 16 MB: large copies reach 55 GB/s on PCIe 5 where the sketch
-// kernel's own 2 KB reads of host memory stay at 44 GB/s; 8 to 64 MB measure the same, 27.3 ms against 31.1 ms for
-// 1000 x 5 Mbp), every chunk records an event, and sketch_sorted launches the
-// kernel chunk by chunk behind them.  Only for sks_all_vs_all_from_host, which keeps the batch to itself, and only from
-// SKS_HOST_STREAM_MIN_MB (default 64) on: below that the in-place route has less to set up.  SKS_HOST_STREAM=0: off.
-static int batch_streamed(sks_ctx *ctx, int n_genomes, const uint32_t *const *packed, const uint64_t *n_bases,
+// A device batch for genomes in host buffers that is filled WHILE it is sketched: the copy engine brings the genomes
+// chunk by chunk (SKS_HOST_CHUNK_MB, default 16 MB: large copies reach 55 GB/s on PCIe 5 where the sketch kernel's own
+// 2 KB reads of host memory stay at 44 GB/s; 8 to 64 MB measure the same, 27.3 ms against 31.1 ms for 1000 x 5 Mbp), every
+// chunk records an event, and sketch_sorted launches the kernel chunk by chunk behind them.
+//   pinned buffers   : all copies are queued here, straight from the caller's memory (a run of equally long, equally
+//                      spaced genomes is one strided copy);
+//   pageable buffers : a feeder thread and its helpers copy chunk after chunk into a ring of three pinned staging
+//                      buffers -- laid out like the device buffer, so that a chunk is one copy -- and queue the copies as
+//                      they go; the consumers wait for "chunk c is queued" (sks_batch::Feed) before they wait for its
+//                      event.  cudaMemcpyAsync from pageable memory goes through the driver's own staging at ~10 GB/s:
+//                      136 ms for 1000 x 5 Mbp, against 28.5 ms this way with 8 threads (59 ms with 2, 35 ms with 4).
+// Only for sks_all_vs_all_from_host, which keeps the batch to itself, and only from SKS_HOST_STREAM_MIN_MB (default 64)
+// on: below that the in-place route / a plain upload have less to set up.  SKS_HOST_STREAM=0: off.
+namespace {
+struct CopyPiece {
+  char *dst;
+  const char *src;
+  size_t bytes;
+};
+// The feeder's helpers: run() hands a list of host copies to all threads (the caller takes part) and returns when done.
+struct CopyTeam {
+  std::vector<std::thread> helpers;
+  std::mutex m;
+  std::condition_variable cv_start, cv_done;
+  const std::vector<CopyPiece> *pieces = nullptr;
+  std::atomic<size_t> next{0};
+  int generation = 0, running = 0;
+  bool stop = false;
+  explicit CopyTeam(int n_helpers) {
+    for (int i = 0; i < n_helpers; ++i) helpers.emplace_back([this] { loop(); });
+  }
+  ~CopyTeam() {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      stop = true;
+    }
+    cv_start.notify_all();
+    for (std::thread &t : helpers) t.join();
+  }
+  void work() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= pieces->size()) return;
+      memcpy((*pieces)[i].dst, (*pieces)[i].src, (*pieces)[i].bytes);
+    }
+  }
+  void loop() {
+    int seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> lk(m);
+      cv_start.wait(lk, [&] { return stop || generation != seen; });
+      if (stop) return;
+      seen = generation;
+      lk.unlock();
+      work();
+      lk.lock();
+      if (--running == 0) cv_done.notify_one();
+    }
+  }
+  void run(const std::vector<CopyPiece> &p) {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      pieces = &p;
+      next = 0;
+      running = (int)helpers.size();
+      ++generation;
+    }
+    cv_start.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m);
+    cv_done.wait(lk, [&] { return running == 0; });
+  }
+};
+}  // namespace
+
+static int batch_streamed(sks_ctx *ctx, int n_genomes, const uint32_t *const *packed, const uint64_t *n_bases, int world,
                           sks_batch **out) {
   // (read at every call: the tests change them)
   const char *e_on = getenv("SKS_HOST_STREAM"), *e_min = getenv("SKS_HOST_STREAM_MIN_MB"), *e_chunk = getenv("SKS_HOST_CHUNK_MB");
+  const char *e_threads = getenv("SKS_HOST_THREADS");
   const bool enabled = !e_on || atoi(e_on) != 0;
   const uint64_t min_bytes = (uint64_t)std::max<long long>(e_min ? atoll(e_min) : 64, 0) << 20;
   const uint64_t chunk_bytes = (uint64_t)std::max<long long>(e_chunk ? atoll(e_chunk) : 16, 1) << 20;
@@ -924,58 +1009,90 @@ static int batch_streamed(sks_ctx *ctx, int n_genomes, const uint32_t *const *pa
     total_bytes += (n_bases[g] + 15) / 16 * 4;
   }
   if (total_bytes < min_bytes) return SKS_ERR_INVALID;
+  int n_pinned = 0, n_pageable = 0;
   for (int g = 0; g < n_genomes; ++g) {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, packed[g]) != cudaSuccess) {
       cudaGetLastError();
       return SKS_ERR_INVALID;
     }
-    if (attr.type != cudaMemoryTypeHost) return SKS_ERR_INVALID;  // pageable: the copies would not be asynchronous
+    if (attr.type == cudaMemoryTypeHost) ++n_pinned;
+    else if (attr.type == cudaMemoryTypeUnregistered) ++n_pageable;
   }
+  const bool staged = n_pageable == n_genomes;
+  if (!staged && n_pinned != n_genomes) return SKS_ERR_INVALID;  // device, managed or mixed memory: the plain upload
   sks_batch *b = new (std::nothrow) sks_batch();
   if (!b) return SKS_ERR_INVALID;
   b->device = ctx->device;
   uint64_t total_words = 0;
   int st = layout_batch(b, n_genomes, n_bases, nullptr, nullptr, &total_words);
-  if (st == SKS_OK) st = alloc_buffer(ctx, (size_t)total_words * 4, &b->words);
+  // chunks: whole genomes, at least chunk_bytes each (but for the last); the device words of chunk [g0, g1) are
+  // [word_off(g0) - kPreWords, word_off(g1 - 1) + n_words(g1 - 1)), the last chunk runs to the end of the buffer
+  struct Chunk {
+    int g0, g1;
+    uint64_t w0, w1;
+  };
+  std::vector<Chunk> chunks;
+  uint64_t slot_words = 0;
+  if (st == SKS_OK) {
+    for (int g = 0; g < n_genomes;) {
+      Chunk c{g, g, 0, 0};
+      uint64_t bytes = 0;
+      while (c.g1 < n_genomes && bytes < chunk_bytes) bytes += (n_bases[c.g1++] + 15) / 16 * 4;
+      c.w0 = b->h_genomes[c.g0].word_off - kPreWords;
+      c.w1 = c.g1 == n_genomes ? total_words : b->h_genomes[c.g1 - 1].word_off + b->h_genomes[c.g1 - 1].n_words;
+      slot_words = std::max(slot_words, c.w1 - c.w0);
+      chunks.push_back(c);
+      g = c.g1;
+    }
+    if (staged && slot_words * 4 > ((uint64_t)256 << 20)) st = SKS_ERR_INVALID;  // one huge genome: not worth a 768 MB ring
+  }
+  if (st != SKS_OK) {
+    delete b;
+    return SKS_ERR_INVALID;
+  }
+  st = alloc_buffer(ctx, (size_t)total_words * 4, &b->words);
   if (st == SKS_OK) st = upload_tables(ctx, b);
   auto fail = [&](cudaError_t e) { return e == cudaSuccess ? SKS_OK : set_error(SKS_ERR_CUDA, "streamed batch: %s", cudaGetErrorString(e)); };
   if (st == SKS_OK && !ctx->copy_stream) st = fail(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  size_t n_events = 0;
-  auto next_event = [&](cudaEvent_t *ev) {
-    if (n_events == ctx->sync_events.size()) {
-      cudaEvent_t e;
-      if (int r = fail(cudaEventCreateWithFlags(&e, cudaEventDisableTiming))) return r;
-      ctx->sync_events.push_back(e);
-    }
-    *ev = ctx->sync_events[n_events++];
-    return (int)SKS_OK;
-  };
+  while (st == SKS_OK && ctx->sync_events.size() < chunks.size() + 1) {
+    cudaEvent_t e;
+    st = fail(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (st == SKS_OK) ctx->sync_events.push_back(e);
+  }
+  if (st == SKS_OK && staged && ctx->stage_ring_bytes < 3 * slot_words * 4) {
+    if (ctx->stage_ring) cudaFreeHost(ctx->stage_ring);
+    ctx->stage_ring = nullptr;
+    ctx->stage_ring_bytes = 0;
+    st = fail(cudaMallocHost(&ctx->stage_ring, 3 * slot_words * 4));
+    if (st == SKS_OK) ctx->stage_ring_bytes = 3 * slot_words * 4;
+  }
+  uint32_t *d = st == SKS_OK ? static_cast<uint32_t *>(b->words->ptr) : nullptr;
   if (st == SKS_OK) {
-    uint32_t *d = static_cast<uint32_t *>(b->words->ptr);
-    // the buffer may have been in use by earlier work of the context's stream: the copies start behind it
-    cudaEvent_t free_ev = nullptr;
-    st = next_event(&free_ev);
-    if (st == SKS_OK) st = fail(cudaEventRecord(free_ev, ctx->stream));
-    if (st == SKS_OK) st = fail(cudaStreamWaitEvent(ctx->copy_stream, free_ev, 0));
-    if (st == SKS_OK) {
-      zero_pads_kernel<<<(unsigned)((n_genomes + 1 + 7) / 8), 256, 0, ctx->stream>>>(d, static_cast<const GenomeDesc *>(b->genomes->ptr),
-                                                                                 n_genomes, (unsigned long long)total_words);
-      st = fail(cudaGetLastError());
-      ctx->launches++;
+    // what lies between the genomes is zeroed here (the pinned route copies the data words only); the buffer may have
+    // been in use by earlier work of the context's stream: the copies start behind all that
+    zero_pads_kernel<<<(unsigned)((n_genomes + 1 + 7) / 8), 256, 0, ctx->stream>>>(d, static_cast<const GenomeDesc *>(b->genomes->ptr),
+                                                                               n_genomes, (unsigned long long)total_words);
+    st = fail(cudaGetLastError());
+    ctx->launches++;
+    if (st == SKS_OK) st = fail(cudaEventRecord(ctx->sync_events[chunks.size()], ctx->stream));
+    if (st == SKS_OK) st = fail(cudaStreamWaitEvent(ctx->copy_stream, ctx->sync_events[chunks.size()], 0));
+  }
+  if (st == SKS_OK)
+    for (size_t c = 0; c < chunks.size(); ++c) {
+      const GenomeDesc &first = b->h_genomes[chunks[c].g0], &last = b->h_genomes[chunks[c].g1 - 1];
+      b->arriving.push_back({first.tile_first, last.tile_first + last.n_tiles, ctx->sync_events[c]});
     }
-    int g = 0;
-    while (g < n_genomes && st == SKS_OK) {
-      const int chunk_first = g;
-      uint64_t bytes = 0;
-      while (g < n_genomes && bytes < chunk_bytes && st == SKS_OK) {
+  if (st == SKS_OK && !staged) {
+    for (size_t c = 0; c < chunks.size() && st == SKS_OK; ++c) {
+      for (int g = chunks[c].g0; g < chunks[c].g1 && st == SKS_OK;) {
         // a run of equally long, equally spaced genomes is one strided copy
         const uint64_t row = (n_bases[g] + 15) / 16 * 4;
         int run = 1;
-        if (g + 1 < n_genomes && n_bases[g + 1] == n_bases[g] && packed[g + 1] > packed[g]) {
+        if (g + 1 < chunks[c].g1 && n_bases[g + 1] == n_bases[g] && packed[g + 1] > packed[g]) {
           const uint64_t pitch = (uint64_t)(reinterpret_cast<const char *>(packed[g + 1]) - reinterpret_cast<const char *>(packed[g]));
           if (pitch >= row && pitch < ((uint64_t)1 << 31)) {
-            while (g + run < n_genomes && n_bases[g + run] == n_bases[g] && bytes + (uint64_t)run * row < chunk_bytes &&
+            while (g + run < chunks[c].g1 && n_bases[g + run] == n_bases[g] &&
                    reinterpret_cast<const char *>(packed[g + run]) == reinterpret_cast<const char *>(packed[g]) + (uint64_t)run * pitch)
               ++run;
             if (run > 1)
@@ -984,17 +1101,61 @@ static int batch_streamed(sks_ctx *ctx, int n_genomes, const uint32_t *const *pa
           }
         }
         if (run == 1) st = fail(cudaMemcpyAsync(d + b->h_genomes[g].word_off, packed[g], (size_t)row, cudaMemcpyHostToDevice, ctx->copy_stream));
-        bytes += (uint64_t)run * row;
         g += run;
       }
-      cudaEvent_t ready = nullptr;
-      if (st == SKS_OK) st = next_event(&ready);
-      if (st == SKS_OK) st = fail(cudaEventRecord(ready, ctx->copy_stream));
-      if (st == SKS_OK) {
-        const GenomeDesc &last = b->h_genomes[g - 1];
-        b->arriving.push_back({b->h_genomes[chunk_first].tile_first, last.tile_first + last.n_tiles, ready});
-      }
+      if (st == SKS_OK) st = fail(cudaEventRecord(b->arriving[c].ready, ctx->copy_stream));
     }
+  }
+  if (st == SKS_OK && staged) {
+    int n_threads = e_threads ? atoi(e_threads) : (int)std::thread::hardware_concurrency() / std::max(world, 1);  // the ranks of a node share its cores
+    n_threads = std::min(std::max(n_threads, 1), 8);
+    b->feed.reset(new (std::nothrow) sks_batch::Feed());
+    if (!b->feed) st = set_error(SKS_ERR_INVALID, "out of host memory");
+  if (st == SKS_OK) {
+    sks_batch::Feed *feed = b->feed.get();
+    const int device = ctx->device;
+    cudaStream_t copy_stream = ctx->copy_stream;
+    char *ring = static_cast<char *>(ctx->stage_ring);
+    const size_t slot_bytes = (size_t)slot_words * 4;
+    std::vector<const uint32_t *> src(packed, packed + n_genomes);
+    const sks_batch *batch = b;
+    feed->worker = std::thread([=]() {
+      auto done = [&](size_t n, int status) {
+        {
+          std::lock_guard<std::mutex> lk(feed->m);
+          feed->n_queued = n;
+          if (status != SKS_OK) feed->status = status;
+        }
+        feed->cv.notify_all();
+      };
+      if (cudaSetDevice(device) != cudaSuccess) return done(chunks.size(), SKS_ERR_CUDA);
+      CopyTeam team(n_threads - 1);
+      std::vector<CopyPiece> pieces;
+      const size_t kPiece = (size_t)256 << 10;
+      for (size_t c = 0; c < chunks.size(); ++c) {
+        char *slot = ring + (c % 3) * slot_bytes;
+        // the copy that read this slot three chunks ago must be over
+        if (c >= 3 && cudaEventSynchronize(batch->arriving[c - 3].ready) != cudaSuccess) return done(chunks.size(), SKS_ERR_CUDA);
+        pieces.clear();
+        uint64_t at = chunks[c].w0;  // device word the next zero gap starts at
+        for (int g = chunks[c].g0; g < chunks[c].g1; ++g) {
+          const GenomeDesc &gd = batch->h_genomes[g];
+          const size_t bytes = (size_t)((gd.n_bases + 15ull) / 16) * 4;
+          memset(slot + (at - chunks[c].w0) * 4, 0, (size_t)(gd.word_off - at) * 4);
+          char *dst = slot + (gd.word_off - chunks[c].w0) * 4;
+          const char *from = reinterpret_cast<const char *>(src[g]);
+          for (size_t o = 0; o < bytes; o += kPiece) pieces.push_back({dst + o, from + o, std::min(kPiece, bytes - o)});
+          at = gd.word_off + bytes / 4;
+        }
+        memset(slot + (at - chunks[c].w0) * 4, 0, (size_t)(chunks[c].w1 - at) * 4);
+        team.run(pieces);
+        if (cudaMemcpyAsync(d + chunks[c].w0, slot, (size_t)(chunks[c].w1 - chunks[c].w0) * 4, cudaMemcpyHostToDevice, copy_stream) != cudaSuccess ||
+            cudaEventRecord(batch->arriving[c].ready, copy_stream) != cudaSuccess)
+          return done(chunks.size(), SKS_ERR_CUDA);
+        done(c + 1, SKS_OK);
+      }
+    });
+  }
   }
   if (st != SKS_OK) {
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);  // nothing of a failed call may touch the caller's buffers later
@@ -1975,7 +2136,7 @@ int sks_all_vs_all_from_host(sks_ctx *ctx, sks_comm *comm, int n_local, const ui
   if (n_local > 0) {
     // pinned and large: copied chunk by chunk under the sketch kernel; pinned and small: read in place by the kernel;
     // pageable (or misaligned): copied up first
-    if (batch_streamed(ctx, n_local, packed, n_bases, &batch) == SKS_OK)
+    if (batch_streamed(ctx, n_local, packed, n_bases, comm ? sks_comm_world(comm) : 1, &batch) == SKS_OK)
       ctx->streamed_calls++;
     else if (batch_in_place(ctx, n_local, packed, n_bases, &batch) != SKS_OK)
       st = sks_batch_upload(ctx, n_local, packed, n_bases, nullptr, nullptr, &batch);
@@ -1983,7 +2144,10 @@ int sks_all_vs_all_from_host(sks_ctx *ctx, sks_comm *comm, int n_local, const ui
     if (st == SKS_OK) st = sks_sketch(ctx, batch, mask, window, pred, SKS_REPR_SORTED, sets.data());
     // sks_sketch has read the counts back: the copies and the kernel are done with the caller's buffers -- unless it
     // failed on the way
-    if (st != SKS_OK && batch && !batch->arriving.empty()) cudaStreamSynchronize(ctx->copy_stream);
+    if (st != SKS_OK && batch && !batch->arriving.empty()) {
+      if (batch->feed && batch->feed->worker.joinable()) batch->feed->worker.join();
+      cudaStreamSynchronize(ctx->copy_stream);
+    }
   }
   if (st == SKS_OK) st = sks_all_vs_all_sharded(ctx, comm, sets.data(), n_local, n_total, out_counts, out_sizes, out_ani);
   for (sks_set *s : sets)

@@ -5,7 +5,10 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <utility>
 #include <string>
 #include <vector>
@@ -208,6 +211,8 @@ struct sks_ctx {
   int64_t streamed_calls = 0;  // sks_all_vs_all_from_host calls whose genomes arrived chunk by chunk under the sketch kernel
   cudaStream_t copy_stream = nullptr;    // host-to-device copies of a batch that is sketched while it arrives
   std::vector<cudaEvent_t> sync_events;  // one per chunk of such a batch (no timing), reused by the next call
+  void *stage_ring = nullptr;            // three pinned staging buffers for pageable sources of such a batch
+  size_t stage_ring_bytes = 0;
   // reusable scratch (grown on demand)
   void *scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -245,6 +250,18 @@ struct sks_batch {
     cudaEvent_t ready;
   };
   std::vector<Arriving> arriving;
+  // pageable sources: a feeder thread stages and queues the copies; chunk c may be waited for once n_queued > c
+  struct Feed {
+    std::mutex m;
+    std::condition_variable cv;
+    size_t n_queued = 0;
+    int status = 0;
+    std::thread worker;
+    ~Feed() {
+      if (worker.joinable()) worker.join();
+    }
+  };
+  std::unique_ptr<Feed> feed;
 };
 
 struct sks_set {

@@ -179,7 +179,8 @@ def test_pinned_host_genomes_are_streamed_under_the_sketch_kernel():
     """sks_all_vs_all_from_host on pinned host buffers above the streaming threshold (csrc/sks_api.cu, batch_streamed): the
     copy engine brings the genomes chunk by chunk, every chunk is sketched behind its own event.  Equally long, equally
     spaced genomes travel as one strided copy, the others one by one; thresholds lowered so that 30 small genomes make
-    several chunks.  Same matrix as from a resident batch; SKS_HOST_STREAM=0 takes the in-place route again."""
+    several chunks.  Pageable buffers go the same way through a feeder thread and pinned staging buffers.  Same matrix as
+    from a resident batch; SKS_HOST_STREAM=0 takes the in-place route / the plain upload again."""
     import os
     import torch
     ctx = sks.Context(0)
@@ -210,7 +211,7 @@ def test_pinned_host_genomes_are_streamed_under_the_sketch_kernel():
     def fresh():
         return np.zeros((n, n), np.int32), np.zeros(n, np.int32), np.zeros((n, n), np.float64)
 
-    saved = {k: os.environ.get(k) for k in ("SKS_HOST_STREAM", "SKS_HOST_STREAM_MIN_MB", "SKS_HOST_CHUNK_MB")}
+    saved = {k: os.environ.get(k) for k in ("SKS_HOST_STREAM", "SKS_HOST_STREAM_MIN_MB", "SKS_HOST_CHUNK_MB", "SKS_HOST_THREADS")}
     try:
         os.environ["SKS_HOST_STREAM_MIN_MB"] = "0"
         os.environ["SKS_HOST_CHUNK_MB"] = "1"
@@ -220,10 +221,24 @@ def test_pinned_host_genomes_are_streamed_under_the_sketch_kernel():
             got = ctx.all_vs_all_from_host(None, ptrs, lens, n, mask, w, pred, fresh())
             assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
         assert ctx.streamed_calls - s0 == 3 and ctx.in_place_calls == p0
+        # pageable memory: a feeder thread stages the chunks through pinned buffers and queues the copies as it goes
+        pageable = np.array(hnp, copy=True)
+        pptrs = [pageable.ctypes.data + 4 * o for o in offs]
+        for threads in ("1", "3", None):
+            if threads is None:
+                os.environ.pop("SKS_HOST_THREADS", None)
+            else:
+                os.environ["SKS_HOST_THREADS"] = threads
+            got = ctx.all_vs_all_from_host(None, pptrs, lens, n, mask, w, pred, fresh())
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]), threads
+        assert ctx.streamed_calls - s0 == 6 and ctx.in_place_calls == p0
         os.environ["SKS_HOST_STREAM"] = "0"
         got = ctx.all_vs_all_from_host(None, ptrs, lens, n, mask, w, pred, fresh())
         assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
-        assert ctx.streamed_calls - s0 == 3 and ctx.in_place_calls == p0 + 1
+        assert ctx.streamed_calls - s0 == 6 and ctx.in_place_calls == p0 + 1
+        got = ctx.all_vs_all_from_host(None, pptrs, lens, n, mask, w, pred, fresh())      # pageable, plain upload
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+        assert ctx.streamed_calls - s0 == 6 and ctx.in_place_calls == p0 + 1
     finally:
         for k, v in saved.items():
             if v is None:

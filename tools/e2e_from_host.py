@@ -30,9 +30,19 @@ def run(tag):
     print(tag, "e2e ms", [round(t, 2) for t in ts], "streamed", ctx.streamed_calls, "in place", ctx.in_place_calls, flush=True)
 os.environ["SKS_HOST_STREAM"] = "0"; run("in place")
 os.environ["SKS_HOST_STREAM"] = "1"
-for mb in (4, 8, 16, 32, 64, 128):
+for mb in (8, 16, 32):
     os.environ["SKS_HOST_CHUNK_MB"] = str(mb); run("chunk %d MB" % mb)
+pageable = np.array(hnp, copy=True)
+pinned_ptrs = ptrs
+ptrs = [pageable.ctypes.data + 4 * g * stride for g in range(G)]
+os.environ["SKS_HOST_CHUNK_MB"] = "16"
+os.environ["SKS_HOST_STREAM"] = "0"; run("pageable, plain upload")
+os.environ["SKS_HOST_STREAM"] = "1"
+for th in (1, 2, 4, 8, 16):
+    os.environ["SKS_HOST_THREADS"] = str(th); run("pageable, staged, %d threads" % th)
+os.environ.pop("SKS_HOST_THREADS")
+ptrs = pinned_ptrs
 ctx.profile(True); ctx.kernel_stats()
-os.environ["SKS_HOST_CHUNK_MB"] = "32"
+os.environ["SKS_HOST_CHUNK_MB"] = "16"
 ctx.all_vs_all_from_host(None, ptrs, [L] * G, G, mask, w, pred, out)
 print({k: (v[0], round(v[1], 3)) for k, v in ctx.kernel_stats().items()})
