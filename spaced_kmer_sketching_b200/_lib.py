@@ -142,6 +142,30 @@ def load():
     return _lib
 
 
+_nccl_preloaded = False
+
+
+def preload_nccl() -> None:
+    """libsks binds NCCL at run time (csrc/sks_comm.cu: SKS_NCCL_LIB, else a libnccl.so.2 already in the process, else
+    the system's).  A Python process that imports torch AFTER its first communicator would then hold the system's NCCL
+    where libtorch_cuda.so expects the newer one of the `nvidia-nccl` wheel and fail to import; so the wheel's library,
+    when there is one, is loaded first."""
+    global _nccl_preloaded
+    if _nccl_preloaded or os.environ.get("SKS_NCCL_LIB"):
+        return
+    _nccl_preloaded = True
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for loc in (spec.submodule_search_locations if spec else []):
+            path = os.path.join(loc, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:      # no wheel, or it does not load here: libsks finds its own
+        pass
+
+
 def check(status: int) -> None:
     if status != SKS_OK:
         raise SksError(status, load().sks_last_error().decode("utf-8", "replace"))

@@ -456,6 +456,7 @@ COMM_ID_BYTES = 128
 def comm_unique_id() -> bytes:
     """The 128-byte NCCL id rank 0 makes; the launcher carries it to the other ranks (multi_gpu.init_comm)."""
     buf = C.create_string_buffer(COMM_ID_BYTES)
+    _lib.preload_nccl()
     check(_lib.load().sks_comm_unique_id(buf))
     return buf.raw
 
@@ -464,6 +465,7 @@ class Comm:
     """One rank's communicator (C ABI: sks_comm_*).  `None` everywhere a Comm is expected means a single rank."""
 
     def __init__(self, ctx: "Context", comm_id: bytes, rank: int, world: int):
+        _lib.preload_nccl()
         self._L = _lib.load()
         self.ctx, self.rank, self.world = ctx, rank, world
         h = C.c_void_p()
@@ -474,6 +476,7 @@ class Comm:
     def init_all(cls, ctxs: Sequence["Context"]) -> List["Comm"]:
         """One process, one context per GPU: communicators for all of them (sks_comm_init_all); the sharded calls are
         then made from one thread per context."""
+        _lib.preload_nccl()
         L = _lib.load()
         n = len(ctxs)
         hs = (C.c_void_p * n)(*[c.h for c in ctxs])

@@ -44,6 +44,22 @@ def test_comm_id_is_made_without_a_gpu():
     assert len(a) == engine.COMM_ID_BYTES == 128 and a != b
 
 
+def test_torch_still_imports_after_the_first_communicator_call():
+    """libsks binds NCCL at run time; a process that touches a communicator entry point before it imports torch must not
+    end up with the system's older libnccl where libtorch_cuda.so needs the wheel's (engine -> _lib.preload_nccl)."""
+    import subprocess
+    import sys
+    code = ("from spaced_kmer_sketching_b200 import engine\n"
+            "assert len(engine.comm_unique_id()) == 128\n"
+            "import torch\n"
+            "import torch.distributed\n"
+            "print('ok', torch.__version__)\n")
+    env = {k: v for k, v in os.environ.items() if k != "SKS_NCCL_LIB"}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
