@@ -420,7 +420,7 @@ def run_b200(args):
         streamed = ctx.streamed_calls - streamed0 == args.steps
         h2d = int(n_loc * words * 4 + n_loc * (32 + 4 + 4))       # packed bases + genome descriptors + segment ends + tile map (per rank)
         d2h = int(n_loc * n * 12 + n * 4)                         # the rank's rows: int32 counts + float64 ANI, and the n sizes
-        # pageable host buffers take the copy path (cudaMemcpyAsync through the driver's staging)
+        # pageable host buffers: staged through pinned ring buffers by host threads, chunk by chunk under the sketch kernel
         pageable = np.array(hnp, copy=True)
         pptrs = [pageable.ctypes.data + 4 * g * stride for g in range(n_loc)]
         pg_wall = []

@@ -947,7 +947,14 @@ struct CopyTeam {
   int generation = 0, running = 0;
   bool stop = false;
   explicit CopyTeam(int n_helpers) {
-    for (int i = 0; i < n_helpers; ++i) helpers.emplace_back([this] { loop(); });
+    helpers.reserve(n_helpers > 0 ? n_helpers : 0);
+    for (int i = 0; i < n_helpers; ++i) {
+      try {
+        helpers.emplace_back([this] { loop(); });
+      } catch (...) {  // no more threads to be had: fewer helpers
+        break;
+      }
+    }
   }
   ~CopyTeam() {
     {
@@ -1119,7 +1126,7 @@ static int batch_streamed(sks_ctx *ctx, int n_genomes, const uint32_t *const *pa
     const size_t slot_bytes = (size_t)slot_words * 4;
     std::vector<const uint32_t *> src(packed, packed + n_genomes);
     const sks_batch *batch = b;
-    feed->worker = std::thread([=]() {
+    auto feeder = [=]() {
       auto done = [&](size_t n, int status) {
         {
           std::lock_guard<std::mutex> lk(feed->m);
@@ -1154,7 +1161,12 @@ static int batch_streamed(sks_ctx *ctx, int n_genomes, const uint32_t *const *pa
           return done(chunks.size(), SKS_ERR_CUDA);
         done(c + 1, SKS_OK);
       }
-    });
+    };
+    try {
+      feed->worker = std::thread(feeder);
+    } catch (...) {
+      st = set_error(SKS_ERR_INVALID, "could not start the thread that stages the host genomes");
+    }
   }
   }
   if (st != SKS_OK) {
