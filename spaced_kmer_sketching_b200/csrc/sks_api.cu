@@ -602,7 +602,11 @@ int sketch_sorted(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
   std::vector<uint64_t> off, count, uoff, ucount;
   uint64_t span = 0;
   bool done = false;
-  if (key_words == 1 && plan.pred_mode != PRED_ALL && pred->modulus > 1) {
+  // (a context whose last attempt overflowed skips the next 63: the genomes of one workload tend to look alike, and a
+  // failed attempt costs a second pass of the sketch kernel)
+  if (ctx->kpart_skip > 0) {
+    --ctx->kpart_skip;
+  } else if (key_words == 1 && plan.pred_mode != PRED_ALL && pred->modulus > 1) {
     // A sparse condition on 8-byte keys: the first level of the bucket sort (histogram + scatter by the keys' top mask
     // bits) is folded into the sketch kernel's emit -- the kept k-mers go straight into per-(genome, bucket) regions,
     // and the sort starts at its bucket kernel.  Nothing is read back in between.  A region that overflows (a genome
@@ -653,6 +657,7 @@ int sketch_sorted(sks_ctx *ctx, const sks_batch *batch, SketchPlan &plan, const 
       plan.p.kpart_bits = 0;
       SKS_TRY(sort_unique_from_buckets(ctx, static_cast<unsigned long long *>(regions->ptr), G, bb, cap, d_cursor, d_flag, total_bound,
                                        &uniq, &uoff, &ucount, &done));
+      if (!done) ctx->kpart_skip = 63;
     }
   }
   if (!done) {

@@ -208,6 +208,7 @@ struct sks_ctx {
   int sm_count = 148;
   int64_t launches = 0;
   int64_t in_place_calls = 0;  // sks_pair_ani calls that read the genomes from pinned host memory
+  int kpart_skip = 0;          // sketch_sorted: calls that still skip the folded sort partition after it overflowed
   int64_t streamed_calls = 0;  // sks_all_vs_all_from_host calls whose genomes arrived chunk by chunk under the sketch kernel
   cudaStream_t copy_stream = nullptr;    // host-to-device copies of a batch that is sketched while it arrives
   std::vector<cudaEvent_t> sync_events;  // one per chunk of such a batch (no timing), reused by the next call
